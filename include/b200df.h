@@ -1,0 +1,246 @@
+/* b200df — B200-native batched state-validity engine for MoveIt's distance-field collision path.
+ *
+ * Thin C ABI between host code (the C++ CollisionEnv mirror in moveit_b200/host/, the MoveIt plugin described in
+ * INTEGRATION.md, ctypes in tests/bench) and the hand-written sm_100a kernels in moveit_b200/csrc/.
+ * Plain pointers and sizes only.  Every call returns a status; nothing throws across this boundary; there is no
+ * CPU fallback: without a CUDA device every compute entry point returns B200DF_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to /root/reference/moveit_core).
+ *
+ * Conventions
+ *   - poses / transforms: row-major 3x4 doubles (rotation | translation), implied last row 0 0 0 1
+ *   - voxel arrays: x-major, z fastest, index = x*(ny*nz) + y*nz + z   (voxel_grid.h:426-429)
+ *   - "host" entry points take host pointers and include the H2D/D2H copies; "_device" entry points take
+ *     device pointers plus a cudaStream_t (passed as void*) and never synchronise the device.
+ */
+#ifndef B200DF_H
+#define B200DF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DF_VERSION 100
+
+enum
+{
+  B200DF_OK = 0,
+  B200DF_ERR_INVALID = 1,     /* bad argument / inconsistent handles */
+  B200DF_ERR_CUDA = 2,        /* CUDA runtime failure or no device */
+  B200DF_ERR_NOMEM = 3,
+  B200DF_ERR_UNSUPPORTED = 4, /* reference leaves it unimplemented too (e.g. continuous checks) */
+};
+
+/* joint types, matching the *JointModel::computeTransform set (robot_model/src/*_joint_model.cpp) */
+enum
+{
+  B200DF_JOINT_FIXED = 0,
+  B200DF_JOINT_REVOLUTE = 1, /* also continuous */
+  B200DF_JOINT_PRISMATIC = 2,
+  B200DF_JOINT_PLANAR = 3,
+  B200DF_JOINT_FLOATING = 4,
+};
+
+/* shapes::ShapeType values this path can rasterise (distance_field.cpp:196-219) */
+enum
+{
+  B200DF_SHAPE_SPHERE = 1,   /* dims: radius */
+  B200DF_SHAPE_CYLINDER = 2, /* dims: radius, length (axis = local z) */
+  B200DF_SHAPE_BOX = 4,      /* dims: x, y, z */
+};
+
+/* which tests a batch runs; evaluation order is irrelevant for a yes/no verdict (logical OR) */
+enum
+{
+  B200DF_CHECK_ROBOT = 1, /* group spheres vs world field      getEnvironmentCollisions  collision_env_distance_field.cpp:1580-1662 */
+  B200DF_CHECK_SELF = 2,  /* group spheres vs self field       getSelfCollisions         :277-356 */
+  B200DF_CHECK_INTRA = 4, /* sphere pairs inside the group     getIntraGroupCollisions   :433-660 */
+};
+
+/* joint-value element type of a batch */
+enum
+{
+  B200DF_Q_F32 = 0,
+  B200DF_Q_F64 = 1,
+};
+
+/* arithmetic of the validity kernels */
+enum
+{
+  B200DF_PRECISION_EXACT = 0, /* fp64 FK + fp64 voxel indexing, operation order of the reference */
+  B200DF_PRECISION_FAST = 1,  /* fp32 fast path; states whose verdict could depend on rounding are re-run EXACT */
+};
+
+/* CollisionType of a gradient entry (collision_distance_field_types.h:57-63) */
+enum
+{
+  B200DF_TYPE_NONE = 0,
+  B200DF_TYPE_SELF = 1,
+  B200DF_TYPE_INTRA = 2,
+  B200DF_TYPE_ENVIRONMENT = 3,
+};
+
+typedef struct b200df_model b200df_model; /* immutable robot description on the device */
+typedef struct b200df_group b200df_group; /* immutable (model, link subset, ACM tables, thresholds) */
+typedef struct b200df_field b200df_field; /* PropagationDistanceField replacement (occupancy + exact EDT) */
+
+/* ---- errors / device ----------------------------------------------------------------------------------- */
+const char* b200df_last_error(void); /* thread-local message of the last failing call on this thread */
+int b200df_version(void);
+int b200df_device_count(int* count);
+int b200df_set_device(int device); /* device used by handles created afterwards on this thread */
+
+/* ---- robot model -----------------------------------------------------------------------------------------
+ * Replaces the slice of moveit::core::RobotModel / LinkModel / JointModel that FK and the sphere decomposition
+ * read: robot_state.cpp:718-755, revolute_joint_model.cpp:66-75,222-259, prismatic_joint_model.cpp:119-144,
+ * fixed_joint_model.cpp:94-97, planar_joint_model.cpp:327-331, floating_joint_model.cpp:224-229, and the
+ * BodyDecomposition per link built by CollisionEnvDistanceField::addLinkBodyDecompositions
+ * (collision_env_distance_field.cpp:1065-1093).  Links are in DFS pre-order (parent index < child index). */
+typedef struct b200df_model_desc
+{
+  int32_t n_links;
+  int32_t n_vars; /* RobotState variable count; a batch row holds n_vars joint values */
+  const int32_t* parent;             /* [L] parent link index, -1 for the root */
+  const int32_t* joint_type;         /* [L] B200DF_JOINT_* of the parent joint */
+  const double* axis;                /* [L][3] joint axis (normalised by the engine like setAxis does) */
+  const double* origin;              /* [L][12] LinkModel::getJointOriginTransform */
+  const int32_t* origin_is_identity; /* [L] LinkModel::jointOriginTransformIsIdentity */
+  const int32_t* var_index;          /* [L] first variable of the parent joint, -1 if it has none */
+  const int32_t* mimic_var;          /* [L] first variable of the mimicked joint, -1 if not a mimic joint */
+  const double* mimic_mult;          /* [L] JointModel::getMimicFactor */
+  const double* mimic_offset;        /* [L] JointModel::getMimicOffset */
+  /* per-link BodyDecomposition */
+  const int32_t* has_geometry;  /* [L] !LinkModel::getShapes().empty() */
+  const int32_t* sphere_offset; /* [L+1] CSR offsets into spheres */
+  const double* spheres;        /* [S][4] CollisionSphere relative_vec_ xyz + radius_ */
+  const double* bsphere;        /* [L][4] BodyDecomposition::getRelativeBoundingSphere centre xyz + radius */
+  const int64_t* point_offset;  /* [L+1] CSR offsets into points (may be NULL when no link has points) */
+  const double* points;         /* [P][3] BodyDecomposition::getCollisionPoints (link frame) */
+} b200df_model_desc;
+
+int b200df_model_create(const b200df_model_desc* desc, b200df_model** out);
+int b200df_model_destroy(b200df_model* model);
+
+/* FK only: RobotState::updateLinkTransforms for n states.  q: host [n][n_vars] (q_dtype), out: host [n][L][12]. */
+int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64_t n, double* link_transforms);
+
+/* BodyDecomposition (collision_distance_field_types.cpp:290-334) for one link / world shape list, host side
+ * set-up helper: spheres along the bounding cylinders (determineCollisionSpheres :46-79), lattice points
+ * (find_internal_points.cpp:39-64, rasterised on the GPU) and the merged bounding sphere.
+ * Two-pass: call with caps 0 to get the counts. */
+int b200df_body_decomposition(int32_t n_shapes, const int32_t* shape_types, const double* dims /*[n][3]*/,
+                              const double* poses /*[n][12]*/, double resolution, double padding,
+                              double* spheres /*[cap][4]*/, int64_t sphere_cap, int64_t* n_spheres,
+                              double* points /*[cap][3]*/, int64_t point_cap, int64_t* n_points,
+                              double* bsphere /*[4]*/);
+
+/* ---- collision group ---------------------------------------------------------------------------------------
+ * Replaces DistanceFieldCacheEntry (collision_common_distance_field.h:56-167) as produced by
+ * CollisionEnvDistanceField::generateDistanceFieldCacheEntry (:728-975): the group's link list, which links
+ * check against the self field and which link pairs are tested (already resolved from the
+ * AllowedCollisionMatrix by the host, getEntry()==ALWAYS semantics :785-805), plus the field parameters the
+ * thresholds depend on. */
+typedef struct b200df_group_desc
+{
+  int32_t n_group_links;
+  const int32_t* group_links;   /* [n] model link indices in model order (getUpdatedLinkModelNames / all links) */
+  const uint8_t* self_enabled;  /* [n] self_collision_enabled_ */
+  const uint8_t* intra_enabled; /* [n][n] intra_group_collision_enabled_ (only j > i is read) */
+  double resolution;                /* fields used with this group must have this resolution */
+  double collision_tolerance;       /* collision_tolerance_ (default 0.0) */
+  double max_propagation_distance;  /* max_propogation_distance_ (default 0.25) */
+} b200df_group_desc;
+
+int b200df_group_create(const b200df_model* model, const b200df_group_desc* desc, b200df_group** out);
+int b200df_group_destroy(b200df_group* group);
+int b200df_group_sphere_count(const b200df_group* group, int32_t* n_spheres); /* S of the gradient outputs */
+
+/* ---- distance field ----------------------------------------------------------------------------------------
+ * Replaces distance_field::PropagationDistanceField (propagation_distance_field.cpp) with an occupancy grid plus
+ * an EXACT clamped squared EDT rebuilt on the GPU (separable passes).  origin is the grid CORNER exactly as in the
+ * PropagationDistanceField constructor; CollisionEnvDistanceField passes centre - size/2 (:946-948, :1804-1806). */
+typedef struct b200df_field_desc
+{
+  double size[3];
+  double origin[3];
+  double resolution;
+  double max_distance;
+  int32_t propagate_negative; /* use_signed_distance_field_ */
+} b200df_field_desc;
+
+int b200df_field_create(const b200df_field_desc* desc, b200df_field** out);
+int b200df_field_destroy(b200df_field* field);
+/* out4 = nx, ny, nz, max_distance_sq_ (propagation_distance_field.cpp:78, voxel_grid.h:387) */
+int b200df_field_dims(const b200df_field* field, int32_t* out4);
+int b200df_field_reset(b200df_field* field);                                        /* reset()                 :507-525 */
+int b200df_field_add_points(b200df_field* field, const double* xyz, int64_t n);     /* addPointsToField       :176-195 */
+int b200df_field_remove_points(b200df_field* field, const double* xyz, int64_t n);  /* removePointsFromField  :197-218 */
+int b200df_field_update_points(b200df_field* field, const double* old_xyz, int64_t n_old, const double* new_xyz,
+                               int64_t n_new);                                      /* updatePointsInField    :120-174 */
+int b200df_field_add_voxels(b200df_field* field, const int32_t* ijk, int64_t n);    /* addNewObstacleVoxels   :220-300 */
+/* addShapeToField / removeShapeFromField (distance_field.cpp:221-226,320-330): findInternalPointsConvex
+ * rasterised on the GPU.  pose = shape pose in the field frame; padding/scale as bodies::Body. */
+int b200df_field_add_shape(b200df_field* field, int32_t shape_type, const double* dims3, const double* pose12,
+                           double scale, double padding);
+int b200df_field_remove_shape(b200df_field* field, int32_t shape_type, const double* dims3, const double* pose12,
+                              double scale, double padding);
+/* BodyDecomposition points of a shape rasterised in its own frame, then posed (the CollisionEnvDistanceField
+ * world-object route: getBodyDecompositionCacheEntry + PosedBodyPointDecomposition, types.cpp:368-379, Q10) */
+int b200df_field_add_posed_body(b200df_field* field, int32_t shape_type, const double* dims3,
+                                const double* pose12, double padding);
+/* occupied octree leaves (centre xyz + edge) -> points per getOcTreePoints (distance_field.cpp:236-280) */
+int b200df_field_add_octree_leaves(b200df_field* field, const double* leaves4, int64_t n);
+/* Rebuilds the EDT if the occupancy changed (queries do this implicitly).  Returns the device time of the
+ * rebuild in milliseconds through *ms when non-NULL. */
+int b200df_field_rebuild(b200df_field* field, float* ms);
+/* d^2 per voxel as int32 (negative != 0: negative_distance_square_) */
+int b200df_field_download_d2(b200df_field* field, int32_t* out, int negative);
+int b200df_field_download_occupancy(b200df_field* field, uint8_t* out);
+/* DistanceField::getDistanceGradient (distance_field.cpp:62-86) for n host points:
+ * dist[n], grad[n][3], in_bounds[n] */
+int b200df_field_distance_gradient(b200df_field* field, const double* xyz, int64_t n, double* dist, double* grad,
+                                   uint8_t* in_bounds);
+/* writeToStream / readFromStream (propagation_distance_field.cpp:636-761): the bit-packed occupancy payload
+ * (before / after zlib, which stays on the host) */
+int b200df_field_pack_occupancy(b200df_field* field, uint8_t* out, int64_t cap, int64_t* n_bytes);
+int b200df_field_unpack_occupancy(b200df_field* field, const uint8_t* bytes, int64_t n_bytes);
+/* device view for replication across GPUs (NCCL broadcast / peer copy of the built arrays) */
+int b200df_field_device_arrays(b200df_field* field, void** d2, void** neg_d2, int64_t* n_bytes, int32_t* elem_size);
+int b200df_field_mark_built(b200df_field* field); /* after the arrays were overwritten by a broadcast */
+int b200df_field_copy_from(b200df_field* dst, b200df_field* src); /* same geometry; peer copy when on two GPUs */
+
+/* ---- batched checks ----------------------------------------------------------------------------------------
+ * N joint vectors -> N verdicts.  Replaces, per state, checkRobotCollision (:1500-1519), checkSelfCollision
+ * (:254-261 -> :182-204) and checkCollision (:1441-1464) with req.contacts == false.
+ * world / self may be NULL when the corresponding flag is not set. */
+int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                       int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict);
+int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q_dev,
+                              int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, void* stream);
+
+/* getCollisionGradients (:1536-1557) for N states, flattened over the group's spheres (links with geometry, in
+ * group order): dist[n][S], grad[n][S][3], type[n][S] (B200DF_TYPE_*), centers[n][S][3] (may be NULL).
+ * flags: B200DF_CHECK_SELF = self field term of getSelfProximityGradients, B200DF_CHECK_INTRA =
+ * getIntraGroupProximityGradients, B200DF_CHECK_ROBOT = getEnvironmentProximityGradients. */
+int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
+                           double* centers);
+
+/* distanceRobot / distanceSelf are stubs in the reference (collision_env_distance_field.h:108-123,178-198, F5).
+ * Defined here as min over group spheres of (field distance - radius); out[n]. */
+int b200df_distance_batch(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
+                          double* min_clearance);
+
+/* posed sphere centres (PosedBodySphereDecomposition::updatePose, types.cpp:390-397): out[n][S][3] */
+int b200df_sphere_centers(const b200df_group* group, const void* q, int q_dtype, int64_t n, double* centers);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t b200df_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DF_H */

@@ -1,0 +1,117 @@
+// Internal declarations shared by the b200df translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200df.h"
+
+namespace b200df
+{
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define B200DF_CUDA(expr)                                                                                          \
+  do                                                                                                               \
+  {                                                                                                                \
+    cudaError_t e__ = (expr);                                                                                      \
+    if (e__ != cudaSuccess)                                                                                        \
+    {                                                                                                              \
+      b200df::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(e__));             \
+      return B200DF_ERR_CUDA;                                                                                      \
+    }                                                                                                              \
+  } while (0)
+
+#define B200DF_REQUIRE(cond, msg)                                                                                  \
+  do                                                                                                               \
+  {                                                                                                                \
+    if (!(cond))                                                                                                   \
+    {                                                                                                              \
+      b200df::set_error("%s (%s) at %s:%d", msg, #cond, __FILE__, __LINE__);                                       \
+      return B200DF_ERR_INVALID;                                                                                   \
+    }                                                                                                              \
+  } while (0)
+
+#define B200DF_LAUNCHED() (b200df::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// RAII device switch
+struct DeviceGuard
+{
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess)
+      ok = false;
+    else if (prev != dev && cudaSetDevice(dev) != cudaSuccess)
+      ok = false;
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+
+int current_device();  // device chosen by b200df_set_device on this thread (default: CUDA current device)
+
+// Geometry of a voxel grid as the kernels see it (voxel_grid.h:367-399).
+struct GridDev
+{
+  double om[3];  // origin_minus_ = origin - 0.5*resolution
+  double oo;     // oo_resolution_ = 1/resolution
+  int n[3];
+  long stride1, stride2;  // ny*nz, nz
+};
+
+// What the validity / gradient kernels read of a field.
+struct FieldDev
+{
+  GridDev g;
+  const void* d2;       // uint8_t or uint16_t per voxel
+  const void* neg;      // same type, nullptr when the field is unsigned
+  const double* sqrt_table;  // sqrt(i)*resolution, i in [0, max_d2]
+  int elem_size;
+  int max_d2;
+  double max_distance;  // getUninitializedDistance()
+  int inv_twice_res;    // int(1/(2*res)) — Q3
+};
+}  // namespace b200df
+
+struct b200df_field
+{
+  int device = 0;
+  b200df_field_desc desc{};
+  b200df::GridDev grid{};
+  long n_voxels = 0;
+  int max_d2 = 0;
+  int radius = 0;  // smallest R with R*R >= max_d2
+  int elem_size = 1;
+  int inv_twice_res = 0;
+  uint8_t* occ = nullptr;      // 1 = obstacle
+  uint8_t* scratch8 = nullptr; // per-voxel marks for updatePointsInField
+  void* d2 = nullptr;
+  void* neg = nullptr;
+  uint16_t* tmp_a = nullptr;
+  uint16_t* tmp_b = nullptr;
+  uint32_t* bits = nullptr;    // occupancy bit rows for the fused z/y pass
+  double* sqrt_table = nullptr;
+  std::vector<double> sqrt_table_host;
+  bool dirty = true;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  float last_rebuild_ms = 0.f;
+};
+
+namespace b200df
+{
+// builds the EDT when dirty; fills the kernel view.  Caller holds no lock.
+int field_prepare(b200df_field* f, FieldDev* view, cudaStream_t wait_on);
+}
