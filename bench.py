@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — state-validity checks/sec on B200 (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 2 — Panda (12 links, 9 variables, 60 collision spheres), robot-vs-world
+against Field A (2 m cube @ 2 cm, 8 boxes + 4 cylinders) plus intra-group sphere pairs from the SRDF-style ACM,
+10 M uniformly random states PER GPU (weak scaling; the state batch shards with no data-path collective).  A step is
+one pass of the hot path over the rank's batch.
+
+  value : whole-job states/s, inputs already resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e   : the same metric through the host-buffer C-ABI call (b200df_check_batch): pinned host joint values in,
+          host verdicts out, copies inside the timed region
+  cpu_baseline / --impl reference : the CPU oracle (faithful restatement of the reference; the reference itself
+          cannot be compiled here) with one thread per host core on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STATES_PER_GPU = 10_000_000
+ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--states", type=int, default=STATES_PER_GPU, help="states per GPU per step")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-edt", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                          ("sw_power_cap", 6)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def build_oracle_env(n_threads_hint=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py
+    from common import OracleSetup
+    from moveit_b200 import robot_description as rd
+    from moveit_b200 import scenarios
+    desc = rd.panda()
+    setup = OracleSetup(oracle_py, desc, scenarios.FIELD_A, scenarios.random_scene(),
+                        self_state=np.zeros(desc.nvar), exact_field=False)
+    return oracle_py, desc, setup
+
+
+def cpu_rate(setup, desc, oracle_py, target_seconds=12.0):
+    """states/s of the oracle with one thread per host core on a bounded sample of the bench workload."""
+    from moveit_b200 import scenarios
+    cores = oracle_py.hardware_concurrency() or os.cpu_count() or 1
+    probe = desc.sample_states(20000, scenarios.SEED_STATES, np.float32).astype(np.float64)
+    _, t = setup.env.check_batch(probe, mode=3, n_threads=cores, return_time=True)
+    rate = len(probe) / max(t, 1e-9)
+    n = int(min(max(rate * target_seconds, 20000), 4_000_000))
+    q = desc.sample_states(n, scenarios.SEED_STATES, np.float32).astype(np.float64)
+    _, t = setup.env.check_batch(q, mode=3, n_threads=cores, return_time=True)
+    return n / t, cores, n, t
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    oracle_py, desc, setup = build_oracle_env()
+    from moveit_b200 import scenarios
+    cores = oracle_py.hardware_concurrency() or os.cpu_count() or 1
+    probe = desc.sample_states(20000, scenarios.SEED_STATES, np.float32).astype(np.float64)
+    _, t = setup.env.check_batch(probe, mode=3, n_threads=cores, return_time=True)
+    per_step = int(min(max(len(probe) / t * 3.0, 20000), 2_000_000))  # ~3 s of CPU work per step
+    q = desc.sample_states(per_step, scenarios.SEED_STATES, np.float32).astype(np.float64)
+    for _ in range(args.warmup):
+        setup.env.check_batch(q, mode=3, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        setup.env.check_batch(q, mode=3, n_threads=cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "state_validity_checks_per_sec", "value": value, "unit": "states/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(per_step),
+        "cpu_baseline": {"value": value, "unit": "states/s", "cores": cores, "kind": "port",
+                         "sample": "%d states per step of the bench batch (same seed), CPU oracle = faithful restatement "
+                                   "of CollisionEnvDistanceField (reference not buildable here), one thread per core"
+                                   % per_step},
+        "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(states_per_gpu):
+    return {"workload": "BASELINE config 2: Panda (12 links, 9 vars, 60 spheres) checkRobotCollision vs Field A "
+                        "(100^3 voxels @ 2 cm, 8 boxes + 4 cylinders) + intra-group sphere pairs (SRDF ACM), "
+                        "uniform random states",
+            "states_per_gpu_per_step": states_per_gpu, "checks": "robot+intra", "q_dtype": "f32",
+            "l2_policy": "inputs larger than L2 (360 MB of joint values per step per GPU)",
+            "parallelism": "states sharded across ranks, field replicated once by NCCL broadcast"}
+
+
+def edt_timings(engine, scenarios, B):
+    """EDT rebuild ms (BASELINE metric's second half): Field A from the bench scene, Field B from the 1 M-point cloud."""
+    out = {}
+    fa = scenarios.FIELD_A
+    f = engine.Field.centered(fa["size"], fa["resolution"], fa["center"], fa["max_distance"])
+    best = 1e9
+    objs = scenarios.random_scene()
+    for _ in range(5):
+        f.reset()
+        for t, dims, pose in objs:
+            f.add_posed_body(t, dims, pose)
+        best = min(best, f.rebuild())
+    out["field_a_2cm_100^3_ms"] = best
+    fb = scenarios.FIELD_B
+    pts = scenarios.synthetic_cloud(1_000_000)
+    g = engine.Field.centered(fb["size"], fb["resolution"], fb["center"], fb["max_distance"])
+    best = 1e9
+    for _ in range(3):
+        g.reset()
+        g.add_points(pts)
+        best = min(best, g.rebuild())
+    out["field_b_1cm_400^3_1Mpts_ms"] = best
+    peak, _ = measured_peak_hbm()
+    algo = 400 ** 3 * 3 + 24 * len(pts)
+    out["field_b_roofline_frac"] = algo / (best * 1e-3) / 1e9 / peak
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from moveit_b200 import binding as B
+    from moveit_b200 import engine, scenarios, sharding
+    from moveit_b200 import robot_description as rd
+
+    if not torch.cuda.is_available() or B.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    B.check(B.load().b200df_set_device(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- set-up (untimed): model, group, world field (built on rank 0, replicated by ONE broadcast)
+    desc = rd.panda()
+    md = engine.assemble_model(desc, engine.body_decomposition, scenarios.FIELD_A["resolution"])
+    model = engine.Model(md)
+    links = desc.group_links("")
+    se, ie = engine.resolve_acm(md, links, desc.acm_entry_matrix())
+    fa = scenarios.FIELD_A
+    group = engine.Group(model, links, se, ie, fa["resolution"], 0.0, fa["max_distance"])
+    world_field = engine.Field.centered(fa["size"], fa["resolution"], fa["center"], fa["max_distance"])
+    replicated_bytes = 0
+    if rank == 0:
+        for t, dims, pose in scenarios.random_scene():
+            world_field.add_posed_body(t, dims, pose)
+        world_field.rebuild()
+    if world > 1:
+        replicated_bytes = sharding.replicate_field(world_field, dist, rank, 0, dev)
+
+    n = args.states
+    lo = rank * n  # each rank draws its own slice of one global SplitMix64 stream
+    from moveit_b200.rng import uniform01
+    lim_lo = np.array([l[0] for l in desc.limits])
+    lim_hi = np.array([l[1] for l in desc.limits])
+    q_host = torch.empty((n, desc.nvar), dtype=torch.float32).pin_memory()
+    chunk = 1_000_000
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        u = uniform01(scenarios.SEED_STATES, m * desc.nvar, offset=(lo + s) * desc.nvar).reshape(m, desc.nvar)
+        qq = lim_lo + (lim_hi - lim_lo) * u
+        qq[:, 8] = qq[:, 7]  # finger2 mimics finger1
+        q_host[s:s + m] = torch.from_numpy(qq.astype(np.float32))
+    q_dev = q_host.to(dev)
+    v_dev = torch.empty(n, dtype=torch.uint8, device=dev)
+    v_host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    flags = B.CHECK_ROBOT | B.CHECK_INTRA
+    precision = B.PRECISION_FAST if args.precision == "fast" else B.PRECISION_EXACT
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        group.check_device(q_dev.data_ptr(), B.Q_F32, n, v_dev.data_ptr(), world_field, None, flags, precision,
+                           stream.cuda_stream)
+
+    def step_host():
+        B.check(B.load().b200df_check_batch(group.h, world_field.h, None, ctypes.c_void_p(q_host.data_ptr()), B.Q_F32,
+                                            n, flags, precision,
+                                            ctypes.cast(v_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8))))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = B.load().b200df_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = B.load().b200df_launch_count() - launches0
+    clocks = sampler.summary()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    colliding = int(v_dev.sum().item())
+
+    # ---- end-to-end through the host-buffer C-ABI call
+    e2e_steps = max(2, min(args.steps, 5))
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    same = bool(torch.equal(v_host.to(dev), v_dev))
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = n * world / (ms_per_step * 1e-3)
+        peak, peak_src = measured_peak_hbm()
+        achieved = ALGO_BYTES_PER_STATE * n / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": "state_validity_checks_per_sec", "value": value, "unit": "states/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == "exact" else "f32+f64",
+            "data": "synthetic", "config": workload_config(n),
+            "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "states/s",
+                    "h2d_bytes_per_step": n * desc.nvar * 4, "d2h_bytes_per_step": n,
+                    "verdicts_match_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "37 algorithmic bytes/state; the fused validity kernel is instruction-issue bound "
+                                 "by construction (see DESIGN.md), HBM fraction is reported for completeness"},
+            "colliding_fraction": colliding / n,
+            "field_replication_bytes": replicated_bytes,
+            "precision": args.precision,
+        }
+        if not args.no_edt:
+            try:
+                line["edt_ms"] = edt_timings(engine, scenarios, B)
+            except Exception as ex:  # keep the headline line even if the big field does not fit
+                line["edt_ms"] = {"error": str(ex)}
+        if world == 1 and not args.no_cpu_baseline:
+            oracle_py, odesc, setup = build_oracle_env()
+            rate, cores, ns, ts = cpu_rate(setup, odesc, oracle_py)
+            line["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d states of the bench batch (%.1f s), CPU oracle, one thread "
+                                              "per host core; omits MoveIt's per-call GSR copies / string-map ACM "
+                                              "look-ups, i.e. faster than stock MoveIt" % (ns, ts)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -211,6 +211,11 @@ int b200df_field_unpack_occupancy(b200df_field* field, const uint8_t* bytes, int
 int b200df_field_device_arrays(b200df_field* field, void** d2, void** neg_d2, int64_t* n_bytes, int32_t* elem_size);
 int b200df_field_mark_built(b200df_field* field); /* after the arrays were overwritten by a broadcast */
 int b200df_field_copy_from(b200df_field* dst, b200df_field* src); /* same geometry; peer copy when on two GPUs */
+/* copies of the built arrays to / from caller-owned device buffers (occupancy: n voxels bytes; d2 / neg_d2:
+ * n_bytes each), e.g. the tensor an NCCL broadcast runs on.  NULL pointers are skipped. */
+int b200df_field_export_device(b200df_field* field, void* occ_dev, void* d2_dev, void* neg_d2_dev, void* stream);
+int b200df_field_import_device(b200df_field* field, const void* occ_dev, const void* d2_dev, const void* neg_d2_dev,
+                               void* stream);
 
 /* ---- batched checks ----------------------------------------------------------------------------------------
  * N joint vectors -> N verdicts.  Replaces, per state, checkRobotCollision (:1500-1519), checkSelfCollision

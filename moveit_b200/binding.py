@@ -86,6 +86,8 @@ SYMBOLS = {
     "b200df_field_device_arrays": (C.c_int, [_VP, _VPP, _VPP, c_i64p, c_i32p]),
     "b200df_field_mark_built": (C.c_int, [_VP]),
     "b200df_field_copy_from": (C.c_int, [_VP, _VP]),
+    "b200df_field_export_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "b200df_field_import_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "b200df_check_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
     "b200df_check_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP]),
     "b200df_gradients_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_dp, c_dp, c_u8p, c_dp]),

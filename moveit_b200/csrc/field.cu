@@ -988,6 +988,46 @@ int b200df_field_copy_from(b200df_field* dst, b200df_field* src)
   return B200DF_OK;
 }
 
+int b200df_field_export_device(b200df_field* f, void* occ_dev, void* d2_dev, void* neg_d2_dev, void* stream)
+{
+  B200DF_REQUIRE(f, "null field");
+  DeviceGuard dg(f->device);
+  std::lock_guard<std::mutex> lk(f->mu);
+  int rc = rebuild_locked(f);
+  if (rc)
+    return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nb = (size_t)f->n_voxels * f->elem_size;
+  if (occ_dev && f->n_voxels)
+    B200DF_CUDA(cudaMemcpyAsync(occ_dev, f->occ, (size_t)f->n_voxels, cudaMemcpyDeviceToDevice, st));
+  if (d2_dev && nb)
+    B200DF_CUDA(cudaMemcpyAsync(d2_dev, f->d2, nb, cudaMemcpyDeviceToDevice, st));
+  if (neg_d2_dev && nb && f->neg)
+    B200DF_CUDA(cudaMemcpyAsync(neg_d2_dev, f->neg, nb, cudaMemcpyDeviceToDevice, st));
+  B200DF_CUDA(cudaStreamSynchronize(st));
+  return B200DF_OK;
+}
+
+int b200df_field_import_device(b200df_field* f, const void* occ_dev, const void* d2_dev, const void* neg_d2_dev,
+                               void* stream)
+{
+  B200DF_REQUIRE(f, "null field");
+  DeviceGuard dg(f->device);
+  std::lock_guard<std::mutex> lk(f->mu);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t nb = (size_t)f->n_voxels * f->elem_size;
+  if (occ_dev && f->n_voxels)
+    B200DF_CUDA(cudaMemcpyAsync(f->occ, occ_dev, (size_t)f->n_voxels, cudaMemcpyDeviceToDevice, st));
+  if (d2_dev && nb)
+    B200DF_CUDA(cudaMemcpyAsync(f->d2, d2_dev, nb, cudaMemcpyDeviceToDevice, st));
+  if (neg_d2_dev && nb && f->neg)
+    B200DF_CUDA(cudaMemcpyAsync(f->neg, neg_d2_dev, nb, cudaMemcpyDeviceToDevice, st));
+  B200DF_CUDA(cudaStreamSynchronize(st));
+  if (d2_dev)
+    f->dirty = false;
+  return B200DF_OK;
+}
+
 // BodyDecomposition (collision_distance_field_types.cpp:290-334)
 int b200df_body_decomposition(int32_t n_shapes, const int32_t* shape_types, const double* dims, const double* poses,
                               double resolution, double padding, double* spheres, int64_t sphere_cap,

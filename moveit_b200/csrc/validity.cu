@@ -112,7 +112,7 @@ struct b200df_group
 namespace
 {
 // ------------------------------------------------------------------------------------------------------------
-// device maths (operation order = oracle/df_oracle.hpp = Eigen 3.3 fixed-size products, left-to-right sums)
+// device maths (operation order = Eigen 3.3 fixed-size products as the reference evaluates them: left-to-right sums)
 // ------------------------------------------------------------------------------------------------------------
 // r = a.affine() * b.matrix() with implied last row (0,0,0,1).  Zero terms are dropped (x + a*0 == x for the
 // finite values that occur here), the "+ a3*1" term is kept as "+ a3".

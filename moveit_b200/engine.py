@@ -346,3 +346,9 @@ class Field:
 
     def copy_from(self, other):
         B.check(B.load().b200df_field_copy_from(self.h, other.h))
+
+    def export_device(self, occ_ptr=None, d2_ptr=None, neg_ptr=None, stream=None):
+        B.check(B.load().b200df_field_export_device(self.h, occ_ptr, d2_ptr, neg_ptr, stream))
+
+    def import_device(self, occ_ptr=None, d2_ptr=None, neg_ptr=None, stream=None):
+        B.check(B.load().b200df_field_import_device(self.h, occ_ptr, d2_ptr, neg_ptr, stream))

@@ -141,6 +141,31 @@ void orc_field_add_voxels(void* f, const int32_t* ijk, long n)
   df->addNewObstacleVoxels(v);
 }
 
+// Replaces the propagated d^2 arrays by the EXACT clamped squared EDT of the field's current zero set (F4): the
+// second oracle of SURVEY.md 8(c).  Occupancy (the zero set) is untouched, so later add/remove calls continue
+// from the same obstacle voxels.
+void orc_field_make_exact(void* f)
+{
+  auto* df = static_cast<PropagationDistanceField*>(f);
+  const int nx = df->g_.num_cells[0], ny = df->g_.num_cells[1], nz = df->g_.num_cells[2];
+  const size_t n = df->cells_.size();
+  std::vector<uint8_t> occ(n);
+  std::vector<int32_t> out(n);
+  for (size_t i = 0; i < n; ++i)
+    occ[i] = df->cells_[i].distance_square == 0;
+  edt_exact(occ.data(), nx, ny, nz, df->max_distance_sq_, out.data());
+  for (size_t i = 0; i < n; ++i)
+    df->cells_[i].distance_square = out[i];
+  if (df->propagate_negative_)
+  {
+    for (size_t i = 0; i < n; ++i)
+      occ[i] = !occ[i];
+    edt_exact(occ.data(), nx, ny, nz, df->max_distance_sq_, out.data());
+    for (size_t i = 0; i < n; ++i)
+      df->cells_[i].negative_distance_square = out[i];
+  }
+}
+
 void orc_edt_exact(const uint8_t* occ, int nx, int ny, int nz, int max_d2, int32_t* out)
 {
   edt_exact(occ, nx, ny, nz, max_d2, out);

@@ -61,6 +61,7 @@ def lib():
         L.orc_field_pack_occupancy.argtypes = [C.c_void_p, c_u8p, C.c_long]
         L.orc_field_unpack_occupancy.argtypes = [C.c_void_p, c_u8p, C.c_long]
         L.orc_field_add_voxels.argtypes = [C.c_void_p, c_i32p, C.c_long]
+        L.orc_field_make_exact.argtypes = [C.c_void_p]
         for n in ("orc_edt_exact", "orc_edt_brute"):
             getattr(L, n).argtypes = [c_u8p, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p]
         L.orc_shape_points.restype = C.c_long
@@ -155,6 +156,10 @@ class Field:
 
     def reset(self):
         lib().orc_field_reset(self.h)
+
+    def make_exact(self):
+        """Swap the propagated distances for the exact clamped EDT of the same zero set (second oracle, F4)."""
+        lib().orc_field_make_exact(self.h)
 
     def d2(self, negative=False):
         out = np.empty(self.dims, dtype=np.int32)

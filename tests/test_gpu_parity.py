@@ -1,0 +1,412 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Everything here needs a B200."""
+import numpy as np
+import pytest
+
+from moveit_b200 import robot_description as rd
+from moveit_b200 import scenarios
+from moveit_b200.binding import CHECK_INTRA, CHECK_ROBOT, CHECK_SELF
+
+from common import EngineSetup, OracleSetup, oracle_world_points, self_field_points
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(size=(1.0, 1.0, 1.0), resolution=0.1, origin=(0.0, 0.0, 0.0), max_distance=0.3)
+POINT1, POINT2, POINT3 = (0.1, 0.0, 0.0), (0.0, 0.1, 0.2), (0.4, 0.0, 0.0)
+
+
+def small_pair(oracle, signed=False):
+    from moveit_b200 import engine
+    g = engine.Field(SMALL["size"], SMALL["resolution"], SMALL["origin"], SMALL["max_distance"], signed)
+    o = oracle.Field(SMALL["size"], SMALL["resolution"], SMALL["origin"], SMALL["max_distance"], signed)
+    return g, o
+
+
+# ------------------------------------------------------------------------------------------------ kernel 5: field
+def test_field_dims_and_empty(gpu, oracle):
+    g, o = small_pair(oracle)
+    assert g.dims == o.dims and g.max_d2 == o.max_d2 == 9
+    assert np.array_equal(g.d2(), o.d2())  # all max_distance_sq_
+    d, grad, inb = g.distance_gradient([(1000.0, 1000.0, 1000.0)])
+    assert abs(d[0] - 0.3) < 1e-4 and not inb[0] and np.all(grad == 0)
+
+
+def test_add_update_remove_points_sequence(gpu, oracle):
+    """test_distance_field.cpp:329-375 on the GPU: zero sets and d2 equal to the oracle after every step."""
+    g, o = small_pair(oracle)
+    for f in (g, o):
+        f.add_points([POINT1, POINT2])
+    assert np.array_equal(g.d2(), o.d2())
+    for f in (g, o):
+        f.update_points([POINT1], [POINT2, POINT3])
+    assert np.array_equal(g.d2(), o.d2())
+    for f in (g, o):
+        f.remove_points([POINT2])
+    assert np.array_equal(g.d2(), o.d2())
+    assert int((g.d2() == 0).sum()) == 1
+
+
+def test_field_gradients_match_oracle(gpu, oracle):
+    g, o = small_pair(oracle)
+    for f in (g, o):
+        f.add_points([POINT1])
+    nx, ny, nz = g.dims
+    pts = np.array([o.grid_to_world(x, y, z) for x in range(nx) for y in range(ny) for z in range(nz)])
+    d, grad, inb = g.distance_gradient(pts)
+    for k in range(0, len(pts), 7):
+        od, og, oi = o.distance_gradient(*pts[k])
+        assert d[k] == od and np.array_equal(grad[k], og) and inb[k] == oi
+
+
+@pytest.mark.parametrize("shape,max_dist,res", [((40, 33, 27), 0.25, 0.02), ((24, 24, 50), 0.25, 0.01)])
+def test_edt_bit_exact_vs_brute_force(gpu, oracle, shape, max_dist, res):
+    from moveit_b200 import engine
+    size = [s * res + 1e-9 for s in shape]
+    g = engine.Field(size, res, (0, 0, 0), max_dist)
+    assert g.dims == shape
+    rng = np.random.default_rng(5)
+    ijk = np.stack([rng.integers(0, s, 60) for s in shape], axis=1)
+    g.add_voxels(ijk)
+    occ = np.zeros(shape, dtype=np.uint8)
+    occ[ijk[:, 0], ijk[:, 1], ijk[:, 2]] = 1
+    assert np.array_equal(g.occupancy(), occ)
+    ref = oracle.edt_exact(occ, g.max_d2, brute=True)
+    assert np.array_equal(g.d2(), ref)
+    assert np.array_equal(oracle.edt_exact(occ, g.max_d2), ref)
+
+
+def test_signed_field_matches_oracle(gpu, oracle):
+    """test_distance_field.cpp:431-499 on the GPU (solid block: propagation == exact)."""
+    g, o = small_pair(oracle, signed=True)
+    lw, hw = o.grid_to_world(1, 1, 1), o.grid_to_world(8, 8, 8)
+    pts = [(x, y, z) for x in np.arange(lw[0], hw[0] + 1e-9, 0.1) for y in np.arange(lw[1], hw[1] + 1e-9, 0.1)
+           for z in np.arange(lw[2], hw[2] + 1e-9, 0.1)]
+    for f in (g, o):
+        f.add_points(pts)
+        f.remove_points([o.grid_to_world(5, 5, 5)])
+    assert np.array_equal(g.d2(), o.d2())
+    assert np.array_equal(g.d2(True), o.d2(True))
+    q = np.array([o.grid_to_world(x, y, z) for x in range(1, 9) for y in range(1, 9) for z in range(1, 9)])
+    d, grad, inb = g.distance_gradient(q)
+    for k in range(0, len(q), 5):
+        od, og, oi = o.distance_gradient(*q[k])
+        assert d[k] == od and np.array_equal(grad[k], og)
+
+
+def test_pack_unpack_occupancy(gpu, oracle):
+    g, o = small_pair(oracle)
+    for f in (g, o):
+        f.add_points([POINT1, POINT2, POINT3])
+    assert np.array_equal(g.pack_occupancy(), o.pack_occupancy())
+    g2, _ = small_pair(oracle)
+    g2.unpack_occupancy(o.pack_occupancy())
+    assert np.array_equal(g2.d2(), o.d2())
+
+
+# ------------------------------------------------------------------------------------------- rasteriser (a14)
+@pytest.mark.parametrize("k", range(3))
+def test_rasteriser_matches_oracle(gpu, oracle, k):
+    from moveit_b200 import engine
+    objs = scenarios.random_scene(seed=100 + k)
+    fa = scenarios.FIELD_A
+    g = engine.Field.centered(fa["size"], fa["resolution"], fa["center"], fa["max_distance"])
+    o = oracle.Field(fa["size"], fa["resolution"], scenarios.field_corner(fa), fa["max_distance"])
+    for t, dims, pose in objs:
+        g.add_posed_body(t, dims, pose)
+    o.add_points(oracle_world_points(oracle, objs, fa["resolution"]))
+    assert np.array_equal(g.occupancy(), (o.d2() == 0).astype(np.uint8))
+    # direct (field-frame) rasterisation: addShapeToField
+    g2 = engine.Field.centered(fa["size"], fa["resolution"], fa["center"], fa["max_distance"])
+    o2 = oracle.Field(fa["size"], fa["resolution"], scenarios.field_corner(fa), fa["max_distance"])
+    for t, dims, pose in objs:
+        g2.add_shape(t, dims, pose)
+        o2.add_points(oracle.shape_points(t, dims, pose, fa["resolution"]))
+    assert np.array_equal(g2.occupancy(), (o2.d2() == 0).astype(np.uint8))
+    g2.remove_shape(*objs[0][:3])
+    o2.remove_points(oracle.shape_points(objs[0][0], objs[0][1], objs[0][2], fa["resolution"]))
+    assert np.array_equal(g2.occupancy(), (o2.d2() == 0).astype(np.uint8))
+
+
+def test_body_decomposition_matches_oracle(gpu, oracle):
+    from moveit_b200 import engine
+    for desc in (rd.panda(), rd.pr2_like()):
+        for i in desc.links_with_geometry():
+            for pad in (0.0, 0.01):
+                s1, p1, b1 = engine.body_decomposition(desc.shapes[i], 0.02, pad)
+                s2, p2, b2 = oracle.body_decomposition(desc.shapes[i], 0.02, pad)
+                assert np.array_equal(s1, s2) and np.array_equal(p1, p2) and np.array_equal(b1, b2)
+    # multi-shape link: merged bounding sphere
+    shapes = [(rd.SHAPE_BOX, (0.1, 0.2, 0.3), rd.rpy_xyz_to_pose((0.1, 0, 0), (0.3, 0.2, 0.1))),
+              (rd.SHAPE_SPHERE, (0.07,), rd.rpy_xyz_to_pose((-0.2, 0.1, 0.0))),
+              (rd.SHAPE_CYLINDER, (0.05, 0.4), rd.rpy_xyz_to_pose((0, 0, 0.3), (1.0, 0, 0)))]
+    s1, p1, b1 = engine.body_decomposition(shapes, 0.02, 0.01)
+    s2, p2, b2 = oracle.body_decomposition(shapes, 0.02, 0.01)
+    assert np.array_equal(s1, s2) and np.array_equal(p1, p2) and np.array_equal(b1, b2)
+
+
+# ------------------------------------------------------------------------------------------------- kernel 1: FK
+@pytest.mark.parametrize("robot", ["one_robot", "panda", "pr2_like"])
+def test_fk_matches_oracle(gpu, oracle, robot):
+    from moveit_b200 import engine
+    desc = getattr(rd, robot)()
+    md = assemble_model(desc, oracle)
+    gm, om = engine.Model(md), oracle.Model(md)
+    q = desc.sample_states(256, 7)
+    T = gm.fk(q)
+    ref = np.stack([om.fk(qi) for qi in q])
+    # identical operation order; only sin/cos may differ in the last ulp between CUDA and glibc
+    assert np.max(np.abs(T - ref)) < 1e-13
+    T32 = gm.fk(q.astype(np.float32))
+    ref32 = np.stack([om.fk(qi) for qi in q.astype(np.float32).astype(np.float64)])
+    assert np.max(np.abs(T32 - ref32)) < 1e-13
+
+
+def assemble_model(desc, oracle, res=0.02):
+    from moveit_b200.engine import assemble_model as am
+    return am(desc, oracle.body_decomposition, res)
+
+
+def test_one_robot_fk_known_answers_on_gpu(gpu, oracle):
+    """robot_state_test.cpp:484-543 through b200df_model_fk."""
+    from moveit_b200 import engine
+    desc = rd.one_robot()
+    gm = engine.Model(assemble_model(desc, oracle))
+    name = {n: i for i, n in enumerate(desc.link_names)}
+    q = np.zeros(7)
+    q[[0, 1, 2, 3, 4]] = (1.0, 1.0, 0.5, -0.5, 0.08)
+    T = gm.fk(q)[0]
+    assert np.allclose(T[name["link_b"]][:, 3], (1, 1.5, 0), atol=1e-5)
+    assert np.allclose(T[name["link_c"]][:, 3], (1.08, 1.4, 0), atol=1e-5)
+    q = np.zeros(7)
+    q[6] = 1.0
+    T = gm.fk(q)[0]
+    assert np.allclose(T[name["link_d"]][:, 3], (1.7, 0.5, 0), atol=1e-5)
+    assert np.allclose(T[name["link_e"]][:, 3], (2.8, 0.6, 0), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------- kernels 2-4: verdicts
+def test_sphere_centers_match_oracle(gpu, oracle):
+    desc = rd.panda()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A)
+    e = EngineSetup(desc, scenarios.FIELD_A, model_desc=o.model_desc)
+    q = desc.sample_states(128, 11)
+    c = e.group.sphere_centers(q)
+    ref = np.stack([o.env.sphere_centers(qi) for qi in q])
+    assert c.shape == ref.shape == (128, 60, 3)
+    assert np.max(np.abs(c - ref)) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_config1_robot_verdicts_bit_exact(gpu, oracle, dtype):
+    """BASELINE config 1: Panda, 10k random states, Field A, 8 boxes + 4 cylinders, checkRobotCollision."""
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs)
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    assert np.array_equal(e.world.d2(), o.env.world.d2()), "exact EDT differs from the reference propagation here"
+    q = desc.sample_states(10000, scenarios.SEED_STATES, dtype)
+    got = e.group.check(q, e.world, flags=CHECK_ROBOT)
+    ref = o.env.check_batch(q.astype(np.float64), mode=1)
+    assert np.array_equal(got, ref)
+    assert 0.05 < ref.mean() < 0.95  # the workload exercises both outcomes
+
+
+def test_config2_robot_plus_self_verdicts_bit_exact(gpu, oracle):
+    """BASELINE config 2 at oracle-sized N: robot + intra-group pairs from the SRDF-style ACM."""
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    q = desc.sample_states(20000, scenarios.SEED_STATES + 7)
+    got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    ref = o.env.check_batch(q, mode=3, n_threads=4)
+    assert np.array_equal(got, ref)
+    intra_only = e.group.check(q, flags=CHECK_INTRA)
+    ref_self = o.env.check_batch(q, mode=2, n_threads=4)
+    assert np.array_equal(intra_only, ref_self)
+    assert 0.02 < ref_self.mean() < 0.98
+    # checkCollision order (self, intra, env) gives the same verdict as the PlanningScene order
+    assert np.array_equal(o.env.check_batch(q[:2000], mode=4), ref[:2000])
+
+
+def test_group_with_self_field(gpu, oracle):
+    """Planning group panda_arm: link0 is outside the group -> its points build the self field (cpp:913-973)."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=77)
+    q0 = np.zeros(desc.nvar)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, group="panda_arm", self_state=q0)
+    sp = self_field_points(o.model_desc, desc, o.group_links, o.model.fk(q0))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, group="panda_arm", self_points=sp)
+    assert np.array_equal(e.self_field.d2(), o.env.self_field().d2())
+    q = desc.sample_states(8000, 99)
+    got = e.group.check(q, e.world, e.self_field, flags=CHECK_ROBOT | CHECK_SELF | CHECK_INTRA)
+    ref = o.env.check_batch(q, mode=3, n_threads=4)
+    assert np.array_equal(got, ref)
+    only_self = e.group.check(q, None, e.self_field, flags=CHECK_SELF)
+    assert only_self.sum() > 0  # arm spheres do reach link0's voxels
+
+
+def test_signed_world_field_verdicts(gpu, oracle):
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=5)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, signed=True)
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, signed=True)
+    assert np.array_equal(e.world.d2(), o.env.world.d2())
+    assert np.array_equal(e.world.d2(True), o.env.world.d2(True))
+    q = desc.sample_states(5000, 3)
+    assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT), o.env.check_batch(q, mode=1))
+
+
+def test_tolerance_and_no_acm(gpu, oracle):
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=9)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, use_acm=False, tol=0.015, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, use_acm=False, tol=0.015)
+    q = desc.sample_states(3000, 4)
+    assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT), o.env.check_batch(q, mode=1))
+    # without an ACM adjacent links are tested too -> (nearly) every state self-collides in both
+    assert np.array_equal(e.group.check(q, flags=CHECK_INTRA), o.env.check_batch(q, mode=2))
+
+
+def test_derived_spheres_from_bounding_cylinders(gpu, oracle):
+    """determineCollisionSpheres route (no link_body_decompositions override), a3."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=21)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, sphere_overrides=False, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, sphere_overrides=False)
+    q = desc.sample_states(4000, 8)
+    assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA),
+                          o.env.check_batch(q, mode=3, n_threads=4))
+
+
+def test_config4_pr2_like_full_acm(gpu, oracle):
+    """BASELINE config 4: PR2-like dual-arm tree, all pairs enabled except parent-child."""
+    desc = rd.pr2_like()
+    objs = scenarios.random_scene(seed=31)
+    fd = scenarios.FIELD_DEFAULT
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, fd, objs)
+    q = desc.sample_states(6000, 12)
+    got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    ref = o.env.check_batch(q, mode=3, n_threads=4)
+    assert np.array_equal(got, ref)
+    arms = desc.group_links("arms")
+    assert len(arms) < desc.n_links
+
+
+def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
+    """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
+    from moveit_b200 import engine
+    r = rd.RobotDescription("test")
+    r.add_link("base", None, "root_joint", rd.JOINT_FIXED)
+    r.add_shape("base", rd.SHAPE_SPHERE, (0.04,))
+    md = engine.assemble_model(r, engine.body_decomposition, 0.02, link_padding=0.04)
+    assert md["spheres"][0][0, 3] == 0.08
+    model = engine.Model(md)
+    grp = engine.Group(model, [0], [1], [[1]], 0.02, 0.0, 0.25)
+    world = engine.Field.centered((0.1, 0.1, 0.2), 0.02, (0, 0, 0), 0.25)
+    assert world.dims == (5, 5, 10)
+    q = np.zeros((1, 0))
+    box = (rd.SHAPE_BOX, (0.02, 0.02, 0.02))
+    expected = [(0.0, 1), (0.08, 1), (0.1, 0)]
+    for z, verdict in expected:
+        world.reset()  # MOVE_SHAPE: old points removed, new points added
+        world.add_posed_body(box[0], box[1], rd.rpy_xyz_to_pose((0, 0, z)))
+        assert grp.check(q, world, flags=CHECK_ROBOT)[0] == verdict, z
+
+
+def test_ragged_and_empty_batches(gpu, oracle):
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    assert len(e.group.check(np.zeros((0, desc.nvar)), e.world)) == 0
+    for n in (1, 31, 33, 127, 129, 1000):
+        q = desc.sample_states(n, 1000 + n)
+        assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA),
+                              o.env.check_batch(q, mode=3))
+    # states far outside the field are "free" (Q4), NaN joints do not crash
+    q = desc.sample_states(4, 1)
+    q[0, :] = np.nan
+    e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+
+
+# ------------------------------------------------------------------------------------------------ gradients
+def test_config5_gradients_within_tolerance(gpu, oracle):
+    """BASELINE config 5 at oracle-sized N: getCollisionGradients (self field + intra + environment)."""
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    q0 = np.zeros(desc.nvar)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=q0)
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    traj = scenarios.chomp_trajectories(desc, 12, 100).reshape(-1, desc.nvar)
+    got = e.group.gradients(traj, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    ref = o.env.gradients_batch(traj, flags=2 | 4)
+    assert np.array_equal(got["type"], ref["type"].astype(np.uint8))
+    fin = ref["dist"] < 1e300
+    assert np.array_equal(fin, got["dist"] < 1e300)
+    assert np.max(np.abs(got["dist"][fin] - ref["dist"][fin])) < 1e-5   # north_star tolerance: 1e-5 m
+    assert np.max(np.abs(got["grad"] - ref["grad"])) < 1e-5
+    assert np.max(np.abs(got["centers"] - ref["centers"])) < 1e-12
+    assert (got["type"] == 3).any() and (got["type"] == 2).any()
+
+
+def test_distance_batch_definition(gpu, oracle):
+    """distanceRobot is a stub in the reference (F5); the engine defines min over spheres of dist - radius."""
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs)
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    q = desc.sample_states(200, 17)
+    got = e.group.distance(q, e.world)
+    radii = np.concatenate([s[:, 3] for s in o.model_desc["spheres"] if len(s)])
+    for k in range(0, 200, 9):
+        c = o.env.sphere_centers(q[k])
+        d = np.array([o.env.world.distance_gradient(*p)[0] for p in c]) - radii
+        assert abs(got[k] - d.min()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ full sizes
+def test_full_size_properties_10m_states(gpu, oracle):
+    """Config 2 at BASELINE size through size-independent properties: chunk invariance (the verdict of a state
+    does not depend on its position in the batch), robot|intra == robot OR intra, and exact agreement with the
+    oracle on a strided sample of the same batch."""
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    n = 10_000_000
+    q = desc.sample_states(n, scenarios.SEED_STATES, np.float32)
+    both = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    robot = e.group.check(q, e.world, flags=CHECK_ROBOT)
+    intra = e.group.check(q, flags=CHECK_INTRA)
+    assert np.array_equal(both, robot | intra)
+    sl = slice(3_333_333, 3_343_333)
+    assert np.array_equal(e.group.check(q[sl], e.world, flags=CHECK_ROBOT | CHECK_INTRA), both[sl])
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    idx = np.arange(0, n, 997)
+    ref = o.env.check_batch(q[idx].astype(np.float64), mode=3, n_threads=8)
+    assert np.array_equal(both[idx], ref)
+
+
+def test_config3_field_b_cloud(gpu, oracle):
+    """Config 3: 1M-point cloud into the 400^3 field; exactness checked by a KD-tree on a voxel sample and by the
+    oracle's exact EDT on a sub-block; mismatch census against the reference propagation on the sub-block."""
+    from scipy.spatial import cKDTree
+    from moveit_b200 import engine
+    fb = scenarios.FIELD_B
+    pts = scenarios.synthetic_cloud(1_000_000)
+    g = engine.Field.centered(fb["size"], fb["resolution"], fb["center"], fb["max_distance"])
+    assert g.dims == (400, 400, 400) and g.max_d2 == 625
+    g.add_points(pts)
+    ms = g.rebuild()
+    d2 = g.d2()
+    occ = g.occupancy()
+    assert (d2 == 0).sum() == occ.sum() > 100_000
+    assert np.array_equal(d2 == 0, occ == 1)
+    vox = np.argwhere(occ)
+    tree = cKDTree(vox)
+    rng = np.random.default_rng(0)
+    sample = rng.integers(0, 400, size=(300_000, 3))
+    dist, _ = tree.query(sample, k=1)
+    want = np.minimum(np.rint(dist * dist).astype(np.int64), 625)
+    assert np.array_equal(d2[sample[:, 0], sample[:, 1], sample[:, 2]], want)
+    print("field B rebuild: %.3f ms" % ms)
