@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Turns an ncu report / launch list brought back in gpurun_out/ into the small text summaries kept in profiles/.
+
+  python profiles/summarize.py rep  gpurun_out/prof.ncu-rep   profiles/<name>.txt
+  python profiles/summarize.py list gpurun_out/launches.csv   profiles/<name>.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed.avg.per_cycle_active", "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "lts__t_sector_hit_rate.pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
+    "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+    "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct",
+]
+
+
+def rep(path, out):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none summary of %s\n" % path)
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+            f.write("\nkernel: %s\n" % name[:200])
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write("  %-75s %s %s\n" % (k, r[i], units[i]))
+
+
+def launch_list(path, out):
+    agg = OrderedDict()
+    with open(path) as fh:
+        lines = [l for l in fh if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = r["Kernel Name"].split("(")[0][-90:]
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v * scale
+    total = sum(a[1] for a in agg.values()) or 1.0
+    with open(out, "w") as f:
+        f.write("# launch list (ncu --metrics gpu__time_duration.sum --clock-control none) of %s\n" % path)
+        f.write("# cold-cache, serialised: compare SHARES, not absolutes\n")
+        f.write("%-92s %8s %14s %8s\n" % ("kernel", "launches", "total_us", "share"))
+        for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-92s %8d %14.1f %7.2f%%\n" % (name, cnt, us, 100 * us / total))
+
+
+if __name__ == "__main__":
+    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
