@@ -1,0 +1,620 @@
+// Generic fp64 sweep (one thread per state, all sphere centres kept in shared memory): FK / sphere-centre /
+// clearance outputs, the gradient kernel of getCollisionGradients, and the round-1 verdict kernel that is kept as an
+// independent cross-check of the fused verdict kernel in validity.cu (precision value 2).
+//
+// Reference being replaced, per state:
+//   RobotState::updateLinkTransformsInternal            robot_state/src/robot_state.cpp:718-755
+//   PosedBodySphereDecomposition::updatePose            collision_distance_field/src/collision_distance_field_types.cpp:390-408
+//   getCollisionSphereGradients                         collision_distance_field_types.cpp:143-204
+//   CollisionEnvDistanceField::getCollisionGradients    collision_env_distance_field.cpp:1536-1557
+//     getSelfProximityGradients :358-431, getIntraGroupProximityGradients :662-727,
+//     getEnvironmentProximityGradients :1664-1700
+//
+// Compiled with --fmad=false so that mul/add round like the reference's non-FMA x86-64 build.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "validity_common.cuh"
+
+using namespace b200df;
+
+namespace
+{
+enum OutMode
+{
+  OUT_VERDICT = 0,
+  OUT_CENTERS = 1,
+  OUT_TRANSFORMS = 2,
+  OUT_CLEARANCE = 3,
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// The EXACT validity kernel
+// ------------------------------------------------------------------------------------------------------------
+template <typename QT, typename FT, int MODE>
+__global__ void validity_exact_kernel(GroupDev g, FieldDev wf, FieldDev sf, const QT* __restrict__ q, long n,
+                                      int flags, uint8_t* __restrict__ verdict, double* __restrict__ out_f64)
+{
+  extern __shared__ double smem[];
+  const int B = blockDim.x;
+  const int tid = threadIdx.x;
+  const long base = (long)blockIdx.x * B;
+  double* qs = smem;                               // [n_vars][B]
+  double* slots = qs + (size_t)g.n_vars * B;       // [n_slots][12][B]
+  double* cen = slots + (size_t)g.n_slots * 12 * B;  // [S][3][B]
+  double* bsc = cen + (size_t)g.n_spheres * 3 * B;   // [n_glinks][3][B]
+
+  // stage the block's joint values: coalesced read, transposed into [var][thread]
+  {
+    const long total = (long)B * g.n_vars;
+    const long limit = (n - base) * g.n_vars;
+    for (long e = tid; e < total; e += B)
+    {
+      const int s = (int)(e / g.n_vars), v = (int)(e % g.n_vars);
+      qs[v * B + s] = (e < limit) ? (double)q[base * g.n_vars + e] : 0.0;
+    }
+  }
+  __syncthreads();
+  const long state = base + tid;
+  const bool active = state < n;
+  const double* my_q = qs + tid;
+  double* my_slots = slots + tid;
+  double* my_cen = cen + tid;
+  double* my_bsc = bsc + tid;
+
+  bool hit = false;
+  double clearance = DBL_MAX;
+  double cur[12];
+  const bool want_pairs = (flags & B200DF_CHECK_INTRA) != 0 && g.n_pairs > 0;
+
+  for (int i = 0; i < g.n_links; ++i)
+  {
+    const DevLink& l = g.links[i];
+    fk_step(l, my_q, my_slots, B, cur);
+    if (MODE == OUT_TRANSFORMS)
+    {
+      if (active)
+      {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+          out_f64[(state * g.n_links + i) * 12 + k] = cur[k];
+      }
+      continue;
+    }
+    const int gs = g.link_gslot[i];
+    if (gs < 0)
+      continue;
+    const DevGroupLink& gl = g.glinks[gs];
+    // PosedBodySphereDecomposition::updatePose
+    if (want_pairs)
+    {
+      double bx, by, bz;
+      iso_apply(cur, gl.bs[0], gl.bs[1], gl.bs[2], bx, by, bz);
+      my_bsc[(gs * 3 + 0) * B] = bx;
+      my_bsc[(gs * 3 + 1) * B] = by;
+      my_bsc[(gs * 3 + 2) * B] = bz;
+    }
+    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    {
+      const double* rel = g.sph + 4 * s;
+      double cx, cy, cz;
+      iso_apply(cur, rel[0], rel[1], rel[2], cx, cy, cz);
+      if (want_pairs)
+      {
+        my_cen[(s * 3 + 0) * B] = cx;
+        my_cen[(s * 3 + 1) * B] = cy;
+        my_cen[(s * 3 + 2) * B] = cz;
+      }
+      if (MODE == OUT_CENTERS)
+      {
+        if (active)
+        {
+          out_f64[(state * g.n_spheres + s) * 3 + 0] = cx;
+          out_f64[(state * g.n_spheres + s) * 3 + 1] = cy;
+          out_f64[(state * g.n_spheres + s) * 3 + 2] = cz;
+        }
+        continue;
+      }
+      if (MODE == OUT_CLEARANCE)
+      {
+        long idx;
+        double d = wf.max_distance;
+        if (inset_cell(wf.g, cx, cy, cz, idx))
+          d = cell_dist<FT>(wf, idx);
+        d = d - rel[3];
+        if (d < clearance)
+          clearance = d;
+        continue;
+      }
+      if (flags & B200DF_CHECK_ROBOT)
+        hit |= sphere_collides<FT>(wf, cx, cy, cz, rel[3], g.sph_thr[s], g.tol, g.max_prop);
+      if ((flags & B200DF_CHECK_SELF) && gl.self_enabled)
+        hit |= sphere_collides<FT>(sf, cx, cy, cz, rel[3], g.sph_thr[s], g.tol, g.max_prop);
+    }
+  }
+  if (MODE == OUT_TRANSFORMS || MODE == OUT_CENTERS)
+    return;
+  if (MODE == OUT_CLEARANCE)
+  {
+    if (active)
+      out_f64[state] = clearance;
+    return;
+  }
+
+  // intra-group sphere pairs (kernel 4).  A warp stops as soon as every one of its states has a verdict.
+  if (want_pairs)
+  {
+    for (int p = 0; p < g.n_pairs; ++p)
+    {
+      if (__all_sync(0xffffffffu, hit || !active))
+        break;
+      const DevPair pr = g.pairs[p];
+      const double dx = my_bsc[(pr.gi * 3 + 0) * B] - my_bsc[(pr.gj * 3 + 0) * B];
+      const double dy = my_bsc[(pr.gi * 3 + 1) * B] - my_bsc[(pr.gj * 3 + 1) * B];
+      const double dz = my_bsc[(pr.gi * 3 + 2) * B] - my_bsc[(pr.gj * 3 + 2) * B];
+      const double d2 = (dx * dx + dy * dy) + dz * dz;
+      // doBoundingSpheresIntersect: squared distance against the UN-squared radius sum (Q2)
+      if (hit || !(d2 < pr.radius_sum))
+        continue;
+      const DevGroupLink& gi = g.glinks[pr.gi];
+      const DevGroupLink& gj = g.glinks[pr.gj];
+      for (int k = gi.sphere_begin; k < gi.sphere_end; ++k)
+      {
+        const double ax = my_cen[(k * 3 + 0) * B], ay = my_cen[(k * 3 + 1) * B], az = my_cen[(k * 3 + 2) * B];
+        const double* thr_row = g.pair_thr + (size_t)g.sph_cls[k] * g.n_cls;
+        for (int m = gj.sphere_begin; m < gj.sphere_end; ++m)
+        {
+          const double ex = ax - my_cen[(m * 3 + 0) * B];
+          const double ey = ay - my_cen[(m * 3 + 1) * B];
+          const double ez = az - my_cen[(m * 3 + 2) * B];
+          const double e2 = (ex * ex + ey * ey) + ez * ez;
+          hit |= e2 < thr_row[g.sph_cls[m]];
+        }
+      }
+    }
+  }
+  if (active)
+    verdict[state] = hit ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gradient kernel (getCollisionGradients :1536-1557): self field, intra group, environment — in that order,
+// each keeping the per-sphere minimum with strict '<' like the reference.
+// ------------------------------------------------------------------------------------------------------------
+template <typename FT>
+__device__ __forceinline__ void field_gradient_update(const FieldDev& f, double x, double y, double z, double max_value,
+                                                      int type, double& best, double& gx, double& gy, double& gz,
+                                                      int& btype)
+{
+  // getCollisionSphereGradients (collision_distance_field_types.cpp:143-204), subtract_radii == false
+  long idx;
+  double dist, dgx = 0.0, dgy = 0.0, dgz = 0.0;
+  if (!inset_cell(f.g, x, y, z, idx))
+    dist = f.max_distance;  // in_bounds = false, gradient 0: the "out of bounds" return is dead (Q4)
+  else
+  {
+    const double itr = (double)f.inv_twice_res;
+    dgx = (cell_dist<FT>(f, idx + f.g.stride1) - cell_dist<FT>(f, idx - f.g.stride1)) * itr;
+    dgy = (cell_dist<FT>(f, idx + f.g.stride2) - cell_dist<FT>(f, idx - f.g.stride2)) * itr;
+    dgz = (cell_dist<FT>(f, idx + 1) - cell_dist<FT>(f, idx - 1)) * itr;
+    dist = cell_dist<FT>(f, idx);
+  }
+  if (dist < max_value && dist < best)
+  {
+    best = dist;
+    gx = dgx;
+    gy = dgy;
+    gz = dgz;
+    btype = type;
+  }
+}
+
+template <typename QT, typename FT>
+__global__ void gradients_kernel(GroupDev g, FieldDev wf, FieldDev sf, const QT* __restrict__ q, long n, int flags,
+                                 double* __restrict__ out_dist, double* __restrict__ out_grad,
+                                 uint8_t* __restrict__ out_type, double* __restrict__ out_cen)
+{
+  extern __shared__ double smem[];
+  const int B = blockDim.x;
+  const int tid = threadIdx.x;
+  const long base = (long)blockIdx.x * B;
+  double* qs = smem;
+  double* slots = qs + (size_t)g.n_vars * B;
+  double* cen = slots + (size_t)g.n_slots * 12 * B;
+  {
+    const long total = (long)B * g.n_vars;
+    const long limit = (n - base) * g.n_vars;
+    for (long e = tid; e < total; e += B)
+    {
+      const int s = (int)(e / g.n_vars), v = (int)(e % g.n_vars);
+      qs[v * B + s] = (e < limit) ? (double)q[base * g.n_vars + e] : 0.0;
+    }
+  }
+  __syncthreads();
+  const long state = base + tid;
+  if (state >= n)
+    return;
+  const double* my_q = qs + tid;
+  double* my_slots = slots + tid;
+  double* my_cen = cen + tid;
+  const int S = g.n_spheres;
+  double* dist = out_dist + state * S;
+  double* grad = out_grad + state * S * 3;
+  uint8_t* type = out_type + state * S;
+
+  double cur[12];
+  for (int i = 0; i < g.n_links; ++i)
+  {
+    const DevLink& l = g.links[i];
+    fk_step(l, my_q, my_slots, B, cur);
+    const int gs = g.link_gslot[i];
+    if (gs < 0)
+      continue;
+    const DevGroupLink& gl = g.glinks[gs];
+    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    {
+      const double* rel = g.sph + 4 * s;
+      double cx, cy, cz;
+      iso_apply(cur, rel[0], rel[1], rel[2], cx, cy, cz);
+      my_cen[(s * 3 + 0) * B] = cx;
+      my_cen[(s * 3 + 1) * B] = cy;
+      my_cen[(s * 3 + 2) * B] = cz;
+      if (out_cen)
+      {
+        out_cen[(state * S + s) * 3 + 0] = cx;
+        out_cen[(state * S + s) * 3 + 1] = cy;
+        out_cen[(state * S + s) * 3 + 2] = cz;
+      }
+      // updateGroupStateRepresentationState :1128-1133
+      double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
+      int bt = B200DF_TYPE_NONE;
+      // getSelfProximityGradients: self field term (:420-422)
+      if ((flags & B200DF_CHECK_SELF) && gl.self_enabled)
+        field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
+      dist[s] = best;
+      grad[3 * s] = gx;
+      grad[3 * s + 1] = gy;
+      grad[3 * s + 2] = gz;
+      type[s] = (uint8_t)bt;
+    }
+  }
+  // getIntraGroupProximityGradients :662-727 — sequential over pairs, both spheres updated with strict '<'
+  if (flags & B200DF_CHECK_INTRA)
+  {
+    for (int p = 0; p < g.n_pairs; ++p)
+    {
+      const DevPair pr = g.pairs[p];
+      const DevGroupLink& gi = g.glinks[pr.gi];
+      const DevGroupLink& gj = g.glinks[pr.gj];
+      for (int k = gi.sphere_begin; k < gi.sphere_end; ++k)
+      {
+        const double ax = my_cen[(k * 3 + 0) * B], ay = my_cen[(k * 3 + 1) * B], az = my_cen[(k * 3 + 2) * B];
+        double dk = dist[k];
+        for (int m = gj.sphere_begin; m < gj.sphere_end; ++m)
+        {
+          const double ex = ax - my_cen[(m * 3 + 0) * B];
+          const double ey = ay - my_cen[(m * 3 + 1) * B];
+          const double ez = az - my_cen[(m * 3 + 2) * B];
+          const double d = sqrt((ex * ex + ey * ey) + ez * ez);
+          if (d < dk)
+          {
+            dk = d;
+            dist[k] = d;
+            grad[3 * k] = ex;
+            grad[3 * k + 1] = ey;
+            grad[3 * k + 2] = ez;
+            type[k] = B200DF_TYPE_INTRA;
+          }
+          if (d < dist[m])
+          {
+            dist[m] = d;
+            grad[3 * m] = -ex;
+            grad[3 * m + 1] = -ey;
+            grad[3 * m + 2] = -ez;
+            type[m] = B200DF_TYPE_INTRA;
+          }
+        }
+      }
+    }
+  }
+  // getEnvironmentProximityGradients :1664-1700
+  if (flags & B200DF_CHECK_ROBOT)
+  {
+    for (int s = 0; s < S; ++s)
+    {
+      double best = dist[s], gx = grad[3 * s], gy = grad[3 * s + 1], gz = grad[3 * s + 2];
+      int bt = type[s];
+      const double before = best;
+      field_gradient_update<FT>(wf, my_cen[(s * 3 + 0) * B], my_cen[(s * 3 + 1) * B], my_cen[(s * 3 + 2) * B],
+                                g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
+      if (best < before)
+      {
+        dist[s] = best;
+        grad[3 * s] = gx;
+        grad[3 * s + 1] = gy;
+        grad[3 * s + 2] = gz;
+        type[s] = (uint8_t)bt;
+      }
+    }
+  }
+}
+
+size_t smem_bytes(const GroupDev& g, int block, bool with_centers, bool with_bsc)
+{
+  size_t d = (size_t)g.n_vars + (size_t)g.n_slots * 12;
+  if (with_centers)
+    d += (size_t)g.n_spheres * 3;
+  if (with_bsc)
+    d += (size_t)g.n_glinks * 3;
+  return d * block * sizeof(double);
+}
+
+int pick_block(const GroupDev& g, bool with_centers, bool with_bsc, int* block, size_t* bytes)
+{
+  // largest block (multiple of 32) whose shared-memory footprint still lets two CTAs share an SM, else one
+  const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
+  for (int b : { 128, 96, 64, 32 })
+  {
+    const size_t s = smem_bytes(g, b, with_centers, with_bsc);
+    if (s <= budget2 || (b == 32 && s <= budget1))
+    {
+      *block = b;
+      *bytes = s;
+      return B200DF_OK;
+    }
+  }
+  set_error("robot too large for the per-state shared-memory layout (%zu bytes for 32 states)",
+            smem_bytes(g, 32, with_centers, with_bsc));
+  return B200DF_ERR_UNSUPPORTED;
+}
+
+template <typename K>
+int set_smem_limit(K kernel, size_t bytes)
+{
+  if (bytes > 48 * 1024)
+    B200DF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return B200DF_OK;
+}
+
+template <typename QT, typename FT, int MODE>
+int launch_exact(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
+                 uint8_t* verdict, double* out_f64, cudaStream_t stream)
+{
+  const bool pairs = MODE == OUT_VERDICT && (flags & B200DF_CHECK_INTRA) && g.n_pairs > 0;
+  int block;
+  size_t bytes;
+  int rc = pick_block(g, pairs, pairs, &block, &bytes);
+  if (rc)
+    return rc;
+  rc = set_smem_limit(validity_exact_kernel<QT, FT, MODE>, bytes);
+  if (rc)
+    return rc;
+  const unsigned grid = (unsigned)((n + block - 1) / block);
+  validity_exact_kernel<QT, FT, MODE>
+      <<<grid, block, bytes, stream>>>(g, wf, sf, static_cast<const QT*>(q), n, flags, verdict, out_f64);
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  return B200DF_OK;
+}
+
+template <int MODE>
+int dispatch_exact(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                   int q_dtype, long n, int flags, uint8_t* verdict, double* out_f64, cudaStream_t stream)
+{
+  if (q_dtype == B200DF_Q_F32)
+  {
+    if (field_elem == 1)
+      return launch_exact<float, uint8_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+    return launch_exact<float, uint16_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+  }
+  if (field_elem == 1)
+    return launch_exact<double, uint8_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+  return launch_exact<double, uint16_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+}
+}  // namespace
+
+namespace b200df
+{
+// round-1 verdict kernel (all centres in shared memory, pair phase after the sweep); cross-check only
+int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                      int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream)
+{
+  return dispatch_exact<OUT_VERDICT>(g, wf, sf, field_elem, q, q_dtype, n, flags, verdict, nullptr, stream);
+}
+}  // namespace b200df
+
+extern "C" {
+
+// shared host wrapper for the fp64-output modes
+static int run_f64_output(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
+                          int mode, size_t out_per_state, double* out)
+{
+  B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && out)), "bad arguments");
+  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
+  if (n == 0)
+    return B200DF_OK;
+  FieldDev wf, sf;
+  std::memset(&wf, 0, sizeof(wf));
+  std::memset(&sf, 0, sizeof(sf));
+  int elem = 1;
+  if (mode == OUT_CLEARANCE)
+  {
+    int rc = prepare_fields(group, world, nullptr, B200DF_CHECK_ROBOT, &wf, &sf, &elem);
+    if (rc)
+      return rc;
+  }
+  DeviceGuard dg(group->device);
+  cudaStream_t stream;
+  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const size_t qbytes = (size_t)n * group->dev.n_vars * q_elem_size(q_dtype);
+  const size_t obytes = (size_t)n * out_per_state * sizeof(double);
+  int rc = B200DF_OK;
+  {
+    ScratchBuffer dq, dout;
+    dq.stream = dout.stream = stream;
+    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMallocAsync(&dout.p, std::max<size_t>(obytes, 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+    {
+      set_error("staging the batch failed: %s", cudaGetErrorString(e));
+      rc = B200DF_ERR_CUDA;
+    }
+    if (!rc)
+    {
+      double* o = static_cast<double*>(dout.p);
+      if (mode == OUT_CENTERS)
+        rc = dispatch_exact<OUT_CENTERS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
+      else if (mode == OUT_TRANSFORMS)
+        rc = dispatch_exact<OUT_TRANSFORMS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
+      else
+        rc = dispatch_exact<OUT_CLEARANCE>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
+    }
+    if (!rc)
+    {
+      e = cudaMemcpyAsync(out, dout.p, obytes, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess)
+      {
+        set_error("reading results back failed: %s", cudaGetErrorString(e));
+        rc = B200DF_ERR_CUDA;
+      }
+    }
+  }
+  cudaStreamSynchronize(stream);
+  cudaStreamDestroy(stream);
+  return rc;
+}
+
+int b200df_sphere_centers(const b200df_group* group, const void* q, int q_dtype, int64_t n, double* centers)
+{
+  B200DF_REQUIRE(group, "null group");
+  return run_f64_output(group, nullptr, q, q_dtype, n, OUT_CENTERS, (size_t)group->dev.n_spheres * 3, centers);
+}
+
+int b200df_distance_batch(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
+                          double* min_clearance)
+{
+  B200DF_REQUIRE(group && world, "null argument");
+  return run_f64_output(group, world, q, q_dtype, n, OUT_CLEARANCE, 1, min_clearance);
+}
+
+int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64_t n, double* link_transforms)
+{
+  B200DF_REQUIRE(model, "null model");
+  // an empty group over the model gives the kernel its link table
+  b200df_group_desc gd{};
+  gd.n_group_links = 0;
+  gd.resolution = 1.0;
+  b200df_group* g = nullptr;
+  int rc = b200df_group_create(model, &gd, &g);
+  if (rc)
+    return rc;
+  rc = run_f64_output(g, nullptr, q, q_dtype, n, OUT_TRANSFORMS, (size_t)model->n_links * 12, link_transforms);
+  b200df_group_destroy(g);
+  return rc;
+}
+
+int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
+                           double* centers)
+{
+  B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && dist && grad && type)), "bad arguments");
+  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
+  if (n == 0)
+    return B200DF_OK;
+  FieldDev wf, sf;
+  int elem;
+  int rc = prepare_fields(group, world, self, flags, &wf, &sf, &elem);
+  if (rc)
+    return rc;
+  const GroupDev& g = group->dev;
+  const size_t S = (size_t)g.n_spheres;
+  DeviceGuard dg(group->device);
+  cudaStream_t stream;
+  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const size_t qbytes = (size_t)n * g.n_vars * q_elem_size(q_dtype);
+  {
+    ScratchBuffer dq, dd, dgr, dt, dc;
+    dq.stream = dd.stream = dgr.stream = dt.stream = dc.stream = stream;
+    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMallocAsync(&dd.p, std::max<size_t>(n * S * sizeof(double), 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMallocAsync(&dgr.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMallocAsync(&dt.p, std::max<size_t>(n * S, 1), stream);
+    if (e == cudaSuccess && centers)
+      e = cudaMallocAsync(&dc.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+    {
+      set_error("staging the batch failed: %s", cudaGetErrorString(e));
+      rc = B200DF_ERR_CUDA;
+    }
+    if (!rc)
+    {
+      int block;
+      size_t bytes;
+      rc = pick_block(g, true, false, &block, &bytes);
+      const unsigned grid = (unsigned)((n + block - 1) / block);
+#define B200DF_LAUNCH_GRAD(QT, FT)                                                                                 \
+  do                                                                                                               \
+  {                                                                                                                \
+    if (!rc)                                                                                                       \
+      rc = set_smem_limit(gradients_kernel<QT, FT>, bytes);                                                        \
+    if (!rc)                                                                                                       \
+      gradients_kernel<QT, FT><<<grid, block, bytes, stream>>>(                                                    \
+          g, wf, sf, static_cast<const QT*>(dq.p), n, flags, static_cast<double*>(dd.p),                           \
+          static_cast<double*>(dgr.p), static_cast<uint8_t*>(dt.p), static_cast<double*>(dc.p));                   \
+  } while (0)
+      if (q_dtype == B200DF_Q_F32 && elem == 1)
+        B200DF_LAUNCH_GRAD(float, uint8_t);
+      else if (q_dtype == B200DF_Q_F32)
+        B200DF_LAUNCH_GRAD(float, uint16_t);
+      else if (elem == 1)
+        B200DF_LAUNCH_GRAD(double, uint8_t);
+      else
+        B200DF_LAUNCH_GRAD(double, uint16_t);
+#undef B200DF_LAUNCH_GRAD
+      if (!rc)
+      {
+        B200DF_LAUNCHED();
+        e = cudaGetLastError();
+        if (e != cudaSuccess)
+        {
+          set_error("gradient kernel launch failed: %s", cudaGetErrorString(e));
+          rc = B200DF_ERR_CUDA;
+        }
+      }
+    }
+    if (!rc)
+    {
+      e = cudaMemcpyAsync(dist, dd.p, n * S * sizeof(double), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(grad, dgr.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(type, dt.p, n * S, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess && centers)
+        e = cudaMemcpyAsync(centers, dc.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess)
+      {
+        set_error("reading gradients back failed: %s", cudaGetErrorString(e));
+        rc = B200DF_ERR_CUDA;
+      }
+    }
+  }
+  cudaStreamSynchronize(stream);
+  cudaStreamDestroy(stream);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,5 +1,5 @@
-// Batched state validity (kernels 1-4): forward kinematics, collision-sphere posing, sphere-vs-field lookups,
-// ACM-pruned intra-group sphere pairs.  EXACT path: fp64 arithmetic in the reference's operation order.
+// Batched state validity (kernels 1-4 fused): forward kinematics, collision-sphere posing, sphere-vs-field lookups
+// and ACM-pruned intra-group sphere pairs, one thread per state, fp64 in the reference's operation order.
 //
 // Reference being replaced, per state:
 //   RobotState::updateLinkTransformsInternal           robot_state/src/robot_state.cpp:718-755
@@ -11,10 +11,12 @@
 //   CollisionEnvDistanceField::getSelfCollisions        :277-356
 //   CollisionEnvDistanceField::getIntraGroupCollisions  :433-660, doBoundingSpheresIntersect types.cpp:410-420
 //
-// Layout: one thread per state.  Model tables are read through uniform (warp-broadcast) loads; every per-state
-// intermediate that has to survive the FK sweep (branch-parent transforms, posed sphere centres, posed bounding
-// sphere centres) lives in shared memory as [item][component][thread], so a thread only ever touches its own
-// column (conflict-free, no block synchronisation after the joint values are staged).
+// Layout of the verdict kernel.  The links are swept once in model (DFS) order.  A verdict is a logical OR over
+// sphere tests, so the intra-group pairs are folded into the same sweep: a link that is the lower-index side of an
+// enabled pair keeps its posed sphere centres in shared memory ("stored" link); when the higher-index partner is
+// swept, each of its freshly posed spheres is tested against the stored spheres of the partners whose bounding
+// spheres pass the reference's prune.  Only stored links occupy shared memory ([item][component][thread], a thread
+// only touches its own column), which is what lets 8-9 warps share an SM instead of 3.
 //
 // Compiled with --fmad=false so that mul/add round like the reference's non-FMA x86-64 build.
 #include <algorithm>
@@ -24,639 +26,240 @@
 #include <map>
 #include <memory>
 
-#include "b200df_internal.cuh"
+#include "validity_common.cuh"
 
 using namespace b200df;
 
 namespace b200df
 {
-struct DevLink
-{
-  int parent;
-  int joint_type;
-  int var;        // first variable read for this joint (already redirected to the mimicked joint)
-  int is_mimic;
-  double mimic_mult, mimic_off;
-  double ax, ay, az, x2, y2, z2, xy, xz, yz;  // RevoluteJointModel::setAxis precompute
-  double origin[12];
-  int origin_is_identity;
-  int parent_is_prev;  // parent == i-1: parent transform is still in registers
-  int store_slot;      // >=0: save this link's transform for a later non-adjacent child
-  int parent_slot;     // slot holding the parent's transform when !parent_is_prev
-};
-
-struct DevGroupLink  // per group link with geometry, in group order
-{
-  int link;  // model link index
-  int sphere_begin, sphere_end;
-  int self_enabled;
-  double bs[4];  // relative bounding sphere centre + radius
-};
-
-struct DevPair  // enabled link pair (i < j), indices into the group-link table
-{
-  int gi, gj;
-  double radius_sum;  // p1_radius + p2_radius of doBoundingSpheresIntersect
-};
-
-struct GroupDev
-{
-  const DevLink* links;
-  int n_links;
-  int n_vars;
-  int n_slots;
-  const int* link_gslot;  // [n_links] index into glinks or -1
-  const DevGroupLink* glinks;
-  int n_glinks;
-  const double* sph;      // [S][4] rel xyz + radius
-  const int* sph_thr;     // [S] unsigned-field verdict threshold: collide iff d2 < thr
-  const int* sph_cls;     // [S] radius class
-  int n_spheres;
-  const DevPair* pairs;
-  int n_pairs;
-  const double* pair_thr;  // [U][U] : ||c1-c2|| < r1+r2  <=>  squaredNorm < pair_thr[cls1][cls2]
-  int n_cls;
-  double tol, max_prop;
-};
-}  // namespace b200df
-
-struct b200df_model
-{
-  int device = 0;
-  int n_links = 0, n_vars = 0;
-  std::vector<DevLink> links;
-  std::vector<int> has_geometry;
-  std::vector<int> sphere_offset;
-  std::vector<double> spheres;
-  std::vector<double> bsphere;
-  std::vector<int64_t> point_offset;
-  std::vector<double> points;
-  int n_slots = 0;
-  DevLink* d_links = nullptr;
-};
-
-struct b200df_group
-{
-  const b200df_model* model = nullptr;
-  int device = 0;
-  b200df_group_desc desc{};
-  std::vector<DevGroupLink> glinks;
-  std::vector<int> link_gslot;
-  std::vector<double> sph;
-  std::vector<DevPair> pairs;
-  int n_cls = 0;
-  GroupDev dev{};
-  std::vector<void*> allocations;
-};
+int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                      int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream);
+}
 
 namespace
 {
-// ------------------------------------------------------------------------------------------------------------
-// device maths (operation order = Eigen 3.3 fixed-size products as the reference evaluates them: left-to-right sums)
-// ------------------------------------------------------------------------------------------------------------
-// r = a.affine() * b.matrix() with implied last row (0,0,0,1).  Zero terms are dropped (x + a*0 == x for the
-// finite values that occur here), the "+ a3*1" term is kept as "+ a3".
-__device__ __forceinline__ void iso_mul(const double* a, const double* b, double* r)
+// what the verdict kernel reads of a field: the fp64 world->grid mapping plus integer bounds
+struct LookupDev
 {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-  {
-    const double a0 = a[4 * i], a1 = a[4 * i + 1], a2 = a[4 * i + 2], a3 = a[4 * i + 3];
-    r[4 * i + 0] = (a0 * b[0] + a1 * b[4]) + a2 * b[8];
-    r[4 * i + 1] = (a0 * b[1] + a1 * b[5]) + a2 * b[9];
-    r[4 * i + 2] = (a0 * b[2] + a1 * b[6]) + a2 * b[10];
-    r[4 * i + 3] = ((a0 * b[3] + a1 * b[7]) + a2 * b[11]) + a3;
-  }
-}
-
-__device__ __forceinline__ void iso_apply(const double* t, double x, double y, double z, double& ox, double& oy,
-                                          double& oz)
-{
-  ox = t[3] + ((t[0] * x + t[1] * y) + t[2] * z);
-  oy = t[7] + ((t[4] * x + t[5] * y) + t[6] * z);
-  oz = t[11] + ((t[8] * x + t[9] * y) + t[10] * z);
-}
-
-template <typename QT>
-__device__ __forceinline__ double joint_value(const DevLink& l, const double* qs, int k, int stride)
-{
-  const double v = qs[(l.var + k) * stride];
-  return l.is_mimic ? l.mimic_mult * v + l.mimic_off : v;
-}
-
-// *JointModel::computeTransform
-template <typename QT>
-__device__ __forceinline__ void joint_transform(const DevLink& l, const double* qs, int stride, double* t)
-{
-  t[0] = 1.0; t[1] = 0.0; t[2] = 0.0; t[3] = 0.0;
-  t[4] = 0.0; t[5] = 1.0; t[6] = 0.0; t[7] = 0.0;
-  t[8] = 0.0; t[9] = 0.0; t[10] = 1.0; t[11] = 0.0;
-  switch (l.joint_type)
-  {
-    case B200DF_JOINT_REVOLUTE:
-    {
-      const double v = joint_value<QT>(l, qs, 0, stride);
-      double s, c;
-      sincos(v, &s, &c);
-      const double tt = 1.0 - c;
-      const double txy = tt * l.xy, txz = tt * l.xz, tyz = tt * l.yz;
-      const double zs = l.az * s, ys = l.ay * s, xs = l.ax * s;
-      t[0] = tt * l.x2 + c;
-      t[4] = txy + zs;
-      t[8] = txz - ys;
-      t[1] = txy - zs;
-      t[5] = tt * l.y2 + c;
-      t[9] = tyz + xs;
-      t[2] = txz + ys;
-      t[6] = tyz - xs;
-      t[10] = tt * l.z2 + c;
-      break;
-    }
-    case B200DF_JOINT_PRISMATIC:
-    {
-      const double v = joint_value<QT>(l, qs, 0, stride);
-      t[3] = l.ax * v;
-      t[7] = l.ay * v;
-      t[11] = l.az * v;
-      break;
-    }
-    case B200DF_JOINT_PLANAR:
-    {
-      const double x = joint_value<QT>(l, qs, 0, stride), y = joint_value<QT>(l, qs, 1, stride),
-                   th = joint_value<QT>(l, qs, 2, stride);
-      double s, c;
-      sincos(th, &s, &c);
-      const double c1 = 1.0 - c;
-      t[0] = c1 * 0.0 * 0.0 + c;
-      t[5] = c1 * 0.0 * 0.0 + c;
-      t[10] = c1 * 1.0 * 1.0 + c;
-      t[1] = c1 * 0.0 * 0.0 - s * 1.0;
-      t[4] = c1 * 0.0 * 0.0 + s * 1.0;
-      t[3] = x;
-      t[7] = y;
-      t[11] = 0.0;
-      break;
-    }
-    case B200DF_JOINT_FLOATING:
-    {
-      double qx = joint_value<QT>(l, qs, 3, stride), qy = joint_value<QT>(l, qs, 4, stride),
-             qz = joint_value<QT>(l, qs, 5, stride), qw = joint_value<QT>(l, qs, 6, stride);
-      const double n = sqrt(((qx * qx + qy * qy) + qz * qz) + qw * qw);
-      qx /= n;
-      qy /= n;
-      qz /= n;
-      qw /= n;
-      const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
-      const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
-      const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
-      const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-      t[0] = 1.0 - (tyy + tzz);
-      t[1] = txy - twz;
-      t[2] = txz + twy;
-      t[4] = txy + twz;
-      t[5] = 1.0 - (txx + tzz);
-      t[6] = tyz - twx;
-      t[8] = txz - twy;
-      t[9] = tyz + twx;
-      t[10] = 1.0 - (txx + tyy);
-      t[3] = joint_value<QT>(l, qs, 0, stride);
-      t[7] = joint_value<QT>(l, qs, 1, stride);
-      t[11] = joint_value<QT>(l, qs, 2, stride);
-      break;
-    }
-    default:
-      break;
-  }
-}
-
-// RobotState::updateLinkTransformsInternal for link i; cur holds link i-1 on entry and link i on exit
-template <typename QT>
-__device__ __forceinline__ void fk_step(const DevLink& l, const double* qs, double* slots, int stride, double* cur)
-{
-  double par[12];
-  if (l.parent >= 0)
-  {
-    if (l.parent_is_prev)
-    {
-#pragma unroll
-      for (int k = 0; k < 12; ++k)
-        par[k] = cur[k];
-    }
-    else
-    {
-#pragma unroll
-      for (int k = 0; k < 12; ++k)
-        par[k] = slots[(l.parent_slot * 12 + k) * stride];
-    }
-  }
-  if (l.joint_type == B200DF_JOINT_FIXED)
-  {
-    if (l.parent >= 0)
-      iso_mul(par, l.origin, cur);
-    else
-    {
-      // root with a fixed joint: origin identity -> J (= identity); else origin.affine() * identity
-      double j[12];
-      joint_transform<QT>(l, qs, stride, j);
-      if (l.origin_is_identity)
-      {
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-          cur[k] = j[k];
-      }
-      else
-        iso_mul(l.origin, j, cur);
-    }
-  }
-  else
-  {
-    double j[12];
-    joint_transform<QT>(l, qs, stride, j);
-    if (l.parent >= 0)
-    {
-      if (l.origin_is_identity)
-        iso_mul(par, j, cur);
-      else
-      {
-        double tmp[12];
-        iso_mul(par, l.origin, tmp);
-        iso_mul(tmp, j, cur);
-      }
-    }
-    else
-    {
-      if (l.origin_is_identity)
-      {
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-          cur[k] = j[k];
-      }
-      else
-        iso_mul(l.origin, j, cur);
-    }
-  }
-  if (l.store_slot >= 0)
-  {
-#pragma unroll
-    for (int k = 0; k < 12; ++k)
-      slots[(l.store_slot * 12 + k) * stride] = cur[k];
-  }
-}
-
-// getDistanceGradient's cell lookup without the gradient: returns false when the centre is outside the
-// 1-cell-inset box (the reference then reports max_distance => never a collision, Q4)
-__device__ __forceinline__ bool inset_cell(const GridDev& g, double x, double y, double z, long& idx)
-{
-  const double fx = floor((x - g.om[0]) * g.oo), fy = floor((y - g.om[1]) * g.oo), fz = floor((z - g.om[2]) * g.oo);
-  if (!(fx >= 1.0 && fy >= 1.0 && fz >= 1.0 && fx < (double)(g.n[0] - 1) && fy < (double)(g.n[1] - 1) &&
-        fz < (double)(g.n[2] - 1)))
-    return false;
-  idx = (long)fx * g.stride1 + (long)fy * g.stride2 + (long)fz;
-  return true;
-}
-
-template <typename FT>
-__device__ __forceinline__ double cell_dist(const FieldDev& f, long idx)
-{
-  double d = f.sqrt_table[static_cast<const FT*>(f.d2)[idx]];
-  if (f.neg)
-    d = d - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
-  else
-    d = d - f.sqrt_table[0];
-  return d;
-}
-
-// getCollisionSphereCollision's per-sphere predicate (collision_distance_field_types.cpp:213-227)
-template <typename FT>
-__device__ __forceinline__ bool sphere_collides(const FieldDev& f, double x, double y, double z, double radius,
-                                                int thr, double tol, double max_prop)
-{
-  long idx;
-  if (!inset_cell(f.g, x, y, z, idx))
-    return false;
-  if (!f.neg)
-    return (int)static_cast<const FT*>(f.d2)[idx] < thr;  // host-resolved, exactly equivalent threshold
-  const double dist = cell_dist<FT>(f, idx);
-  return (max_prop > dist) && (radius - dist > tol);
-}
-
-enum OutMode
-{
-  OUT_VERDICT = 0,
-  OUT_CENTERS = 1,
-  OUT_TRANSFORMS = 2,
-  OUT_CLEARANCE = 3,
+  double om[3];      // origin_minus_
+  double oo;         // oo_resolution_
+  unsigned lim[3];   // n-2 (0 when n < 2): cell c is inside the 1-cell inset box iff (unsigned)(c-1) < lim
+  int stride1, stride2;
+  const void* d2;
+  const void* neg;
+  const double* sqrt_table;
 };
 
-// ------------------------------------------------------------------------------------------------------------
-// The EXACT validity kernel
-// ------------------------------------------------------------------------------------------------------------
-template <typename QT, typename FT, int MODE>
-__global__ void validity_exact_kernel(GroupDev g, FieldDev wf, FieldDev sf, const QT* __restrict__ q, long n,
-                                      int flags, uint8_t* __restrict__ verdict, double* __restrict__ out_f64)
+LookupDev make_lookup(const FieldDev& f)
+{
+  LookupDev l{};
+  for (int i = 0; i < 3; ++i)
+  {
+    l.om[i] = f.g.om[i];
+    l.lim[i] = f.g.n[i] >= 2 ? (unsigned)(f.g.n[i] - 2) : 0u;
+  }
+  l.oo = f.g.oo;
+  l.stride1 = (int)f.g.stride1;
+  l.stride2 = (int)f.g.stride2;
+  l.d2 = f.d2;
+  l.neg = f.neg;
+  l.sqrt_table = f.sqrt_table;
+  return l;
+}
+
+// getCollisionSphereCollision's per-sphere predicate (collision_distance_field_types.cpp:213-227) on top of
+// getDistanceGradient's cell lookup (distance_field.cpp:62-86, voxel_grid.h:515-532).
+// floor((p - origin_minus) * oo) is evaluated in fp64 exactly like the reference; cvt.rmi.s32.f64 IS that floor for
+// every value inside the grid and saturates outside (NaN -> 0), where the unsigned range test fails anyway.
+// A centre outside the 1-cell inset box reads as "max distance" in the reference => never a collision (Q4).
+// world->grid cell of a sphere centre: flat voxel index (0 when outside) + "inside the 1-cell inset box"
+__device__ __forceinline__ unsigned cell_index(const LookupDev& f, double x, double y, double z, bool& in)
+{
+  const int ix = __double2int_rd((x - f.om[0]) * f.oo);
+  const int iy = __double2int_rd((y - f.om[1]) * f.oo);
+  const int iz = __double2int_rd((z - f.om[2]) * f.oo);
+  in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
+  return in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
+}
+
+template <typename FT>
+__device__ __forceinline__ bool voxel_hits(const LookupDev& f, unsigned idx, bool in, int d2, double radius, int thr,
+                                           double tol, double max_prop)
+{
+  if (!f.neg)
+    return in & (d2 < thr);  // host-resolved threshold, exactly equivalent to the fp64 predicate
+  const double dist = f.sqrt_table[d2] - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
+  return in && (max_prop > dist) && (radius - dist > tol);
+}
+
+constexpr int kBatch = 4;  // spheres posed / looked up / pair-tested together (independent chains for the fp64 pipe)
+
+template <typename QT, typename FT, int B>
+__global__ void __launch_bounds__(B) validity_kernel(GroupDev g, LookupDev wf, LookupDev sf, const QT* __restrict__ q,
+                                                     long n, int flags, uint8_t* __restrict__ verdict)
 {
   extern __shared__ double smem[];
-  const int B = blockDim.x;
   const int tid = threadIdx.x;
   const long base = (long)blockIdx.x * B;
-  double* qs = smem;                               // [n_vars][B]
-  double* slots = qs + (size_t)g.n_vars * B;       // [n_slots][12][B]
-  double* cen = slots + (size_t)g.n_slots * 12 * B;  // [S][3][B]
-  double* bsc = cen + (size_t)g.n_spheres * 3 * B;   // [n_glinks][3][B]
+  const bool do_pairs = (flags & B200DF_CHECK_INTRA) != 0 && g.n_partners > 0;
+  double* slots = smem;                                                           // [n_slots][12][B]
+  double* stc = slots + (size_t)g.n_slots * 12 * B;                               // [n_store_spheres][3][B]
+  double* stb = stc + (do_pairs ? (size_t)g.n_store_spheres * 3 * B : 0);         // [n_store_links][3][B]
+  QT* qs = reinterpret_cast<QT*>(stb + (do_pairs ? (size_t)g.n_store_links * 3 * B : 0));  // [B][n_vars]
 
-  // stage the block's joint values: coalesced read, transposed into [var][thread]
   {
-    const long total = (long)B * g.n_vars;
+    // the tile's joint values are one contiguous run of the batch: straight coalesced copy, rows stay rows
+    const int total = B * g.n_vars;
     const long limit = (n - base) * g.n_vars;
-    for (long e = tid; e < total; e += B)
-    {
-      const int s = (int)(e / g.n_vars), v = (int)(e % g.n_vars);
-      qs[v * B + s] = (e < limit) ? (double)q[base * g.n_vars + e] : 0.0;
-    }
+    const QT* src = q + base * g.n_vars;
+    for (int e = tid; e < total; e += B)
+      qs[e] = (e < limit) ? src[e] : QT(0);
   }
   __syncthreads();
   const long state = base + tid;
   const bool active = state < n;
-  const double* my_q = qs + tid;
+  const QT* my_q = qs + (size_t)tid * g.n_vars;
   double* my_slots = slots + tid;
-  double* my_cen = cen + tid;
-  double* my_bsc = bsc + tid;
+  double* my_stc = stc + tid;
+  double* my_stb = stb + tid;
 
-  bool hit = false;
-  double clearance = DBL_MAX;
+  const bool do_robot = (flags & B200DF_CHECK_ROBOT) != 0;
+  const bool do_self = (flags & B200DF_CHECK_SELF) != 0;
+  bool hit = !active;  // padding lanes never contribute work
   double cur[12];
-  const bool want_pairs = (flags & B200DF_CHECK_INTRA) != 0 && g.n_pairs > 0;
 
   for (int i = 0; i < g.n_links; ++i)
   {
-    const DevLink& l = g.links[i];
-    fk_step<QT>(l, my_q, my_slots, B, cur);
-    if (MODE == OUT_TRANSFORMS)
-    {
-      if (active)
-      {
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-          out_f64[(state * g.n_links + i) * 12 + k] = cur[k];
-      }
-      continue;
-    }
+    fk_step_sparse(g.links[i], my_q, my_slots, 1, B, cur);
     const int gs = g.link_gslot[i];
     if (gs < 0)
       continue;
     const DevGroupLink& gl = g.glinks[gs];
-    // PosedBodySphereDecomposition::updatePose
-    if (want_pairs)
+    const int np = do_pairs ? gl.partner_end - gl.partner_begin : 0;
+    const bool stored = do_pairs && gl.store_link >= 0;
+    const bool self_here = do_self && gl.self_enabled;
+    double bx = 0.0, by = 0.0, bz = 0.0;
+    if (np > 0 || stored)
     {
-      double bx, by, bz;
-      iso_apply(cur, gl.bs[0], gl.bs[1], gl.bs[2], bx, by, bz);
-      my_bsc[(gs * 3 + 0) * B] = bx;
-      my_bsc[(gs * 3 + 1) * B] = by;
-      my_bsc[(gs * 3 + 2) * B] = bz;
+      iso_apply(cur, gl.bs[0], gl.bs[1], gl.bs[2], bx, by, bz);  // posed bounding-sphere centre (types.cpp:398-399)
+      if (stored)
+      {
+        my_stb[(gl.store_link * 3 + 0) * B] = bx;
+        my_stb[(gl.store_link * 3 + 1) * B] = by;
+        my_stb[(gl.store_link * 3 + 2) * B] = bz;
+      }
     }
-    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    // partners are handled 32 at a time so that one bit mask per lane says which of them passed the prune
+    const int n_chunks = np > 0 ? (np + 31) / 32 : 1;
+    for (int c = 0; c < n_chunks; ++c)
     {
-      const double* rel = g.sph + 4 * s;
-      double cx, cy, cz;
-      iso_apply(cur, rel[0], rel[1], rel[2], cx, cy, cz);
-      if (want_pairs)
+      const int p0 = gl.partner_begin + 32 * c;
+      unsigned lane_mask = 0u;
+      if (np > 0)
       {
-        my_cen[(s * 3 + 0) * B] = cx;
-        my_cen[(s * 3 + 1) * B] = cy;
-        my_cen[(s * 3 + 2) * B] = cz;
-      }
-      if (MODE == OUT_CENTERS)
-      {
-        if (active)
+        const int pc = min(32, gl.partner_end - p0);
+#pragma unroll 2
+        for (int b = 0; b < pc; ++b)
         {
-          out_f64[(state * g.n_spheres + s) * 3 + 0] = cx;
-          out_f64[(state * g.n_spheres + s) * 3 + 1] = cy;
-          out_f64[(state * g.n_spheres + s) * 3 + 2] = cz;
-        }
-        continue;
-      }
-      if (MODE == OUT_CLEARANCE)
-      {
-        long idx;
-        double d = wf.max_distance;
-        if (inset_cell(wf.g, cx, cy, cz, idx))
-          d = cell_dist<FT>(wf, idx);
-        d = d - rel[3];
-        if (d < clearance)
-          clearance = d;
-        continue;
-      }
-      if (flags & B200DF_CHECK_ROBOT)
-        hit |= sphere_collides<FT>(wf, cx, cy, cz, rel[3], g.sph_thr[s], g.tol, g.max_prop);
-      if ((flags & B200DF_CHECK_SELF) && gl.self_enabled)
-        hit |= sphere_collides<FT>(sf, cx, cy, cz, rel[3], g.sph_thr[s], g.tol, g.max_prop);
-    }
-  }
-  if (MODE == OUT_TRANSFORMS || MODE == OUT_CENTERS)
-    return;
-  if (MODE == OUT_CLEARANCE)
-  {
-    if (active)
-      out_f64[state] = clearance;
-    return;
-  }
-
-  // intra-group sphere pairs (kernel 4).  A warp stops as soon as every one of its states has a verdict.
-  if (want_pairs)
-  {
-    for (int p = 0; p < g.n_pairs; ++p)
-    {
-      if (__all_sync(0xffffffffu, hit || !active))
-        break;
-      const DevPair pr = g.pairs[p];
-      const double dx = my_bsc[(pr.gi * 3 + 0) * B] - my_bsc[(pr.gj * 3 + 0) * B];
-      const double dy = my_bsc[(pr.gi * 3 + 1) * B] - my_bsc[(pr.gj * 3 + 1) * B];
-      const double dz = my_bsc[(pr.gi * 3 + 2) * B] - my_bsc[(pr.gj * 3 + 2) * B];
-      const double d2 = (dx * dx + dy * dy) + dz * dz;
-      // doBoundingSpheresIntersect: squared distance against the UN-squared radius sum (Q2)
-      if (hit || !(d2 < pr.radius_sum))
-        continue;
-      const DevGroupLink& gi = g.glinks[pr.gi];
-      const DevGroupLink& gj = g.glinks[pr.gj];
-      for (int k = gi.sphere_begin; k < gi.sphere_end; ++k)
-      {
-        const double ax = my_cen[(k * 3 + 0) * B], ay = my_cen[(k * 3 + 1) * B], az = my_cen[(k * 3 + 2) * B];
-        const double* thr_row = g.pair_thr + (size_t)g.sph_cls[k] * g.n_cls;
-        for (int m = gj.sphere_begin; m < gj.sphere_end; ++m)
-        {
-          const double ex = ax - my_cen[(m * 3 + 0) * B];
-          const double ey = ay - my_cen[(m * 3 + 1) * B];
-          const double ez = az - my_cen[(m * 3 + 2) * B];
-          const double e2 = (ex * ex + ey * ey) + ez * ez;
-          hit |= e2 < thr_row[g.sph_cls[m]];
+          const DevPartner& pr = g.partners[p0 + b];
+          const double dx = my_stb[(pr.store_link * 3 + 0) * B] - bx;
+          const double dy = my_stb[(pr.store_link * 3 + 1) * B] - by;
+          const double dz = my_stb[(pr.store_link * 3 + 2) * B] - bz;
+          const double d2 = (dx * dx + dy * dy) + dz * dz;
+          // doBoundingSpheresIntersect compares the SQUARED distance with the UN-squared radius sum (Q2);
+          // tight2 additionally drops link pairs none of whose spheres can touch (never changes a verdict)
+          const bool pass = !hit && (d2 < pr.radius_sum) && (d2 < pr.tight2);
+          lane_mask |= (pass ? 1u : 0u) << b;
         }
       }
+      const unsigned warp_mask = __reduce_or_sync(0xffffffffu, lane_mask);
+      for (int s0 = gl.sphere_begin; s0 < gl.sphere_end; s0 += kBatch)
+      {
+        const int cnt = min(kBatch, gl.sphere_end - s0);  // warp-uniform
+        double cx[kBatch], cy[kBatch], cz[kBatch];
+        unsigned widx[kBatch], sidx[kBatch];
+        bool win[kBatch], sin_[kBatch];
+        int wv[kBatch], sv[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+        {
+          if (k < cnt)
+          {
+            const double* rel = g.sph + 4 * (s0 + k);
+            iso_apply(cur, rel[0], rel[1], rel[2], cx[k], cy[k], cz[k]);  // updatePose (types.cpp:393-396)
+            if (c == 0)
+            {
+              // the voxel loads are issued here and consumed after the pair tests of this batch
+              if (do_robot)
+              {
+                widx[k] = cell_index(wf, cx[k], cy[k], cz[k], win[k]);
+                wv[k] = (int)static_cast<const FT*>(wf.d2)[widx[k]];
+              }
+              if (self_here)
+              {
+                sidx[k] = cell_index(sf, cx[k], cy[k], cz[k], sin_[k]);
+                sv[k] = (int)static_cast<const FT*>(sf.d2)[sidx[k]];
+              }
+              if (stored)
+              {
+                const int slot = gl.store_sphere + (s0 + k - gl.sphere_begin);
+                my_stc[(slot * 3 + 0) * B] = cx[k];
+                my_stc[(slot * 3 + 1) * B] = cy[k];
+                my_stc[(slot * 3 + 2) * B] = cz[k];
+              }
+            }
+          }
+        }
+        unsigned mm = warp_mask;
+        const double* t_row = g.pair_T + gl.pair_const_begin + (long)(s0 - gl.sphere_begin) * gl.pair_const_stride;
+        while (mm)
+        {
+          const int b = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const DevPartner& pr = g.partners[p0 + b];
+          const double* t = t_row + pr.const_offset;
+          const double* pc = my_stc + (size_t)pr.store_sphere * 3 * B;
+          const int stride = gl.pair_const_stride;
+          bool h = false;
+          for (int m = 0; m < pr.count; ++m)
+          {
+            const double px = pc[(m * 3 + 0) * B], py = pc[(m * 3 + 1) * B], pz = pc[(m * 3 + 2) * B];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)
+            {
+              if (k < cnt)
+              {
+                const double ex = cx[k] - px, ey = cy[k] - py, ez = cz[k] - pz;
+                const double e2 = (ex * ex + ey * ey) + ez * ez;
+                h |= e2 < t[k * stride + m];  // ||c1-c2|| < r1+r2 (:574-584), sqrt-free, bit-equivalent threshold
+              }
+            }
+          }
+          hit |= h && ((lane_mask >> b) & 1u);
+        }
+        if (c == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+          {
+            if (k < cnt)
+            {
+              const double radius = g.sph[4 * (s0 + k) + 3];
+              const int thr = g.sph_thr[s0 + k];
+              if (do_robot)
+                hit |= voxel_hits<FT>(wf, widx[k], win[k], wv[k], radius, thr, g.tol, g.max_prop);
+              if (self_here)
+                hit |= voxel_hits<FT>(sf, sidx[k], sin_[k], sv[k], radius, thr, g.tol, g.max_prop);
+            }
+          }
+        }
+      }
     }
+    if (__all_sync(0xffffffffu, hit))
+      break;  // every state of this warp already has its verdict
   }
   if (active)
     verdict[state] = hit ? 1 : 0;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// Gradient kernel (getCollisionGradients :1536-1557): self field, intra group, environment — in that order,
-// each keeping the per-sphere minimum with strict '<' like the reference.
-// ------------------------------------------------------------------------------------------------------------
-template <typename FT>
-__device__ __forceinline__ void field_gradient_update(const FieldDev& f, double x, double y, double z, double max_value,
-                                                      int type, double& best, double& gx, double& gy, double& gz,
-                                                      int& btype)
-{
-  // getCollisionSphereGradients (collision_distance_field_types.cpp:143-204), subtract_radii == false
-  long idx;
-  double dist, dgx = 0.0, dgy = 0.0, dgz = 0.0;
-  if (!inset_cell(f.g, x, y, z, idx))
-    dist = f.max_distance;  // in_bounds = false, gradient 0: the "out of bounds" return is dead (Q4)
-  else
-  {
-    const double itr = (double)f.inv_twice_res;
-    dgx = (cell_dist<FT>(f, idx + f.g.stride1) - cell_dist<FT>(f, idx - f.g.stride1)) * itr;
-    dgy = (cell_dist<FT>(f, idx + f.g.stride2) - cell_dist<FT>(f, idx - f.g.stride2)) * itr;
-    dgz = (cell_dist<FT>(f, idx + 1) - cell_dist<FT>(f, idx - 1)) * itr;
-    dist = cell_dist<FT>(f, idx);
-  }
-  if (dist < max_value && dist < best)
-  {
-    best = dist;
-    gx = dgx;
-    gy = dgy;
-    gz = dgz;
-    btype = type;
-  }
-}
-
-template <typename QT, typename FT>
-__global__ void gradients_kernel(GroupDev g, FieldDev wf, FieldDev sf, const QT* __restrict__ q, long n, int flags,
-                                 double* __restrict__ out_dist, double* __restrict__ out_grad,
-                                 uint8_t* __restrict__ out_type, double* __restrict__ out_cen)
-{
-  extern __shared__ double smem[];
-  const int B = blockDim.x;
-  const int tid = threadIdx.x;
-  const long base = (long)blockIdx.x * B;
-  double* qs = smem;
-  double* slots = qs + (size_t)g.n_vars * B;
-  double* cen = slots + (size_t)g.n_slots * 12 * B;
-  {
-    const long total = (long)B * g.n_vars;
-    const long limit = (n - base) * g.n_vars;
-    for (long e = tid; e < total; e += B)
-    {
-      const int s = (int)(e / g.n_vars), v = (int)(e % g.n_vars);
-      qs[v * B + s] = (e < limit) ? (double)q[base * g.n_vars + e] : 0.0;
-    }
-  }
-  __syncthreads();
-  const long state = base + tid;
-  if (state >= n)
-    return;
-  const double* my_q = qs + tid;
-  double* my_slots = slots + tid;
-  double* my_cen = cen + tid;
-  const int S = g.n_spheres;
-  double* dist = out_dist + state * S;
-  double* grad = out_grad + state * S * 3;
-  uint8_t* type = out_type + state * S;
-
-  double cur[12];
-  for (int i = 0; i < g.n_links; ++i)
-  {
-    const DevLink& l = g.links[i];
-    fk_step<QT>(l, my_q, my_slots, B, cur);
-    const int gs = g.link_gslot[i];
-    if (gs < 0)
-      continue;
-    const DevGroupLink& gl = g.glinks[gs];
-    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
-    {
-      const double* rel = g.sph + 4 * s;
-      double cx, cy, cz;
-      iso_apply(cur, rel[0], rel[1], rel[2], cx, cy, cz);
-      my_cen[(s * 3 + 0) * B] = cx;
-      my_cen[(s * 3 + 1) * B] = cy;
-      my_cen[(s * 3 + 2) * B] = cz;
-      if (out_cen)
-      {
-        out_cen[(state * S + s) * 3 + 0] = cx;
-        out_cen[(state * S + s) * 3 + 1] = cy;
-        out_cen[(state * S + s) * 3 + 2] = cz;
-      }
-      // updateGroupStateRepresentationState :1128-1133
-      double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
-      int bt = B200DF_TYPE_NONE;
-      // getSelfProximityGradients: self field term (:420-422)
-      if ((flags & B200DF_CHECK_SELF) && gl.self_enabled)
-        field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
-      dist[s] = best;
-      grad[3 * s] = gx;
-      grad[3 * s + 1] = gy;
-      grad[3 * s + 2] = gz;
-      type[s] = (uint8_t)bt;
-    }
-  }
-  // getIntraGroupProximityGradients :662-727 — sequential over pairs, both spheres updated with strict '<'
-  if (flags & B200DF_CHECK_INTRA)
-  {
-    for (int p = 0; p < g.n_pairs; ++p)
-    {
-      const DevPair pr = g.pairs[p];
-      const DevGroupLink& gi = g.glinks[pr.gi];
-      const DevGroupLink& gj = g.glinks[pr.gj];
-      for (int k = gi.sphere_begin; k < gi.sphere_end; ++k)
-      {
-        const double ax = my_cen[(k * 3 + 0) * B], ay = my_cen[(k * 3 + 1) * B], az = my_cen[(k * 3 + 2) * B];
-        double dk = dist[k];
-        for (int m = gj.sphere_begin; m < gj.sphere_end; ++m)
-        {
-          const double ex = ax - my_cen[(m * 3 + 0) * B];
-          const double ey = ay - my_cen[(m * 3 + 1) * B];
-          const double ez = az - my_cen[(m * 3 + 2) * B];
-          const double d = sqrt((ex * ex + ey * ey) + ez * ez);
-          if (d < dk)
-          {
-            dk = d;
-            dist[k] = d;
-            grad[3 * k] = ex;
-            grad[3 * k + 1] = ey;
-            grad[3 * k + 2] = ez;
-            type[k] = B200DF_TYPE_INTRA;
-          }
-          if (d < dist[m])
-          {
-            dist[m] = d;
-            grad[3 * m] = -ex;
-            grad[3 * m + 1] = -ey;
-            grad[3 * m + 2] = -ez;
-            type[m] = B200DF_TYPE_INTRA;
-          }
-        }
-      }
-    }
-  }
-  // getEnvironmentProximityGradients :1664-1700
-  if (flags & B200DF_CHECK_ROBOT)
-  {
-    for (int s = 0; s < S; ++s)
-    {
-      double best = dist[s], gx = grad[3 * s], gy = grad[3 * s + 1], gz = grad[3 * s + 2];
-      int bt = type[s];
-      const double before = best;
-      field_gradient_update<FT>(wf, my_cen[(s * 3 + 0) * B], my_cen[(s * 3 + 1) * B], my_cen[(s * 3 + 2) * B],
-                                g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
-      if (best < before)
-      {
-        dist[s] = best;
-        grad[3 * s] = gx;
-        grad[3 * s + 1] = gy;
-        grad[3 * s + 2] = gz;
-        type[s] = (uint8_t)bt;
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -688,90 +291,159 @@ int upload(b200df_group* grp, const std::vector<T>& host, const T** dev)
   return B200DF_OK;
 }
 
-struct ScratchBuffer
+size_t verdict_smem_bytes(const GroupDev& g, int block, bool pairs, size_t q_elem)
 {
-  void* p = nullptr;
-  cudaStream_t stream = nullptr;
-  ~ScratchBuffer()
-  {
-    if (p)
-      cudaFreeAsync(p, stream);
-  }
-};
-
-size_t smem_bytes(const GroupDev& g, int block, bool with_centers, bool with_bsc)
-{
-  size_t d = (size_t)g.n_vars + (size_t)g.n_slots * 12;
-  if (with_centers)
-    d += (size_t)g.n_spheres * 3;
-  if (with_bsc)
-    d += (size_t)g.n_glinks * 3;
-  return d * block * sizeof(double);
+  size_t d = (size_t)g.n_slots * 12;
+  if (pairs)
+    d += (size_t)g.n_store_spheres * 3 + (size_t)g.n_store_links * 3;
+  return d * block * sizeof(double) + (size_t)g.n_vars * block * q_elem;
 }
 
-int pick_block(const GroupDev& g, bool with_centers, bool with_bsc, int* block, size_t* bytes)
-{
-  // largest block (multiple of 32) whose shared-memory footprint still lets two CTAs share an SM, else one
-  const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
-  for (int b : { 128, 96, 64, 32 })
-  {
-    const size_t s = smem_bytes(g, b, with_centers, with_bsc);
-    if (s <= budget2 || (b == 32 && s <= budget1))
-    {
-      *block = b;
-      *bytes = s;
-      return B200DF_OK;
-    }
-  }
-  set_error("robot too large for the per-state shared-memory layout (%zu bytes for 32 states)",
-            smem_bytes(g, 32, with_centers, with_bsc));
-  return B200DF_ERR_UNSUPPORTED;
-}
-
-template <typename K>
-int set_smem_limit(K kernel, size_t bytes)
+template <typename QT, typename FT, int B>
+int launch_verdict_block(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
+                         uint8_t* verdict, size_t bytes, cudaStream_t stream)
 {
   if (bytes > 48 * 1024)
-    B200DF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return B200DF_OK;
-}
-
-template <typename QT, typename FT, int MODE>
-int launch_exact(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
-                 uint8_t* verdict, double* out_f64, cudaStream_t stream)
-{
-  const bool pairs = MODE == OUT_VERDICT && (flags & B200DF_CHECK_INTRA) && g.n_pairs > 0;
-  int block;
-  size_t bytes;
-  int rc = pick_block(g, pairs, pairs, &block, &bytes);
-  if (rc)
-    return rc;
-  rc = set_smem_limit(validity_exact_kernel<QT, FT, MODE>, bytes);
-  if (rc)
-    return rc;
-  const unsigned grid = (unsigned)((n + block - 1) / block);
-  validity_exact_kernel<QT, FT, MODE>
-      <<<grid, block, bytes, stream>>>(g, wf, sf, static_cast<const QT*>(q), n, flags, verdict, out_f64);
+    B200DF_CUDA(cudaFuncSetAttribute(validity_kernel<QT, FT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bytes));
+  const unsigned grid = (unsigned)((n + B - 1) / B);
+  validity_kernel<QT, FT, B><<<grid, B, bytes, stream>>>(g, make_lookup(wf), make_lookup(sf),
+                                                         static_cast<const QT*>(q), n, flags, verdict);
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
 }
 
-template <int MODE>
-int dispatch_exact(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
-                   int q_dtype, long n, int flags, uint8_t* verdict, double* out_f64, cudaStream_t stream)
+template <typename QT, typename FT>
+int launch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
+                   uint8_t* verdict, cudaStream_t stream)
+{
+  const bool pairs = (flags & B200DF_CHECK_INTRA) && g.n_partners > 0;
+  // 64 states per CTA when four or more such CTAs fit an SM, else one warp per CTA
+  size_t bytes = verdict_smem_bytes(g, 64, pairs, sizeof(QT));
+  if (bytes <= 56 * 1024)
+    return launch_verdict_block<QT, FT, 64>(g, wf, sf, q, n, flags, verdict, bytes, stream);
+  bytes = verdict_smem_bytes(g, 32, pairs, sizeof(QT));
+  if (bytes > 220 * 1024)
+  {
+    set_error("robot too large for the per-state shared-memory layout (%zu bytes for 32 states)", bytes);
+    return B200DF_ERR_UNSUPPORTED;
+  }
+  return launch_verdict_block<QT, FT, 32>(g, wf, sf, q, n, flags, verdict, bytes, stream);
+}
+
+int dispatch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                     int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream)
 {
   if (q_dtype == B200DF_Q_F32)
   {
     if (field_elem == 1)
-      return launch_exact<float, uint8_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
-    return launch_exact<float, uint16_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+      return launch_verdict<float, uint8_t>(g, wf, sf, q, n, flags, verdict, stream);
+    return launch_verdict<float, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
   }
   if (field_elem == 1)
-    return launch_exact<double, uint8_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
-  return launch_exact<double, uint16_t, MODE>(g, wf, sf, q, n, flags, verdict, out_f64, stream);
+    return launch_verdict<double, uint8_t>(g, wf, sf, q, n, flags, verdict, stream);
+  return launch_verdict<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
 }
 
+constexpr int kPrecisionV1 = 2;  // undocumented: the round-1 kernel, kept as an independent cross-check
+
+int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int elem, const void* q_dev,
+                int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, cudaStream_t stream)
+{
+  if (precision == kPrecisionV1)
+    return launch_verdict_v1(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+  return dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// Staging contexts of the host-buffer entry point: a batch is cut into chunks that travel H2D -> kernel -> D2H on
+// two streams, so the PCIe copies of one chunk overlap the kernel of the other.  Contexts are cached per group
+// (checks may run concurrently from several threads: each call takes its own context).
+// ------------------------------------------------------------------------------------------------------------
+struct b200df_group::StagePool
+{
+  struct Ctx
+  {
+    cudaStream_t stream[2] = { nullptr, nullptr };
+    void* q[2] = { nullptr, nullptr };
+    uint8_t* v[2] = { nullptr, nullptr };
+    size_t q_bytes = 0, v_bytes = 0;
+  };
+  std::mutex mu;
+  std::vector<Ctx*> free_list;
+  ~StagePool()
+  {
+    for (Ctx* c : free_list)
+      release(c);
+  }
+  static void release(Ctx* c)
+  {
+    for (int i = 0; i < 2; ++i)
+    {
+      cudaFree(c->q[i]);
+      cudaFree(c->v[i]);
+      if (c->stream[i])
+        cudaStreamDestroy(c->stream[i]);
+    }
+    delete c;
+  }
+  Ctx* acquire()
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!free_list.empty())
+    {
+      Ctx* c = free_list.back();
+      free_list.pop_back();
+      return c;
+    }
+    return new Ctx;
+  }
+  void give_back(Ctx* c)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    free_list.push_back(c);
+  }
+};
+
+namespace
+{
+constexpr int64_t kChunkStates = 1 << 20;
+
+int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
+{
+  for (int i = 0; i < 2; ++i)
+  {
+    if (!c->stream[i])
+      B200DF_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+  }
+  if (q_bytes > c->q_bytes)
+  {
+    for (int i = 0; i < 2; ++i)
+    {
+      cudaFree(c->q[i]);
+      c->q[i] = nullptr;
+      B200DF_CUDA(cudaMalloc(&c->q[i], q_bytes));
+    }
+    c->q_bytes = q_bytes;
+  }
+  if (v_bytes > c->v_bytes)
+  {
+    for (int i = 0; i < 2; ++i)
+    {
+      cudaFree(c->v[i]);
+      c->v[i] = nullptr;
+      B200DF_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->v[i]), v_bytes));
+    }
+    c->v_bytes = v_bytes;
+  }
+  return B200DF_OK;
+}
+}  // namespace
+
+namespace b200df
+{
 int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field* self, int flags, FieldDev* wf,
                    FieldDev* sf, int* elem)
 {
@@ -782,6 +454,7 @@ int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field*
   auto check = [&](b200df_field* f, FieldDev* v) -> int {
     B200DF_REQUIRE(f->device == group->device, "field and group live on different devices");
     B200DF_REQUIRE(f->desc.resolution == group->desc.resolution, "field resolution differs from the group's");
+    B200DF_REQUIRE(f->n_voxels < (1L << 31), "field too large for 32-bit voxel indices");
     int rc = field_prepare(f, v, nullptr);
     if (rc)
       return rc;
@@ -807,12 +480,7 @@ int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field*
   }
   return B200DF_OK;
 }
-
-size_t q_elem_size(int q_dtype)
-{
-  return q_dtype == B200DF_Q_F32 ? sizeof(float) : sizeof(double);
-}
-}  // namespace
+}  // namespace b200df
 
 extern "C" {
 
@@ -877,6 +545,16 @@ int b200df_model_create(const b200df_model_desc* d, b200df_model** out)
     l.xy = l.ax * l.ay;
     l.xz = l.ax * l.az;
     l.yz = l.ay * l.az;
+    l.jkind = 0;
+    if (l.joint_type == B200DF_JOINT_REVOLUTE)
+    {
+      if (std::fabs(l.ax) == 1.0 && l.ay == 0.0 && l.az == 0.0)
+        l.jkind = 1;
+      else if (l.ax == 0.0 && std::fabs(l.ay) == 1.0 && l.az == 0.0)
+        l.jkind = 2;
+      else if (l.ax == 0.0 && l.ay == 0.0 && std::fabs(l.az) == 1.0)
+        l.jkind = 3;
+    }
     std::memcpy(l.origin, d->origin + 12 * i, sizeof(l.origin));
     l.origin_is_identity = d->origin_is_identity[i];
     l.parent_is_prev = (l.parent >= 0 && l.parent == i - 1);
@@ -944,7 +622,7 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     prev_link = li;
     if (!model->has_geometry[li])
       continue;  // link_has_geometry_ false: skipped by every loop of the reference
-    DevGroupLink gl;
+    DevGroupLink gl{};
     gl.link = li;
     gl.sphere_begin = (int)(g->sph.size() / 4);
     for (int s = model->sphere_offset[li]; s < model->sphere_offset[li + 1]; ++s)
@@ -978,6 +656,7 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     gl.sphere_end = (int)(g->sph.size() / 4);
     gl.self_enabled = d->self_enabled[i] ? 1 : 0;
     std::memcpy(gl.bs, &model->bsphere[(size_t)li * 4], sizeof(gl.bs));
+    gl.store_link = gl.store_sphere = -1;
     gslot_of_pos[i] = (int)g->glinks.size();
     g->link_gslot[li] = (int)g->glinks.size();
     g->glinks.push_back(gl);
@@ -1000,11 +679,73 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
       }
   }
   const int U = (int)radii.size();
-  g->n_cls = U;
   std::vector<double> pair_thr((size_t)U * U);
   for (int a = 0; a < U; ++a)
     for (int b = 0; b < U; ++b)
       pair_thr[(size_t)a * U + b] = sqrt_less_threshold(radii[a] + radii[b]);
+
+  // ---- tables of the fused sweep.  A pair only matters when both links have spheres.
+  const int G = (int)g->glinks.size();
+  auto count_of = [&](int gs) { return g->glinks[gs].sphere_end - g->glinks[gs].sphere_begin; };
+  // radius around the reference's bounding-sphere centre that really encloses the link's collision spheres
+  // (the spheres may come from a link_body_decompositions override and stick out of the shape's bounding sphere)
+  std::vector<double> enclosing(G, 0.0);
+  for (int gs = 0; gs < G; ++gs)
+  {
+    const DevGroupLink& gl = g->glinks[gs];
+    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    {
+      const double* sp = &g->sph[(size_t)s * 4];
+      const double dx = sp[0] - gl.bs[0], dy = sp[1] - gl.bs[1], dz = sp[2] - gl.bs[2];
+      enclosing[gs] = std::max(enclosing[gs], std::sqrt(dx * dx + dy * dy + dz * dz) + sp[3]);
+    }
+  }
+  std::vector<std::vector<int>> lower(G);  // lower-index partners of each link, ascending
+  for (const DevPair& p : g->pairs)
+    if (count_of(p.gi) > 0 && count_of(p.gj) > 0)
+      lower[p.gj].push_back(p.gi);
+  int n_store_links = 0, n_store_spheres = 0;
+  for (int gs = 0; gs < G; ++gs)
+  {
+    bool is_lower = false;
+    for (int h = gs + 1; h < G && !is_lower; ++h)
+      is_lower = std::find(lower[h].begin(), lower[h].end(), gs) != lower[h].end();
+    if (is_lower)
+    {
+      g->glinks[gs].store_link = n_store_links++;
+      g->glinks[gs].store_sphere = n_store_spheres;
+      n_store_spheres += count_of(gs);
+    }
+  }
+  std::vector<DevPartner> partners;
+  std::vector<double> pair_T;
+  for (int gs = 0; gs < G; ++gs)
+  {
+    DevGroupLink& gl = g->glinks[gs];
+    gl.partner_begin = (int)partners.size();
+    int stride = 0;
+    for (int lo : lower[gs])
+    {
+      DevPartner pr{};
+      pr.store_link = g->glinks[lo].store_link;
+      pr.store_sphere = g->glinks[lo].store_sphere;
+      pr.count = count_of(lo);
+      pr.const_offset = stride;
+      pr.radius_sum = g->glinks[lo].bs[3] + gl.bs[3];
+      const double reach = (enclosing[lo] + enclosing[gs]) * (1.0 + 1e-9) + 1e-9;  // slack >> any fp64 rounding here
+      pr.tight2 = reach * reach;
+      stride += pr.count;
+      partners.push_back(pr);
+    }
+    gl.partner_end = (int)partners.size();
+    gl.pair_const_begin = (int)pair_T.size();
+    gl.pair_const_stride = stride;
+    for (int s = gl.sphere_begin; s < gl.sphere_end && stride > 0; ++s)
+      for (int lo : lower[gs])
+        for (int m = g->glinks[lo].sphere_begin; m < g->glinks[lo].sphere_end; ++m)
+          pair_T.push_back(pair_thr[(size_t)sph_cls[s] * U + sph_cls[m]]);
+  }
+  B200DF_REQUIRE(pair_T.size() < (size_t)1 << 31, "too many sphere pairs");
 
   DeviceGuard dg(g->device);
   GroupDev& dev = g->dev;
@@ -1012,10 +753,14 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
   dev.n_links = L;
   dev.n_vars = model->n_vars;
   dev.n_slots = model->n_slots;
-  dev.n_glinks = (int)g->glinks.size();
+  dev.n_glinks = G;
   dev.n_spheres = (int)(g->sph.size() / 4);
   dev.n_pairs = (int)g->pairs.size();
   dev.n_cls = U;
+  dev.n_store_links = n_store_links;
+  dev.n_store_spheres = n_store_spheres;
+  dev.n_partners = (int)partners.size();
+  dev.n_pair_consts = (long)pair_T.size();
   dev.tol = d->collision_tolerance;
   dev.max_prop = d->max_propagation_distance;
   int rc;
@@ -1033,6 +778,11 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     return rc;
   if ((rc = upload(g.get(), pair_thr, &dev.pair_thr)))
     return rc;
+  if ((rc = upload(g.get(), partners, &dev.partners)))
+    return rc;
+  if ((rc = upload(g.get(), pair_T, &dev.pair_T)))
+    return rc;
+  g->stage = new b200df_group::StagePool;
   *out = g.release();
   return B200DF_OK;
 }
@@ -1042,6 +792,7 @@ int b200df_group_destroy(b200df_group* g)
   if (!g)
     return B200DF_OK;
   DeviceGuard dg(g->device);
+  delete g->stage;
   for (void* p : g->allocations)
     cudaFree(p);
   delete g;
@@ -1060,7 +811,8 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q_dev && verdict_dev)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
-  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST, "unknown precision");
+  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1,
+                 "unknown precision");
   if (n == 0)
     return B200DF_OK;
   FieldDev wf, sf;
@@ -1069,8 +821,8 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
   if (rc)
     return rc;
   DeviceGuard dg(group->device);
-  return dispatch_exact<OUT_VERDICT>(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, nullptr,
-                                     static_cast<cudaStream_t>(stream));
+  return run_verdict(group, wf, sf, elem, q_dev, q_dtype, n, flags, precision, verdict_dev,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q, int q_dtype,
@@ -1078,145 +830,8 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && verdict)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
-  if (n == 0)
-    return B200DF_OK;
-  DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  const size_t qbytes = (size_t)n * group->dev.n_vars * q_elem_size(q_dtype);
-  int rc = B200DF_OK;
-  {
-    ScratchBuffer dq, dv;
-    dq.stream = dv.stream = stream;
-    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dv.p, (size_t)n, stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
-    {
-      set_error("staging the batch failed: %s", cudaGetErrorString(e));
-      rc = B200DF_ERR_CUDA;
-    }
-    if (!rc)
-      rc = b200df_check_batch_device(group, world, self, dq.p, q_dtype, n, flags, precision,
-                                     static_cast<uint8_t*>(dv.p), stream);
-    if (!rc)
-    {
-      e = cudaMemcpyAsync(verdict, dv.p, (size_t)n, cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess)
-      {
-        set_error("reading the verdicts back failed: %s", cudaGetErrorString(e));
-        rc = B200DF_ERR_CUDA;
-      }
-    }
-  }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
-  return rc;
-}
-
-// shared host wrapper for the fp64-output modes
-static int run_f64_output(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
-                          int mode, size_t out_per_state, double* out)
-{
-  B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && out)), "bad arguments");
-  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
-  if (n == 0)
-    return B200DF_OK;
-  FieldDev wf, sf;
-  std::memset(&wf, 0, sizeof(wf));
-  std::memset(&sf, 0, sizeof(sf));
-  int elem = 1;
-  if (mode == OUT_CLEARANCE)
-  {
-    int rc = prepare_fields(group, world, nullptr, B200DF_CHECK_ROBOT, &wf, &sf, &elem);
-    if (rc)
-      return rc;
-  }
-  DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  const size_t qbytes = (size_t)n * group->dev.n_vars * q_elem_size(q_dtype);
-  const size_t obytes = (size_t)n * out_per_state * sizeof(double);
-  int rc = B200DF_OK;
-  {
-    ScratchBuffer dq, dout;
-    dq.stream = dout.stream = stream;
-    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dout.p, std::max<size_t>(obytes, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
-    {
-      set_error("staging the batch failed: %s", cudaGetErrorString(e));
-      rc = B200DF_ERR_CUDA;
-    }
-    if (!rc)
-    {
-      double* o = static_cast<double*>(dout.p);
-      if (mode == OUT_CENTERS)
-        rc = dispatch_exact<OUT_CENTERS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-      else if (mode == OUT_TRANSFORMS)
-        rc = dispatch_exact<OUT_TRANSFORMS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-      else
-        rc = dispatch_exact<OUT_CLEARANCE>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-    }
-    if (!rc)
-    {
-      e = cudaMemcpyAsync(out, dout.p, obytes, cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess)
-      {
-        set_error("reading results back failed: %s", cudaGetErrorString(e));
-        rc = B200DF_ERR_CUDA;
-      }
-    }
-  }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
-  return rc;
-}
-
-int b200df_sphere_centers(const b200df_group* group, const void* q, int q_dtype, int64_t n, double* centers)
-{
-  B200DF_REQUIRE(group, "null group");
-  return run_f64_output(group, nullptr, q, q_dtype, n, OUT_CENTERS, (size_t)group->dev.n_spheres * 3, centers);
-}
-
-int b200df_distance_batch(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
-                          double* min_clearance)
-{
-  B200DF_REQUIRE(group && world, "null argument");
-  return run_f64_output(group, world, q, q_dtype, n, OUT_CLEARANCE, 1, min_clearance);
-}
-
-int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64_t n, double* link_transforms)
-{
-  B200DF_REQUIRE(model, "null model");
-  // an empty group over the model gives the kernel its link table
-  b200df_group_desc gd{};
-  gd.n_group_links = 0;
-  gd.resolution = 1.0;
-  b200df_group* g = nullptr;
-  int rc = b200df_group_create(model, &gd, &g);
-  if (rc)
-    return rc;
-  rc = run_f64_output(g, nullptr, q, q_dtype, n, OUT_TRANSFORMS, (size_t)model->n_links * 12, link_transforms);
-  b200df_group_destroy(g);
-  return rc;
-}
-
-int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
-                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
-                           double* centers)
-{
-  B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && dist && grad && type)), "bad arguments");
-  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
+  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1,
+                 "unknown precision");
   if (n == 0)
     return B200DF_OK;
   FieldDev wf, sf;
@@ -1224,87 +839,39 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
   int rc = prepare_fields(group, world, self, flags, &wf, &sf, &elem);
   if (rc)
     return rc;
-  const GroupDev& g = group->dev;
-  const size_t S = (size_t)g.n_spheres;
   DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  const size_t qbytes = (size_t)n * g.n_vars * q_elem_size(q_dtype);
+  const size_t row = (size_t)group->dev.n_vars * q_elem_size(q_dtype);
+  const int64_t chunk = std::min<int64_t>(n, kChunkStates);
+  b200df_group::StagePool::Ctx* ctx = group->stage->acquire();
+  rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
+  cudaError_t e = cudaSuccess;
+  int k = 0;
+  for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k ^= 1)
   {
-    ScratchBuffer dq, dd, dgr, dt, dc;
-    dq.stream = dd.stream = dgr.stream = dt.stream = dc.stream = stream;
-    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dd.p, std::max<size_t>(n * S * sizeof(double), 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dgr.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dt.p, std::max<size_t>(n * S, 1), stream);
-    if (e == cudaSuccess && centers)
-      e = cudaMallocAsync(&dc.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
+    const int64_t m = std::min<int64_t>(chunk, n - s);
+    cudaStream_t st = ctx->stream[k];
+    // the stream order protects the buffers of slot k: this H2D runs after the D2H of the chunk before last
+    e = cudaMemcpyAsync(ctx->q[k], static_cast<const char*>(q) + (size_t)s * row, (size_t)m * row,
+                        cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess)
-    {
-      set_error("staging the batch failed: %s", cudaGetErrorString(e));
-      rc = B200DF_ERR_CUDA;
-    }
-    if (!rc)
-    {
-      int block;
-      size_t bytes;
-      rc = pick_block(g, true, false, &block, &bytes);
-      const unsigned grid = (unsigned)((n + block - 1) / block);
-#define B200DF_LAUNCH_GRAD(QT, FT)                                                                                 \
-  do                                                                                                               \
-  {                                                                                                                \
-    if (!rc)                                                                                                       \
-      rc = set_smem_limit(gradients_kernel<QT, FT>, bytes);                                                        \
-    if (!rc)                                                                                                       \
-      gradients_kernel<QT, FT><<<grid, block, bytes, stream>>>(                                                    \
-          g, wf, sf, static_cast<const QT*>(dq.p), n, flags, static_cast<double*>(dd.p),                           \
-          static_cast<double*>(dgr.p), static_cast<uint8_t*>(dt.p), static_cast<double*>(dc.p));                   \
-  } while (0)
-      if (q_dtype == B200DF_Q_F32 && elem == 1)
-        B200DF_LAUNCH_GRAD(float, uint8_t);
-      else if (q_dtype == B200DF_Q_F32)
-        B200DF_LAUNCH_GRAD(float, uint16_t);
-      else if (elem == 1)
-        B200DF_LAUNCH_GRAD(double, uint8_t);
-      else
-        B200DF_LAUNCH_GRAD(double, uint16_t);
-#undef B200DF_LAUNCH_GRAD
-      if (!rc)
-      {
-        B200DF_LAUNCHED();
-        e = cudaGetLastError();
-        if (e != cudaSuccess)
-        {
-          set_error("gradient kernel launch failed: %s", cudaGetErrorString(e));
-          rc = B200DF_ERR_CUDA;
-        }
-      }
-    }
-    if (!rc)
-    {
-      e = cudaMemcpyAsync(dist, dd.p, n * S * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(grad, dgr.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(type, dt.p, n * S, cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess && centers)
-        e = cudaMemcpyAsync(centers, dc.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess)
-      {
-        set_error("reading gradients back failed: %s", cudaGetErrorString(e));
-        rc = B200DF_ERR_CUDA;
-      }
-    }
+      break;
+    rc = run_verdict(group, wf, sf, elem, ctx->q[k], q_dtype, m, flags, precision, ctx->v[k], st);
+    if (rc)
+      break;
+    e = cudaMemcpyAsync(verdict + s, ctx->v[k], (size_t)m, cudaMemcpyDeviceToHost, st);
   }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
+  for (int i = 0; i < 2; ++i)
+  {
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream[i]);
+    if (e == cudaSuccess)
+      e = es;
+  }
+  group->stage->give_back(ctx);
+  if (!rc && e != cudaSuccess)
+  {
+    set_error("batched check failed while staging / running / reading back: %s", cudaGetErrorString(e));
+    rc = B200DF_ERR_CUDA;
+  }
   return rc;
 }
 

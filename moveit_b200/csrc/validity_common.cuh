@@ -1,0 +1,490 @@
+// Device-side model tables and the FK / sphere-vs-field primitives shared by the validity and gradient kernels.
+//
+// Reference being replaced (paths relative to /root/reference/moveit_core):
+//   RobotState::updateLinkTransformsInternal   robot_state/src/robot_state.cpp:718-755
+//   *JointModel::computeTransform               robot_model/src/{revolute,prismatic,fixed,planar,floating}_joint_model.cpp
+//   DistanceField::getDistanceGradient          distance_field/src/distance_field.cpp:62-86
+//   getCollisionSphereCollision                 collision_distance_field/src/collision_distance_field_types.cpp:206-231
+//
+// Everything here is fp64 in the reference's operation order; the including translation units are compiled with
+// --fmad=false so mul/add round like the reference's non-FMA x86-64 build.
+#pragma once
+#include <cfloat>
+
+#include "b200df_internal.cuh"
+
+namespace b200df
+{
+struct DevLink
+{
+  int parent;
+  int joint_type;
+  int var;  // first variable read for this joint (already redirected to the mimicked joint)
+  int is_mimic;
+  double mimic_mult, mimic_off;
+  double ax, ay, az, x2, y2, z2, xy, xz, yz;  // RevoluteJointModel::setAxis precompute
+  double origin[12];
+  int origin_is_identity;
+  int parent_is_prev;  // parent == i-1: the parent transform is still in registers
+  int store_slot;      // >=0: save this link's transform for a later non-adjacent child
+  int parent_slot;     // slot holding the parent's transform when !parent_is_prev
+  int jkind;           // revolute joints: 1/2/3 = axis exactly +-x/+-y/+-z (sparse joint matrix), 0 = general
+};
+
+// One group link with geometry, in group order.  Links that are the lower-index side of an enabled pair are
+// "stored": their posed sphere centres stay in shared memory until the higher-index partner is swept.
+struct DevGroupLink
+{
+  int link;  // model link index
+  int sphere_begin, sphere_end;
+  int self_enabled;
+  double bs[4];  // relative bounding sphere centre + radius
+  int store_link;    // index among stored links, -1 if not stored
+  int store_sphere;  // first stored-sphere slot, -1 if not stored
+  int partner_begin, partner_end;  // lower-index partners of this link (range in GroupDev::partners)
+  int pair_const_begin;            // offset of this link's first sphere in the pair-constant arrays
+  int pair_const_stride;           // pair constants per sphere of this link (sum of the partners' sphere counts)
+};
+
+struct DevPartner
+{
+  int store_link;    // stored-link index of the partner (bounding-sphere centre slot)
+  int store_sphere;  // first stored-sphere slot of the partner
+  int count;         // its sphere count
+  int const_offset;  // offset of this partner's thresholds inside one sphere's stride of pair_T
+  double radius_sum;  // p1_radius + p2_radius of doBoundingSpheresIntersect (compared with the SQUARED distance, Q2)
+  double tight2;      // (R'_i + R'_j)^2, R' = radius around the same centre that really encloses the link's spheres:
+                      // a sphere pair can only touch when the squared centre distance is below it (exact cull)
+};
+
+struct DevPair  // enabled link pair (gi < gj), indices into the group-link table (gradient kernel order)
+{
+  int gi, gj;
+  double radius_sum;
+};
+
+struct GroupDev
+{
+  const DevLink* links;
+  int n_links;
+  int n_vars;
+  int n_slots;
+  const int* link_gslot;  // [n_links] index into glinks or -1
+  const DevGroupLink* glinks;
+  int n_glinks;
+  const double* sph;   // [S][4] rel xyz + radius
+  const int* sph_thr;  // [S] unsigned-field verdict threshold: collide iff d2 < thr
+  int n_spheres;
+  int n_store_links, n_store_spheres;
+  const DevPartner* partners;
+  int n_partners;
+  const double* pair_T;  // ||c1-c2|| < r1+r2  <=>  squaredNorm < pair_T; [own sphere][partner][partner sphere]
+  long n_pair_consts;
+  // tables of the generic sweep (gradient kernel, FK / centre / clearance outputs)
+  const int* sph_cls;      // [S] radius class
+  const double* pair_thr;  // [U][U] thresholds by radius class
+  int n_cls;
+  const DevPair* pairs;  // link pairs in the reference's (i, j>i) loop order
+  int n_pairs;
+  double tol, max_prop;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// maths: Eigen 3.3 fixed-size products as the reference evaluates them (left-to-right sums, no FMA)
+// ------------------------------------------------------------------------------------------------------------
+// r = a.affine() * b.matrix() with implied last row (0,0,0,1).  Zero terms are dropped (x + a*0 == x for the
+// finite values that occur here), the "+ a3*1" term is kept as "+ a3".
+__device__ __forceinline__ void iso_mul(const double* a, const double* b, double* r)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const double a0 = a[4 * i], a1 = a[4 * i + 1], a2 = a[4 * i + 2], a3 = a[4 * i + 3];
+    r[4 * i + 0] = (a0 * b[0] + a1 * b[4]) + a2 * b[8];
+    r[4 * i + 1] = (a0 * b[1] + a1 * b[5]) + a2 * b[9];
+    r[4 * i + 2] = (a0 * b[2] + a1 * b[6]) + a2 * b[10];
+    r[4 * i + 3] = ((a0 * b[3] + a1 * b[7]) + a2 * b[11]) + a3;
+  }
+}
+
+// Isometry3d * Vector3d: t + ((r0*x + r1*y) + r2*z)   (collision_distance_field_types.cpp:393-396)
+__device__ __forceinline__ void iso_apply(const double* t, double x, double y, double z, double& ox, double& oy,
+                                          double& oz)
+{
+  ox = t[3] + ((t[0] * x + t[1] * y) + t[2] * z);
+  oy = t[7] + ((t[4] * x + t[5] * y) + t[6] * z);
+  oz = t[11] + ((t[8] * x + t[9] * y) + t[10] * z);
+}
+
+template <typename QT>
+__device__ __forceinline__ double joint_value(const DevLink& l, const QT* qs, int k, int stride)
+{
+  const double v = (double)qs[(l.var + k) * stride];
+  return l.is_mimic ? l.mimic_mult * v + l.mimic_off : v;  // robot_state.h:1856-1861
+}
+
+// *JointModel::computeTransform
+template <typename QT>
+__device__ __forceinline__ void joint_transform(const DevLink& l, const QT* qs, int stride, double* t)
+{
+  t[0] = 1.0; t[1] = 0.0; t[2] = 0.0; t[3] = 0.0;
+  t[4] = 0.0; t[5] = 1.0; t[6] = 0.0; t[7] = 0.0;
+  t[8] = 0.0; t[9] = 0.0; t[10] = 1.0; t[11] = 0.0;
+  switch (l.joint_type)
+  {
+    case B200DF_JOINT_REVOLUTE:  // revolute_joint_model.cpp:222-259
+    {
+      const double v = joint_value(l, qs, 0, stride);
+      double s, c;
+      sincos(v, &s, &c);
+      const double tt = 1.0 - c;
+      const double txy = tt * l.xy, txz = tt * l.xz, tyz = tt * l.yz;
+      const double zs = l.az * s, ys = l.ay * s, xs = l.ax * s;
+      t[0] = tt * l.x2 + c;
+      t[4] = txy + zs;
+      t[8] = txz - ys;
+      t[1] = txy - zs;
+      t[5] = tt * l.y2 + c;
+      t[9] = tyz + xs;
+      t[2] = txz + ys;
+      t[6] = tyz - xs;
+      t[10] = tt * l.z2 + c;
+      break;
+    }
+    case B200DF_JOINT_PRISMATIC:  // prismatic_joint_model.cpp:119-144
+    {
+      const double v = joint_value(l, qs, 0, stride);
+      t[3] = l.ax * v;
+      t[7] = l.ay * v;
+      t[11] = l.az * v;
+      break;
+    }
+    case B200DF_JOINT_PLANAR:  // planar_joint_model.cpp:327-331 (Translation * AngleAxis(theta, UnitZ))
+    {
+      const double x = joint_value(l, qs, 0, stride), y = joint_value(l, qs, 1, stride),
+                   th = joint_value(l, qs, 2, stride);
+      double s, c;
+      sincos(th, &s, &c);
+      const double c1 = 1.0 - c;
+      t[0] = c1 * 0.0 * 0.0 + c;
+      t[5] = c1 * 0.0 * 0.0 + c;
+      t[10] = c1 * 1.0 * 1.0 + c;
+      t[1] = c1 * 0.0 * 0.0 - s * 1.0;
+      t[4] = c1 * 0.0 * 0.0 + s * 1.0;
+      t[3] = x;
+      t[7] = y;
+      t[11] = 0.0;
+      break;
+    }
+    case B200DF_JOINT_FLOATING:  // floating_joint_model.cpp:224-229
+    {
+      double qx = joint_value(l, qs, 3, stride), qy = joint_value(l, qs, 4, stride),
+             qz = joint_value(l, qs, 5, stride), qw = joint_value(l, qs, 6, stride);
+      const double n = sqrt(((qx * qx + qy * qy) + qz * qz) + qw * qw);
+      qx /= n;
+      qy /= n;
+      qz /= n;
+      qw /= n;
+      const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
+      const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+      const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+      const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+      t[0] = 1.0 - (tyy + tzz);
+      t[1] = txy - twz;
+      t[2] = txz + twy;
+      t[4] = txy + twz;
+      t[5] = 1.0 - (txx + tzz);
+      t[6] = tyz - twx;
+      t[8] = txz - twy;
+      t[9] = tyz + twx;
+      t[10] = 1.0 - (txx + tyy);
+      t[3] = joint_value(l, qs, 0, stride);
+      t[7] = joint_value(l, qs, 1, stride);
+      t[11] = joint_value(l, qs, 2, stride);
+      break;
+    }
+    default:  // fixed_joint_model.cpp:94-97
+      break;
+  }
+}
+
+// RobotState::updateLinkTransformsInternal for link i; cur holds link i-1 on entry and link i on exit.
+// slots: per-thread column of saved branch-parent transforms, [slot*12 + k] * stride.
+template <typename QT>
+__device__ __forceinline__ void fk_step(const DevLink& l, const QT* qs, double* slots, int qstride, int stride,
+                                        double* cur)
+{
+  double par[12];
+  if (l.parent >= 0)
+  {
+    if (l.parent_is_prev)
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        par[k] = cur[k];
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        par[k] = slots[(l.parent_slot * 12 + k) * stride];
+    }
+  }
+  if (l.joint_type == B200DF_JOINT_FIXED && l.parent >= 0)
+  {
+    iso_mul(par, l.origin, cur);  // robot_state.cpp:727-729
+  }
+  else
+  {
+    double j[12];
+    joint_transform(l, qs, qstride, j);
+    if (l.parent >= 0)
+    {
+      if (l.origin_is_identity)
+        iso_mul(par, j, cur);  // :732-734
+      else
+      {
+        double tmp[12];
+        iso_mul(par, l.origin, tmp);  // :735-738, evaluated left to right
+        iso_mul(tmp, j, cur);
+      }
+    }
+    else
+    {
+      if (l.origin_is_identity)  // :743-744
+      {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+          cur[k] = j[k];
+      }
+      else
+        iso_mul(l.origin, j, cur);  // :745-747
+    }
+  }
+  if (l.store_slot >= 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      slots[(l.store_slot * 12 + k) * stride] = cur[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Sparse variant of fk_step for the verdict kernel.  A revolute joint about a coordinate axis has a joint matrix
+// with structural zeros; the dropped terms are exact zeros, so every entry has the same VALUE as the full product
+// (only the sign of a zero result can differ, which no later mul/add/compare/floor can observe).
+// ------------------------------------------------------------------------------------------------------------
+// r = a * J for J = rotation about +-x / +-y / +-z (kind 1/2/3); j = the 9 rotation entries of J, row-major
+__device__ __forceinline__ void iso_mul_axis(const double* a, const double* j, int kind, double* r)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const double a0 = a[4 * i], a1 = a[4 * i + 1], a2 = a[4 * i + 2];
+    if (kind == 3)
+    {
+      r[4 * i + 0] = a0 * j[0] + a1 * j[3];
+      r[4 * i + 1] = a0 * j[1] + a1 * j[4];
+      r[4 * i + 2] = a2 * j[8];
+    }
+    else if (kind == 2)
+    {
+      r[4 * i + 0] = a0 * j[0] + a2 * j[6];
+      r[4 * i + 1] = a1 * j[4];
+      r[4 * i + 2] = a0 * j[2] + a2 * j[8];
+    }
+    else
+    {
+      r[4 * i + 0] = a0 * j[0];
+      r[4 * i + 1] = a1 * j[4] + a2 * j[7];
+      r[4 * i + 2] = a1 * j[5] + a2 * j[8];
+    }
+    r[4 * i + 3] = a[4 * i + 3];
+  }
+}
+
+template <typename QT>
+__device__ __forceinline__ void fk_step_sparse(const DevLink& l, const QT* qs, double* slots, int qstride, int stride,
+                                               double* cur)
+{
+  if (l.parent < 0 || l.joint_type == B200DF_JOINT_FIXED ||
+      !((l.joint_type == B200DF_JOINT_REVOLUTE && l.jkind != 0) || l.joint_type == B200DF_JOINT_PRISMATIC))
+  {
+    fk_step(l, qs, slots, qstride, stride, cur);
+    return;
+  }
+  double par[12];
+  if (l.parent_is_prev)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      par[k] = cur[k];
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      par[k] = slots[(l.parent_slot * 12 + k) * stride];
+  }
+  double base[12];
+  if (l.origin_is_identity)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      base[k] = par[k];
+  }
+  else
+    iso_mul(par, l.origin, base);
+  const double v = joint_value(l, qs, 0, qstride);
+  if (l.joint_type == B200DF_JOINT_PRISMATIC)
+  {
+    // J = identity rotation + translation axis*v: the rotation block passes through unchanged
+    const double tx = l.ax * v, ty = l.ay * v, tz = l.az * v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+      cur[4 * i + 0] = base[4 * i + 0];
+      cur[4 * i + 1] = base[4 * i + 1];
+      cur[4 * i + 2] = base[4 * i + 2];
+      cur[4 * i + 3] = ((base[4 * i] * tx + base[4 * i + 1] * ty) + base[4 * i + 2] * tz) + base[4 * i + 3];
+    }
+  }
+  else
+  {
+    double s, c;
+    sincos(v, &s, &c);
+    const double tt = 1.0 - c;
+    const double txy = tt * l.xy, txz = tt * l.xz, tyz = tt * l.yz;
+    const double zs = l.az * s, ys = l.ay * s, xs = l.ax * s;
+    double j[9];
+    j[0] = tt * l.x2 + c;
+    j[3] = txy + zs;
+    j[6] = txz - ys;
+    j[1] = txy - zs;
+    j[4] = tt * l.y2 + c;
+    j[7] = tyz + xs;
+    j[2] = txz + ys;
+    j[5] = tyz - xs;
+    j[8] = tt * l.z2 + c;
+    iso_mul_axis(base, j, l.jkind, cur);
+  }
+  if (l.store_slot >= 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      slots[(l.store_slot * 12 + k) * stride] = cur[k];
+  }
+}
+
+template <typename QT>
+__device__ __forceinline__ void fk_step(const DevLink& l, const QT* qs, double* slots, int stride, double* cur)
+{
+  fk_step(l, qs, slots, stride, stride, cur);
+}
+
+// getDistanceGradient's cell lookup without the gradient: false when the centre is outside the 1-cell-inset
+// box (the reference then reports max_distance => never a collision, Q4).  NaN fails every comparison.
+__device__ __forceinline__ bool inset_cell(const GridDev& g, double x, double y, double z, long& idx)
+{
+  const double fx = floor((x - g.om[0]) * g.oo), fy = floor((y - g.om[1]) * g.oo), fz = floor((z - g.om[2]) * g.oo);
+  if (!(fx >= 1.0 && fy >= 1.0 && fz >= 1.0 && fx < (double)(g.n[0] - 1) && fy < (double)(g.n[1] - 1) &&
+        fz < (double)(g.n[2] - 1)))
+    return false;
+  idx = (long)fx * g.stride1 + (long)fy * g.stride2 + (long)fz;
+  return true;
+}
+
+// PropagationDistanceField::getDistance (propagation_distance_field.h:597-600)
+template <typename FT>
+__device__ __forceinline__ double cell_dist(const FieldDev& f, long idx)
+{
+  double d = f.sqrt_table[static_cast<const FT*>(f.d2)[idx]];
+  if (f.neg)
+    d = d - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
+  else
+    d = d - f.sqrt_table[0];
+  return d;
+}
+
+// getCollisionSphereCollision's per-sphere predicate (collision_distance_field_types.cpp:213-227)
+template <typename FT>
+__device__ __forceinline__ bool sphere_collides(const FieldDev& f, double x, double y, double z, double radius,
+                                                int thr, double tol, double max_prop)
+{
+  long idx;
+  if (!inset_cell(f.g, x, y, z, idx))
+    return false;
+  if (!f.neg)
+    return (int)static_cast<const FT*>(f.d2)[idx] < thr;  // host-resolved, exactly equivalent threshold
+  const double dist = cell_dist<FT>(f, idx);
+  return (max_prop > dist) && (radius - dist > tol);
+}
+
+// stage one tile of joint values into shared memory as [var][thread] (coalesced global read)
+template <typename QT>
+__device__ __forceinline__ void stage_q(const QT* __restrict__ q, long base, long n, int n_vars, int B, int tid,
+                                        QT* qs)
+{
+  const long total = (long)B * n_vars;
+  const long limit = (n - base) * n_vars;
+  for (long e = tid; e < total; e += B)
+  {
+    const int s = (int)(e / n_vars), v = (int)(e % n_vars);
+    qs[v * B + s] = (e < limit) ? q[base * n_vars + e] : QT(0);
+  }
+}
+}  // namespace b200df
+
+// host-side handles (shared by validity.cu and gradients.cu)
+struct b200df_model
+{
+  int device = 0;
+  int n_links = 0, n_vars = 0;
+  std::vector<b200df::DevLink> links;
+  std::vector<int> has_geometry;
+  std::vector<int> sphere_offset;
+  std::vector<double> spheres;
+  std::vector<double> bsphere;
+  std::vector<int64_t> point_offset;
+  std::vector<double> points;
+  int n_slots = 0;
+  b200df::DevLink* d_links = nullptr;
+};
+
+struct b200df_group
+{
+  const b200df_model* model = nullptr;
+  int device = 0;
+  b200df_group_desc desc{};
+  std::vector<b200df::DevGroupLink> glinks;
+  std::vector<int> link_gslot;
+  std::vector<double> sph;
+  std::vector<b200df::DevPair> pairs;
+  b200df::GroupDev dev{};
+  std::vector<void*> allocations;
+  struct StagePool;  // host<->device staging contexts of the pipelined host-buffer entry points (validity.cu)
+  StagePool* stage = nullptr;
+};
+
+namespace b200df
+{
+// fills wf / sf for the requested flags (rebuilding dirty fields) and checks they fit the group
+int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field* self, int flags, FieldDev* wf,
+                   FieldDev* sf, int* elem);
+
+inline size_t q_elem_size(int q_dtype)
+{
+  return q_dtype == B200DF_Q_F32 ? sizeof(float) : sizeof(double);
+}
+
+struct ScratchBuffer  // stream-ordered scratch
+{
+  void* p = nullptr;
+  cudaStream_t stream = nullptr;
+  ~ScratchBuffer()
+  {
+    if (p)
+      cudaFreeAsync(p, stream);
+  }
+};
+}  // namespace b200df

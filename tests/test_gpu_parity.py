@@ -293,6 +293,41 @@ def test_config4_pr2_like_full_acm(gpu, oracle):
     assert len(arms) < desc.n_links
 
 
+@pytest.mark.parametrize("robot", ["panda", "pr2_like"])
+def test_fused_kernel_agrees_with_independent_sweep(gpu, oracle, robot):
+    """The fused verdict kernel (pairs folded into the FK sweep, sparse joint products, tight link cull) against the
+    independently written round-1 sweep (precision value 2) on 1 M states, every flag combination."""
+    desc = rd.panda() if robot == "panda" else rd.pr2_like()
+    fd = scenarios.FIELD_A if robot == "panda" else scenarios.FIELD_DEFAULT
+    e = EngineSetup(desc, fd, scenarios.random_scene(seed=17))
+    q = desc.sample_states(1_000_000 if robot == "panda" else 200_000, 4242, np.float32)
+    for flags in (CHECK_ROBOT, CHECK_INTRA, CHECK_ROBOT | CHECK_INTRA):
+        a = e.group.check(q, e.world, flags=flags, precision=0)
+        b = e.group.check(q, e.world, flags=flags, precision=2)
+        assert np.array_equal(a, b), "flags=%d: %d differences" % (flags, int((a != b).sum()))
+        assert a.sum() > 0
+
+
+def test_host_buffer_entry_is_chunk_invariant(gpu, oracle):
+    """b200df_check_batch pipelines 2^20-state chunks over two streams: ragged sizes around the chunk edge give the
+    same verdicts as the device entry point on one launch."""
+    import torch
+    from moveit_b200 import binding as B
+    desc = rd.panda()
+    e = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
+    n = (1 << 21) + 12345
+    q = desc.sample_states(n, 777, np.float32)
+    host = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    qd = torch.from_numpy(q).cuda()
+    vd = torch.empty(n, dtype=torch.uint8, device="cuda")
+    e.group.check_device(qd.data_ptr(), B.Q_F32, n, vd.data_ptr(), e.world, None, CHECK_ROBOT | CHECK_INTRA,
+                         B.PRECISION_EXACT, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(host, vd.cpu().numpy())
+    for m in (1, 31, 33, (1 << 20) - 1, (1 << 20) + 1):
+        assert np.array_equal(e.group.check(q[:m], e.world, flags=CHECK_ROBOT | CHECK_INTRA), host[:m])
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine
