@@ -9,6 +9,7 @@
 // and voxel boundaries by construction.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -239,6 +240,163 @@ __global__ void edt_pass_axis_kernel(const uint16_t* __restrict__ in, OutT* __re
     out[i] = (OutT)(best > max_d2 ? kInf16 : best);  // anything beyond the clamp can never win later
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fast path of the same exact EDT (nz even, R <= 31): bit-packed occupancy, z pass by bit scans, y and x passes as
+// "marching" min-plus passes on packed u16x2 voxel pairs with the DPX add-min instruction (VIADDMNMX.U16x2).
+//
+//   pack   : occ u8 -> 1 bit per voxel, rows of ceil(nz/32) words                 (reads V bytes, writes V/8)
+//   z pass : nearest set bit within +-31 of each voxel -> dz^2 (or INF)            (reads the bits, writes 2V)
+//   march  : a thread owns two z-adjacent voxels and walks the y (then x) axis once.  Input row t is added to the
+//            2R+1 open outputs t-R..t+R (one register each, ring indexed statically by unrolling 2R+1 steps);
+//            output t-R is complete after input t and is written out.  One VIADDMNMX per (input, output) pair and
+//            voxel pair, no re-reads: each pass reads 2V and writes 2V bytes (the last one writes sizeof(d2)*V).
+// Values above max_d2 are kept (they only grow) and clamped by the last pass; INF = 0x4000 leaves head-room for two
+// additions of R*R <= 961 in 16 bits.  The result equals the windowed passes above bit for bit.
+// ------------------------------------------------------------------------------------------------------------
+constexpr unsigned kInfPair = 0x40004000u;
+
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int nz, int wpr,
+                                 long n_words, bool invert)
+{
+  const long gw = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;  // one warp per output word
+  if (gw >= n_words)
+    return;
+  const int lane = threadIdx.x & 31;
+  const long row = gw / wpr;
+  const int z = 32 * (int)(gw % wpr) + lane;
+  const bool o = z < nz && ((occ[row * nz + z] != 0) != invert);
+  const unsigned m = __ballot_sync(0xffffffffu, o);
+  if (lane == 0)
+    bits[gw] = m;
+}
+
+// nz % 16 == 0: a thread turns 16 occupancy bytes (one 16-byte load; occupancy bytes are 0 or 1) into one half-word
+// of the bit row.  Block = (32, 8): threadIdx.y picks the row, threadIdx.x strides over the row's 16-voxel groups.
+__global__ void pack_bits16_kernel(const uint4* __restrict__ occ, uint16_t* __restrict__ bits16, int groups, int wpr,
+                                   long n_rows, bool invert)
+{
+  const long row = blockIdx.x * (long)blockDim.y + threadIdx.y;
+  if (row >= n_rows)
+    return;
+  const unsigned flip = invert ? 0x01010101u : 0u;
+  for (int h = threadIdx.x; h < groups; h += 32)
+  {
+    const uint4 v = occ[row * groups + h];
+    const unsigned n0 = ((((v.x & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
+    const unsigned n1 = ((((v.y & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
+    const unsigned n2 = ((((v.z & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
+    const unsigned n3 = ((((v.w & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
+    bits16[row * (2 * wpr) + h] = (uint16_t)(n0 | (n1 << 4) | (n2 << 8) | (n3 << 12));
+  }
+}
+
+__device__ __forceinline__ unsigned z_dist2(unsigned lo, unsigned hi, int R)
+{
+  // lo = bits [z-32, z) (bit 31 is z-1), hi = bits [z, z+32) (bit 0 is z)
+  const int up = hi ? __ffs(hi) - 1 : 64;
+  const int dn = lo ? __clz(lo) + 1 : 64;
+  const int d = min(up, dn);
+  return d <= R ? (unsigned)(d * d) : 0x4000u;
+}
+
+// Block = (64, 4): threadIdx.y picks the row, threadIdx.x strides over the row's voxel pairs.
+__global__ void edt_z_from_bits_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ out, int half, int wpr,
+                                       long n_rows, int R)
+{
+  const long row = blockIdx.x * (long)blockDim.y + threadIdx.y;
+  if (row >= n_rows)
+    return;
+  const uint32_t* br = bits + row * wpr;
+  uint32_t* orow = out + row * half;
+  for (int p = threadIdx.x; p < half; p += 64)
+  {
+    const int z0 = 2 * p;
+    const int wi = (z0 - 32) >> 5;  // -1 for the first 32 voxels of a row
+    const int o = z0 & 31;
+    const unsigned w0 = wi >= 0 ? br[wi] : 0u;
+    const unsigned w1 = br[wi + 1];
+    const unsigned w2 = wi + 2 < wpr ? br[wi + 2] : 0u;
+    const unsigned v0 = z_dist2(__funnelshift_r(w0, w1, o), __funnelshift_r(w1, w2, o), R);
+    const unsigned v1 = z_dist2(__funnelshift_r(w0, w1, o + 1), __funnelshift_r(w1, w2, o + 1), R);
+    orow[p] = v0 | (v1 << 16);
+  }
+}
+
+// Lines: line L -> first pair (L / inner) * outer_stride + (L % inner), then `stride` pairs per step along the axis.
+// The 2R+1 steps of one ring revolution are cut into three chunks; the inputs of the next chunk are loaded while
+// the current one is consumed, so a thread always has (2R+1)/3 loads in flight.
+template <int R, typename OutT, bool FINAL>
+__global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __restrict__ in, void* __restrict__ out_v,
+                                                       long n_lines, long inner, long outer_stride, long stride,
+                                                       int n_axis, int max_d2)
+{
+  constexpr int W = 2 * R + 1;
+  constexpr int C = W / 3;
+  static_assert(C * 3 == W, "ring length must be a multiple of 3");
+  const long line0 = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long line = line0 < n_lines ? line0 : n_lines - 1;  // surplus lanes shadow the last line (keeps votes full)
+  const long base = (line / inner) * outer_stride + (line % inner);
+  const uint32_t* src = in + base;
+  unsigned acc[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    acc[j] = kInfPair;
+  const unsigned clamp = (unsigned)max_d2 * 0x00010001u;
+  unsigned nxt[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j)
+    nxt[j] = j < n_axis ? src[(long)j * stride] : kInfPair;
+  for (int t0 = 0; t0 < n_axis + R; t0 += W)
+  {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+    {
+      unsigned cur[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        cur[j] = nxt[j];
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+      {
+        const int tn = t0 + (c + 1) * C + j;
+        nxt[j] = tn < n_axis ? src[(long)tn * stride] : kInfPair;
+      }
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+      {
+        const int u = c * C + j;
+        const int t = t0 + u;
+        const unsigned f = cur[j];
+        // rows without any obstacle within reach contribute nothing: skip them warp-wide
+        if (__any_sync(0xffffffffu, f != kInfPair))
+        {
+#pragma unroll
+          for (int d = -R; d <= R; ++d)
+            acc[(u + d + W) % W] = __viaddmin_u16x2(f, (unsigned)(d * d) * 0x00010001u, acc[(u + d + W) % W]);
+        }
+        // output t-R has now seen every input within +-R of it
+        const int yo = t - R;
+        const int slot = (u + R + 1) % W;  // == (u - R) mod W
+        if (yo >= 0 && yo < n_axis && line0 < n_lines)
+        {
+          unsigned v = acc[slot];
+          if (FINAL)
+          {
+            v = __vminu2(v, clamp);
+            if (sizeof(OutT) == 1)
+              static_cast<uint16_t*>(out_v)[base + (long)yo * stride] = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));
+            else
+              static_cast<uint32_t*>(out_v)[base + (long)yo * stride] = v;
+          }
+          else
+            static_cast<uint32_t*>(out_v)[base + (long)yo * stride] = v;
+        }
+        acc[slot] = kInfPair;
+      }
+    }
+  }
+}
+
 __global__ void fill_kernel_u8(uint8_t* p, long n, uint8_t v)
 {
   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -464,6 +622,24 @@ int rasterize_into(b200df_field* f, int shape_type, const double* dims3, const d
   return B200DF_OK;
 }
 
+template <int R, typename T>
+int run_edt_march(b200df_field* f, T* out)
+{
+  const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
+  const long half = nz / 2;
+  const int threads = 64;
+  // y pass: lines = (x, z pair); x pass: lines = (y, z pair)
+  const long lines_y = (long)nx * half, lines_x = (long)ny * half;
+  edt_march_kernel<R, uint16_t, false><<<blocks_for(lines_y, threads), threads, 0, f->stream>>>(
+      reinterpret_cast<const uint32_t*>(f->tmp_a), f->tmp_b, lines_y, half, (long)ny * half, half, ny, f->max_d2);
+  B200DF_LAUNCHED();
+  edt_march_kernel<R, T, true><<<blocks_for(lines_x, threads), threads, 0, f->stream>>>(
+      reinterpret_cast<const uint32_t*>(f->tmp_b), out, lines_x, lines_x, 0, (long)ny * half, nx, f->max_d2);
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  return B200DF_OK;
+}
+
 template <typename T>
 int run_edt(b200df_field* f, bool invert, T* out)
 {
@@ -471,6 +647,31 @@ int run_edt(b200df_field* f, bool invert, T* out)
   const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
   const int threads = 256;
   const unsigned blocks = blocks_for(n, threads);
+  if (f->bits && nz % 2 == 0 && f->radius <= 31)
+  {
+    const int wpr = (nz + 31) / 32;
+    const long n_rows = (long)nx * ny;
+    if (nz % 16 == 0)
+    {
+      pack_bits16_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
+          reinterpret_cast<const uint4*>(f->occ), reinterpret_cast<uint16_t*>(f->bits), nz / 16, wpr, n_rows, invert);
+    }
+    else
+    {
+      const long n_words = n_rows * wpr;
+      pack_bits_kernel<<<blocks_for(n_words * 32, threads), threads, 0, f->stream>>>(f->occ, f->bits, nz, wpr, n_words,
+                                                                                    invert);
+    }
+    B200DF_LAUNCHED();
+    edt_z_from_bits_kernel<<<blocks_for(n_rows, 4), dim3(64, 4), 0, f->stream>>>(
+        f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), nz / 2, wpr, n_rows, f->radius);
+    B200DF_LAUNCHED();
+    if (f->radius <= 13)
+      return run_edt_march<13, T>(f, out);
+    if (f->radius <= 25)
+      return run_edt_march<25, T>(f, out);
+    return run_edt_march<31, T>(f, out);
+  }
   if (invert)
     edt_pass_z_kernel<true><<<blocks, threads, 0, f->stream>>>(f->occ, f->tmp_a, nz, n, f->radius);
   else
@@ -608,6 +809,12 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out)
     B200DF_CUDA(cudaMalloc(&f->neg, nv * f->elem_size));
   B200DF_CUDA(cudaMalloc(&f->tmp_a, nv * sizeof(uint16_t)));
   B200DF_CUDA(cudaMalloc(&f->tmp_b, nv * sizeof(uint16_t)));
+  if (total > 0 && f->grid.n[2] % 2 == 0 && f->radius <= 31 && !getenv("B200DF_EDT_WINDOWED"))
+  {
+    const size_t bit_bytes = (size_t)f->grid.n[0] * f->grid.n[1] * ((f->grid.n[2] + 31) / 32) * sizeof(uint32_t);
+    B200DF_CUDA(cudaMalloc(&f->bits, bit_bytes));
+    B200DF_CUDA(cudaMemset(f->bits, 0, bit_bytes));  // padding bits of a row stay 0 (= no obstacle) forever
+  }
   B200DF_CUDA(cudaMalloc(&f->sqrt_table, f->sqrt_table_host.size() * sizeof(double)));
   B200DF_CUDA(cudaMemcpy(f->sqrt_table, f->sqrt_table_host.data(), f->sqrt_table_host.size() * sizeof(double),
                          cudaMemcpyHostToDevice));
