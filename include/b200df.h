@@ -34,7 +34,7 @@ enum
   B200DF_ERR_UNSUPPORTED = 4, /* reference leaves it unimplemented too (e.g. continuous checks) */
 };
 
-/* joint types, matching the *JointModel::computeTransform set (robot_model/src/*_joint_model.cpp) */
+/* joint types, matching the *JointModel::computeTransform set (robot_model/src/<type>_joint_model.cpp) */
 enum
 {
   B200DF_JOINT_FIXED = 0,
@@ -191,6 +191,10 @@ int b200df_field_remove_shape(b200df_field* field, int32_t shape_type, const dou
  * world-object route: getBodyDecompositionCacheEntry + PosedBodyPointDecomposition, types.cpp:368-379, Q10) */
 int b200df_field_add_posed_body(b200df_field* field, int32_t shape_type, const double* dims3,
                                 const double* pose12, double padding);
+/* the removePointsFromField half of notifyObjectChange (collision_env_distance_field.cpp:1731-1743) for the same
+ * decomposition; voxels shared with another object are cleared as well, like the reference (no ref-count) */
+int b200df_field_remove_posed_body(b200df_field* field, int32_t shape_type, const double* dims3,
+                                   const double* pose12, double padding);
 /* occupied octree leaves (centre xyz + edge) -> points per getOcTreePoints (distance_field.cpp:236-280) */
 int b200df_field_add_octree_leaves(b200df_field* field, const double* leaves4, int64_t n);
 /* Rebuilds the EDT if the occupancy changed (queries do this implicitly).  Returns the device time of the

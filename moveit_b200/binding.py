@@ -76,6 +76,7 @@ SYMBOLS = {
     "b200df_field_add_shape": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double, C.c_double]),
     "b200df_field_remove_shape": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double, C.c_double]),
     "b200df_field_add_posed_body": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double]),
+    "b200df_field_remove_posed_body": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double]),
     "b200df_field_add_octree_leaves": (C.c_int, [_VP, c_dp, C.c_int64]),
     "b200df_field_rebuild": (C.c_int, [_VP, c_fp]),
     "b200df_field_download_d2": (C.c_int, [_VP, c_i32p, C.c_int]),

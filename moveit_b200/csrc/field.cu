@@ -972,6 +972,14 @@ int b200df_field_add_posed_body(b200df_field* f, int32_t shape_type, const doubl
   return rasterize_into(f, shape_type, dims3, identity, pose12, 1.0, padding, 1);
 }
 
+int b200df_field_remove_posed_body(b200df_field* f, int32_t shape_type, const double* dims3, const double* pose12,
+                                   double padding)
+{
+  B200DF_REQUIRE(f && dims3 && pose12, "null argument");
+  static const double identity[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+  return rasterize_into(f, shape_type, dims3, identity, pose12, 1.0, padding, 0);  // Q8: shared voxels are cleared too
+}
+
 int b200df_field_add_octree_leaves(b200df_field* f, const double* leaves4, int64_t n)
 {
   B200DF_REQUIRE(f && (leaves4 || n == 0) && n >= 0, "bad arguments");

@@ -1,0 +1,1199 @@
+// CollisionEnvB200 — host-side C++ mirror of collision_detection::CollisionEnvDistanceField over the b200df C ABI.
+//
+// This is the code a MoveIt maintainer drops behind the plugin loader: same class and method
+// names, argument meaning and result conventions as the reference, every GPU interaction through include/b200df.h.
+// MoveIt's own headers (Eigen, RobotModel/RobotState, World, pluginlib ...) are not in this image, so the types the
+// reference takes from moveit_core are small stand-ins with the same member names.  Swapping them for the real
+// headers is mechanical; nothing below depends on more than the members declared here.
+//
+// Reference (paths relative to /root/reference/moveit_core):
+//   collision_distance_field/include/moveit/collision_distance_field/collision_env_distance_field.h:48-303
+//   collision_distance_field/src/collision_env_distance_field.cpp   (cited per method)
+//   collision_distance_field/include/.../collision_common_distance_field.h:56-167   DistanceFieldCacheEntry, GSR
+//   collision_distance_field/include/.../collision_distance_field_types.h:57-105      CollisionType, GradientInfo
+//   collision_detection/include/moveit/collision_detection/collision_common.h:146-390 request / result / contact
+//   collision_detection/src/collision_matrix.cpp:113-145                              AllowedCollisionMatrix
+//   collision_detection/include/moveit/collision_detection/world.h:305-318            World observers
+//   collision_detection/include/.../collision_detector_allocator.h:46-98              allocator template
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b200df.h"
+
+namespace collision_detection_b200
+{
+// ------------------------------------------------------------------------------------------------------------
+// stand-ins for moveit_core / Eigen / geometric_shapes types
+// ------------------------------------------------------------------------------------------------------------
+struct Vector3d
+{
+  double x = 0.0, y = 0.0, z = 0.0;
+};
+
+struct Isometry3d  // row-major 3x4, implied last row 0 0 0 1
+{
+  double m[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+  static Isometry3d Identity()
+  {
+    return Isometry3d();
+  }
+  bool isIdentity() const
+  {
+    static const double id[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+    return std::memcmp(m, id, sizeof(m)) == 0;
+  }
+  // Isometry3d * Vector3d the way Eigen evaluates it: t + ((r0*x + r1*y) + r2*z)
+  Vector3d operator*(const Vector3d& p) const
+  {
+    Vector3d r;
+    r.x = m[3] + ((m[0] * p.x + m[1] * p.y) + m[2] * p.z);
+    r.y = m[7] + ((m[4] * p.x + m[5] * p.y) + m[6] * p.z);
+    r.z = m[11] + ((m[8] * p.x + m[9] * p.y) + m[10] * p.z);
+    return r;
+  }
+};
+
+namespace shapes
+{
+enum ShapeType  // geometric_shapes/shapes.h values
+{
+  SPHERE = B200DF_SHAPE_SPHERE,
+  CYLINDER = B200DF_SHAPE_CYLINDER,
+  BOX = B200DF_SHAPE_BOX,
+};
+struct Shape
+{
+  ShapeType type = BOX;
+  double dims[3] = { 0, 0, 0 };  // sphere: radius; cylinder: radius, length; box: x, y, z
+};
+using ShapeConstPtr = std::shared_ptr<const Shape>;
+}  // namespace shapes
+
+namespace core
+{
+enum JointType
+{
+  FIXED = B200DF_JOINT_FIXED,
+  REVOLUTE = B200DF_JOINT_REVOLUTE,
+  PRISMATIC = B200DF_JOINT_PRISMATIC,
+  PLANAR = B200DF_JOINT_PLANAR,
+  FLOATING = B200DF_JOINT_FLOATING,
+};
+
+struct LinkModel  // a link together with its parent joint, as RobotModel stores them in DFS order
+{
+  std::string name, joint_name;
+  int parent = -1;
+  JointType joint_type = FIXED;
+  double axis[3] = { 0, 0, 1 };
+  Isometry3d joint_origin;
+  std::string mimic_joint;  // empty: none
+  double mimic_factor = 1.0, mimic_offset = 0.0;
+  std::vector<shapes::Shape> shapes;
+  std::vector<Isometry3d> shape_origins;
+  int first_variable = -1;
+};
+
+class RobotModel
+{
+public:
+  explicit RobotModel(std::string name) : name_(std::move(name))
+  {
+  }
+  // links must be added parent before child (RobotModel::buildModel order, robot_model.cpp:783-838)
+  int addLink(const LinkModel& l)
+  {
+    static const int nv[5] = { 0, 1, 1, 3, 7 };
+    LinkModel c = l;
+    if (c.parent >= (int)links_.size())
+      throw std::invalid_argument("parent link must be added before its child");
+    c.first_variable = nv[c.joint_type] ? variable_count_ : -1;
+    variable_count_ += nv[c.joint_type];
+    link_index_[c.name] = (int)links_.size();
+    joint_index_[c.joint_name] = (int)links_.size();
+    links_.push_back(c);
+    return (int)links_.size() - 1;
+  }
+  void addJointModelGroup(const std::string& group, const std::vector<std::string>& joints)
+  {
+    groups_[group] = joints;
+  }
+  bool hasJointModelGroup(const std::string& g) const
+  {
+    return groups_.count(g) != 0;
+  }
+  const std::vector<LinkModel>& getLinkModels() const
+  {
+    return links_;
+  }
+  std::vector<std::string> getLinkModelNames() const
+  {
+    std::vector<std::string> n;
+    for (const LinkModel& l : links_)
+      n.push_back(l.name);
+    return n;
+  }
+  int getLinkIndex(const std::string& n) const
+  {
+    auto it = link_index_.find(n);
+    return it == link_index_.end() ? -1 : it->second;
+  }
+  int getJointIndex(const std::string& n) const
+  {
+    auto it = joint_index_.find(n);
+    return it == joint_index_.end() ? -1 : it->second;
+  }
+  int getVariableCount() const
+  {
+    return variable_count_;
+  }
+  // JointModelGroup::getUpdatedLinkModelNames (joint_model_group.cpp:223-247): every link moved by a group joint
+  std::vector<int> getUpdatedLinkModelIndices(const std::string& group) const
+  {
+    const std::vector<std::string>& joints = groups_.at(group);
+    std::set<int> moved;
+    for (int i = 0; i < (int)links_.size(); ++i)
+      if (std::find(joints.begin(), joints.end(), links_[i].joint_name) != joints.end() ||
+          (links_[i].parent >= 0 && moved.count(links_[i].parent)))
+        moved.insert(i);
+    return std::vector<int>(moved.begin(), moved.end());
+  }
+  // the variables the group's active joints own (generateDistanceFieldCacheEntry :881-896 "updated_map")
+  std::set<int> getGroupVariableIndices(const std::string& group) const
+  {
+    static const int nv[5] = { 0, 1, 1, 3, 7 };
+    std::set<int> v;
+    for (const LinkModel& l : links_)
+    {
+      const bool in = group.empty() || std::find(groups_.at(group).begin(), groups_.at(group).end(), l.joint_name) !=
+                                           groups_.at(group).end();
+      if (in && l.mimic_joint.empty())
+        for (int k = 0; k < nv[l.joint_type]; ++k)
+          v.insert(l.first_variable + k);
+    }
+    return v;
+  }
+  const std::string& getName() const
+  {
+    return name_;
+  }
+
+private:
+  std::string name_;
+  std::vector<LinkModel> links_;
+  std::map<std::string, int> link_index_, joint_index_;
+  std::map<std::string, std::vector<std::string>> groups_;
+  int variable_count_ = 0;
+};
+using RobotModelConstPtr = std::shared_ptr<const RobotModel>;
+
+class RobotState  // the slice of moveit::core::RobotState the collision env reads: the variable vector
+{
+public:
+  explicit RobotState(const RobotModelConstPtr& model) : model_(model), position_(model->getVariableCount(), 0.0)
+  {
+  }
+  void setVariablePositions(const double* p)
+  {
+    std::copy(p, p + position_.size(), position_.begin());
+  }
+  const double* getVariablePositions() const
+  {
+    return position_.data();
+  }
+  double getVariablePosition(int i) const
+  {
+    return position_[i];
+  }
+  std::size_t getVariableCount() const
+  {
+    return position_.size();
+  }
+  const RobotModelConstPtr& getRobotModel() const
+  {
+    return model_;
+  }
+
+private:
+  RobotModelConstPtr model_;
+  std::vector<double> position_;
+};
+}  // namespace core
+
+namespace AllowedCollision
+{
+enum Type
+{
+  NEVER,
+  ALWAYS,
+  CONDITIONAL,
+};
+}
+
+class AllowedCollisionMatrix  // collision_matrix.cpp:46-64, 113-145
+{
+public:
+  AllowedCollisionMatrix() = default;
+  AllowedCollisionMatrix(const std::vector<std::string>& names, bool allowed)
+  {
+    for (std::size_t i = 0; i < names.size(); ++i)
+      for (std::size_t j = i; j < names.size(); ++j)
+        setEntry(names[i], names[j], allowed);
+  }
+  void setEntry(const std::string& a, const std::string& b, bool allowed)
+  {
+    entries_[a][b] = entries_[b][a] = allowed ? AllowedCollision::ALWAYS : AllowedCollision::NEVER;
+  }
+  bool getEntry(const std::string& a, const std::string& b, AllowedCollision::Type& t) const
+  {
+    auto i = entries_.find(a);
+    if (i == entries_.end())
+      return false;
+    auto j = i->second.find(b);
+    if (j == i->second.end())
+      return false;
+    t = j->second;
+    return true;
+  }
+  bool operator==(const AllowedCollisionMatrix& o) const
+  {
+    return entries_ == o.entries_;
+  }
+
+private:
+  std::map<std::string, std::map<std::string, AllowedCollision::Type>> entries_;
+};
+
+class World  // collision_detection/world.h: objects + synchronous observers
+{
+public:
+  enum ActionBits
+  {
+    UNINITIALIZED = 0,
+    CREATE = 1,
+    DESTROY = 2,
+    MOVE_SHAPE = 4,
+    ADD_SHAPE = 8,
+    REMOVE_SHAPE = 16,
+  };
+  using Action = int;
+  struct Object
+  {
+    std::string id_;
+    std::vector<shapes::ShapeConstPtr> shapes_;
+    std::vector<Isometry3d> shape_poses_;  // global shape transforms
+  };
+  using ObjectConstPtr = std::shared_ptr<const Object>;
+  using ObserverCallbackFn = std::function<void(const ObjectConstPtr&, Action)>;
+  using ObserverHandle = int;
+
+  void addToObject(const std::string& id, const shapes::ShapeConstPtr& shape, const Isometry3d& pose)
+  {
+    std::shared_ptr<Object>& o = objects_[id];
+    Action a = ADD_SHAPE;
+    if (!o)
+    {
+      o = std::make_shared<Object>();
+      o->id_ = id;
+      a |= CREATE;
+    }
+    else
+      o = std::make_shared<Object>(*o);  // copy on write like World::ensureUnique
+    o->shapes_.push_back(shape);
+    o->shape_poses_.push_back(pose);
+    notify(o, a);
+  }
+  bool moveShapeInObject(const std::string& id, std::size_t shape_index, const Isometry3d& pose)
+  {
+    auto it = objects_.find(id);
+    if (it == objects_.end() || shape_index >= it->second->shapes_.size())
+      return false;
+    it->second = std::make_shared<Object>(*it->second);
+    it->second->shape_poses_[shape_index] = pose;
+    notify(it->second, MOVE_SHAPE);
+    return true;
+  }
+  bool removeObject(const std::string& id)
+  {
+    auto it = objects_.find(id);
+    if (it == objects_.end())
+      return false;
+    ObjectConstPtr o = it->second;
+    objects_.erase(it);
+    notify(o, DESTROY);
+    return true;
+  }
+  ObjectConstPtr getObject(const std::string& id) const
+  {
+    auto it = objects_.find(id);
+    return it == objects_.end() ? ObjectConstPtr() : ObjectConstPtr(it->second);
+  }
+  ObserverHandle addObserver(const ObserverCallbackFn& cb)
+  {
+    observers_[++next_handle_] = cb;
+    return next_handle_;
+  }
+  void removeObserver(ObserverHandle h)
+  {
+    observers_.erase(h);
+  }
+  void notifyObserverAllObjects(ObserverHandle h, Action a) const
+  {
+    auto it = observers_.find(h);
+    if (it != observers_.end())
+      for (const auto& kv : objects_)
+        it->second(kv.second, a);
+  }
+
+private:
+  void notify(const ObjectConstPtr& o, Action a)
+  {
+    for (auto& kv : observers_)
+      kv.second(o, a);
+  }
+  std::map<std::string, std::shared_ptr<Object>> objects_;
+  std::map<ObserverHandle, ObserverCallbackFn> observers_;
+  ObserverHandle next_handle_ = 0;
+};
+using WorldPtr = std::shared_ptr<World>;
+
+namespace BodyTypes
+{
+enum Type
+{
+  ROBOT_LINK,
+  ROBOT_ATTACHED,
+  WORLD_OBJECT,
+};
+}
+
+struct Contact  // collision_common.h:79-120; the distance-field env fills pos and the body names/types only
+{
+  Vector3d pos;
+  std::string body_name_1, body_name_2;
+  BodyTypes::Type body_type_1 = BodyTypes::ROBOT_LINK, body_type_2 = BodyTypes::WORLD_OBJECT;
+};
+
+struct CollisionRequest  // collision_common.h:146-196
+{
+  std::string group_name;
+  bool distance = false;
+  bool cost = false;
+  bool contacts = false;
+  std::size_t max_contacts = 1;
+  std::size_t max_contacts_per_pair = 1;
+  bool verbose = false;
+};
+
+struct CollisionResult  // collision_common.h:350-390
+{
+  using ContactMap = std::map<std::pair<std::string, std::string>, std::vector<Contact>>;
+  bool collision = false;
+  double distance = std::numeric_limits<double>::max();
+  std::size_t contact_count = 0;
+  ContactMap contacts;
+  void clear()
+  {
+    collision = false;
+    distance = std::numeric_limits<double>::max();
+    contact_count = 0;
+    contacts.clear();
+  }
+};
+
+struct CollisionSphere  // collision_distance_field_types.h:66-76
+{
+  Vector3d relative_vec_;
+  double radius_ = 0.0;
+};
+
+enum CollisionType  // collision_distance_field_types.h:57-63
+{
+  NONE = B200DF_TYPE_NONE,
+  SELF = B200DF_TYPE_SELF,
+  INTRA = B200DF_TYPE_INTRA,
+  ENVIRONMENT = B200DF_TYPE_ENVIRONMENT,
+};
+
+struct GradientInfo  // collision_distance_field_types.h:78-105
+{
+  double closest_distance = DBL_MAX;
+  bool collision = false;
+  std::vector<Vector3d> sphere_locations;
+  std::vector<double> distances;
+  std::vector<Vector3d> gradients;
+  std::vector<CollisionType> types;
+  std::vector<double> sphere_radii;
+  std::string joint_name;
+};
+
+struct GroupStateRepresentation  // collision_common_distance_field.h:120-167 (what CHOMP reads of it)
+{
+  std::vector<std::string> link_names_;
+  std::vector<GradientInfo> gradients_;
+};
+using GroupStateRepresentationPtr = std::shared_ptr<GroupStateRepresentation>;
+
+static const double DEFAULT_SIZE_X = 3.0;  // collision_env_distance_field.h:48-54
+static const double DEFAULT_SIZE_Y = 3.0;
+static const double DEFAULT_SIZE_Z = 4.0;
+static const bool DEFAULT_USE_SIGNED_DISTANCE_FIELD = false;
+static const double DEFAULT_RESOLUTION = .02;
+static const double DEFAULT_COLLISION_TOLERANCE = 0.0;
+static const double DEFAULT_MAX_PROPOGATION_DISTANCE = .25;
+static const double EPSILON = 0.001f;  // collision_env_distance_field.cpp:54 (a float literal stored in a double, Q16)
+
+class B200Error : public std::runtime_error
+{
+public:
+  explicit B200Error(const std::string& what) : std::runtime_error(what)
+  {
+  }
+};
+
+inline void checkStatus(int rc, const char* what)
+{
+  if (rc != B200DF_OK)
+    throw B200Error(std::string(what) + ": " + b200df_last_error());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CollisionEnvB200
+// ------------------------------------------------------------------------------------------------------------
+class CollisionEnvB200
+{
+public:
+  using LinkSpheres = std::map<std::string, std::vector<CollisionSphere>>;
+
+  // (robot_model) constructor, collision_env_distance_field.h:62-72 / .cpp:58-75: a private empty world, padding
+  // forced to 0 (Q18)
+  explicit CollisionEnvB200(const core::RobotModelConstPtr& robot_model, const LinkSpheres& link_body_decompositions = {},
+                            double size_x = DEFAULT_SIZE_X, double size_y = DEFAULT_SIZE_Y,
+                            double size_z = DEFAULT_SIZE_Z, const Vector3d& origin = Vector3d(),
+                            bool use_signed_distance_field = DEFAULT_USE_SIGNED_DISTANCE_FIELD,
+                            double resolution = DEFAULT_RESOLUTION,
+                            double collision_tolerance = DEFAULT_COLLISION_TOLERANCE,
+                            double max_propogation_distance = DEFAULT_MAX_PROPOGATION_DISTANCE, double /*padding*/ = 0.0,
+                            double /*scale*/ = 1.0)
+    : CollisionEnvB200(robot_model, std::make_shared<World>(), link_body_decompositions, size_x, size_y, size_z, origin,
+                       use_signed_distance_field, resolution, collision_tolerance, max_propogation_distance, 0.0, 1.0)
+  {
+  }
+
+  // (robot_model, world) constructor, .h:74-84 / .cpp:77-93
+  CollisionEnvB200(const core::RobotModelConstPtr& robot_model, const WorldPtr& world,
+                   const LinkSpheres& link_body_decompositions = {}, double size_x = DEFAULT_SIZE_X,
+                   double size_y = DEFAULT_SIZE_Y, double size_z = DEFAULT_SIZE_Z, const Vector3d& origin = Vector3d(),
+                   bool use_signed_distance_field = DEFAULT_USE_SIGNED_DISTANCE_FIELD,
+                   double resolution = DEFAULT_RESOLUTION, double collision_tolerance = DEFAULT_COLLISION_TOLERANCE,
+                   double max_propogation_distance = DEFAULT_MAX_PROPOGATION_DISTANCE, double padding = 0.0,
+                   double /*scale*/ = 1.0)
+    : robot_model_(robot_model), world_(world), link_padding_(padding)
+  {
+    size_[0] = size_x;
+    size_[1] = size_y;
+    size_[2] = size_z;
+    origin_ = origin;
+    initialize(link_body_decompositions, use_signed_distance_field, resolution, collision_tolerance,
+               max_propogation_distance);
+    world_field_ = newField();  // generateDistanceFieldCacheEntryWorld :1800-1816
+    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
+      notifyObjectChange(o, a);
+    });
+    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+  }
+
+  // copy onto another world, .h:86 / .cpp:95-116 (the allocator's allocateEnv(orig, world))
+  CollisionEnvB200(const CollisionEnvB200& other, const WorldPtr& world)
+    : robot_model_(other.robot_model_), world_(world), link_padding_(other.link_padding_)
+  {
+    std::copy(other.size_, other.size_ + 3, size_);
+    origin_ = other.origin_;
+    initialize(other.link_spheres_, other.use_signed_distance_field_, other.resolution_, other.collision_tolerance_,
+               other.max_propogation_distance_);
+    world_field_ = newField();
+    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
+      notifyObjectChange(o, a);
+    });
+    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+  }
+
+  CollisionEnvB200(const CollisionEnvB200&) = delete;
+  CollisionEnvB200& operator=(const CollisionEnvB200&) = delete;
+
+  ~CollisionEnvB200()  // .cpp:118-121
+  {
+    world_->removeObserver(observer_handle_);
+    dfce_.reset();
+    b200df_field_destroy(world_field_);
+    b200df_model_destroy(model_);
+  }
+
+  // ---- single-state API of CollisionEnv (each call is a batch of one) -----------------------------------
+  void checkSelfCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
+  {
+    checkSelfCollisionHelper(req, res, state, nullptr);  // .cpp:238-244
+  }
+  void checkSelfCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                          const AllowedCollisionMatrix& acm) const
+  {
+    checkSelfCollisionHelper(req, res, state, &acm);  // .cpp:254-261
+  }
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
+  {
+    run(req, res, state, nullptr, B200DF_CHECK_ROBOT, false);  // .cpp:1466-1487 (no self field generated, Q13)
+  }
+  void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                           const AllowedCollisionMatrix& acm) const
+  {
+    run(req, res, state, &acm, B200DF_CHECK_ROBOT, true);  // .cpp:1500-1519
+  }
+  // continuous check: unimplemented in the reference too (.cpp:1521-1534)
+  void checkRobotCollision(const CollisionRequest&, CollisionResult&, const core::RobotState&, const core::RobotState&,
+                           const AllowedCollisionMatrix&) const
+  {
+    last_error_ = "Continuous collision checking not implemented";
+  }
+  void checkCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
+  {
+    run(req, res, state, nullptr, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT, true);  // .cpp:1401-1416
+  }
+  void checkCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                      const AllowedCollisionMatrix& acm) const
+  {
+    run(req, res, state, &acm, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT, true);  // .cpp:1441-1464
+  }
+  // distanceRobot / distanceSelf are stubs in the reference (.h:108-123,178-198); defined here as the minimum over
+  // the group's spheres of (world-field distance - radius)
+  double distanceRobot(const core::RobotState& state, const std::string& group_name = "") const
+  {
+    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(group_name, state, nullptr, false);
+    double d = 0.0;
+    checkStatus(b200df_distance_batch(e->group, world_field_, state.getVariablePositions(), B200DF_Q_F64, 1, &d),
+                "b200df_distance_batch");
+    return d;
+  }
+
+  // getCollisionGradients .cpp:1536-1557 — the CHOMP entry point
+  void getCollisionGradients(const CollisionRequest& req, CollisionResult& /*res*/, const core::RobotState& state,
+                             const AllowedCollisionMatrix* acm, GroupStateRepresentationPtr& gsr) const
+  {
+    std::vector<GroupStateRepresentationPtr> one;
+    getCollisionGradientsBatch(req, state.getVariablePositions(), 1, acm, one, &state);
+    gsr = one[0];
+  }
+
+  // ---- batched entry points (new): N states, row-major [n][variable count] -------------------------------
+  // verdict[i] = res.collision of the corresponding single-state call with req.contacts == false.
+  // which: B200DF_CHECK_ROBOT = checkRobotCollision, SELF|INTRA = checkSelfCollision, all three = checkCollision.
+  // The non-group links are posed by reference_state (the scene's current state) for the self field, exactly
+  // like the cache entry of the reference, which is built from the first state it sees and then reused while the
+  // non-group joints stay within EPSILON.
+  void checkCollisionBatch(const CollisionRequest& req, const double* states, std::int64_t n,
+                           const AllowedCollisionMatrix* acm, int which, const core::RobotState& reference_state,
+                           std::uint8_t* verdict) const
+  {
+    const bool need_self = (which & B200DF_CHECK_SELF) != 0;
+    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, need_self);
+    int flags = which;
+    if (!e->self_field)
+      flags &= ~B200DF_CHECK_SELF;
+    checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
+                                   B200DF_PRECISION_EXACT, verdict),
+                "b200df_check_batch");
+  }
+
+  void getCollisionGradientsBatch(const CollisionRequest& req, const double* states, std::int64_t n,
+                                  const AllowedCollisionMatrix* acm, std::vector<GroupStateRepresentationPtr>& out,
+                                  const core::RobotState* reference_state = nullptr) const
+  {
+    core::RobotState ref(robot_model_);
+    if (reference_state)
+      ref = *reference_state;
+    else if (n > 0)
+      ref.setVariablePositions(states);
+    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, ref, acm, true);
+    const std::size_t S = e->sphere_radii.size();
+    std::vector<double> dist(n * S), grad(n * S * 3), cen(n * S * 3);
+    std::vector<std::uint8_t> type(n * S);
+    int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
+    checkStatus(b200df_gradients_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
+                                       dist.data(), grad.data(), type.data(), cen.data()),
+                "b200df_gradients_batch");
+    out.clear();
+    for (std::int64_t i = 0; i < n; ++i)
+    {
+      auto gsr = std::make_shared<GroupStateRepresentation>();
+      gsr->link_names_ = e->link_names;
+      gsr->gradients_.resize(e->link_names.size());
+      for (std::size_t l = 0; l < e->link_names.size(); ++l)
+      {
+        GradientInfo& gi = gsr->gradients_[l];
+        gi.joint_name = e->joint_names[l];
+        for (int s = e->sphere_begin[l]; s < e->sphere_begin[l + 1]; ++s)
+        {
+          const std::size_t k = i * S + s;
+          gi.sphere_radii.push_back(e->sphere_radii[s]);
+          gi.sphere_locations.push_back(Vector3d{ cen[3 * k], cen[3 * k + 1], cen[3 * k + 2] });
+          gi.distances.push_back(dist[k]);
+          gi.gradients.push_back(Vector3d{ grad[3 * k], grad[3 * k + 1], grad[3 * k + 2] });
+          gi.types.push_back(static_cast<CollisionType>(type[k]));
+          gi.closest_distance = std::min(gi.closest_distance, dist[k]);
+        }
+      }
+      out.push_back(gsr);
+    }
+  }
+
+  void setWorld(const WorldPtr& world)  // .cpp:1702-1721
+  {
+    if (world == world_)
+      return;
+    world_->removeObserver(observer_handle_);
+    world_ = world;
+    checkStatus(b200df_field_reset(world_field_), "b200df_field_reset");
+    posed_objects_.clear();
+    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
+      notifyObjectChange(o, a);
+    });
+    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+  }
+  const WorldPtr& getWorld() const
+  {
+    return world_;
+  }
+  b200df_field* getDistanceField() const  // .h:200-203 (the world field)
+  {
+    return world_field_;
+  }
+  float rebuildWorldField() const  // forces the pending EDT rebuild; returns its device time in ms
+  {
+    float ms = 0.f;
+    checkStatus(b200df_field_rebuild(world_field_, &ms), "b200df_field_rebuild");
+    return ms;
+  }
+  const std::string& lastError() const
+  {
+    return last_error_;
+  }
+
+private:
+  struct CacheEntry  // DistanceFieldCacheEntry, collision_common_distance_field.h:56-118
+  {
+    std::string group_name;
+    bool has_acm = false;
+    AllowedCollisionMatrix acm;
+    std::vector<double> state_values;
+    std::vector<int> state_check_indices;
+    std::vector<int> link_indices;  // group links in model order
+    std::vector<std::string> link_names, joint_names;  // links WITH geometry, in group order (sphere layout)
+    std::vector<int> sphere_begin;
+    std::vector<double> sphere_radii;
+    std::vector<int> geom_model_index;           // model link index of each link with geometry
+    std::vector<std::uint8_t> geom_self_enabled;  // self_collision_enabled_ of those links
+    std::vector<std::uint8_t> geom_intra;         // intra_group_collision_enabled_ between them, [g][g]
+    b200df_group* group = nullptr;
+    b200df_field* self_field = nullptr;
+    ~CacheEntry()
+    {
+      b200df_group_destroy(group);
+      b200df_field_destroy(self_field);
+    }
+  };
+
+  // initialize .cpp:123-161 + addLinkBodyDecompositions .cpp:1065-1093
+  void initialize(const LinkSpheres& link_body_decompositions, bool use_signed_distance_field, double resolution,
+                  double collision_tolerance, double max_propogation_distance)
+  {
+    use_signed_distance_field_ = use_signed_distance_field;
+    resolution_ = resolution;
+    collision_tolerance_ = collision_tolerance;
+    max_propogation_distance_ = max_propogation_distance;
+    link_spheres_ = link_body_decompositions;
+    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    const int L = (int)links.size();
+    std::vector<int32_t> parent(L), jtype(L), ident(L), var(L), mimic_var(L, -1), has_geom(L), sph_off(L + 1, 0);
+    std::vector<int64_t> pt_off(L + 1, 0);
+    std::vector<double> axis(3 * L), origin(12 * L), mmult(L, 1.0), moff(L, 0.0), spheres, points, bsphere(4 * L, 0.0);
+    for (int i = 0; i < L; ++i)
+    {
+      const core::LinkModel& l = links[i];
+      parent[i] = l.parent;
+      jtype[i] = l.joint_type;
+      std::copy(l.axis, l.axis + 3, &axis[3 * i]);
+      std::copy(l.joint_origin.m, l.joint_origin.m + 12, &origin[12 * i]);
+      ident[i] = l.joint_origin.isIdentity() ? 1 : 0;
+      var[i] = l.first_variable;
+      if (!l.mimic_joint.empty())
+      {
+        const int src = robot_model_->getJointIndex(l.mimic_joint);
+        if (src < 0)
+          throw B200Error("unknown mimic joint " + l.mimic_joint);
+        mimic_var[i] = links[src].first_variable;
+        mmult[i] = l.mimic_factor;
+        moff[i] = l.mimic_offset;
+      }
+      has_geom[i] = l.shapes.empty() ? 0 : 1;
+      if (has_geom[i])
+      {
+        // BodyDecomposition(shapes, poses, resolution, getLinkPadding(link)) .cpp:1078-1083
+        std::vector<int32_t> types;
+        std::vector<double> dims, poses;
+        for (std::size_t s = 0; s < l.shapes.size(); ++s)
+        {
+          types.push_back(l.shapes[s].type);
+          dims.insert(dims.end(), l.shapes[s].dims, l.shapes[s].dims + 3);
+          poses.insert(poses.end(), l.shape_origins[s].m, l.shape_origins[s].m + 12);
+        }
+        int64_t ns = 0, np = 0;
+        checkStatus(b200df_body_decomposition((int32_t)types.size(), types.data(), dims.data(), poses.data(),
+                                              resolution_, link_padding_, nullptr, 0, &ns, nullptr, 0, &np,
+                                              &bsphere[4 * i]),
+                    "b200df_body_decomposition");
+        std::vector<double> sph(std::max<int64_t>(ns, 1) * 4), pts(std::max<int64_t>(np, 1) * 3);
+        checkStatus(b200df_body_decomposition((int32_t)types.size(), types.data(), dims.data(), poses.data(),
+                                              resolution_, link_padding_, sph.data(), ns, &ns, pts.data(), np, &np,
+                                              &bsphere[4 * i]),
+                    "b200df_body_decomposition");
+        sph.resize(ns * 4);
+        pts.resize(np * 3);
+        auto over = link_body_decompositions.find(l.name);  // replaceCollisionSpheres .cpp:1085-1088
+        if (over != link_body_decompositions.end())
+        {
+          sph.clear();
+          for (const CollisionSphere& cs : over->second)
+            sph.insert(sph.end(), { cs.relative_vec_.x, cs.relative_vec_.y, cs.relative_vec_.z, cs.radius_ });
+        }
+        spheres.insert(spheres.end(), sph.begin(), sph.end());
+        points.insert(points.end(), pts.begin(), pts.end());
+      }
+      sph_off[i + 1] = (int32_t)(spheres.size() / 4);
+      pt_off[i + 1] = (int64_t)(points.size() / 3);
+    }
+    link_points_ = points;
+    link_point_offset_ = pt_off;
+    link_sphere_offset_ = sph_off;
+    link_spheres_flat_ = spheres;
+    link_bsphere_ = bsphere;
+    b200df_model_desc d{};
+    d.n_links = L;
+    d.n_vars = robot_model_->getVariableCount();
+    d.parent = parent.data();
+    d.joint_type = jtype.data();
+    d.axis = axis.data();
+    d.origin = origin.data();
+    d.origin_is_identity = ident.data();
+    d.var_index = var.data();
+    d.mimic_var = mimic_var.data();
+    d.mimic_mult = mmult.data();
+    d.mimic_offset = moff.data();
+    d.has_geometry = has_geom.data();
+    d.sphere_offset = sph_off.data();
+    d.spheres = spheres.data();
+    d.bsphere = bsphere.data();
+    d.point_offset = pt_off.data();
+    d.points = points.data();
+    checkStatus(b200df_model_create(&d, &model_), "b200df_model_create");
+  }
+
+  b200df_field* newField() const  // PropagationDistanceField(size, resolution, origin - size/2, ...) .cpp:946-948, Q14
+  {
+    b200df_field_desc fd{};
+    const double o[3] = { origin_.x, origin_.y, origin_.z };
+    for (int i = 0; i < 3; ++i)
+    {
+      fd.size[i] = size_[i];
+      fd.origin[i] = o[i] - 0.5 * size_[i];
+    }
+    fd.resolution = resolution_;
+    fd.max_distance = max_propogation_distance_;
+    fd.propagate_negative = use_signed_distance_field_ ? 1 : 0;
+    b200df_field* f = nullptr;
+    checkStatus(b200df_field_create(&fd, &f), "b200df_field_create");
+    return f;
+  }
+
+  // notifyObjectChange .cpp:1723-1747 + updateDistanceObject :1749-1798.  Every shape goes through the
+  // BodyDecomposition route with the default padding 0.01 (collision_distance_field_types.h:227, Q10).
+  void notifyObjectChange(const World::ObjectConstPtr& obj, World::Action action)
+  {
+    std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+    auto cur = posed_objects_.find(obj->id_);
+    if (cur != posed_objects_.end() && (action == World::DESTROY || (action & (World::MOVE_SHAPE | World::REMOVE_SHAPE))))
+      for (std::size_t i = 0; i < cur->second->shapes_.size(); ++i)
+        checkStatus(b200df_field_remove_posed_body(world_field_, cur->second->shapes_[i]->type,
+                                                   cur->second->shapes_[i]->dims, cur->second->shape_poses_[i].m, 0.01),
+                    "b200df_field_remove_posed_body");
+    World::ObjectConstPtr now = world_->getObject(obj->id_);
+    if (now)
+    {
+      if (action != World::DESTROY)
+      {
+        // CREATE / ADD_SHAPE re-add every shape of the object like the reference (add_points holds all of them)
+        for (std::size_t i = 0; i < now->shapes_.size(); ++i)
+          checkStatus(b200df_field_add_posed_body(world_field_, now->shapes_[i]->type, now->shapes_[i]->dims,
+                                                  now->shape_poses_[i].m, 0.01),
+                      "b200df_field_add_posed_body");
+      }
+      posed_objects_[obj->id_] = now;
+    }
+    else
+      posed_objects_.erase(obj->id_);
+  }
+
+  // getDistanceFieldCacheEntry .cpp:206-236 (one cached entry, regenerated when group / ACM / non-group joints
+  // change) + generateDistanceFieldCacheEntry :728-975
+  std::shared_ptr<const CacheEntry> getDistanceFieldCacheEntry(const std::string& group_name,
+                                                                const core::RobotState& state,
+                                                                const AllowedCollisionMatrix* acm,
+                                                                bool generate_distance_field) const
+  {
+    std::lock_guard<std::mutex> lk(update_cache_lock_);
+    std::shared_ptr<const CacheEntry> cur = dfce_;
+    if (cur && cur->group_name == group_name && compareCacheEntryToState(*cur, state) &&
+        compareCacheEntryToAllowedCollisionMatrix(*cur, acm) && (!generate_distance_field || cur->self_field ||
+                                                                  !hasNonGroupGeometry(*cur)))
+      return cur;
+    dfce_ = generateDistanceFieldCacheEntry(group_name, state, acm, generate_distance_field);
+    return dfce_;
+  }
+
+  bool compareCacheEntryToState(const CacheEntry& e, const core::RobotState& state) const  // .cpp:1270-1310
+  {
+    for (int i : e.state_check_indices)
+      if (std::fabs(e.state_values[i] - state.getVariablePosition(i)) > EPSILON)
+        return false;
+    return true;
+  }
+  static bool compareCacheEntryToAllowedCollisionMatrix(const CacheEntry& e, const AllowedCollisionMatrix* acm)
+  {
+    if (!acm)
+      return !e.has_acm;
+    return e.has_acm && e.acm == *acm;  // .cpp:1341-1389 compares the entries name by name
+  }
+  bool hasNonGroupGeometry(const CacheEntry& e) const
+  {
+    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    std::set<int> in(e.link_indices.begin(), e.link_indices.end());
+    for (int i = 0; i < (int)links.size(); ++i)
+      if (!links[i].shapes.empty() && !in.count(i))
+        return true;
+    return false;
+  }
+
+  std::shared_ptr<CacheEntry> generateDistanceFieldCacheEntry(const std::string& group_name,
+                                                              const core::RobotState& state,
+                                                              const AllowedCollisionMatrix* acm,
+                                                              bool generate_distance_field) const
+  {
+    auto e = std::make_shared<CacheEntry>();
+    e->group_name = group_name;
+    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    if (group_name.empty())  // :736-739
+      for (int i = 0; i < (int)links.size(); ++i)
+        e->link_indices.push_back(i);
+    else
+      e->link_indices = robot_model_->getUpdatedLinkModelIndices(group_name);
+    if (acm)
+    {
+      e->has_acm = true;
+      e->acm = *acm;
+    }
+    const int n = (int)e->link_indices.size();
+    std::vector<std::uint8_t> self_enabled(n, 1), intra(n * n, 1);
+    e->sphere_begin.push_back(0);
+    for (int i = 0; i < n; ++i)
+    {
+      const core::LinkModel& li = links[e->link_indices[i]];
+      if (li.shapes.empty())  // :846-852
+      {
+        self_enabled[i] = 0;
+        std::fill(intra.begin() + i * n, intra.begin() + (i + 1) * n, 0);
+        continue;
+      }
+      e->link_names.push_back(li.name);
+      e->joint_names.push_back(li.joint_name);
+      for (int s = link_sphere_offset_[e->link_indices[i]]; s < link_sphere_offset_[e->link_indices[i] + 1]; ++s)
+        e->sphere_radii.push_back(link_spheres_flat_[4 * s + 3]);
+      e->sphere_begin.push_back((int)e->sphere_radii.size());
+      if (!acm)
+        continue;  // :840-844 all enabled
+      AllowedCollision::Type t;
+      if (acm->getEntry(li.name, li.name, t) && t == AllowedCollision::ALWAYS)  // :785-790
+        self_enabled[i] = 0;
+      for (int j = i + 1; j < n; ++j)  // :793-805; only explicit ALWAYS entries disable a pair (Q12)
+        if (acm->getEntry(li.name, links[e->link_indices[j]].name, t) && t == AllowedCollision::ALWAYS)
+          intra[i * n + j] = 0;
+    }
+    {
+      std::vector<int> pos;  // position in the group list of each link with geometry
+      for (int i = 0; i < n; ++i)
+        if (!links[e->link_indices[i]].shapes.empty())
+          pos.push_back(i);
+      const std::size_t g = pos.size();
+      e->geom_intra.assign(g * g, 0);
+      for (std::size_t a = 0; a < g; ++a)
+      {
+        e->geom_model_index.push_back(e->link_indices[pos[a]]);
+        e->geom_self_enabled.push_back(self_enabled[pos[a]]);
+        for (std::size_t b = a + 1; b < g; ++b)
+          e->geom_intra[a * g + b] = intra[pos[a] * n + pos[b]];
+      }
+    }
+    // :898-908 — the non-group variables that invalidate the entry when they move
+    const std::set<int> group_vars = robot_model_->getGroupVariableIndices(group_name);
+    for (int v = 0; v < (int)state.getVariableCount(); ++v)
+    {
+      e->state_values.push_back(state.getVariablePosition(v));
+      if (!group_vars.count(v))
+        e->state_check_indices.push_back(v);
+    }
+    b200df_group_desc gd{};
+    std::vector<int32_t> gl(e->link_indices.begin(), e->link_indices.end());
+    gd.n_group_links = n;
+    gd.group_links = gl.data();
+    gd.self_enabled = self_enabled.data();
+    gd.intra_enabled = intra.data();
+    gd.resolution = resolution_;
+    gd.collision_tolerance = collision_tolerance_;
+    gd.max_propagation_distance = max_propogation_distance_;
+    checkStatus(b200df_group_create(model_, &gd, &e->group), "b200df_group_create");
+    if (generate_distance_field)  // :910-973: the links outside the group, posed by this state, as one point set
+    {
+      std::set<int> in(e->link_indices.begin(), e->link_indices.end());
+      std::vector<double> T(links.size() * 12);
+      checkStatus(b200df_model_fk(model_, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
+      std::vector<double> all_points;
+      bool any = false;
+      for (int li = 0; li < (int)links.size(); ++li)
+      {
+        if (links[li].shapes.empty() || in.count(li))
+          continue;
+        any = true;
+        Isometry3d pose;
+        std::copy(&T[12 * li], &T[12 * li] + 12, pose.m);
+        for (int64_t p = link_point_offset_[li]; p < link_point_offset_[li + 1]; ++p)
+        {
+          // PosedBodyPointDecomposition::updatePose, collision_distance_field_types.cpp:368-379
+          const Vector3d w = pose * Vector3d{ link_points_[3 * p], link_points_[3 * p + 1], link_points_[3 * p + 2] };
+          all_points.insert(all_points.end(), { w.x, w.y, w.z });
+        }
+      }
+      if (any)
+      {
+        e->self_field = newField();
+        checkStatus(b200df_field_add_points(e->self_field, all_points.data(), (int64_t)(all_points.size() / 3)),
+                    "b200df_field_add_points");
+      }
+    }
+    return e;
+  }
+
+  void checkSelfCollisionHelper(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                                const AllowedCollisionMatrix* acm) const  // .cpp:182-204
+  {
+    run(req, res, state, acm, B200DF_CHECK_SELF | B200DF_CHECK_INTRA, true);
+  }
+
+  // one state through the batched kernels.  req.contacts == false: the verdict kernel.  req.contacts == true: the
+  // posed sphere centres and per-sphere field distances come from the GPU and the contact bookkeeping of
+  // getSelfCollisions :277-356 / getIntraGroupCollisions :433-660 / getEnvironmentCollisions :1580-1662 is replayed
+  // on them in the reference's order (self field, intra group, environment for checkCollision).
+  void run(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+           const AllowedCollisionMatrix* acm, int which, bool generate_distance_field) const
+  {
+    std::shared_ptr<const CacheEntry> e =
+        getDistanceFieldCacheEntry(req.group_name, state, acm, generate_distance_field && (which & B200DF_CHECK_SELF));
+    int flags = which;
+    if (!e->self_field)
+      flags &= ~B200DF_CHECK_SELF;
+    if (!req.contacts)
+    {
+      std::uint8_t v = 0;
+      checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, state.getVariablePositions(), B200DF_Q_F64,
+                                     1, flags, B200DF_PRECISION_EXACT, &v),
+                  "b200df_check_batch");
+      if (v)
+        res.collision = true;
+      return;
+    }
+    contactsFromSpheres(req, res, state, *e, flags);
+  }
+
+  void contactsFromSpheres(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                           const CacheEntry& e, int flags) const
+  {
+    const std::size_t S = e.sphere_radii.size();
+    std::vector<double> cen(S * 3), dist(S), grad(S * 3);
+    std::vector<std::uint8_t> type(S);
+    auto field_pass = [&](int flag, b200df_field* world, b200df_field* self) {
+      checkStatus(b200df_gradients_batch(e.group, world, self, state.getVariablePositions(), B200DF_Q_F64, 1, flag,
+                                         dist.data(), grad.data(), type.data(), cen.data()),
+                  "b200df_gradients_batch");
+    };
+    // per-sphere predicate of getCollisionSphereCollision (types.cpp:233-267): the gradient pass leaves DBL_MAX
+    // where the field distance is not below max_propogation_distance
+    auto sphere_hits = [&](std::size_t s) { return dist[s] != DBL_MAX && e.sphere_radii[s] - dist[s] > collision_tolerance_; };
+    auto field_contacts = [&](const char* other, BodyTypes::Type other_type, const std::vector<std::uint8_t>* enabled) {
+      for (std::size_t l = 0; l < e.link_names.size(); ++l)
+      {
+        if (enabled && !(*enabled)[l])
+          continue;
+        const std::size_t allowed = std::min(req.max_contacts_per_pair, req.max_contacts - res.contact_count);
+        std::size_t found = 0;
+        for (int s = e.sphere_begin[l]; s < e.sphere_begin[l + 1] && found < allowed; ++s)
+        {
+          if (!sphere_hits(s))
+            continue;
+          Contact con;
+          con.pos = Vector3d{ cen[3 * s], cen[3 * s + 1], cen[3 * s + 2] };
+          con.body_name_1 = e.link_names[l];
+          con.body_type_1 = BodyTypes::ROBOT_LINK;
+          con.body_name_2 = other;
+          con.body_type_2 = other_type;
+          res.contacts[std::make_pair(con.body_name_1, con.body_name_2)].push_back(con);
+          res.contact_count++;
+          res.collision = true;
+          ++found;
+        }
+        if (res.contact_count >= req.max_contacts)
+          return true;
+      }
+      return res.contact_count >= req.max_contacts;
+    };
+    bool done = false;
+    if ((flags & B200DF_CHECK_SELF) && e.self_field)
+    {
+      field_pass(B200DF_CHECK_SELF, nullptr, e.self_field);
+      done = field_contacts("self", BodyTypes::ROBOT_LINK, &e.geom_self_enabled);
+    }
+    else
+      field_pass(0, nullptr, nullptr);  // posed centres only
+    if (!done && (flags & B200DF_CHECK_INTRA))
+      done = intraContacts(req, res, state, e, cen);
+    if (!done && (flags & B200DF_CHECK_ROBOT))
+    {
+      field_pass(B200DF_CHECK_ROBOT, world_field_, nullptr);
+      field_contacts("environment", BodyTypes::WORLD_OBJECT, nullptr);
+    }
+  }
+
+  // getIntraGroupCollisions .cpp:433-660 with req.contacts == true, replayed on the exact GPU-posed sphere centres;
+  // the bounding-sphere prune (doBoundingSpheresIntersect, types.cpp:410-420, Q2) uses GPU link transforms
+  bool intraContacts(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                     const CacheEntry& e, const std::vector<double>& cen) const
+  {
+    const std::size_t n = e.link_names.size();
+    std::vector<double> T(robot_model_->getLinkModels().size() * 12);
+    checkStatus(b200df_model_fk(model_, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
+    std::vector<Vector3d> bcen(n);
+    for (std::size_t i = 0; i < n; ++i)
+    {
+      const int li = e.geom_model_index[i];
+      Isometry3d pose;
+      std::copy(&T[12 * li], &T[12 * li] + 12, pose.m);
+      bcen[i] = pose * Vector3d{ link_bsphere_[4 * li], link_bsphere_[4 * li + 1], link_bsphere_[4 * li + 2] };
+    }
+    for (std::size_t i = 0; i < n; ++i)
+      for (std::size_t j = i + 1; j < n; ++j)
+      {
+        if (!e.geom_intra[i * n + j])
+          continue;
+        const double bx = bcen[i].x - bcen[j].x, by = bcen[i].y - bcen[j].y, bz = bcen[i].z - bcen[j].z;
+        const double p_dist = (bx * bx + by * by) + bz * bz;  // squaredNorm vs the un-squared radius sum (Q2)
+        if (!(p_dist < link_bsphere_[4 * e.geom_model_index[i] + 3] + link_bsphere_[4 * e.geom_model_index[j] + 3]))
+          continue;
+        auto key = std::make_pair(e.link_names[i], e.link_names[j]);
+        std::size_t num_pair = res.contacts.count(key) ? res.contacts[key].size() : 0;
+        for (int k = e.sphere_begin[i]; k < e.sphere_begin[i + 1] && num_pair < req.max_contacts_per_pair; ++k)
+          for (int l = e.sphere_begin[j]; l < e.sphere_begin[j + 1] && num_pair < req.max_contacts_per_pair; ++l)
+          {
+            const double gx = cen[3 * k] - cen[3 * l], gy = cen[3 * k + 1] - cen[3 * l + 1],
+                         gz = cen[3 * k + 2] - cen[3 * l + 2];
+            const double d = std::sqrt((gx * gx + gy * gy) + gz * gz);
+            if (d < e.sphere_radii[k] + e.sphere_radii[l])
+            {
+              Contact con;
+              con.pos = Vector3d{ cen[3 * k], cen[3 * k + 1], cen[3 * k + 2] };
+              con.body_name_1 = e.link_names[i];
+              con.body_name_2 = e.link_names[j];
+              con.body_type_1 = con.body_type_2 = BodyTypes::ROBOT_LINK;
+              res.collision = true;
+              res.contact_count++;
+              res.contacts[key].push_back(con);
+              ++num_pair;
+              if (res.contact_count >= req.max_contacts)
+                return true;
+            }
+          }
+      }
+    return false;
+  }
+
+  core::RobotModelConstPtr robot_model_;
+  WorldPtr world_;
+  double size_[3] = { DEFAULT_SIZE_X, DEFAULT_SIZE_Y, DEFAULT_SIZE_Z };
+  Vector3d origin_;
+  bool use_signed_distance_field_ = DEFAULT_USE_SIGNED_DISTANCE_FIELD;
+  double resolution_ = DEFAULT_RESOLUTION;
+  double collision_tolerance_ = DEFAULT_COLLISION_TOLERANCE;
+  double max_propogation_distance_ = DEFAULT_MAX_PROPOGATION_DISTANCE;
+  double link_padding_ = 0.0;
+  LinkSpheres link_spheres_;
+  std::vector<double> link_points_, link_spheres_flat_, link_bsphere_;
+  std::vector<int64_t> link_point_offset_;
+  std::vector<int32_t> link_sphere_offset_;
+  b200df_model* model_ = nullptr;
+  b200df_field* world_field_ = nullptr;
+  std::map<std::string, World::ObjectConstPtr> posed_objects_;  // posed_body_point_decompositions_ of the world entry
+  World::ObserverHandle observer_handle_ = 0;
+  mutable std::mutex update_cache_lock_, update_cache_lock_world_;  // .h:295,302
+  mutable std::shared_ptr<const CacheEntry> dfce_;
+  mutable std::string last_error_;
+};
+using CollisionEnvB200Ptr = std::shared_ptr<CollisionEnvB200>;
+
+// CollisionDetectorAllocatorTemplate<CollisionEnvB200, CollisionDetectorAllocatorB200>, collision_detector_allocator.h:73-98
+class CollisionDetectorAllocatorB200
+{
+public:
+  static const std::string& NAME()
+  {
+    static const std::string name = "B200DistanceField";
+    return name;
+  }
+  const std::string& getName() const
+  {
+    return NAME();
+  }
+  CollisionEnvB200Ptr allocateEnv(const WorldPtr& world, const core::RobotModelConstPtr& robot_model) const
+  {
+    return std::make_shared<CollisionEnvB200>(robot_model, world);
+  }
+  CollisionEnvB200Ptr allocateEnv(const std::shared_ptr<const CollisionEnvB200>& orig, const WorldPtr& world) const
+  {
+    return std::make_shared<CollisionEnvB200>(*orig, world);
+  }
+  CollisionEnvB200Ptr allocateEnv(const core::RobotModelConstPtr& robot_model) const
+  {
+    return std::make_shared<CollisionEnvB200>(robot_model);
+  }
+  static std::shared_ptr<CollisionDetectorAllocatorB200> create()
+  {
+    return std::make_shared<CollisionDetectorAllocatorB200>();
+  }
+};
+}  // namespace collision_detection_b200

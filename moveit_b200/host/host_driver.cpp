@@ -1,0 +1,257 @@
+// Test / demo driver of the C++ host mirror (collision_env_b200.hpp): reads a scenario written by
+// moveit_b200/scenario_io.py, builds RobotModel + World + AllowedCollisionMatrix through the reference-shaped API,
+// allocates the env through CollisionDetectorAllocatorB200 and writes verdicts / contacts / gradients that
+// tests/test_host_mirror.py compares with the CPU oracle.  Everything numeric happens on the GPU via libb200df.so.
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "collision_env_b200.hpp"
+
+using namespace collision_detection_b200;
+
+namespace
+{
+Isometry3d readPose(std::istream& in)
+{
+  Isometry3d p;
+  for (double& v : p.m)
+    in >> v;
+  return p;
+}
+
+template <typename T>
+void writeFile(const std::string& path, const std::vector<T>& v)
+{
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+}
+}  // namespace
+
+int main(int argc, char** argv)
+{
+  if (argc < 4)
+  {
+    std::fprintf(stderr, "usage: host_driver <scenario.txt> <states.f64> <out_prefix>\n");
+    return 2;
+  }
+  try
+  {
+    std::ifstream in(argv[1]);
+    if (!in)
+      throw std::runtime_error("cannot open scenario");
+    in.precision(17);
+    std::string tok, robot_name;
+    int n_links = 0;
+    in >> tok >> robot_name >> n_links;
+    auto model = std::make_shared<core::RobotModel>(robot_name);
+    CollisionEnvB200::LinkSpheres overrides;
+    for (int i = 0; i < n_links; ++i)
+    {
+      core::LinkModel l;
+      int jt, n_shapes, n_spheres;
+      in >> tok >> l.name >> l.parent >> l.joint_name >> jt >> l.axis[0] >> l.axis[1] >> l.axis[2];
+      l.joint_type = static_cast<core::JointType>(jt);
+      l.joint_origin = readPose(in);
+      in >> l.mimic_joint >> l.mimic_factor >> l.mimic_offset;
+      if (l.mimic_joint == "-")
+        l.mimic_joint.clear();
+      in >> n_shapes;
+      for (int s = 0; s < n_shapes; ++s)
+      {
+        shapes::Shape sh;
+        int t;
+        in >> t >> sh.dims[0] >> sh.dims[1] >> sh.dims[2];
+        sh.type = static_cast<shapes::ShapeType>(t);
+        l.shapes.push_back(sh);
+        l.shape_origins.push_back(readPose(in));
+      }
+      in >> n_spheres;
+      if (n_spheres >= 0)
+      {
+        std::vector<CollisionSphere>& v = overrides[l.name];
+        for (int s = 0; s < n_spheres; ++s)
+        {
+          CollisionSphere cs;
+          in >> cs.relative_vec_.x >> cs.relative_vec_.y >> cs.relative_vec_.z >> cs.radius_;
+          v.push_back(cs);
+        }
+      }
+      model->addLink(l);
+    }
+    int n_groups = 0;
+    in >> tok >> n_groups;
+    for (int g = 0; g < n_groups; ++g)
+    {
+      std::string name;
+      int nj;
+      in >> name >> nj;
+      std::vector<std::string> joints(nj);
+      for (std::string& j : joints)
+        in >> j;
+      model->addJointModelGroup(name, joints);
+    }
+    // default ACM of a PlanningScene: every pair NEVER, SRDF disable_collisions pairs ALWAYS
+    int use_acm = 0, n_disabled = 0;
+    in >> tok >> use_acm >> n_disabled;
+    AllowedCollisionMatrix acm(model->getLinkModelNames(), false);
+    for (int k = 0; k < n_disabled; ++k)
+    {
+      std::string a, b;
+      in >> a >> b;
+      acm.setEntry(a, b, true);
+    }
+    double size[3], center[3], res, max_dist, tol;
+    int use_signed;
+    in >> tok >> size[0] >> size[1] >> size[2] >> center[0] >> center[1] >> center[2] >> res >> max_dist >>
+        use_signed >> tol;
+    int n_objects = 0;
+    in >> tok >> n_objects;
+    auto world = std::make_shared<World>();
+    std::vector<std::string> object_ids;
+    for (int k = 0; k < n_objects; ++k)
+    {
+      std::string id;
+      int t;
+      auto sh = std::make_shared<shapes::Shape>();
+      in >> id >> t >> sh->dims[0] >> sh->dims[1] >> sh->dims[2];
+      sh->type = static_cast<shapes::ShapeType>(t);
+      const Isometry3d pose = readPose(in);
+      world->addToObject(id, sh, pose);
+      object_ids.push_back(id);
+    }
+    std::string group_name;
+    int n_single = 0, n_contacts = 0, n_grad = 0, mutate = 0;
+    std::size_t max_contacts = 1, max_per_pair = 1;
+    in >> tok >> group_name >> n_single >> n_contacts >> max_contacts >> max_per_pair >> n_grad >> mutate;
+    if (group_name == "-")
+      group_name.clear();
+    if (!in)
+      throw std::runtime_error("scenario parse error");
+
+    // states
+    std::ifstream sf(argv[2], std::ios::binary | std::ios::ate);
+    const std::streamsize bytes = sf.tellg();
+    sf.seekg(0);
+    const int nvar = model->getVariableCount();
+    const std::int64_t n = bytes / (std::streamsize)(sizeof(double) * nvar);
+    std::vector<double> q((std::size_t)n * nvar);
+    sf.read(reinterpret_cast<char*>(q.data()), bytes);
+
+    // the env is created the way PlanningScene does it: through the allocator, on an already populated world
+    auto alloc = CollisionDetectorAllocatorB200::create();
+    const Vector3d origin{ center[0], center[1], center[2] };
+    CollisionEnvB200Ptr env = std::make_shared<CollisionEnvB200>(model, world, overrides, size[0], size[1], size[2],
+                                                                 origin, use_signed != 0, res, tol, max_dist);
+    const std::string prefix = argv[3];
+    const AllowedCollisionMatrix* acm_ptr = use_acm ? &acm : nullptr;
+    CollisionRequest req;
+    req.group_name = group_name;
+    core::RobotState ref_state(model);  // all-zero scene state poses the non-group links
+    std::vector<std::uint8_t> v(n);
+    env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_ROBOT, ref_state, v.data());
+    writeFile(prefix + ".robot.u8", v);
+    env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_SELF | B200DF_CHECK_INTRA, ref_state, v.data());
+    writeFile(prefix + ".self.u8", v);
+    env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT,
+                             ref_state, v.data());
+    writeFile(prefix + ".all.u8", v);
+
+    // single-state CollisionEnv API
+    std::vector<std::uint8_t> single;
+    for (std::int64_t i = 0; i < std::min<std::int64_t>(n_single, n); ++i)
+    {
+      core::RobotState st(model);
+      st.setVariablePositions(&q[(std::size_t)i * nvar]);
+      CollisionResult r1, r2, r3;
+      if (acm_ptr)
+      {
+        env->checkRobotCollision(req, r1, st, acm);
+        env->checkSelfCollision(req, r2, st, acm);
+        env->checkCollision(req, r3, st, acm);
+      }
+      else
+      {
+        env->checkRobotCollision(req, r1, st);
+        env->checkSelfCollision(req, r2, st);
+        env->checkCollision(req, r3, st);
+      }
+      single.push_back((r1.collision ? 1 : 0) | (r2.collision ? 2 : 0) | (r3.collision ? 4 : 0));
+    }
+    writeFile(prefix + ".single.u8", single);
+
+    // contacts
+    {
+      std::ofstream cf(prefix + ".contacts.txt");
+      cf.precision(17);
+      CollisionRequest creq = req;
+      creq.contacts = true;
+      creq.max_contacts = max_contacts;
+      creq.max_contacts_per_pair = max_per_pair;
+      for (std::int64_t i = 0; i < std::min<std::int64_t>(n_contacts, n); ++i)
+      {
+        core::RobotState st(model);
+        st.setVariablePositions(&q[(std::size_t)i * nvar]);
+        CollisionResult r;
+        if (acm_ptr)
+          env->checkCollision(creq, r, st, acm);
+        else
+          env->checkCollision(creq, r, st);
+        cf << "state " << i << " " << (r.collision ? 1 : 0) << " " << r.contact_count << "\n";
+        for (const auto& kv : r.contacts)
+          for (const Contact& c : kv.second)
+            cf << "contact " << c.body_name_1 << " " << c.body_name_2 << " " << c.pos.x << " " << c.pos.y << " "
+               << c.pos.z << "\n";
+      }
+    }
+
+    // gradients (CHOMP entry point), flattened per state: S x (dist, gx, gy, gz, type, cx, cy, cz)
+    {
+      std::vector<double> out;
+      for (std::int64_t i = 0; i < std::min<std::int64_t>(n_grad, n); ++i)
+      {
+        core::RobotState st(model);
+        st.setVariablePositions(&q[(std::size_t)i * nvar]);
+        CollisionResult r;
+        GroupStateRepresentationPtr gsr;
+        // the reference entry is built from the first state it sees; pose the non-group links with the scene state
+        std::vector<GroupStateRepresentationPtr> one;
+        env->getCollisionGradientsBatch(req, st.getVariablePositions(), 1, acm_ptr, one, &ref_state);
+        gsr = one[0];
+        for (const GradientInfo& gi : gsr->gradients_)
+          for (std::size_t s = 0; s < gi.distances.size(); ++s)
+            out.insert(out.end(), { gi.distances[s], gi.gradients[s].x, gi.gradients[s].y, gi.gradients[s].z,
+                                    (double)gi.types[s], gi.sphere_locations[s].x, gi.sphere_locations[s].y,
+                                    gi.sphere_locations[s].z });
+      }
+      writeFile(prefix + ".grad.f64", out);
+    }
+
+    // world mutation through the observer: move the first object by +0.1 m in x, destroy the second
+    if (mutate && object_ids.size() >= 2)
+    {
+      World::ObjectConstPtr o = world->getObject(object_ids[0]);
+      Isometry3d moved = o->shape_poses_[0];
+      moved.m[3] += 0.1;
+      world->moveShapeInObject(object_ids[0], 0, moved);
+      world->removeObject(object_ids[1]);
+      env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_ROBOT, ref_state, v.data());
+      writeFile(prefix + ".robot2.u8", v);
+      // a second env allocated from the first on the same world must agree (allocateEnv(orig, world))
+      CollisionEnvB200Ptr copy = alloc->allocateEnv(env, world);
+      std::vector<std::uint8_t> v2(n);
+      copy->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_ROBOT, ref_state, v2.data());
+      if (v2 != v)
+        throw std::runtime_error("env copied onto the same world disagrees with the original");
+    }
+    std::printf("host_driver ok: %s, %lld states, detector %s, %lld kernel launches\n", robot_name.c_str(),
+                (long long)n, alloc->getName().c_str(), (long long)b200df_launch_count());
+    return 0;
+  }
+  catch (const std::exception& ex)
+  {
+    std::fprintf(stderr, "host_driver failed: %s\n", ex.what());
+    return 1;
+  }
+}

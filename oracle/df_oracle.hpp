@@ -1767,6 +1767,112 @@ public:
     return false;
   }
 
+  // ---- req.contacts == true ------------------------------------------------------------------------------
+  // One contact: the group-link index of body 1, body 2 (a group-link index, kSelf or kEnvironment), the sphere of
+  // body 1 whose centre is Contact::pos, and that centre.  res.contacts is a std::map keyed by the name pair; the
+  // caller re-keys by name, the insertion order inside a key is the order below.
+  enum
+  {
+    kSelf = -1,
+    kEnvironment = -2,
+  };
+  struct ContactRec
+  {
+    int link1, body2, sphere;
+    V3 pos;
+  };
+  struct ContactResult
+  {
+    bool collision = false;
+    size_t contact_count = 0;
+    std::vector<ContactRec> contacts;
+    size_t pairCount(int a, int b) const
+    {
+      size_t n = 0;
+      for (const ContactRec& c : contacts)
+        n += (c.link1 == a && c.body2 == b);
+      return n;
+    }
+  };
+  // getSelfCollisions :277-356 / getEnvironmentCollisions :1580-1662 with req.contacts
+  bool fieldContacts(const PropagationDistanceField* df, const GroupStateRepresentation& gsr, bool self, int body2,
+                     size_t max_contacts, size_t max_contacts_per_pair, ContactResult& res) const
+  {
+    for (size_t i = 0; i < dfce_->link_indices.size(); i++)
+    {
+      if (!dfce_->link_has_geometry[i] || (self && !dfce_->self_collision_enabled[i]))
+        continue;
+      const LinkGeom& g = model_->geom[dfce_->link_indices[i]];
+      std::vector<unsigned int> colls;
+      bool coll = getCollisionSphereCollision(df, g.spheres, gsr.sphere_centers[i], p_.max_propagation_distance,
+                                              p_.collision_tolerance,
+                                              (unsigned int)std::min(max_contacts_per_pair, max_contacts - res.contact_count),
+                                              colls);
+      if (coll)
+      {
+        res.collision = true;
+        for (unsigned int col : colls)
+        {
+          res.contacts.push_back(ContactRec{ (int)i, body2, (int)col, gsr.sphere_centers[i][col] });
+          res.contact_count++;
+        }
+        if (res.contact_count >= max_contacts)
+          return true;
+      }
+    }
+    return res.contact_count >= max_contacts;
+  }
+  // getIntraGroupCollisions :433-660 with req.contacts, no attached bodies
+  bool intraContacts(const GroupStateRepresentation& gsr, size_t max_contacts, size_t max_contacts_per_pair,
+                     ContactResult& res) const
+  {
+    const size_t num_links = dfce_->link_indices.size();
+    for (size_t i = 0; i < num_links; i++)
+      for (size_t j = i + 1; j < num_links; j++)
+      {
+        if (!dfce_->link_has_geometry[i] || !dfce_->link_has_geometry[j])
+          continue;
+        if (!dfce_->intra_group_collision_enabled[i][j])
+          continue;
+        if (!doBoundingSpheresIntersect(gsr, i, j))
+          continue;
+        int num_pair = (int)res.pairCount((int)i, (int)j);
+        const auto& s1 = model_->geom[dfce_->link_indices[i]].spheres;
+        const auto& s2 = model_->geom[dfce_->link_indices[j]].spheres;
+        for (size_t k = 0; k < s1.size() && num_pair < (int)max_contacts_per_pair; k++)
+          for (size_t l = 0; l < s2.size() && num_pair < (int)max_contacts_per_pair; l++)
+          {
+            V3 gradient = gsr.sphere_centers[i][k] - gsr.sphere_centers[j][l];
+            double dist = norm(gradient);
+            if (dist < s1[k].radius + s2[l].radius)
+            {
+              res.collision = true;
+              res.contacts.push_back(ContactRec{ (int)i, (int)j, (int)k, gsr.sphere_centers[i][k] });
+              res.contact_count++;
+              num_pair++;
+              if (res.contact_count >= max_contacts)
+                return true;
+            }
+          }
+      }
+    return false;
+  }
+  // checkCollision :1441-1464 with req.contacts == true
+  ContactResult checkCollisionContacts(const double* q, size_t max_contacts, size_t max_contacts_per_pair) const
+  {
+    GroupStateRepresentation gsr;
+    poseGroup(q, gsr);
+    ContactResult res;
+    bool done = false;
+    if (dfce_->distance_field)
+      done = fieldContacts(dfce_->distance_field.get(), gsr, true, kSelf, max_contacts, max_contacts_per_pair, res);
+    if (!done)
+      done = intraContacts(gsr, max_contacts, max_contacts_per_pair, res);
+    if (!done)
+      done = fieldContacts(world_field_.get(), gsr, false, kEnvironment, max_contacts, max_contacts_per_pair, res);
+    return res;
+  }
+
   // per-link PosedDistanceField, getGroupStateRepresentation :1196-1213
   void buildLinkFields()
   {

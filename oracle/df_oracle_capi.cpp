@@ -470,6 +470,33 @@ double orc_env_gradients_batch(void* h, const double* q, long N, int flags, doub
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// checkCollision with req.contacts == true for one state.  out: rows of (link1, body2, sphere, x, y, z) as doubles;
+// body2 -1 = "self", -2 = "environment".  Returns the contact count (may exceed cap; only cap rows are written);
+// *collision receives res.collision.
+long orc_env_check_contacts(void* h, const double* q, long max_contacts, long max_contacts_per_pair, double* out,
+                            long cap, int* collision)
+{
+  auto& env = *static_cast<EnvHandle*>(h)->env;
+  auto res = env.checkCollisionContacts(q, (size_t)max_contacts, (size_t)max_contacts_per_pair);
+  *collision = res.collision ? 1 : 0;
+  long k = 0;
+  for (const auto& c : res.contacts)
+  {
+    if (k < cap)
+    {
+      double* r = out + 6 * k;
+      r[0] = c.link1;
+      r[1] = c.body2;
+      r[2] = c.sphere;
+      r[3] = c.pos.x;
+      r[4] = c.pos.y;
+      r[5] = c.pos.z;
+    }
+    ++k;
+  }
+  return k;
+}
+
 int orc_hardware_concurrency()
 {
   return (int)std::thread::hardware_concurrency();

@@ -92,6 +92,8 @@ def lib():
         L.orc_env_check_batch.argtypes = [C.c_void_p, c_dp, C.c_long, C.c_int, c_u8p, C.c_int]
         L.orc_env_gradients_batch.restype = C.c_double
         L.orc_env_gradients_batch.argtypes = [C.c_void_p, c_dp, C.c_long, C.c_int, c_dp, c_dp, c_i32p, c_dp, c_dp]
+        L.orc_env_check_contacts.restype = C.c_long
+        L.orc_env_check_contacts.argtypes = [C.c_void_p, c_dp, C.c_long, C.c_long, c_dp, C.c_long, c_ip]
         L.orc_hardware_concurrency.restype = C.c_int
         _lib = L
     return _lib
@@ -346,6 +348,18 @@ class Env:
         out = np.empty(n, dtype=np.uint8)
         t = lib().orc_env_check_batch(self.h, pq, n, mode, out.ctypes.data_as(c_u8p), n_threads)
         return (out, t) if return_time else out
+
+    def check_contacts(self, q, max_contacts=1, max_contacts_per_pair=1):
+        """checkCollision with req.contacts == true for ONE state -> (collision, [(link1, body2, sphere, pos[3])]);
+        link indices are positions in the group's link list, body2 -1 = "self", -2 = "environment"."""
+        _, pq = _d(q)
+        cap = max(int(max_contacts), 1) + 8
+        out = np.zeros((cap, 6))
+        col = C.c_int(0)
+        n = lib().orc_env_check_contacts(self.h, pq, int(max_contacts), int(max_contacts_per_pair),
+                                         out.ctypes.data_as(c_dp), cap, C.byref(col))
+        assert n <= cap
+        return bool(col.value), [(int(r[0]), int(r[1]), int(r[2]), r[3:6].copy()) for r in out[:n]]
 
     def gradients_batch(self, q, flags=7):
         q, N = _states(q, self.model.nvar)

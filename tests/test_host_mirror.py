@@ -1,0 +1,136 @@
+"""The C++ host mirror (moveit_b200/host/collision_env_b200.hpp: CollisionEnvB200 + CollisionDetectorAllocatorB200,
+the reference-shaped plugin body) driven end to end by host_driver and compared with the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from moveit_b200 import robot_description as rd
+from moveit_b200 import scenario_io, scenarios
+
+from common import OracleSetup, oracle_world_points, self_field_points
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build_driver():
+    import runpy
+    mod = runpy.run_path(os.path.join(ROOT, "moveit_b200", "host", "build_host.py"))
+    return mod["build"]()
+
+
+def test_host_driver_compiles_against_the_c_abi():
+    """g++ -std=c++17 -Wall -Wextra over the header-only mirror; links libb200df.so only (no torch, no oracle)."""
+    exe = _build_driver()
+    assert os.access(exe, os.X_OK)
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libb200df.so" in out and "liboracle" not in out and "torch" not in out
+
+
+def test_scenario_writer_round_trips_doubles(tmp_path):
+    desc = rd.panda()
+    p = tmp_path / "s.txt"
+    scenario_io.write_scenario(str(p), desc, scenarios.FIELD_A, scenarios.random_scene())
+    toks = open(p).read().split()
+    assert toks[0] == "robot" and int(toks[2]) == desc.n_links
+    i = toks.index("obj0")
+    assert float(toks[i + 2]) == scenarios.random_scene()[0][1][0]
+
+
+def _run(tmp_path, desc, field, objs, q, **kw):
+    exe = _build_driver()
+    scen, states, prefix = str(tmp_path / "scen.txt"), str(tmp_path / "q.f64"), str(tmp_path / "out")
+    scenario_io.write_scenario(scen, desc, field, objs, **kw)
+    np.ascontiguousarray(q, dtype=np.float64).tofile(states)
+    r = subprocess.run([exe, scen, states, prefix], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "B200DistanceField" in r.stdout
+    return prefix
+
+
+@pytest.mark.gpu
+def test_panda_arm_group_through_the_cpp_env(gpu, oracle, tmp_path):
+    """Planning group panda_arm with the SRDF ACM: batched and single-state verdicts, contacts, gradients and a
+    world mutation through the observer, all against the oracle."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=41)
+    fa = scenarios.FIELD_A
+    n = 4000
+    q = desc.sample_states(n, 2024)
+    q0 = np.zeros(desc.nvar)
+    prefix = _run(tmp_path, desc, fa, objs, q, group="panda_arm", n_single=64, n_contacts=200, max_contacts=10,
+                  max_contacts_per_pair=2, n_grad=50, mutate=True)
+    o = OracleSetup(oracle, desc, fa, objs, group="panda_arm", self_state=q0)
+    robot = np.fromfile(prefix + ".robot.u8", dtype=np.uint8)
+    self_ = np.fromfile(prefix + ".self.u8", dtype=np.uint8)
+    both = np.fromfile(prefix + ".all.u8", dtype=np.uint8)
+    assert np.array_equal(robot, o.env.check_batch(q, mode=1, n_threads=4))
+    assert np.array_equal(self_, o.env.check_batch(q, mode=2, n_threads=4))
+    assert np.array_equal(both, o.env.check_batch(q, mode=4, n_threads=4))
+    assert 0 < robot.sum() < n and self_.sum() > 0  # link1 always touches link0's voxels in the self field
+    single = np.fromfile(prefix + ".single.u8", dtype=np.uint8)
+    assert np.array_equal(single & 1, robot[:64]) and np.array_equal((single >> 1) & 1, self_[:64])
+    assert np.array_equal((single >> 2) & 1, both[:64])
+
+    # contacts: same pairs, same order inside a pair, same positions
+    names = [desc.link_names[i] for i in o.group_links]
+    got, cur = {}, None
+    for line in open(prefix + ".contacts.txt"):
+        t = line.split()
+        if t[0] == "state":
+            cur = int(t[1])
+            got[cur] = dict(collision=int(t[2]), count=int(t[3]), contacts=[])
+        else:
+            got[cur]["contacts"].append((t[1], t[2], np.array([float(t[3]), float(t[4]), float(t[5])])))
+    n_with = 0
+    for i in range(200):
+        col, recs = o.env.check_contacts(q[i], 10, 2)
+        want = {}
+        for (l1, b2, _, pos) in recs:
+            key = (names[l1], "self" if b2 == -1 else "environment" if b2 == -2 else names[b2])
+            want.setdefault(key, []).append(pos)
+        assert got[i]["collision"] == int(col) and got[i]["count"] == len(recs)
+        flat = [(k[0], k[1], p) for k in sorted(want) for p in want[k]]  # std::map iteration order
+        assert len(flat) == len(got[i]["contacts"])
+        for (a, b, p), (ga, gb, gp) in zip(flat, got[i]["contacts"]):
+            assert (a, b) == (ga, gb) and np.max(np.abs(p - gp)) < 1e-12  # CUDA vs glibc sincos: <= 2 ulp
+        n_with += bool(recs)
+    assert n_with > 20
+
+    # gradients (self field + intra + environment; the per-link PosedDistanceField term is not part of the engine,
+    # and the oracle only adds it after build_link_fields())
+    g = np.fromfile(prefix + ".grad.f64").reshape(50, -1, 8)
+    ref = o.env.gradients_batch(q[:50], flags=7)
+    assert g.shape[1] == ref["dist"].shape[1]
+    assert np.max(np.abs(g[:, :, 5:8] - ref["centers"])) < 1e-12
+    assert np.array_equal(g[:, :, 4].astype(np.int32), ref["type"])
+    fin = ref["dist"] < 1e300
+    assert np.array_equal(fin, g[:, :, 0] < 1e300)
+    assert np.max(np.abs(g[:, :, 0][fin] - ref["dist"][fin])) < 1e-5
+    assert np.max(np.abs(g[:, :, 1:4] - ref["grad"])) < 1e-5
+
+    # world mutation: object 0 moved by +0.1 m in x, object 1 destroyed (removePointsFromField + addPointsToField)
+    pts = [oracle_world_points(oracle, [ob], fa["resolution"]) for ob in objs]
+    moved = (objs[0][0], objs[0][1], np.array(objs[0][2]) + np.array([[0, 0, 0, 0.1]] * 3) * np.array([[1], [0], [0]]))
+    o.env.world.remove_points(pts[0])
+    o.env.world.add_points(oracle_world_points(oracle, [moved], fa["resolution"]))
+    o.env.world.remove_points(pts[1])
+    o.env.world.make_exact()
+    robot2 = np.fromfile(prefix + ".robot2.u8", dtype=np.uint8)
+    assert np.array_equal(robot2, o.env.check_batch(q, mode=1, n_threads=4))
+    assert not np.array_equal(robot2, robot)
+
+
+@pytest.mark.gpu
+def test_whole_robot_no_acm_and_derived_spheres(gpu, oracle, tmp_path):
+    """group "" (all links), null ACM branch, spheres from determineCollisionSpheres, collision tolerance."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=43)
+    q = desc.sample_states(1500, 5)
+    prefix = _run(tmp_path, desc, scenarios.FIELD_A, objs, q, group="", use_acm=False, sphere_overrides=False,
+                  tol=0.01, n_single=8)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, use_acm=False, sphere_overrides=False, tol=0.01,
+                    self_state=np.zeros(desc.nvar))
+    assert np.array_equal(np.fromfile(prefix + ".robot.u8", dtype=np.uint8), o.env.check_batch(q, mode=1, n_threads=4))
+    assert np.array_equal(np.fromfile(prefix + ".all.u8", dtype=np.uint8), o.env.check_batch(q, mode=4, n_threads=4))
