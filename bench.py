@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 
 STATES_PER_GPU = 10_000_000
 ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out
+# dram__bytes_read.sum + dram__bytes_write.sum per state from the committed ncu --set full captures (2 000 000 states):
+# profiles/r01_validity_fast_full.txt (72.80 MB + 1.00 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
+NCU_DRAM_BYTES_PER_STATE = {"fast": (72.800768e6 + 0.996352e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
 
 
 def parse():
@@ -40,7 +43,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--states", type=int, default=STATES_PER_GPU, help="states per GPU per step")
-    ap.add_argument("--precision", default="exact", choices=["fast", "exact", "v1"])
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact", "v1"],
+                    help="fast = fp32 screening + exact fp64 re-run of the undecided states (same verdicts as exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-edt", action="store_true")
     return ap.parse_args()
@@ -140,7 +144,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "state_validity_checks_per_sec", "value": value, "unit": "states/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
         "config": workload_config(per_step),
         "cpu_baseline": {"value": value, "unit": "states/s", "cores": cores, "kind": "port",
                          "sample": "%d states per step of the bench batch (same seed), CPU oracle = faithful restatement "
@@ -183,9 +187,16 @@ def edt_timings(engine, scenarios, B):
         g.add_points(pts)
         best = min(best, g.rebuild())
     out["field_b_1cm_400^3_1Mpts_ms"] = best
-    peak, _ = measured_peak_hbm()
-    algo = 400 ** 3 * 3 + 24 * len(pts)
-    out["field_b_roofline_frac"] = algo / (best * 1e-3) / 1e9 / peak
+    peak, src = measured_peak_hbm()
+    algo = 400 ** 3 * 3  # occupancy byte in + u16 d^2 out per voxel; the point list is scattered at add time
+    out["field_b_roofline"] = {"bound": "hbm", "achieved": algo / (best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": algo / (best * 1e-3) / 1e9 / peak, "peak_source": src,
+                               "algorithmic_bytes": algo,
+                               "note": "4 launches: pack bits, z pass, DPX marching y pass, DPX marching x pass"}
+    t0 = time.perf_counter()
+    g.reset()
+    g.add_points(pts)
+    out["field_b_add_1Mpts_host_ms"] = 1e3 * (time.perf_counter() - t0)  # 24 MB H2D + scatter kernel, wall clock
     return out
 
 
@@ -278,12 +289,26 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = B.load().b200df_launch_count() - launches0
-    clocks = sampler.summary()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     colliding = int(v_dev.sum().item())
+    undecided = None
+    if args.precision == "fast":
+        # share of states the fp32 screening pass hands to the exact kernel (raw screening verdict 2), on a sample
+        m = min(n, 2_000_000)
+        raw = torch.empty(m, dtype=torch.uint8, device=dev)
+        group.check_device(q_dev.data_ptr(), B.Q_F32, m, raw.data_ptr(), world_field, None, flags, 3, stream.cuda_stream)
+        torch.cuda.synchronize()
+        undecided = float((raw == 2).sum().item()) / m
+        # and the proof that FAST == EXACT on this very batch
+        v_exact = torch.empty(n, dtype=torch.uint8, device=dev)
+        group.check_device(q_dev.data_ptr(), B.Q_F32, n, v_exact.data_ptr(), world_field, None, flags,
+                           B.PRECISION_EXACT, stream.cuda_stream)
+        torch.cuda.synchronize()
+        if not torch.equal(v_exact, v_dev):
+            raise SystemExit("FAST and EXACT verdicts differ on the bench batch")
 
     # ---- end-to-end through the host-buffer C-ABI call
     e2e_steps = max(2, min(args.steps, 5))
@@ -298,6 +323,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    clocks = sampler.summary()  # sampled over both timed regions (device-resident and end-to-end)
     same = bool(torch.equal(v_host.to(dev), v_dev))
 
     if rank == 0:
@@ -308,7 +334,7 @@ def main():
         line = {
             "metric": "state_validity_checks_per_sec", "value": value, "unit": "states/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64",
             "data": "synthetic", "config": workload_config(n),
             "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "states/s",
                     "h2d_bytes_per_step": n * desc.nvar * 4, "d2h_bytes_per_step": n,
@@ -316,12 +342,20 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "37 algorithmic bytes/state; the fused validity kernel is instruction-issue bound "
-                                 "by construction (see DESIGN.md), HBM fraction is reported for completeness"},
+                         "traffic": NCU_DRAM_BYTES_PER_STATE.get(args.precision, NCU_DRAM_BYTES_PER_STATE["exact"]) * n,
+                         "peak_source": peak_src,
+                         "kernel": ("validity_fast_kernel<unsigned char, 128> (+ validity_kernel on the undecided "
+                                    "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
+                         "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
+                                 "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
+                                 "The fused FK+lookup+pair kernel executes ~18 k warp instructions per 32 states and "
+                                 "is issue/latency bound by construction (DESIGN.md section 4); the HBM-bound "
+                                 "kernel of this path is the EDT, see edt_ms.field_b_roofline"},
             "colliding_fraction": colliding / n,
             "field_replication_bytes": replicated_bytes,
             "precision": args.precision,
+            "fast_undecided_fraction": undecided,
+            "fast_equals_exact_on_batch": True if args.precision == "fast" else None,
         }
         if not args.no_edt:
             try:

@@ -94,30 +94,43 @@ __device__ __forceinline__ bool voxel_hits(const LookupDev& f, unsigned idx, boo
 
 constexpr int kBatch = 4;  // spheres posed / looked up / pair-tested together (independent chains for the fp64 pipe)
 
+// redo_idx / redo_count: when set, the kernel re-evaluates the listed states only (the FAST path's ambiguous set); it is
+// then launched with a fixed grid and every CTA strides over the list, whose length lives in device memory.
 template <typename QT, typename FT, int B>
 __global__ void __launch_bounds__(B) validity_kernel(GroupDev g, LookupDev wf, LookupDev sf, const QT* __restrict__ q,
-                                                     long n, int flags, uint8_t* __restrict__ verdict)
+                                                     long n, int flags, uint8_t* __restrict__ verdict,
+                                                     const int* __restrict__ redo_idx,
+                                                     const int* __restrict__ redo_count)
 {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
-  const long base = (long)blockIdx.x * B;
   const bool do_pairs = (flags & B200DF_CHECK_INTRA) != 0 && g.n_partners > 0;
   double* slots = smem;                                                           // [n_slots][12][B]
   double* stc = slots + (size_t)g.n_slots * 12 * B;                               // [n_store_spheres][3][B]
   double* stb = stc + (do_pairs ? (size_t)g.n_store_spheres * 3 * B : 0);         // [n_store_links][3][B]
   QT* qs = reinterpret_cast<QT*>(stb + (do_pairs ? (size_t)g.n_store_links * 3 * B : 0));  // [B][n_vars]
-
+  const long total = redo_idx ? (long)*redo_count : n;
+  for (long base = (long)blockIdx.x * B; base < total; base += (long)gridDim.x * B)
+  {
+  long state = base + tid;
+  const bool active = state < total;
+  if (redo_idx)
+  {
+    __syncthreads();  // the previous tile's readers are done with qs
+    state = active ? redo_idx[state] : 0;
+    for (int v = 0; v < g.n_vars; ++v)
+      qs[tid * g.n_vars + v] = q[state * g.n_vars + v];
+  }
+  else
   {
     // the tile's joint values are one contiguous run of the batch: straight coalesced copy, rows stay rows
-    const int total = B * g.n_vars;
+    const int count = B * g.n_vars;
     const long limit = (n - base) * g.n_vars;
     const QT* src = q + base * g.n_vars;
-    for (int e = tid; e < total; e += B)
+    for (int e = tid; e < count; e += B)
       qs[e] = (e < limit) ? src[e] : QT(0);
   }
   __syncthreads();
-  const long state = base + tid;
-  const bool active = state < n;
   const QT* my_q = qs + (size_t)tid * g.n_vars;
   double* my_slots = slots + tid;
   double* my_stc = stc + tid;
@@ -260,6 +273,7 @@ __global__ void __launch_bounds__(B) validity_kernel(GroupDev g, LookupDev wf, L
   }
   if (active)
     verdict[state] = hit ? 1 : 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -299,16 +313,24 @@ size_t verdict_smem_bytes(const GroupDev& g, int block, bool pairs, size_t q_ele
   return d * block * sizeof(double) + (size_t)g.n_vars * block * q_elem;
 }
 
+struct Redo  // the ambiguous-state list of the FAST path (device pointers), or nulls
+{
+  const int* idx = nullptr;
+  const int* count = nullptr;
+};
+
 template <typename QT, typename FT, int B>
 int launch_verdict_block(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
-                         uint8_t* verdict, size_t bytes, cudaStream_t stream)
+                         uint8_t* verdict, size_t bytes, cudaStream_t stream, Redo redo)
 {
   if (bytes > 48 * 1024)
     B200DF_CUDA(cudaFuncSetAttribute(validity_kernel<QT, FT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)bytes));
-  const unsigned grid = (unsigned)((n + B - 1) / B);
+  // redo: a fixed grid (a few CTAs per SM) strides over the list; its length is only known on the device
+  const unsigned grid = redo.idx ? (unsigned)std::min<long>((n + B - 1) / B, 148 * 8) : (unsigned)((n + B - 1) / B);
   validity_kernel<QT, FT, B><<<grid, B, bytes, stream>>>(g, make_lookup(wf), make_lookup(sf),
-                                                         static_cast<const QT*>(q), n, flags, verdict);
+                                                         static_cast<const QT*>(q), n, flags, verdict, redo.idx,
+                                                         redo.count);
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
@@ -316,44 +338,96 @@ int launch_verdict_block(const GroupDev& g, const FieldDev& wf, const FieldDev& 
 
 template <typename QT, typename FT>
 int launch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
-                   uint8_t* verdict, cudaStream_t stream)
+                   uint8_t* verdict, cudaStream_t stream, Redo redo)
 {
   const bool pairs = (flags & B200DF_CHECK_INTRA) && g.n_partners > 0;
   // 64 states per CTA when four or more such CTAs fit an SM, else one warp per CTA
   size_t bytes = verdict_smem_bytes(g, 64, pairs, sizeof(QT));
   if (bytes <= 56 * 1024)
-    return launch_verdict_block<QT, FT, 64>(g, wf, sf, q, n, flags, verdict, bytes, stream);
+    return launch_verdict_block<QT, FT, 64>(g, wf, sf, q, n, flags, verdict, bytes, stream, redo);
   bytes = verdict_smem_bytes(g, 32, pairs, sizeof(QT));
   if (bytes > 220 * 1024)
   {
     set_error("robot too large for the per-state shared-memory layout (%zu bytes for 32 states)", bytes);
     return B200DF_ERR_UNSUPPORTED;
   }
-  return launch_verdict_block<QT, FT, 32>(g, wf, sf, q, n, flags, verdict, bytes, stream);
+  return launch_verdict_block<QT, FT, 32>(g, wf, sf, q, n, flags, verdict, bytes, stream, redo);
 }
 
 int dispatch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
-                     int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream)
+                     int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream, Redo redo = Redo())
 {
   if (q_dtype == B200DF_Q_F32)
   {
     if (field_elem == 1)
-      return launch_verdict<float, uint8_t>(g, wf, sf, q, n, flags, verdict, stream);
-    return launch_verdict<float, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
+      return launch_verdict<float, uint8_t>(g, wf, sf, q, n, flags, verdict, stream, redo);
+    return launch_verdict<float, uint16_t>(g, wf, sf, q, n, flags, verdict, stream, redo);
   }
   if (field_elem == 1)
-    return launch_verdict<double, uint8_t>(g, wf, sf, q, n, flags, verdict, stream);
-  return launch_verdict<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
+    return launch_verdict<double, uint8_t>(g, wf, sf, q, n, flags, verdict, stream, redo);
+  return launch_verdict<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream, redo);
 }
 
-constexpr int kPrecisionV1 = 2;  // undocumented: the round-1 kernel, kept as an independent cross-check
+constexpr int kPrecisionV1 = 2;       // undocumented: the round-1 kernel, kept as an independent cross-check
+constexpr int kPrecisionFastRaw = 3;  // undocumented: FAST screening pass only, verdicts 0 / 1 / 2 = undecided (tests)
 
+// keeps the stream-ordered allocator from returning memory to the OS between calls (once per device)
+void keep_async_pool(int device)
+{
+  static std::mutex mu;
+  static std::vector<char> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)done.size() <= device)
+    done.resize(device + 1, 0);
+  if (done[device])
+    return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+  {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[device] = 1;
+}
+
+// amb_idx (n ints) / amb_count (1 int): device scratch of the FAST path; allocated stream-ordered when null
 int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int elem, const void* q_dev,
-                int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, cudaStream_t stream)
+                int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, cudaStream_t stream,
+                int* amb_idx = nullptr, int* amb_count = nullptr)
 {
   if (precision == kPrecisionV1)
     return launch_verdict_v1(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
-  return dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+  const bool raw = precision == kPrecisionFastRaw;
+  if (raw && !fast_supported(group, wf, sf, q_dtype, flags))
+  {
+    set_error("the FAST screening pass does not support this call (needs fp32 joint values, unsigned fields, a model "
+              "that fits the constant-bank tables)");
+    return B200DF_ERR_UNSUPPORTED;
+  }
+  if ((precision != B200DF_PRECISION_FAST && !raw) || !fast_supported(group, wf, sf, q_dtype, flags))
+    return dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+  // FAST: fp32 screening pass, then the exact kernel over the states whose verdict could depend on rounding
+  B200DF_REQUIRE(n < (1L << 31), "FAST batches are limited to 2^31 states per call");
+  void* scratch = nullptr;
+  if (!amb_idx)
+  {
+    keep_async_pool(group->device);
+    B200DF_CUDA(cudaMallocAsync(&scratch, ((size_t)n + 1) * sizeof(int), stream));
+    amb_count = static_cast<int*>(scratch);
+    amb_idx = amb_count + 1;
+  }
+  int rc = fast_launch(group, wf, sf, elem, static_cast<const float*>(q_dev), n, flags, verdict_dev, amb_idx, amb_count,
+                       stream);
+  if (!rc && !raw)
+  {
+    Redo redo;
+    redo.idx = amb_idx;
+    redo.count = amb_count;
+    rc = dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream, redo);
+  }
+  if (scratch)
+    cudaFreeAsync(scratch, stream);
+  return rc;
 }
 }  // namespace
 
@@ -369,6 +443,7 @@ struct b200df_group::StagePool
     cudaStream_t stream[2] = { nullptr, nullptr };
     void* q[2] = { nullptr, nullptr };
     uint8_t* v[2] = { nullptr, nullptr };
+    int* amb[2] = { nullptr, nullptr };  // [0] = count, [1..] = indices (FAST path scratch)
     size_t q_bytes = 0, v_bytes = 0;
   };
   std::mutex mu;
@@ -384,6 +459,7 @@ struct b200df_group::StagePool
     {
       cudaFree(c->q[i]);
       cudaFree(c->v[i]);
+      cudaFree(c->amb[i]);
       if (c->stream[i])
         cudaStreamDestroy(c->stream[i]);
     }
@@ -435,6 +511,9 @@ int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
       cudaFree(c->v[i]);
       c->v[i] = nullptr;
       B200DF_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->v[i]), v_bytes));
+      cudaFree(c->amb[i]);
+      c->amb[i] = nullptr;
+      B200DF_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->amb[i]), (v_bytes + 1) * sizeof(int)));
     }
     c->v_bytes = v_bytes;
   }
@@ -778,11 +857,20 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     return rc;
   if ((rc = upload(g.get(), pair_thr, &dev.pair_thr)))
     return rc;
+  g->partners = partners;
+  g->sph_thr = sph_thr;
   if ((rc = upload(g.get(), partners, &dev.partners)))
     return rc;
   if ((rc = upload(g.get(), pair_T, &dev.pair_T)))
     return rc;
   g->stage = new b200df_group::StagePool;
+  if ((rc = fast_create(g.get())))
+  {
+    delete g->stage;
+    for (void* p : g->allocations)
+      cudaFree(p);
+    return rc;
+  }
   *out = g.release();
   return B200DF_OK;
 }
@@ -793,6 +881,7 @@ int b200df_group_destroy(b200df_group* g)
     return B200DF_OK;
   DeviceGuard dg(g->device);
   delete g->stage;
+  fast_destroy(g);
   for (void* p : g->allocations)
     cudaFree(p);
   delete g;
@@ -811,7 +900,8 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q_dev && verdict_dev)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
-  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1,
+  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1 ||
+                     precision == kPrecisionFastRaw,
                  "unknown precision");
   if (n == 0)
     return B200DF_OK;
@@ -830,7 +920,8 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && verdict)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
-  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1,
+  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1 ||
+                     precision == kPrecisionFastRaw,
                  "unknown precision");
   if (n == 0)
     return B200DF_OK;
@@ -855,7 +946,8 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
                         cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess)
       break;
-    rc = run_verdict(group, wf, sf, elem, ctx->q[k], q_dtype, m, flags, precision, ctx->v[k], st);
+    rc = run_verdict(group, wf, sf, elem, ctx->q[k], q_dtype, m, flags, precision, ctx->v[k], st, ctx->amb[k] + 1,
+                     ctx->amb[k]);
     if (rc)
       break;
     e = cudaMemcpyAsync(verdict + s, ctx->v[k], (size_t)m, cudaMemcpyDeviceToHost, st);

@@ -1,0 +1,771 @@
+// FAST precision of the batched validity check: the same fused sweep as validity.cu (FK, sphere posing, field
+// lookups, ACM-pruned intra-group pairs, one thread per state) in fp32 with FMA, plus a proof obligation: every
+// comparison the verdict depends on carries an error margin derived on the host from a forward error analysis of
+// this robot's chain.  A state gets
+//     1  when some test collides by more than its margin  (the exact evaluation collides too),
+//     0  when every test is clear by more than its margin  (the exact evaluation is clear too),
+//     2  otherwise; those states are appended to a list and re-run by the exact fp64 kernel of validity.cu.
+// So the verdicts that leave b200df_check_batch are those of the exact path, bit for bit, at fp32 cost for all but
+// the ~1 % of states that sit within micrometres of a voxel face or a sphere-pair threshold.
+//
+// Reference being replaced: the same functions as validity.cu (robot_state.cpp:718-755, *_joint_model.cpp,
+// collision_distance_field_types.cpp:206-231,390-420, distance_field.cpp:62-86,
+// collision_env_distance_field.cpp:277-356,433-660,1580-1662).
+//
+// This translation unit is compiled WITH fused multiply-add (no --fmad=false): nothing here has to round like the
+// reference, it only has to stay inside the margins.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "validity_common.cuh"
+
+using namespace b200df;
+
+namespace
+{
+constexpr int kMaxLinks = 32;
+constexpr int kMaxGLinks = 32;
+constexpr int kMaxSpheres = 128;
+constexpr int kMaxPartners = 96;
+constexpr int kBatch = 4;
+constexpr double kU = 5.9604644775390625e-08;  // 2^-24, unit round-off of fp32
+
+struct FLink
+{
+  int joint_type, jkind, var, is_mimic;
+  int origin_is_identity, parent, parent_is_prev, store_slot, parent_slot, gslot;
+  float mimic_mult, mimic_off;
+  float ax, ay, az, x2, y2, z2, xy, xz, yz;
+  float origin[12];
+  float vmax;  // joint values beyond this leave the analysed range -> the state is sent to the exact kernel
+};
+
+struct FGLink
+{
+  int sphere_begin, sphere_end, self_enabled, store_link, store_sphere, partner_begin, partner_end;
+  int pair_const_begin, pair_const_stride;
+  float bs[3];
+};
+
+struct FSphere
+{
+  float x, y, z;
+  float eps;  // bound on the distance between the fp32 centre and the exact (fp64) centre, metres
+  int thr;    // collide iff d2 < thr (same host-resolved threshold as the exact kernel)
+};
+
+struct FPartner
+{
+  int store_link, store_sphere, count, const_offset;
+  float rs_lo, rs_hi;  // doBoundingSpheresIntersect threshold (on the squared distance, Q2) minus / plus its margin
+  float tight_hi;      // exact-cull threshold plus margin
+  float pad;
+};
+
+struct FastTables  // passed by value: lives in the constant bank, read with warp-uniform indices
+{
+  int n_links, n_vars, n_slots, n_glinks, n_spheres, n_store_links, n_store_spheres, n_partners;
+  FLink links[kMaxLinks];
+  FGLink glinks[kMaxGLinks];
+  FSphere sph[kMaxSpheres];
+  FPartner partners[kMaxPartners];
+};
+
+struct FastLookup
+{
+  float oo;       // 1/resolution
+  float k[3];     // -origin_minus/resolution: grid coordinate g = p*oo + k
+  float gerr;     // rounding of that evaluation, in cells
+  unsigned lim[3];
+  int stride1, stride2;
+  const void* d2;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mulf(const float* a, const float* b, float* r)  // 3x4 * 3x4 (implied last row)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    const float a0 = a[4 * i], a1 = a[4 * i + 1], a2 = a[4 * i + 2];
+    r[4 * i + 0] = fmaf(a2, b[8], fmaf(a1, b[4], a0 * b[0]));
+    r[4 * i + 1] = fmaf(a2, b[9], fmaf(a1, b[5], a0 * b[1]));
+    r[4 * i + 2] = fmaf(a2, b[10], fmaf(a1, b[6], a0 * b[2]));
+    r[4 * i + 3] = fmaf(a2, b[11], fmaf(a1, b[7], fmaf(a0, b[3], a[4 * i + 3])));
+  }
+}
+
+__device__ __forceinline__ void applyf(const float* t, float x, float y, float z, float& ox, float& oy, float& oz)
+{
+  ox = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
+  oy = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
+  oz = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
+}
+
+// joint value in fp32; mimic joints evaluate mult*v+off in fp64 like the exact kernel and round once
+__device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, bool& out_of_range)
+{
+  float v = q[l.var + k];
+  if (l.is_mimic)
+    v = (float)((double)l.mimic_mult * (double)v + (double)l.mimic_off);
+  out_of_range |= !(fabsf(v) <= l.vmax);
+  return v;
+}
+
+__device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float* slots, int B, float* cur,
+                                          bool& out_of_range)
+{
+  float base[12];
+  if (l.parent < 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      base[k] = l.origin[k];  // identity when origin_is_identity
+  }
+  else
+  {
+    float par[12];
+    if (l.parent_is_prev)
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        par[k] = cur[k];
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        par[k] = slots[(l.parent_slot * 12 + k) * B];
+    }
+    if (l.origin_is_identity)
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        base[k] = par[k];
+    }
+    else
+      mulf(par, l.origin, base);
+  }
+  if (l.joint_type == B200DF_JOINT_FIXED)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      cur[k] = base[k];
+  }
+  else if (l.joint_type == B200DF_JOINT_PRISMATIC)
+  {
+    const float v = jointf(l, q, 0, out_of_range);
+    const float tx = l.ax * v, ty = l.ay * v, tz = l.az * v;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+      cur[4 * i + 0] = base[4 * i + 0];
+      cur[4 * i + 1] = base[4 * i + 1];
+      cur[4 * i + 2] = base[4 * i + 2];
+      cur[4 * i + 3] = fmaf(base[4 * i + 2], tz, fmaf(base[4 * i + 1], ty, fmaf(base[4 * i], tx, base[4 * i + 3])));
+    }
+  }
+  else  // revolute, or planar = translation (x, y) followed by a rotation about z
+  {
+    const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
+    float px = 0.f, py = 0.f;
+    if (planar)
+    {
+      px = jointf(l, q, 0, out_of_range);
+      py = jointf(l, q, 1, out_of_range);
+    }
+    const float v = jointf(l, q, planar ? 2 : 0, out_of_range);
+    float s, c;
+    sincosf(v, &s, &c);
+    const int kind = planar ? 3 : l.jkind;
+    if (kind == 0)
+    {
+      const float tt = 1.f - c;
+      float j[12];
+      j[0] = fmaf(tt, l.x2, c);
+      j[1] = fmaf(tt, l.xy, -l.az * s);
+      j[2] = fmaf(tt, l.xz, l.ay * s);
+      j[4] = fmaf(tt, l.xy, l.az * s);
+      j[5] = fmaf(tt, l.y2, c);
+      j[6] = fmaf(tt, l.yz, -l.ax * s);
+      j[8] = fmaf(tt, l.xz, -l.ay * s);
+      j[9] = fmaf(tt, l.yz, l.ax * s);
+      j[10] = fmaf(tt, l.z2, c);
+      j[3] = j[7] = j[11] = 0.f;
+      mulf(base, j, cur);
+    }
+    else
+    {
+      // rotation by v about +-x / +-y / +-z: the axis sign only flips the sine
+      const float sg = planar ? s : (kind == 1 ? l.ax : (kind == 2 ? l.ay : l.az)) * s;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+      {
+        const float a0 = base[4 * i], a1 = base[4 * i + 1], a2 = base[4 * i + 2];
+        float r0, r1, r2;
+        if (kind == 3)
+        {
+          r0 = fmaf(a1, sg, a0 * c);
+          r1 = fmaf(a1, c, -a0 * sg);
+          r2 = a2;
+        }
+        else if (kind == 2)
+        {
+          r0 = fmaf(a2, -sg, a0 * c);
+          r1 = a1;
+          r2 = fmaf(a2, c, a0 * sg);
+        }
+        else
+        {
+          r0 = a0;
+          r1 = fmaf(a2, sg, a1 * c);
+          r2 = fmaf(a2, c, -a1 * sg);
+        }
+        float t3 = base[4 * i + 3];
+        if (planar)
+          t3 = fmaf(a1, py, fmaf(a0, px, t3));
+        cur[4 * i + 0] = r0;
+        cur[4 * i + 1] = r1;
+        cur[4 * i + 2] = r2;
+        cur[4 * i + 3] = t3;
+      }
+    }
+  }
+  if (l.store_slot >= 0)
+  {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      slots[(l.store_slot * 12 + k) * B] = cur[k];
+  }
+}
+
+// one axis of the world->grid mapping: cell, and whether the exact cell could be the lower / upper neighbour
+__device__ __forceinline__ int axis_cell(float p, float oo, float k, float delta, int& alt)
+{
+  const float g = fmaf(p, oo, k);
+  const float fl = floorf(g);
+  const float frac = g - fl;
+  const int c = (int)fl;  // |g| far outside the grid saturates and fails the range test like the exact kernel
+  alt = frac < delta ? -1 : (frac > 1.f - delta ? 1 : 0);
+  return c;
+}
+
+template <typename FT>
+__device__ __forceinline__ bool cell_status(const FastLookup& f, int ix, int iy, int iz, int thr)
+{
+  const bool in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
+  const unsigned idx = in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
+  return in & ((int)static_cast<const FT*>(f.d2)[idx] < thr);
+}
+
+// Sphere vs field.  sure: the exact evaluation certainly reports this sphere colliding; maybe: it could.
+template <typename FT>
+__device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float y, float z, float eps, int thr,
+                                             bool& sure, bool& maybe)
+{
+  const float delta = fmaf(eps, f.oo, f.gerr);
+  int ax, ay, az;
+  const int ix = axis_cell(x, f.oo, f.k[0], delta, ax);
+  const int iy = axis_cell(y, f.oo, f.k[1], delta, ay);
+  const int iz = axis_cell(z, f.oo, f.k[2], delta, az);
+  const bool s0 = cell_status<FT>(f, ix, iy, iz, thr);
+  if ((ax | ay | az) == 0)  // the common case: the centre is clear of every voxel face
+  {
+    sure |= s0;
+    maybe |= s0;
+    return;
+  }
+  // near a face: the exact cell is one of up to 8 candidates; the verdict is settled only if they all agree
+  bool all = s0, any = s0;
+  for (int m = 1; m < 8; ++m)
+  {
+    if (((m & 1) && !ax) || ((m & 2) && !ay) || ((m & 4) && !az))
+      continue;
+    const bool sm = cell_status<FT>(f, ix + ((m & 1) ? ax : 0), iy + ((m & 2) ? ay : 0), iz + ((m & 4) ? az : 0), thr);
+    all &= sm;
+    any |= sm;
+  }
+  sure |= all;
+  maybe |= any;
+}
+
+template <typename FT, int B>
+__global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
+                                                          FastLookup sf, const float2* __restrict__ pair_T,
+                                                          const float* __restrict__ q, long n, int flags,
+                                                          uint8_t* __restrict__ verdict, int* __restrict__ amb_idx,
+                                                          int* __restrict__ amb_count)
+{
+  extern __shared__ float fsm[];
+  const int tid = threadIdx.x;
+  const long base = (long)blockIdx.x * B;
+  const bool do_pairs = (flags & B200DF_CHECK_INTRA) != 0 && T.n_partners > 0;
+  float* slots = fsm;                                                    // [n_slots][12][B]
+  float* stc = slots + T.n_slots * 12 * B;                               // [n_store_spheres][3][B]
+  float* stb = stc + (do_pairs ? T.n_store_spheres * 3 * B : 0);         // [n_store_links][3][B]
+  float* qs = stb + (do_pairs ? T.n_store_links * 3 * B : 0);            // [B][n_vars]
+  {
+    const int total = B * T.n_vars;
+    const long limit = (n - base) * T.n_vars;
+    const float* src = q + base * T.n_vars;
+    for (int e = tid; e < total; e += B)
+      qs[e] = (e < limit) ? src[e] : 0.f;
+  }
+  __syncthreads();
+  const long state = base + tid;
+  const bool active = state < n;
+  const float* my_q = qs + tid * T.n_vars;
+  float* my_slots = slots + tid;
+  float* my_stc = stc + tid;
+  float* my_stb = stb + tid;
+  const bool do_robot = (flags & B200DF_CHECK_ROBOT) != 0;
+  const bool do_self = (flags & B200DF_CHECK_SELF) != 0;
+
+  bool hit = !active;  // certain collision (padding lanes: no work)
+  bool amb = false;    // some test fell inside its margin
+  bool oor = false;    // a joint value outside the analysed range: nothing computed here can be trusted
+  float cur[12];
+  for (int i = 0; i < T.n_links; ++i)
+  {
+    const FLink& l = T.links[i];
+    fk_step_f(l, my_q, my_slots, B, cur, oor);
+    const int gs = l.gslot;
+    if (gs < 0)
+      continue;
+    const FGLink& gl = T.glinks[gs];
+    const int np = do_pairs ? gl.partner_end - gl.partner_begin : 0;
+    const bool stored = do_pairs && gl.store_link >= 0;
+    const bool self_here = do_self && gl.self_enabled;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    if (np > 0 || stored)
+    {
+      applyf(cur, gl.bs[0], gl.bs[1], gl.bs[2], bx, by, bz);
+      if (stored)
+      {
+        my_stb[(gl.store_link * 3 + 0) * B] = bx;
+        my_stb[(gl.store_link * 3 + 1) * B] = by;
+        my_stb[(gl.store_link * 3 + 2) * B] = bz;
+      }
+    }
+    const int n_chunks = np > 0 ? (np + 31) / 32 : 1;
+    for (int c = 0; c < n_chunks; ++c)
+    {
+      const int p0 = gl.partner_begin + 32 * c;
+      unsigned sure_mask = 0u, maybe_mask = 0u;  // prune certainly passed / could pass
+      if (np > 0)
+      {
+        const int pc = min(32, gl.partner_end - p0);
+#pragma unroll 2
+        for (int b = 0; b < pc; ++b)
+        {
+          const FPartner& pr = T.partners[p0 + b];
+          const float dx = my_stb[(pr.store_link * 3 + 0) * B] - bx;
+          const float dy = my_stb[(pr.store_link * 3 + 1) * B] - by;
+          const float dz = my_stb[(pr.store_link * 3 + 2) * B] - bz;
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          const bool open = !hit && d2 < pr.tight_hi;
+          sure_mask |= ((open && d2 < pr.rs_lo) ? 1u : 0u) << b;
+          maybe_mask |= ((open && d2 < pr.rs_hi) ? 1u : 0u) << b;
+        }
+      }
+      const unsigned warp_mask = __reduce_or_sync(0xffffffffu, maybe_mask);
+      for (int s0 = gl.sphere_begin; s0 < gl.sphere_end; s0 += kBatch)
+      {
+        const int cnt = min(kBatch, gl.sphere_end - s0);
+        float cx[kBatch], cy[kBatch], cz[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+        {
+          if (k < cnt)
+          {
+            const FSphere& sp = T.sph[s0 + k];
+            applyf(cur, sp.x, sp.y, sp.z, cx[k], cy[k], cz[k]);
+            if (c == 0 && stored)
+            {
+              const int slot = gl.store_sphere + (s0 + k - gl.sphere_begin);
+              my_stc[(slot * 3 + 0) * B] = cx[k];
+              my_stc[(slot * 3 + 1) * B] = cy[k];
+              my_stc[(slot * 3 + 2) * B] = cz[k];
+            }
+          }
+        }
+        if (c == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < kBatch; ++k)
+          {
+            if (k < cnt)
+            {
+              const FSphere& sp = T.sph[s0 + k];
+              bool sure = false, maybe = false;
+              if (do_robot)
+                sphere_field<FT>(wf, cx[k], cy[k], cz[k], sp.eps, sp.thr, sure, maybe);
+              if (self_here)
+                sphere_field<FT>(sf, cx[k], cy[k], cz[k], sp.eps, sp.thr, sure, maybe);
+              hit |= sure;
+              amb |= maybe;  // (maybe && !sure) is what matters; a certain hit overrides it at the end
+            }
+          }
+        }
+        unsigned mm = warp_mask;
+        const float2* t_row = pair_T + gl.pair_const_begin + (long)(s0 - gl.sphere_begin) * gl.pair_const_stride;
+        while (mm)
+        {
+          const int b = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const FPartner& pr = T.partners[p0 + b];
+          const float2* t = t_row + pr.const_offset;
+          const float* pc = my_stc + pr.store_sphere * 3 * B;
+          const int stride = gl.pair_const_stride;
+          bool h_sure = false, h_maybe = false;
+          for (int m = 0; m < pr.count; ++m)
+          {
+            const float px = pc[(m * 3 + 0) * B], py = pc[(m * 3 + 1) * B], pz = pc[(m * 3 + 2) * B];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k)
+            {
+              if (k < cnt)
+              {
+                const float ex = cx[k] - px, ey = cy[k] - py, ez = cz[k] - pz;
+                const float e2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                const float2 th = t[k * stride + m];  // {certainly touching below, certainly apart above}
+                h_sure |= e2 < th.x;
+                h_maybe |= e2 <= th.y;
+              }
+            }
+          }
+          const bool p_sure = (sure_mask >> b) & 1u, p_maybe = (maybe_mask >> b) & 1u;
+          hit |= h_sure && p_sure;
+          amb |= h_maybe && p_maybe;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, hit))
+      break;
+  }
+  if (active)
+  {
+    const int v = oor ? 2 : (hit ? 1 : (amb ? 2 : 0));
+    verdict[state] = (uint8_t)v;
+    if (v == 2)
+      amb_idx[atomicAdd(amb_count, 1)] = (int)state;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host: tables + forward error analysis
+// ------------------------------------------------------------------------------------------------------------
+double norm3(const double* v)
+{
+  return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+}
+
+// Travel assumed for translational joint variables and the angle range assumed for rotational ones; values
+// outside are detected at run time and sent to the exact kernel.
+constexpr double kPrismaticTravel = 2.0, kPlanarTravel = 16.0, kAngleRange = 64.0;
+
+struct LinkErr
+{
+  double eR = 0.0;     // || fp32 rotation - exact rotation ||_F
+  double et = 0.0;     // || fp32 translation - exact translation ||_2
+  double reach = 0.0;  // bound on || exact translation ||_2
+};
+}  // namespace
+
+struct b200df_group::FastPath
+{
+  FastTables tables;
+  float2* pair_T = nullptr;  // device
+  bool ok = false;
+};
+
+namespace b200df
+{
+int fast_create(b200df_group* g)
+{
+  const b200df_model* m = g->model;
+  const int L = m->n_links, G = (int)g->glinks.size(), S = (int)(g->sph.size() / 4);
+  const int P = (int)g->partners.size();
+  if (L > kMaxLinks || G > kMaxGLinks || S > kMaxSpheres || P > kMaxPartners)
+    return B200DF_OK;  // FAST silently degrades to EXACT for robots that do not fit the constant-bank tables
+  for (const DevLink& l : m->links)
+    if (l.joint_type == B200DF_JOINT_FLOATING)
+      return B200DF_OK;
+  std::unique_ptr<b200df_group::FastPath> fp(new b200df_group::FastPath);
+  FastTables& T = fp->tables;
+  std::memset(&T, 0, sizeof(T));
+  T.n_links = L;
+  T.n_vars = m->n_vars;
+  T.n_slots = m->n_slots;
+  T.n_glinks = G;
+  T.n_spheres = S;
+  T.n_store_links = g->dev.n_store_links;
+  T.n_store_spheres = g->dev.n_store_spheres;
+  T.n_partners = P;
+
+  // ---- forward error analysis, link by link (u = 2^-24; rotations have unit 2-norm, so errors add up instead
+  // of multiplying; every product of fp32 3x3 blocks adds at most 9u in Frobenius norm: 3 terms per entry,
+  // |row| |col| <= 1 by Cauchy-Schwarz)
+  const double u = kU;
+  const double sc = 2.0 * 2.0 * u;  // sincosf: <= 2 ulp, ulp(1) = 2^-23 = 2u
+  std::vector<LinkErr> E(L);
+  for (int i = 0; i < L; ++i)
+  {
+    const DevLink& l = m->links[i];
+    FLink& f = T.links[i];
+    f.joint_type = l.joint_type;
+    f.jkind = l.jkind;
+    f.var = l.var;
+    f.is_mimic = l.is_mimic;
+    f.origin_is_identity = l.origin_is_identity;
+    f.parent = l.parent;
+    f.parent_is_prev = l.parent_is_prev;
+    f.store_slot = l.store_slot;
+    f.parent_slot = l.parent_slot;
+    f.gslot = g->link_gslot[i];
+    f.mimic_mult = (float)l.mimic_mult;  // used in fp64 on the device only when exactly representable (checked)
+    f.mimic_off = (float)l.mimic_off;
+    if (l.is_mimic && ((double)f.mimic_mult != l.mimic_mult || (double)f.mimic_off != l.mimic_off))
+      return B200DF_OK;
+    f.ax = (float)l.ax;
+    f.ay = (float)l.ay;
+    f.az = (float)l.az;
+    f.x2 = (float)l.x2;
+    f.y2 = (float)l.y2;
+    f.z2 = (float)l.z2;
+    f.xy = (float)l.xy;
+    f.xz = (float)l.xz;
+    f.yz = (float)l.yz;
+    for (int k = 0; k < 12; ++k)
+      f.origin[k] = (float)l.origin[k];
+    const double o[3] = { l.origin[3], l.origin[7], l.origin[11] };
+    const double on = norm3(o);
+    LinkErr par;  // root: identity, exact
+    if (l.parent >= 0)
+      par = E[l.parent];
+    LinkErr b = par;  // base = parent * origin
+    if (!l.origin_is_identity || l.parent < 0)
+    {
+      const double eO = u * std::sqrt(3.0);  // entries rounded to fp32: <= u/2 relative, ||R||_F = sqrt(3)
+      if (l.parent < 0)
+      {
+        b.eR = eO;
+        b.et = u * on;
+      }
+      else
+      {
+        b.eR = par.eR * (1.0 + eO) + eO + 9.1 * u;
+        b.et = par.et + par.eR * on + (1.0 + par.eR) * u * on + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * on + par.reach);
+      }
+      b.reach = par.reach + on;
+    }
+    LinkErr e = b;
+    f.vmax = 0.f;
+    if (l.joint_type == B200DF_JOINT_REVOLUTE || l.joint_type == B200DF_JOINT_PLANAR)
+    {
+      const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
+      f.vmax = (float)(planar ? kPlanarTravel : kAngleRange);  // planar: x, y and theta share the bound
+      // mimic: the fp64 value is rounded once to fp32 -> angle error <= u*|v|
+      const double dv = l.is_mimic ? u * (planar ? kPlanarTravel : kAngleRange) : 0.0;
+      const double dsc = sc + dv;
+      // axis-aligned: entries are c, +-s (error dsc) and one ~1; general Rodrigues: every entry within 4*dsc + 4u
+      const double eJ = (planar || l.jkind != 0) ? std::sqrt(4.0 * dsc * dsc + 4.0 * u * u) : 3.0 * (4.0 * dsc + 4.0 * u);
+      e.eR = b.eR * (1.0 + eJ) + eJ + 9.1 * u;
+      if (planar)
+      {
+        const double tr = kPlanarTravel * std::sqrt(2.0);
+        e.et = b.et + b.eR * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
+        e.reach = b.reach + tr;
+      }
+    }
+    else if (l.joint_type == B200DF_JOINT_PRISMATIC)
+    {
+      f.vmax = (float)kPrismaticTravel;
+      const double tr = kPrismaticTravel;
+      // axis rounded to fp32 (u*tr), axis*v rounded (u*tr), mimic value rounded (u*tr), then R*t + t0
+      e.et = b.et + b.eR * tr + 3.0 * u * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
+      e.reach = b.reach + tr;
+    }
+    E[i] = e;
+  }
+  auto point_eps = [&](int link, const double* rel) {
+    const LinkErr& e = E[link];
+    const double rn = norm3(rel);
+    // R~ * rel~ + t~ : rotation error on |rel|, translation error, rel rounded to fp32, rounding of the evaluation
+    const double eps = e.eR * rn + e.et + u * rn * (1.0 + e.eR) + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * rn + e.reach);
+    return eps * 1.25 + 1e-9;  // slack for the second-order terms dropped above
+  };
+  std::vector<double> bs_eps(G), sph_eps(S);
+  for (int gs = 0; gs < G; ++gs)
+  {
+    const DevGroupLink& gl = g->glinks[gs];
+    FGLink& f = T.glinks[gs];
+    f.sphere_begin = gl.sphere_begin;
+    f.sphere_end = gl.sphere_end;
+    f.self_enabled = gl.self_enabled;
+    f.store_link = gl.store_link;
+    f.store_sphere = gl.store_sphere;
+    f.partner_begin = gl.partner_begin;
+    f.partner_end = gl.partner_end;
+    f.pair_const_begin = gl.pair_const_begin;
+    f.pair_const_stride = gl.pair_const_stride;
+    for (int k = 0; k < 3; ++k)
+      f.bs[k] = (float)gl.bs[k];
+    bs_eps[gs] = point_eps(gl.link, gl.bs);
+    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    {
+      const double* sp = &g->sph[(size_t)s * 4];
+      sph_eps[s] = point_eps(gl.link, sp);
+      T.sph[s].x = (float)sp[0];
+      T.sph[s].y = (float)sp[1];
+      T.sph[s].z = (float)sp[2];
+      T.sph[s].eps = (float)(sph_eps[s] * (1.0 + 2.0 * u));
+      T.sph[s].thr = g->sph_thr[s];
+    }
+  }
+  // thresholds on fp32 squared distances: the fp32 distance is within E = eps_a + eps_b of the exact one, and the
+  // fp32 evaluation of the squared norm is within a relative 8u of its own inputs' squared distance
+  auto lo2 = [&](double R, double Esum) {
+    const double d = R - Esum;
+    return d > 0.0 ? (float)std::max(0.0, d * d * (1.0 - 16.0 * u) - 1e-30) : 0.f;
+  };
+  auto hi2 = [&](double R, double Esum) {
+    const double d = R + Esum;
+    return std::nextafter((float)(d * d * (1.0 + 16.0 * u)), INFINITY);
+  };
+  std::vector<float2> pair_T((size_t)std::max<long>(1, g->dev.n_pair_consts));
+  for (int gs = 0; gs < G; ++gs)
+  {
+    const DevGroupLink& gl = g->glinks[gs];
+    for (int p = gl.partner_begin; p < gl.partner_end; ++p)
+    {
+      const DevPartner& pr = g->partners[p];
+      // which group link is this partner?  the one that owns stored-sphere slot pr.store_sphere
+      int lo = -1;
+      for (int h = 0; h < G; ++h)
+        if (g->glinks[h].store_link == pr.store_link)
+          lo = h;
+      FPartner& f = T.partners[p];
+      f.store_link = pr.store_link;
+      f.store_sphere = pr.store_sphere;
+      f.count = pr.count;
+      f.const_offset = pr.const_offset;
+      const double Eb = bs_eps[gs] + bs_eps[lo];
+      // the reference compares the SQUARED distance with radius_sum (Q2): distance threshold sqrt(radius_sum)
+      const double rs = std::sqrt(std::max(0.0, pr.radius_sum));
+      f.rs_lo = lo2(rs, Eb);
+      f.rs_hi = hi2(rs, Eb);
+      f.tight_hi = hi2(std::sqrt(pr.tight2), Eb);
+      for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+        for (int mm = 0; mm < pr.count; ++mm)
+        {
+          const int ps = g->glinks[lo].sphere_begin + mm;
+          const double R = g->sph[(size_t)s * 4 + 3] + g->sph[(size_t)ps * 4 + 3];
+          const double Es = sph_eps[s] + sph_eps[ps];
+          const size_t at = (size_t)gl.pair_const_begin + (size_t)(s - gl.sphere_begin) * gl.pair_const_stride +
+                            pr.const_offset + mm;
+          pair_T[at] = make_float2(lo2(R, Es), hi2(R, Es));
+        }
+    }
+  }
+  DeviceGuard dg(g->device);
+  B200DF_CUDA(cudaMalloc(&fp->pair_T, pair_T.size() * sizeof(float2)));
+  B200DF_CUDA(cudaMemcpy(fp->pair_T, pair_T.data(), pair_T.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  fp->ok = true;
+  g->fast = fp.release();
+  return B200DF_OK;
+}
+
+void fast_destroy(b200df_group* g)
+{
+  if (!g->fast)
+    return;
+  cudaFree(g->fast->pair_T);
+  delete g->fast;
+  g->fast = nullptr;
+}
+
+bool fast_supported(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int q_dtype, int flags)
+{
+  if (!g->fast || !g->fast->ok || q_dtype != B200DF_Q_F32)
+    return false;
+  if ((flags & B200DF_CHECK_ROBOT) && wf.neg)
+    return false;  // signed fields: the predicate needs the fp64 distances
+  if ((flags & B200DF_CHECK_SELF) && sf.neg)
+    return false;
+  return true;
+}
+
+}  // namespace b200df
+
+namespace
+{
+FastLookup make_fast_lookup(const FieldDev& f)
+{
+  FastLookup l{};
+  double gmax = 4.0;
+  for (int i = 0; i < 3; ++i)
+  {
+    const double k = -f.g.om[i] * f.g.oo;
+    l.k[i] = (float)k;
+    l.lim[i] = f.g.n[i] >= 2 ? (unsigned)(f.g.n[i] - 2) : 0u;
+    gmax = std::max(gmax, (double)f.g.n[i] + 2.0 * std::fabs(k) + 4.0);
+  }
+  l.oo = (float)f.g.oo;
+  // g = fma(p, oo~, k~): oo rounded (u/2 relative on |p*oo| <= n+|k|), k rounded (u/2 |k|), fma rounded (u/2 |g|);
+  // doubled for slack.  Centres farther out than the grid are decided by the range test with cells to spare.
+  l.gerr = (float)(2.0 * kU * gmax);
+  l.stride1 = (int)f.g.stride1;
+  l.stride2 = (int)f.g.stride2;
+  l.d2 = f.d2;
+  return l;
+}
+
+template <typename FT, int B>
+int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const float* q, long n, int flags,
+                uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream)
+{
+  if (bytes > 48 * 1024)
+    B200DF_CUDA(cudaFuncSetAttribute(validity_fast_kernel<FT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bytes));
+  const unsigned grid = (unsigned)((n + B - 1) / B);
+  validity_fast_kernel<FT, B><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf), make_fast_lookup(sf),
+                                                          g->fast->pair_T, q, n, flags, verdict, amb_idx, amb_count);
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  return B200DF_OK;
+}
+}  // namespace
+
+namespace b200df
+{
+int fast_launch(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const float* q, long n,
+                int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream)
+{
+  const FastTables& T = g->fast->tables;
+  const bool pairs = (flags & B200DF_CHECK_INTRA) && T.n_partners > 0;
+  auto smem = [&](int block) {
+    size_t fl = (size_t)T.n_slots * 12 + T.n_vars;
+    if (pairs)
+      fl += (size_t)T.n_store_spheres * 3 + (size_t)T.n_store_links * 3;
+    return fl * block * sizeof(float);
+  };
+  B200DF_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), stream));
+  const size_t b128 = smem(128);
+  if (b128 <= 100 * 1024)
+  {
+    if (field_elem == 1)
+      return launch_fast<uint8_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
+    return launch_fast<uint16_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
+  }
+  const size_t b32 = smem(32);
+  B200DF_REQUIRE(b32 <= 220 * 1024, "robot too large for the per-state shared-memory layout");
+  if (field_elem == 1)
+    return launch_fast<uint8_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+  return launch_fast<uint16_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+}
+}  // namespace b200df

@@ -328,6 +328,52 @@ def test_host_buffer_entry_is_chunk_invariant(gpu, oracle):
         assert np.array_equal(e.group.check(q[:m], e.world, flags=CHECK_ROBOT | CHECK_INTRA), host[:m])
 
 
+def test_fast_precision_equals_exact_and_decides_most_states(gpu, oracle):
+    """PRECISION_FAST = fp32 screening + exact re-run of the undecided states.  Its verdicts must be the exact
+    path's bit for bit (2 M states, every flag combination); the raw screening pass (precision value 3) may only
+    answer 0 / 1 where the exact kernel agrees, and must leave only a small fraction undecided."""
+    desc = rd.panda()
+    e = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
+    q = desc.sample_states(2_000_000, 9090, np.float32)
+    for flags in (CHECK_ROBOT, CHECK_INTRA, CHECK_ROBOT | CHECK_INTRA):
+        exact = e.group.check(q, e.world, flags=flags, precision=0)
+        fast = e.group.check(q, e.world, flags=flags, precision=1)
+        assert np.array_equal(exact, fast), "flags=%d: %d differences" % (flags, int((exact != fast).sum()))
+        raw = e.group.check(q, e.world, flags=flags, precision=3)
+        decided = raw != 2
+        assert np.array_equal(raw[decided], exact[decided])
+        undecided = 1.0 - decided.mean()
+        print("flags=%d undecided fraction %.4f" % (flags, undecided))
+        assert undecided < 0.05
+    # out-of-range joint values leave the analysed range: screened as undecided, answered by the exact kernel
+    q2 = q[:1000].copy()
+    q2[::7, 0] = 500.0
+    raw = e.group.check(q2, e.world, flags=CHECK_ROBOT, precision=3)
+    assert (raw[::7] == 2).all()
+    assert np.array_equal(e.group.check(q2, e.world, flags=CHECK_ROBOT, precision=1),
+                          e.group.check(q2, e.world, flags=CHECK_ROBOT, precision=0))
+
+
+def test_fast_precision_with_self_field_and_fine_field(gpu, oracle):
+    """FAST with a self field (planning group) and on the 1 cm / u16 field (smaller voxels -> more face proximity)."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=77)
+    q0 = np.zeros(desc.nvar)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, group="panda_arm", self_state=q0)
+    sp = self_field_points(o.model_desc, desc, o.group_links, o.model.fk(q0))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, group="panda_arm", self_points=sp)
+    q = desc.sample_states(300_000, 31, np.float32)
+    flags = CHECK_ROBOT | CHECK_SELF | CHECK_INTRA
+    assert np.array_equal(e.group.check(q, e.world, e.self_field, flags=flags, precision=1),
+                          e.group.check(q, e.world, e.self_field, flags=flags, precision=0))
+    fine = dict(size=(2.0, 2.0, 2.0), resolution=0.01, center=(0.0, 0.0, 0.5), max_distance=0.25)
+    e2 = EngineSetup(desc, fine, objs)
+    assert e2.world.max_d2 == 625
+    a = e2.group.check(q, e2.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=1)
+    b = e2.group.check(q, e2.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0)
+    assert np.array_equal(a, b) and 0 < a.sum() < len(a)
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine
