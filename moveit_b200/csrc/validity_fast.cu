@@ -36,7 +36,7 @@ struct FLink
 {
   int joint_type, jkind, var, is_mimic;
   int origin_is_identity, parent, parent_is_prev, store_slot, parent_slot, gslot;
-  float mimic_mult, mimic_off;
+  double mimic_mult, mimic_off;  // evaluated in fp64 like the exact kernel, then rounded once
   float ax, ay, az, x2, y2, z2, xy, xz, yz;
   float origin[12];
   float vmax;  // joint values beyond this leave the analysed range -> the state is sent to the exact kernel
@@ -111,7 +111,7 @@ __device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, b
 {
   float v = q[l.var + k];
   if (l.is_mimic)
-    v = (float)((double)l.mimic_mult * (double)v + (double)l.mimic_off);
+    v = (float)(l.mimic_mult * (double)v + l.mimic_off);
   out_of_range |= !(fabsf(v) <= l.vmax);
   return v;
 }
@@ -527,10 +527,8 @@ int fast_create(b200df_group* g)
     f.store_slot = l.store_slot;
     f.parent_slot = l.parent_slot;
     f.gslot = g->link_gslot[i];
-    f.mimic_mult = (float)l.mimic_mult;  // used in fp64 on the device only when exactly representable (checked)
-    f.mimic_off = (float)l.mimic_off;
-    if (l.is_mimic && ((double)f.mimic_mult != l.mimic_mult || (double)f.mimic_off != l.mimic_off))
-      return B200DF_OK;
+    f.mimic_mult = l.mimic_mult;
+    f.mimic_off = l.mimic_off;
     f.ax = (float)l.ax;
     f.ay = (float)l.ay;
     f.az = (float)l.az;

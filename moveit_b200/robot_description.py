@@ -296,6 +296,54 @@ def one_robot():
     return r
 
 
+def mobile_arm():
+    """Small synthetic mobile manipulator that exercises every joint code path of the kernels at once: planar base,
+    revolute joints about x, y, -z and an oblique axis, a prismatic lift, a revolute mimic joint (x1.5 + 0.1), a
+    branch (two grippers) and non-trivial rpy origins.  Fits the constant-bank tables of the FAST kernel."""
+    hp = math.pi / 2.0
+    r = RobotDescription("mobile_arm")
+    r.add_link("base", None, "world_joint", JOINT_PLANAR, limits=[(-0.4, 0.4), (-0.4, 0.4), (-math.pi, math.pi)])
+    r.add_shape("base", SHAPE_BOX, (0.5, 0.4, 0.2), (0, 0, 0.1))
+    r.add_link("lift", "base", "lift_joint", JOINT_PRISMATIC, (0.1, 0, 0.2), axis=(0, 0, 1), limits=(0.0, 0.4))
+    r.add_shape("lift", SHAPE_CYLINDER, (0.07, 0.3), (0, 0, 0.15))
+    r.add_link("shoulder", "lift", "shoulder_joint", JOINT_REVOLUTE, (0, 0, 0.32), (0.1, -0.2, 0.3), axis=(0, 0, -1),
+               limits=(-2.5, 2.5))
+    r.add_shape("shoulder", SHAPE_CYLINDER, (0.06, 0.16), (0, 0, 0.06))
+    r.add_link("upper", "shoulder", "upper_joint", JOINT_REVOLUTE, (0, 0, 0.12), (0, 0, 0), axis=(0, 1, 0),
+               limits=(-1.8, 1.8))
+    r.add_shape("upper", SHAPE_CYLINDER, (0.05, 0.3), (0.15, 0, 0), (0, hp, 0))
+    r.add_link("fore", "upper", "fore_joint", JOINT_REVOLUTE, (0.3, 0, 0), (hp, 0, 0), axis=(1, 0, 0),
+               limits=(-3.0, 3.0))
+    r.add_shape("fore", SHAPE_BOX, (0.25, 0.08, 0.08), (0.12, 0, 0))
+    r.add_link("wrist", "fore", "wrist_joint", JOINT_REVOLUTE, (0.25, 0, 0), (0, 0.3, -0.4), axis=(0.3, 0.5, 0.8),
+               limits=(-2.0, 2.0))
+    r.add_shape("wrist", SHAPE_SPHERE, (0.05,), (0.03, 0, 0))
+    r.add_link("palm", "wrist", "palm_joint", JOINT_FIXED, (0.06, 0, 0), (0, 0, 0.5))
+    r.add_shape("palm", SHAPE_BOX, (0.04, 0.12, 0.04))
+    r.add_link("finger_l", "palm", "finger_l_joint", JOINT_REVOLUTE, (0.03, 0.05, 0), axis=(0, 0, 1), limits=(-0.5, 0.5))
+    r.add_shape("finger_l", SHAPE_BOX, (0.08, 0.015, 0.03), (0.04, 0, 0))
+    r.add_link("finger_r", "palm", "finger_r_joint", JOINT_REVOLUTE, (0.03, -0.05, 0), axis=(0, 0, 1),
+               limits=(-0.65, 0.85), mimic=("finger_l_joint", 1.5, 0.1))
+    r.add_shape("finger_r", SHAPE_BOX, (0.08, 0.015, 0.03), (0.04, 0, 0))
+    r.set_spheres("base", [(-0.15, -0.1, 0.1, 0.14), (0.15, -0.1, 0.1, 0.14), (-0.15, 0.1, 0.1, 0.14),
+                           (0.15, 0.1, 0.1, 0.14)])
+    r.set_spheres("lift", [(0, 0, 0.05, 0.075), (0, 0, 0.15, 0.075), (0, 0, 0.25, 0.075)])
+    r.set_spheres("shoulder", [(0, 0, 0.03, 0.065), (0, 0, 0.1, 0.065)])
+    r.set_spheres("upper", [(0.05, 0, 0, 0.055), (0.13, 0, 0, 0.055), (0.21, 0, 0, 0.055), (0.28, 0, 0, 0.055)])
+    r.set_spheres("fore", [(0.04, 0, 0, 0.05), (0.12, 0, 0, 0.05), (0.2, 0, 0, 0.05)])
+    r.set_spheres("wrist", [(0.03, 0, 0, 0.05)])
+    r.set_spheres("palm", [(0, -0.04, 0, 0.025), (0, 0, 0, 0.025), (0, 0.04, 0, 0.025)])
+    r.set_spheres("finger_l", [(0.02, 0, 0, 0.015), (0.05, 0, 0, 0.015), (0.075, 0, 0, 0.012)])
+    r.set_spheres("finger_r", [(0.02, 0, 0, 0.015), (0.05, 0, 0, 0.015), (0.075, 0, 0, 0.012)])
+    P = [("base", "lift"), ("lift", "shoulder"), ("shoulder", "upper"), ("upper", "fore"), ("fore", "wrist"),
+         ("wrist", "palm"), ("palm", "finger_l"), ("palm", "finger_r"), ("fore", "palm"), ("base", "shoulder"),
+         ("wrist", "finger_l"), ("wrist", "finger_r")]
+    r.disabled_pairs = list(P)
+    r.groups = {"arm": ["shoulder_joint", "upper_joint", "fore_joint", "wrist_joint", "finger_l_joint",
+                        "finger_r_joint"]}
+    return r
+
+
 def pr2_like():
     """PR2-like dual-arm tree (the real PR2 URDF lives in moveit_resources, F3):
     planar base, prismatic torso, head pan/tilt, two 7-DoF arms with 4-finger-link grippers driven by mimic joints."""

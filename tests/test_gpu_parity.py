@@ -374,6 +374,28 @@ def test_fast_precision_with_self_field_and_fine_field(gpu, oracle):
     assert np.array_equal(a, b) and 0 < a.sum() < len(a)
 
 
+def test_mobile_arm_every_joint_type_fast_exact_oracle(gpu, oracle):
+    """Planar base, prismatic lift, revolute about -z / y / x / an oblique axis, a mimic joint with offset and a
+    branch: the oracle, the exact kernel, the independent round-1 sweep and the FAST path must all agree."""
+    desc = rd.mobile_arm()
+    fd = scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene(seed=57, n_boxes=3, n_cylinders=1)
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, fd, objs)
+    q = desc.sample_states(200_000, 606, np.float32)
+    flags = CHECK_ROBOT | CHECK_INTRA
+    exact = e.group.check(q, e.world, flags=flags, precision=0)
+    assert np.array_equal(exact[:30000], o.env.check_batch(q[:30000].astype(np.float64), mode=3, n_threads=8))
+    assert np.array_equal(exact, e.group.check(q, e.world, flags=flags, precision=2))
+    assert np.array_equal(exact, e.group.check(q, e.world, flags=flags, precision=1))
+    raw = e.group.check(q, e.world, flags=flags, precision=3)  # the FAST tables do cover this robot
+    assert np.array_equal(raw[raw != 2], exact[raw != 2]) and (raw == 2).mean() < 0.05
+    assert 0 < exact.sum() < len(exact)
+    T = e.model.fk(q[:2000].astype(np.float64))
+    ref = np.stack([o.model.fk(x) for x in q[:2000].astype(np.float64)])
+    assert np.max(np.abs(T - ref)) < 1e-12
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine
