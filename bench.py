@@ -59,7 +59,8 @@ def measured_peak_hbm():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML in-process every 5 ms (nvidia_ml_py),
+    falling back to polling nvidia-smi when NVML is not importable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -68,34 +69,69 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
+        self.max_mhz = None
         self.stop_flag = threading.Event()
+        self.source = "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            self.source = "nvidia-smi"
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                pass
+        return index
+
+    def _sample_nvml(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.samples.append((mhz, bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        if len(p) >= 7:
+            act = [x.lower().startswith("active") for x in p[3:7]]
+            self.samples.append((float(p[0]), act[0], act[1], act[2], act[3]))
+            self.max_mhz = float(p[1])
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.005 if self.nv is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
-                          ("sw_power_cap", 6)):
-            if any(s[col].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [name for k, name in ((1, "hw_slowdown"), (2, "hw_thermal_slowdown"), (3, "sw_thermal_slowdown"),
+                                        (4, "sw_power_cap")) if any(s[k] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def build_oracle_env(n_threads_hint=None):
