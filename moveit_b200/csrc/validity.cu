@@ -323,9 +323,7 @@ template <typename QT, typename FT, int B>
 int launch_verdict_block(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
                          uint8_t* verdict, size_t bytes, cudaStream_t stream, Redo redo)
 {
-  if (bytes > 48 * 1024)
-    B200DF_CUDA(cudaFuncSetAttribute(validity_kernel<QT, FT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bytes));
+  B200DF_CUDA(allow_dynamic_smem(validity_kernel<QT, FT, B>, bytes));
   // redo: a fixed grid (a few CTAs per SM) strides over the list; its length is only known on the device
   const unsigned grid = redo.idx ? (unsigned)std::min<long>((n + B - 1) / B, 148 * 8) : (unsigned)((n + B - 1) / B);
   validity_kernel<QT, FT, B><<<grid, B, bytes, stream>>>(g, make_lookup(wf), make_lookup(sf),
@@ -432,18 +430,20 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
-// Staging contexts of the host-buffer entry point: a batch is cut into chunks that travel H2D -> kernel -> D2H on
-// two streams, so the PCIe copies of one chunk overlap the kernel of the other.  Contexts are cached per group
+// Staging contexts of the host-buffer entry point: a batch is cut into 2^18-state chunks that travel H2D -> kernel ->
+// D2H on three streams, so the PCIe copies of one chunk overlap the kernel of another.  Contexts are cached per group
 // (checks may run concurrently from several threads: each call takes its own context).
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kSlots = 3;  // chunks in flight: H2D of one overlaps the kernel of another and the D2H of a third
+
 struct b200df_group::StagePool
 {
   struct Ctx
   {
-    cudaStream_t stream[2] = { nullptr, nullptr };
-    void* q[2] = { nullptr, nullptr };
-    uint8_t* v[2] = { nullptr, nullptr };
-    int* amb[2] = { nullptr, nullptr };  // [0] = count, [1..] = indices (FAST path scratch)
+    cudaStream_t stream[kSlots] = {};
+    void* q[kSlots] = {};
+    uint8_t* v[kSlots] = {};
+    int* amb[kSlots] = {};  // [0] = count, [1..] = indices (FAST path scratch)
     size_t q_bytes = 0, v_bytes = 0;
   };
   std::mutex mu;
@@ -455,7 +455,7 @@ struct b200df_group::StagePool
   }
   static void release(Ctx* c)
   {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kSlots; ++i)
     {
       cudaFree(c->q[i]);
       cudaFree(c->v[i]);
@@ -485,18 +485,18 @@ struct b200df_group::StagePool
 
 namespace
 {
-constexpr int64_t kChunkStates = 1 << 20;
+constexpr int64_t kChunkStates = 1 << 18;
 
 int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
 {
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kSlots; ++i)
   {
     if (!c->stream[i])
       B200DF_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
   }
   if (q_bytes > c->q_bytes)
   {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kSlots; ++i)
     {
       cudaFree(c->q[i]);
       c->q[i] = nullptr;
@@ -506,7 +506,7 @@ int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
   }
   if (v_bytes > c->v_bytes)
   {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kSlots; ++i)
     {
       cudaFree(c->v[i]);
       c->v[i] = nullptr;
@@ -937,7 +937,7 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
   rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
   cudaError_t e = cudaSuccess;
   int k = 0;
-  for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k ^= 1)
+  for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k = (k + 1) % kSlots)
   {
     const int64_t m = std::min<int64_t>(chunk, n - s);
     cudaStream_t st = ctx->stream[k];
@@ -952,7 +952,7 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
       break;
     e = cudaMemcpyAsync(verdict + s, ctx->v[k], (size_t)m, cudaMemcpyDeviceToHost, st);
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kSlots; ++i)
   {
     const cudaError_t es = cudaStreamSynchronize(ctx->stream[i]);
     if (e == cudaSuccess)

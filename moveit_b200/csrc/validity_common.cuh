@@ -10,6 +10,8 @@
 // --fmad=false so mul/add round like the reference's non-FMA x86-64 build.
 #pragma once
 #include <cfloat>
+#include <map>
+#include <utility>
 
 #include "b200df_internal.cuh"
 
@@ -489,6 +491,34 @@ int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field*
 inline size_t q_elem_size(int q_dtype)
 {
   return q_dtype == B200DF_Q_F32 ? sizeof(float) : sizeof(double);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device, size growth): the driver
+// call is too slow to repeat on every chunk of a pipelined batch
+inline cudaError_t allow_dynamic_smem_impl(const void* kernel, size_t bytes)
+{
+  if (bytes <= 48 * 1024)
+    return cudaSuccess;
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;  // (kernel, device) -> bytes already allowed
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = granted[std::make_pair(kernel, dev)];
+  if (bytes <= have)
+    return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess)
+    have = bytes;
+  return e;
+}
+
+template <typename K>
+cudaError_t allow_dynamic_smem(K kernel, size_t bytes)
+{
+  return allow_dynamic_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 struct ScratchBuffer  // stream-ordered scratch

@@ -727,9 +727,7 @@ template <typename FT, int B>
 int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const float* q, long n, int flags,
                 uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream)
 {
-  if (bytes > 48 * 1024)
-    B200DF_CUDA(cudaFuncSetAttribute(validity_fast_kernel<FT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bytes));
+  B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B>, bytes));
   const unsigned grid = (unsigned)((n + B - 1) / B);
   validity_fast_kernel<FT, B><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf), make_fast_lookup(sf),
                                                           g->fast->pair_T, q, n, flags, verdict, amb_idx, amb_count);
