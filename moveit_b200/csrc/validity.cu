@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -430,7 +431,7 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
-// Staging contexts of the host-buffer entry point: a batch is cut into 2^18-state chunks that travel H2D -> kernel ->
+// Staging contexts of the host-buffer entry point: a batch is cut into 2^20-state chunks that travel H2D -> kernel ->
 // D2H on three streams, so the PCIe copies of one chunk overlap the kernel of another.  Contexts are cached per group
 // (checks may run concurrently from several threads: each call takes its own context).
 // ------------------------------------------------------------------------------------------------------------
@@ -485,7 +486,18 @@ struct b200df_group::StagePool
 
 namespace
 {
-constexpr int64_t kChunkStates = 1 << 18;
+constexpr int64_t kChunkStates = 1 << 20;
+
+// B200DF_CHUNK_STATES overrides the pipeline's chunk size (tuning knob, read once)
+int64_t chunk_states()
+{
+  static const int64_t v = [] {
+    const char* e = getenv("B200DF_CHUNK_STATES");
+    const long long x = e ? atoll(e) : 0;
+    return x >= 1024 ? (int64_t)x : kChunkStates;
+  }();
+  return v;
+}
 
 int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
 {
@@ -932,7 +944,7 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
     return rc;
   DeviceGuard dg(group->device);
   const size_t row = (size_t)group->dev.n_vars * q_elem_size(q_dtype);
-  const int64_t chunk = std::min<int64_t>(n, kChunkStates);
+  const int64_t chunk = std::min<int64_t>(n, chunk_states());
   b200df_group::StagePool::Ctx* ctx = group->stage->acquire();
   rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
   cudaError_t e = cudaSuccess;
