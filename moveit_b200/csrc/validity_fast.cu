@@ -293,12 +293,12 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
   maybe |= any;
 }
 
-template <typename FT, int B>
+template <typename FT, int B, bool PAIR_SMEM>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
-                                                          FastLookup sf, const float2* __restrict__ pair_T,
+                                                          FastLookup sf, const float2* __restrict__ pair_T_global,
                                                           const float* __restrict__ q, long n, int flags,
                                                           uint8_t* __restrict__ verdict, int* __restrict__ amb_idx,
-                                                          int* __restrict__ amb_count)
+                                                          int* __restrict__ amb_count, int n_pair_smem)
 {
   extern __shared__ float fsm[];
   const int tid = threadIdx.x;
@@ -314,6 +314,14 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
     const float* src = q + base * T.n_vars;
     for (int e = tid; e < total; e += B)
       qs[e] = (e < limit) ? src[e] : 0.f;
+  }
+  // the pair thresholds are read once per sphere-pair test by every warp: keep them in shared memory when they fit
+  // (L1 is nearly all shared-memory carve-out here and what is left is thrashed by the voxel gathers)
+  float2* pair_T_shared = reinterpret_cast<float2*>(qs + B * T.n_vars);
+  if (PAIR_SMEM)
+  {
+    for (int e = tid; e < n_pair_smem; e += B)
+      pair_T_shared[e] = pair_T_global[e];
   }
   __syncthreads();
   const long state = base + tid;
@@ -412,7 +420,8 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
           }
         }
         unsigned mm = warp_mask;
-        const float2* t_row = pair_T + gl.pair_const_begin + (long)(s0 - gl.sphere_begin) * gl.pair_const_stride;
+        const float2* t_row = (PAIR_SMEM ? pair_T_shared : pair_T_global) + gl.pair_const_begin +
+                              (long)(s0 - gl.sphere_begin) * gl.pair_const_stride;
         while (mm)
         {
           const int b = __ffs(mm) - 1;
@@ -723,14 +732,30 @@ FastLookup make_fast_lookup(const FieldDev& f)
   return l;
 }
 
+constexpr long kPairSmemMax = 1024;  // sphere pairs whose thresholds are staged in shared memory (8 KB)
+
 template <typename FT, int B>
 int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const float* q, long n, int flags,
                 uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream)
 {
-  B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B>, bytes));
+  const bool pairs = (flags & B200DF_CHECK_INTRA) && g->fast->tables.n_partners > 0;
+  const int n_pair_smem = (pairs && g->dev.n_pair_consts <= kPairSmemMax) ? (int)g->dev.n_pair_consts : 0;
+  bytes += (size_t)n_pair_smem * sizeof(float2);
   const unsigned grid = (unsigned)((n + B - 1) / B);
-  validity_fast_kernel<FT, B><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf), make_fast_lookup(sf),
-                                                          g->fast->pair_T, q, n, flags, verdict, amb_idx, amb_count);
+  if (n_pair_smem > 0)
+  {
+    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B, true>, bytes));
+    validity_fast_kernel<FT, B, true><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
+                                                                  make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
+                                                                  verdict, amb_idx, amb_count, n_pair_smem);
+  }
+  else
+  {
+    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B, false>, bytes));
+    validity_fast_kernel<FT, B, false><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
+                                                                   make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
+                                                                   verdict, amb_idx, amb_count, 0);
+  }
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
