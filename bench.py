@@ -47,6 +47,7 @@ def parse():
                     help="fast = fp32 screening + exact fp64 re-run of the undecided states (same verdicts as exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-edt", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (BASELINE configs 1, 4, 5)")
     return ap.parse_args()
 
 
@@ -398,6 +399,13 @@ def main():
                 line["edt_ms"] = edt_timings(engine, scenarios, B)
             except Exception as ex:  # keep the headline line even if the big field does not fit
                 line["edt_ms"] = {"error": str(ex)}
+        if world == 1 and not args.no_extras:
+            try:  # secondary workloads; their CPU figures belong to the cpu_baseline leg (oracle = the checker's port)
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import extras_bench
+                line["extras"] = extras_bench.run(with_oracle=not args.no_cpu_baseline)
+            except Exception as ex:
+                line["extras"] = {"error": str(ex)}
         if world == 1 and not args.no_cpu_baseline:
             oracle_py, odesc, setup = build_oracle_env()
             rate, cores, ns, ts = cpu_rate(setup, odesc, oracle_py)

@@ -238,6 +238,12 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
                            int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
                            double* centers);
 
+/* the same on device buffers (q, dist, grad, type, centers all device pointers; centers may be NULL); never
+ * synchronises — for consumers that keep the gradients on the GPU */
+int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self,
+                                  const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
+                                  double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream);
+
 /* distanceRobot / distanceSelf are stubs in the reference (collision_env_distance_field.h:108-123,178-198, F5).
  * Defined here as min over group spheres of (field distance - radius); out[n]. */
 int b200df_distance_batch(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,
@@ -245,6 +251,11 @@ int b200df_distance_batch(const b200df_group* group, b200df_field* world, const 
 
 /* posed sphere centres (PosedBodySphereDecomposition::updatePose, types.cpp:390-397): out[n][S][3] */
 int b200df_sphere_centers(const b200df_group* group, const void* q, int q_dtype, int64_t n, double* centers);
+
+/* page-locked host memory for batch inputs / results: the host-buffer entry points copy at PCIe speed from / to such
+ * buffers (pageable memory costs an extra staging copy in the driver; 342 MB of CHOMP gradients: 8 ms vs 78 ms) */
+int b200df_host_alloc(size_t bytes, void** out);
+int b200df_host_free(void* p);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t b200df_launch_count(void);

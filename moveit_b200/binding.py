@@ -92,8 +92,11 @@ SYMBOLS = {
     "b200df_check_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
     "b200df_check_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP]),
     "b200df_gradients_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_dp, c_dp, c_u8p, c_dp]),
+    "b200df_gradients_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "b200df_distance_batch": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int64, c_dp]),
     "b200df_sphere_centers": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, c_dp]),
+    "b200df_host_alloc": (C.c_int, [C.c_size_t, _VPP]),
+    "b200df_host_free": (C.c_int, [_VP]),
     "b200df_launch_count": (C.c_int64, []),
 }
 

@@ -64,6 +64,21 @@ int b200df_set_device(int device)
   return B200DF_OK;
 }
 
+int b200df_host_alloc(size_t bytes, void** out)
+{
+  B200DF_REQUIRE(out, "null argument");
+  *out = nullptr;
+  B200DF_CUDA(cudaHostAlloc(out, bytes > 0 ? bytes : 1, cudaHostAllocDefault));
+  return B200DF_OK;
+}
+
+int b200df_host_free(void* p)
+{
+  if (p)
+    B200DF_CUDA(cudaFreeHost(p));
+  return B200DF_OK;
+}
+
 int64_t b200df_launch_count(void)
 {
   return b200df::g_launches.load();

@@ -180,8 +180,8 @@ __global__ void validity_exact_kernel(GroupDev g, FieldDev wf, FieldDev sf, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Gradient kernel (getCollisionGradients :1536-1557): self field, intra group, environment — in that order,
-// each keeping the per-sphere minimum with strict '<' like the reference.
+// getCollisionGradients :1536-1557: self field, intra group, environment — in that order, each keeping the
+// per-sphere minimum with strict '<' like the reference.
 // ------------------------------------------------------------------------------------------------------------
 template <typename FT>
 __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double x, double y, double z, double max_value,
@@ -211,132 +211,123 @@ __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Gradient kernel, gather form.  Phase 1: one thread per state runs FK and poses every sphere into shared memory.
+// Phase 2: one thread per (state, sphere) replays, for ITS sphere only, the candidate sequence the reference's loops
+// produce for it — self field, then every sphere of every enabled partner link (lower-index partners ascending, then
+// higher-index partners ascending: exactly the order in which getIntraGroupProximityGradients :662-727 touches this
+// sphere), then the environment field — keeping the minimum with strict '<' like the reference.  Outputs are written
+// by consecutive threads to consecutive spheres of a state: coalesced, no read-modify-write of global memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGradStates = 32;    // states per CTA
+constexpr int kGradThreads = 256;
+
 template <typename QT, typename FT>
-__global__ void gradients_kernel(GroupDev g, FieldDev wf, FieldDev sf, const QT* __restrict__ q, long n, int flags,
-                                 double* __restrict__ out_dist, double* __restrict__ out_grad,
-                                 uint8_t* __restrict__ out_type, double* __restrict__ out_cen)
+__global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
+                                                                        const QT* __restrict__ q, long n, int flags,
+                                                                        double* __restrict__ out_dist,
+                                                                        double* __restrict__ out_grad,
+                                                                        uint8_t* __restrict__ out_type,
+                                                                        double* __restrict__ out_cen)
 {
   extern __shared__ double smem[];
-  const int B = blockDim.x;
   const int tid = threadIdx.x;
-  const long base = (long)blockIdx.x * B;
-  double* qs = smem;
-  double* slots = qs + (size_t)g.n_vars * B;
-  double* cen = slots + (size_t)g.n_slots * 12 * B;
+  const long base = (long)blockIdx.x * kGradStates;
+  const int S = g.n_spheres;
+  double* cen = smem;                                          // [state][S][3]
+  double* slots = cen + (size_t)kGradStates * S * 3;           // [n_slots][12][state]
+  QT* qs = reinterpret_cast<QT*>(slots + (size_t)g.n_slots * 12 * kGradStates);  // [state][n_vars]
   {
-    const long total = (long)B * g.n_vars;
+    const int total = kGradStates * g.n_vars;
     const long limit = (n - base) * g.n_vars;
-    for (long e = tid; e < total; e += B)
+    const QT* src = q + base * g.n_vars;
+    for (int e = tid; e < total; e += kGradThreads)
+      qs[e] = (e < limit) ? src[e] : QT(0);
+  }
+  __syncthreads();
+  if (tid < kGradStates)
+  {
+    double cur[12];
+    double* my_cen = cen + (size_t)tid * S * 3;
+    for (int i = 0; i < g.n_links; ++i)
     {
-      const int s = (int)(e / g.n_vars), v = (int)(e % g.n_vars);
-      qs[v * B + s] = (e < limit) ? (double)q[base * g.n_vars + e] : 0.0;
+      fk_step(g.links[i], qs + (size_t)tid * g.n_vars, slots + tid, 1, kGradStates, cur);
+      const int gs = g.link_gslot[i];
+      if (gs < 0)
+        continue;
+      const DevGroupLink& gl = g.glinks[gs];
+      for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+      {
+        const double* rel = g.sph + 4 * s;
+        iso_apply(cur, rel[0], rel[1], rel[2], my_cen[3 * s], my_cen[3 * s + 1], my_cen[3 * s + 2]);
+      }
     }
   }
   __syncthreads();
-  const long state = base + tid;
-  if (state >= n)
-    return;
-  const double* my_q = qs + tid;
-  double* my_slots = slots + tid;
-  double* my_cen = cen + tid;
-  const int S = g.n_spheres;
-  double* dist = out_dist + state * S;
-  double* grad = out_grad + state * S * 3;
-  uint8_t* type = out_type + state * S;
-
-  double cur[12];
-  for (int i = 0; i < g.n_links; ++i)
+  const int items = kGradStates * S;
+  for (int it = tid; it < items; it += kGradThreads)
   {
-    const DevLink& l = g.links[i];
-    fk_step(l, my_q, my_slots, B, cur);
-    const int gs = g.link_gslot[i];
-    if (gs < 0)
-      continue;
-    const DevGroupLink& gl = g.glinks[gs];
-    for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
+    const int st = it / S, k = it - st * S;
+    const long state = base + st;
+    if (state >= n)
+      break;
+    const double* sc = cen + (size_t)st * S * 3;
+    const double cx = sc[3 * k], cy = sc[3 * k + 1], cz = sc[3 * k + 2];
+    const int gs = g.sph_glink[k];
+    // updateGroupStateRepresentationState :1128-1133
+    double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
+    int bt = B200DF_TYPE_NONE;
+    // getSelfProximityGradients: self field term (:420-422)
+    if ((flags & B200DF_CHECK_SELF) && g.glinks[gs].self_enabled)
+      field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
+    if (flags & B200DF_CHECK_INTRA)
     {
-      const double* rel = g.sph + 4 * s;
-      double cx, cy, cz;
-      iso_apply(cur, rel[0], rel[1], rel[2], cx, cy, cz);
-      my_cen[(s * 3 + 0) * B] = cx;
-      my_cen[(s * 3 + 1) * B] = cy;
-      my_cen[(s * 3 + 2) * B] = cz;
-      if (out_cen)
+      // sqrt is only taken for candidates that can still win: e2 > bound  =>  sqrt(e2) > best
+      double bound = best * best * 1.000000000000001;
+      for (int nb = g.nbr_off[gs]; nb < g.nbr_off[gs + 1]; ++nb)
       {
-        out_cen[(state * S + s) * 3 + 0] = cx;
-        out_cen[(state * S + s) * 3 + 1] = cy;
-        out_cen[(state * S + s) * 3 + 2] = cz;
-      }
-      // updateGroupStateRepresentationState :1128-1133
-      double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
-      int bt = B200DF_TYPE_NONE;
-      // getSelfProximityGradients: self field term (:420-422)
-      if ((flags & B200DF_CHECK_SELF) && gl.self_enabled)
-        field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
-      dist[s] = best;
-      grad[3 * s] = gx;
-      grad[3 * s + 1] = gy;
-      grad[3 * s + 2] = gz;
-      type[s] = (uint8_t)bt;
-    }
-  }
-  // getIntraGroupProximityGradients :662-727 — sequential over pairs, both spheres updated with strict '<'
-  if (flags & B200DF_CHECK_INTRA)
-  {
-    for (int p = 0; p < g.n_pairs; ++p)
-    {
-      const DevPair pr = g.pairs[p];
-      const DevGroupLink& gi = g.glinks[pr.gi];
-      const DevGroupLink& gj = g.glinks[pr.gj];
-      for (int k = gi.sphere_begin; k < gi.sphere_end; ++k)
-      {
-        const double ax = my_cen[(k * 3 + 0) * B], ay = my_cen[(k * 3 + 1) * B], az = my_cen[(k * 3 + 2) * B];
-        double dk = dist[k];
-        for (int m = gj.sphere_begin; m < gj.sphere_end; ++m)
+        const int2 o = g.nbr[nb];
+        const DevGroupLink& ol = g.glinks[o.x];
+        for (int m = ol.sphere_begin; m < ol.sphere_end; ++m)
         {
-          const double ex = ax - my_cen[(m * 3 + 0) * B];
-          const double ey = ay - my_cen[(m * 3 + 1) * B];
-          const double ez = az - my_cen[(m * 3 + 2) * B];
-          const double d = sqrt((ex * ex + ey * ey) + ez * ez);
-          if (d < dk)
+          // gradient = centre(first link of the pair) - centre(second link); the second link's sphere gets -gradient
+          double ex = sc[3 * m] - cx, ey = sc[3 * m + 1] - cy, ez = sc[3 * m + 2] - cz;
+          if (!o.y)
           {
-            dk = d;
-            dist[k] = d;
-            grad[3 * k] = ex;
-            grad[3 * k + 1] = ey;
-            grad[3 * k + 2] = ez;
-            type[k] = B200DF_TYPE_INTRA;
+            ex = -ex;  // this sphere is on the first link: (cx - other), computed as the reference does
+            ey = -ey;
+            ez = -ez;
           }
-          if (d < dist[m])
+          const double e2 = (ex * ex + ey * ey) + ez * ez;
+          if (e2 > bound)
+            continue;
+          const double d = sqrt(e2);
+          if (d < best)
           {
-            dist[m] = d;
-            grad[3 * m] = -ex;
-            grad[3 * m + 1] = -ey;
-            grad[3 * m + 2] = -ez;
-            type[m] = B200DF_TYPE_INTRA;
+            best = d;
+            bound = d * d * 1.000000000000001;
+            gx = o.y ? -ex : ex;
+            gy = o.y ? -ey : ey;
+            gz = o.y ? -ez : ez;
+            bt = B200DF_TYPE_INTRA;
           }
         }
       }
     }
-  }
-  // getEnvironmentProximityGradients :1664-1700
-  if (flags & B200DF_CHECK_ROBOT)
-  {
-    for (int s = 0; s < S; ++s)
+    // getEnvironmentProximityGradients :1664-1700
+    if (flags & B200DF_CHECK_ROBOT)
+      field_gradient_update<FT>(wf, cx, cy, cz, g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
+    const long o = state * S + k;
+    out_dist[o] = best;
+    out_grad[3 * o] = gx;
+    out_grad[3 * o + 1] = gy;
+    out_grad[3 * o + 2] = gz;
+    out_type[o] = (uint8_t)bt;
+    if (out_cen)
     {
-      double best = dist[s], gx = grad[3 * s], gy = grad[3 * s + 1], gz = grad[3 * s + 2];
-      int bt = type[s];
-      const double before = best;
-      field_gradient_update<FT>(wf, my_cen[(s * 3 + 0) * B], my_cen[(s * 3 + 1) * B], my_cen[(s * 3 + 2) * B],
-                                g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
-      if (best < before)
-      {
-        dist[s] = best;
-        grad[3 * s] = gx;
-        grad[3 * s + 1] = gy;
-        grad[3 * s + 2] = gz;
-        type[s] = (uint8_t)bt;
-      }
+      out_cen[3 * o] = cx;
+      out_cen[3 * o + 1] = cy;
+      out_cen[3 * o + 2] = cz;
     }
   }
 }
@@ -424,6 +415,48 @@ int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf,
   return dispatch_exact<OUT_VERDICT>(g, wf, sf, field_elem, q, q_dtype, n, flags, verdict, nullptr, stream);
 }
 }  // namespace b200df
+
+namespace
+{
+size_t gather_smem_bytes(const GroupDev& g, size_t q_elem)
+{
+  return ((size_t)kGradStates * g.n_spheres * 3 + (size_t)g.n_slots * 12 * kGradStates) * sizeof(double) +
+         (size_t)kGradStates * g.n_vars * q_elem;
+}
+
+template <typename QT, typename FT>
+int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n, int flags,
+                         double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
+{
+  const size_t bytes = gather_smem_bytes(g, sizeof(QT));
+  if (bytes > 220 * 1024)
+  {
+    set_error("robot too large for the gradient kernel's shared-memory layout (%zu bytes)", bytes);
+    return B200DF_ERR_UNSUPPORTED;
+  }
+  B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT>, bytes));
+  const unsigned grid = (unsigned)((n + kGradStates - 1) / kGradStates);
+  gradients_gather_kernel<QT, FT><<<grid, kGradThreads, bytes, stream>>>(g, wf, sf, static_cast<const QT*>(q), n, flags,
+                                                                         dist, grad, type, centers);
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  return B200DF_OK;
+}
+
+int dispatch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int elem, const void* q,
+                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
+                           double* centers, cudaStream_t stream)
+{
+  if (q_dtype == B200DF_Q_F32 && elem == 1)
+    return launch_gather<float, uint8_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+  if (q_dtype == B200DF_Q_F32)
+    return launch_gather<float, uint16_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+  if (elem == 1)
+    return launch_gather<double, uint8_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+  return launch_gather<double, uint16_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -520,6 +553,26 @@ int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64
   return rc;
 }
 
+int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self,
+                                  const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
+                                  double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream)
+{
+  B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q_dev && dist_dev && grad_dev && type_dev)), "bad arguments");
+  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
+  if (n == 0)
+    return B200DF_OK;
+  FieldDev wf, sf;
+  int elem;
+  int rc = prepare_fields(group, world, self, flags, &wf, &sf, &elem);
+  if (rc)
+    return rc;
+  DeviceGuard dg(group->device);
+  return dispatch_gather(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, dist_dev, grad_dev, type_dev, centers_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+// Host-buffer entry: chunks of states travel H2D -> kernel -> D2H on two streams, so the (large) result copies of
+// one chunk overlap the kernel of the next.
 int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
                            int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
                            double* centers)
@@ -536,84 +589,81 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
   const GroupDev& g = group->dev;
   const size_t S = (size_t)g.n_spheres;
   DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  const size_t qbytes = (size_t)n * g.n_vars * q_elem_size(q_dtype);
+  const size_t row = (size_t)g.n_vars * q_elem_size(q_dtype);
+  const int64_t chunk = std::min<int64_t>(n, 16384);
+  struct Slot
   {
-    ScratchBuffer dq, dd, dgr, dt, dc;
-    dq.stream = dd.stream = dgr.stream = dt.stream = dc.stream = stream;
-    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
+    cudaStream_t stream = nullptr;
+    ScratchBuffer q, d, gr, t, c;
+  } slot[2];
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k)
+  {
+    e = cudaStreamCreateWithFlags(&slot[k].stream, cudaStreamNonBlocking);
+    Slot& sl = slot[k];
+    sl.q.stream = sl.d.stream = sl.gr.stream = sl.t.stream = sl.c.stream = sl.stream;
     if (e == cudaSuccess)
-      e = cudaMallocAsync(&dd.p, std::max<size_t>(n * S * sizeof(double), 1), stream);
+      e = cudaMallocAsync(&sl.q.p, std::max<size_t>(chunk * row, 1), sl.stream);
     if (e == cudaSuccess)
-      e = cudaMallocAsync(&dgr.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
+      e = cudaMallocAsync(&sl.d.p, std::max<size_t>(chunk * S * sizeof(double), 1), sl.stream);
     if (e == cudaSuccess)
-      e = cudaMallocAsync(&dt.p, std::max<size_t>(n * S, 1), stream);
+      e = cudaMallocAsync(&sl.gr.p, std::max<size_t>(chunk * S * 3 * sizeof(double), 1), sl.stream);
+    if (e == cudaSuccess)
+      e = cudaMallocAsync(&sl.t.p, std::max<size_t>(chunk * S, 1), sl.stream);
     if (e == cudaSuccess && centers)
-      e = cudaMallocAsync(&dc.p, std::max<size_t>(n * S * 3 * sizeof(double), 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
+      e = cudaMallocAsync(&sl.c.p, std::max<size_t>(chunk * S * 3 * sizeof(double), 1), sl.stream);
+  }
+  int k = 0;
+  for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k ^= 1)
+  {
+    const int64_t m = std::min<int64_t>(chunk, n - s);
+    Slot& sl = slot[k];
+    e = cudaMemcpyAsync(sl.q.p, static_cast<const char*>(q) + (size_t)s * row, (size_t)m * row, cudaMemcpyHostToDevice,
+                        sl.stream);
     if (e != cudaSuccess)
+      break;
+    rc = dispatch_gather(g, wf, sf, elem, sl.q.p, q_dtype, m, flags, static_cast<double*>(sl.d.p),
+                         static_cast<double*>(sl.gr.p), static_cast<uint8_t*>(sl.t.p), static_cast<double*>(sl.c.p),
+                         sl.stream);
+    if (rc)
+      break;
+    e = cudaMemcpyAsync(dist + s * S, sl.d.p, m * S * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(grad + s * S * 3, sl.gr.p, m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(type + s * S, sl.t.p, m * S, cudaMemcpyDeviceToHost, sl.stream);
+    if (e == cudaSuccess && centers)
+      e = cudaMemcpyAsync(centers + s * S * 3, sl.c.p, m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+  }
+  for (int i = 0; i < 2; ++i)
+  {
+    if (!slot[i].stream)
+      continue;
+    const cudaError_t es = cudaStreamSynchronize(slot[i].stream);
+    if (e == cudaSuccess)
+      e = es;
+  }
+  if (!rc && e != cudaSuccess)
+  {
+    set_error("gradient batch failed while staging / running / reading back: %s", cudaGetErrorString(e));
+    rc = B200DF_ERR_CUDA;
+  }
+  // the scratch buffers are freed stream-ordered by their destructors before the streams go away
+  for (int i = 0; i < 2; ++i)
+  {
+    Slot& sl = slot[i];
+    for (ScratchBuffer* b : { &sl.q, &sl.d, &sl.gr, &sl.t, &sl.c })
     {
-      set_error("staging the batch failed: %s", cudaGetErrorString(e));
-      rc = B200DF_ERR_CUDA;
+      if (b->p)
+        cudaFreeAsync(b->p, sl.stream);
+      b->p = nullptr;
     }
-    if (!rc)
+    if (sl.stream)
     {
-      int block;
-      size_t bytes;
-      rc = pick_block(g, true, false, &block, &bytes);
-      const unsigned grid = (unsigned)((n + block - 1) / block);
-#define B200DF_LAUNCH_GRAD(QT, FT)                                                                                 \
-  do                                                                                                               \
-  {                                                                                                                \
-    if (!rc)                                                                                                       \
-      rc = set_smem_limit(gradients_kernel<QT, FT>, bytes);                                                        \
-    if (!rc)                                                                                                       \
-      gradients_kernel<QT, FT><<<grid, block, bytes, stream>>>(                                                    \
-          g, wf, sf, static_cast<const QT*>(dq.p), n, flags, static_cast<double*>(dd.p),                           \
-          static_cast<double*>(dgr.p), static_cast<uint8_t*>(dt.p), static_cast<double*>(dc.p));                   \
-  } while (0)
-      if (q_dtype == B200DF_Q_F32 && elem == 1)
-        B200DF_LAUNCH_GRAD(float, uint8_t);
-      else if (q_dtype == B200DF_Q_F32)
-        B200DF_LAUNCH_GRAD(float, uint16_t);
-      else if (elem == 1)
-        B200DF_LAUNCH_GRAD(double, uint8_t);
-      else
-        B200DF_LAUNCH_GRAD(double, uint16_t);
-#undef B200DF_LAUNCH_GRAD
-      if (!rc)
-      {
-        B200DF_LAUNCHED();
-        e = cudaGetLastError();
-        if (e != cudaSuccess)
-        {
-          set_error("gradient kernel launch failed: %s", cudaGetErrorString(e));
-          rc = B200DF_ERR_CUDA;
-        }
-      }
-    }
-    if (!rc)
-    {
-      e = cudaMemcpyAsync(dist, dd.p, n * S * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(grad, dgr.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(type, dt.p, n * S, cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess && centers)
-        e = cudaMemcpyAsync(centers, dc.p, n * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess)
-      {
-        set_error("reading gradients back failed: %s", cudaGetErrorString(e));
-        rc = B200DF_ERR_CUDA;
-      }
+      cudaStreamSynchronize(sl.stream);
+      cudaStreamDestroy(sl.stream);
     }
   }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
   return rc;
 }
 

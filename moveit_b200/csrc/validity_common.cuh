@@ -88,6 +88,11 @@ struct GroupDev
   int n_cls;
   const DevPair* pairs;  // link pairs in the reference's (i, j>i) loop order
   int n_pairs;
+  // per-sphere gather form of the intra-group pairs (gradient kernel): for group link gs, the enabled partner links
+  // in the order the reference's pair loop touches gs (lower-index partners ascending, then higher-index ascending)
+  const int* sph_glink;  // [S] group-link slot of each sphere
+  const int* nbr_off;    // [n_glinks + 1]
+  const int2* nbr;       // {partner group-link slot, 1 if the partner is the lower-index (first) link of the pair}
   double tol, max_prop;
 };
 

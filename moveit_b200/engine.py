@@ -200,13 +200,18 @@ class Group:
                                                    flags, precision, C.c_void_p(verdict_ptr),
                                                    C.c_void_p(stream) if stream else None))
 
-    def gradients(self, q, world=None, self_field=None, flags=B.CHECK_ROBOT | B.CHECK_INTRA, want_centers=True):
+    def gradients(self, q, world=None, self_field=None, flags=B.CHECK_ROBOT | B.CHECK_INTRA, want_centers=True,
+                  out=None):
+        """out: optional dict of preallocated C-contiguous arrays (dist, grad, type, centers), e.g. views of pinned
+        host memory, to keep the result copies off the pageable path."""
         q, dt = _q_array(q, self.model.n_vars)
         N, S = len(q), self.n_spheres
-        dist = np.empty((N, S))
-        grad = np.empty((N, S, 3))
-        typ = np.empty((N, S), dtype=np.uint8)
-        cen = np.empty((N, S, 3)) if want_centers else None
+        out = out or {}
+        dist = out.get("dist") if out.get("dist") is not None else np.empty((N, S))
+        grad = out.get("grad") if out.get("grad") is not None else np.empty((N, S, 3))
+        typ = out.get("type") if out.get("type") is not None else np.empty((N, S), dtype=np.uint8)
+        cen = (out.get("centers") if out.get("centers") is not None else np.empty((N, S, 3))) if want_centers else None
+        assert dist.shape == (N, S) and grad.shape == (N, S, 3) and typ.shape == (N, S)
         B.check(B.load().b200df_gradients_batch(self.h, world.h if world else None,
                                                 self_field.h if self_field else None, q.ctypes.data_as(C.c_void_p), dt,
                                                 N, flags, B.ptr(dist, C.c_double), B.ptr(grad, C.c_double),

@@ -470,6 +470,41 @@ inline void checkStatus(int rc, const char* what)
     throw B200Error(std::string(what) + ": " + b200df_last_error());
 }
 
+// page-locked host buffer (b200df_host_alloc): batch results are copied back at PCIe speed
+template <typename T>
+class PinnedBuffer
+{
+public:
+  explicit PinnedBuffer(std::size_t n) : n_(n)
+  {
+    void* p = nullptr;
+    checkStatus(b200df_host_alloc(n * sizeof(T), &p), "b200df_host_alloc");
+    p_ = static_cast<T*>(p);
+  }
+  ~PinnedBuffer()
+  {
+    b200df_host_free(p_);
+  }
+  PinnedBuffer(const PinnedBuffer&) = delete;
+  PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+  T* data()
+  {
+    return p_;
+  }
+  const T& operator[](std::size_t i) const
+  {
+    return p_[i];
+  }
+  std::size_t size() const
+  {
+    return n_;
+  }
+
+private:
+  T* p_ = nullptr;
+  std::size_t n_ = 0;
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // CollisionEnvB200
 // ------------------------------------------------------------------------------------------------------------
@@ -627,8 +662,8 @@ public:
       ref.setVariablePositions(states);
     std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, ref, acm, true);
     const std::size_t S = e->sphere_radii.size();
-    std::vector<double> dist(n * S), grad(n * S * 3), cen(n * S * 3);
-    std::vector<std::uint8_t> type(n * S);
+    PinnedBuffer<double> dist(n * S), grad(n * S * 3), cen(n * S * 3);
+    PinnedBuffer<std::uint8_t> type(n * S);
     int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
     checkStatus(b200df_gradients_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
                                        dist.data(), grad.data(), type.data(), cen.data()),

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs 1, 4, 5) timed through the host-buffer C ABI, with the CPU oracle
+beside them on a bounded sample.  Not the headline metric; bench.py embeds the result under "extras"."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(with_oracle=True):
+    from moveit_b200 import binding as B
+    from moveit_b200 import engine, scenarios
+    from moveit_b200 import robot_description as rd
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import EngineSetup, OracleSetup
+    out = {}
+    oracle = None
+    if with_oracle:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as oracle
+    cores = (oracle.hardware_concurrency() if oracle else 0) or os.cpu_count() or 1
+
+    def best_of(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    # config 1: 10 k Panda states, checkRobotCollision
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    q = desc.sample_states(10000, scenarios.SEED_STATES, np.float32)
+    e.group.check(q, e.world, flags=B.CHECK_ROBOT, precision=B.PRECISION_FAST)
+    t = best_of(lambda: e.group.check(q, e.world, flags=B.CHECK_ROBOT, precision=B.PRECISION_FAST), 5)
+    out["config1_10k_robot_ms"] = 1e3 * t
+
+    # config 5: CHOMP gradients, 1000 trajectories x 100 waypoints
+    traj = scenarios.chomp_trajectories(desc, 1000, 100).reshape(-1, desc.nvar)
+    fl = B.CHECK_ROBOT | B.CHECK_INTRA
+    e.group.gradients(traj[:1000], e.world, flags=fl)
+    t = best_of(lambda: e.group.gradients(traj, e.world, flags=fl), 3)
+    out["config5_chomp_gradients"] = {"states": len(traj), "ms": 1e3 * t, "states_per_s": len(traj) / t,
+                                      "spheres": int(e.group.n_spheres),
+                                      "d2h_bytes": len(traj) * int(e.group.n_spheres) * (8 + 24 + 1 + 24)}
+    try:  # the same with pinned result buffers, and the device-resident entry point
+        import torch
+        N, S = len(traj), int(e.group.n_spheres)
+        pin = dict(dist=torch.empty((N, S), dtype=torch.float64).pin_memory().numpy(),
+                   grad=torch.empty((N, S, 3), dtype=torch.float64).pin_memory().numpy(),
+                   type=torch.empty((N, S), dtype=torch.uint8).pin_memory().numpy(),
+                   centers=torch.empty((N, S, 3), dtype=torch.float64).pin_memory().numpy())
+        tq = torch.from_numpy(traj).pin_memory().numpy()
+        e.group.gradients(tq, e.world, flags=fl, out=pin)
+        t = best_of(lambda: e.group.gradients(tq, e.world, flags=fl, out=pin), 3)
+        out["config5_chomp_gradients"]["pinned_ms"] = 1e3 * t
+        out["config5_chomp_gradients"]["pinned_states_per_s"] = N / t
+        import ctypes as C
+        qd = torch.from_numpy(traj).cuda()
+        dd = torch.empty((N, S), dtype=torch.float64, device="cuda")
+        gd = torch.empty((N, S, 3), dtype=torch.float64, device="cuda")
+        td = torch.empty((N, S), dtype=torch.uint8, device="cuda")
+        cd = torch.empty((N, S, 3), dtype=torch.float64, device="cuda")
+        st = torch.cuda.current_stream()
+
+        def dev():
+            B.check(B.load().b200df_gradients_batch_device(e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F64,
+                                                           N, fl, C.c_void_p(dd.data_ptr()), C.c_void_p(gd.data_ptr()),
+                                                           C.c_void_p(td.data_ptr()), C.c_void_p(cd.data_ptr()),
+                                                           C.c_void_p(st.cuda_stream)))
+        dev()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dev()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out["config5_chomp_gradients"]["device_resident_ms"] = ms
+        out["config5_chomp_gradients"]["device_resident_states_per_s"] = N / (ms * 1e-3)
+        assert np.array_equal(dd.cpu().numpy(), pin["dist"]) and np.array_equal(td.cpu().numpy(), pin["type"])
+    except ImportError:
+        pass
+
+    # config 4: PR2-like dual-arm tree, full ACM
+    pr2 = rd.pr2_like()
+    e4 = EngineSetup(pr2, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=31))
+    q4 = pr2.sample_states(200_000, 12, np.float32)
+    e4.group.check(q4[:1000], e4.world, flags=fl)
+    t = best_of(lambda: e4.group.check(q4, e4.world, flags=fl), 3)
+    out["config4_pr2_like"] = {"states": len(q4), "ms": 1e3 * t, "states_per_s": len(q4) / t,
+                               "links": pr2.n_links, "spheres": int(e4.group.n_spheres)}
+    if oracle:
+        o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+        sample = traj[:20000]
+        t0 = time.perf_counter()
+        o.env.gradients_batch(sample, flags=2 | 4)
+        out["config5_chomp_gradients"]["cpu_oracle_states_per_s_1_thread"] = len(sample) / (time.perf_counter() - t0)
+        o4 = OracleSetup(oracle, pr2, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=31),
+                         self_state=np.zeros(pr2.nvar))
+        s4 = q4[:20000].astype(np.float64)
+        _, tt = o4.env.check_batch(s4, mode=3, n_threads=cores, return_time=True)
+        out["config4_pr2_like"]["cpu_oracle_states_per_s"] = len(s4) / tt
+        out["config4_pr2_like"]["cpu_cores"] = cores
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(run("--no-oracle" not in sys.argv)))
