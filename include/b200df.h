@@ -58,6 +58,8 @@ enum
   B200DF_CHECK_ROBOT = 1, /* group spheres vs world field      getEnvironmentCollisions  collision_env_distance_field.cpp:1580-1662 */
   B200DF_CHECK_SELF = 2,  /* group spheres vs self field       getSelfCollisions         :277-356 */
   B200DF_CHECK_INTRA = 4, /* sphere pairs inside the group     getIntraGroupCollisions   :433-660 */
+  B200DF_CHECK_LINK_FIELDS = 8, /* gradients only: per-link PosedDistanceField term of getSelfProximityGradients
+                                   :395-418 (needs b200df_group_set_link_fields) */
 };
 
 /* joint-value element type of a batch */
@@ -157,6 +159,14 @@ typedef struct b200df_group_desc
 int b200df_group_create(const b200df_model* model, const b200df_group_desc* desc, b200df_group** out);
 int b200df_group_destroy(b200df_group* group);
 int b200df_group_sphere_count(const b200df_group* group, int32_t* n_spheres); /* S of the gradient outputs */
+/* The per-link distance fields of GroupStateRepresentation::link_distance_fields_
+ * (getGroupStateRepresentation, collision_env_distance_field.cpp:1187-1210): for each group link WITH geometry, in
+ * group order, a field in the link's own frame (cube of edge 2*bounding radius around the relative bounding-sphere
+ * centre, filled with the link's BodyDecomposition points), or NULL.  enabled[i*G+j] != 0 when the ACM lets link j's
+ * field act on link i's spheres (entry absent or NEVER, :388-404); pass NULL fields to switch the term off.
+ * The fields must stay alive and unmodified while the group uses them.  G = links with geometry, at most 32. */
+int b200df_group_link_count(const b200df_group* group, int32_t* n_links_with_geometry);
+int b200df_group_set_link_fields(b200df_group* group, b200df_field* const* fields, const uint8_t* enabled);
 
 /* ---- distance field ----------------------------------------------------------------------------------------
  * Replaces distance_field::PropagationDistanceField (propagation_distance_field.cpp) with an occupancy grid plus

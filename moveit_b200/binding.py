@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200df.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-CHECK_ROBOT, CHECK_SELF, CHECK_INTRA = 1, 2, 4
+CHECK_ROBOT, CHECK_SELF, CHECK_INTRA, CHECK_LINK_FIELDS = 1, 2, 4, 8
 Q_F32, Q_F64 = 0, 1
 PRECISION_EXACT, PRECISION_FAST = 0, 1
 TYPE_NONE, TYPE_SELF, TYPE_INTRA, TYPE_ENVIRONMENT = 0, 1, 2, 3
@@ -65,6 +65,8 @@ SYMBOLS = {
     "b200df_group_create": (C.c_int, [_VP, C.POINTER(GroupDesc), _VPP]),
     "b200df_group_destroy": (C.c_int, [_VP]),
     "b200df_group_sphere_count": (C.c_int, [_VP, c_i32p]),
+    "b200df_group_link_count": (C.c_int, [_VP, c_i32p]),
+    "b200df_group_set_link_fields": (C.c_int, [_VP, _VPP, c_u8p]),
     "b200df_field_create": (C.c_int, [C.POINTER(FieldDesc), _VPP]),
     "b200df_field_destroy": (C.c_int, [_VP]),
     "b200df_field_dims": (C.c_int, [_VP, c_i32p]),

@@ -222,7 +222,24 @@ __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double 
 constexpr int kGradStates = 32;    // states per CTA
 constexpr int kGradThreads = 256;
 
-template <typename QT, typename FT>
+// PosedDistanceField::getDistanceGradient's point mapping (collision_distance_field_types.h:156-160):
+// rel = pose.inverse() * p with Eigen's isometry inverse (R^T, -(R^T t))
+__device__ __forceinline__ void posed_rel(const double* pose, double x, double y, double z, double& rx, double& ry,
+                                          double& rz)
+{
+  double inv[12];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    inv[4 * i + 0] = pose[i];
+    inv[4 * i + 1] = pose[4 + i];
+    inv[4 * i + 2] = pose[8 + i];
+    inv[4 * i + 3] = -((inv[4 * i] * pose[3] + inv[4 * i + 1] * pose[7]) + inv[4 * i + 2] * pose[11]);
+  }
+  iso_apply(inv, x, y, z, rx, ry, rz);
+}
+
+template <typename QT, typename FT, bool LF>
 __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
                                                                         const QT* __restrict__ q, long n, int flags,
                                                                         double* __restrict__ out_dist,
@@ -234,9 +251,13 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
   const int tid = threadIdx.x;
   const long base = (long)blockIdx.x * kGradStates;
   const int S = g.n_spheres;
+  const int G = g.n_glinks;
   double* cen = smem;                                          // [state][S][3]
   double* slots = cen + (size_t)kGradStates * S * 3;           // [n_slots][12][state]
-  QT* qs = reinterpret_cast<QT*>(slots + (size_t)g.n_slots * 12 * kGradStates);  // [state][n_vars]
+  double* poses = slots + (size_t)g.n_slots * 12 * kGradStates;  // LF: [state][G][12] link poses
+  unsigned* can = reinterpret_cast<unsigned*>(poses + (LF ? (size_t)kGradStates * G * 12 : 0));  // LF: [state][S]
+  unsigned* abt = can + (LF ? (size_t)kGradStates * S : 0);                                       // LF: [state][S]
+  QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)kGradStates * S : 0));  // [state][n_vars]
   {
     const int total = kGradStates * g.n_vars;
     const long limit = (n - base) * g.n_vars;
@@ -261,10 +282,62 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
         const double* rel = g.sph + 4 * s;
         iso_apply(cur, rel[0], rel[1], rel[2], my_cen[3 * s], my_cen[3 * s + 1], my_cen[3 * s + 2]);
       }
+      if (LF)
+      {
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+          poses[((size_t)tid * G + gs) * 12 + k] = cur[k];  // PosedDistanceField::updatePose
+      }
     }
   }
   __syncthreads();
   const int items = kGradStates * S;
+  if (LF)
+  {
+    // Which link fields may act on which sphere.  PosedDistanceField::getCollisionSphereGradients
+    // (collision_distance_field_types.cpp:81-141) walks a link's spheres in order and RETURNS at the first sphere
+    // that is outside the other link's field (Q7; the "gradient norm > 0" guard is the norm of pose * 0 = the
+    // pose's translation, Q6), so sphere k sees field j only if it is inside AND no earlier sphere of its link aborted.
+    for (int it = tid; it < items; it += kGradThreads)
+    {
+      const int st = it / S, k = it - st * S;
+      const double* sc = cen + (size_t)st * S * 3;
+      const int gs = g.sph_glink[k];
+      unsigned allowed = g.glinks[gs].self_enabled ? (g.lf_enabled[gs] & ~(1u << gs)) : 0u;
+      unsigned inb = 0u, ab = 0u;
+      while (allowed)
+      {
+        const int j = __ffs(allowed) - 1;
+        allowed &= allowed - 1;
+        const FieldDev& f = g.link_fields[j];
+        if (!f.d2)
+          continue;
+        const double* pose = poses + ((size_t)st * G + j) * 12;
+        double rx, ry, rz;
+        posed_rel(pose, sc[3 * k], sc[3 * k + 1], sc[3 * k + 2], rx, ry, rz);
+        long idx;
+        if (inset_cell(f.g, rx, ry, rz, idx))
+          inb |= 1u << j;
+        else if (sqrt((pose[3] * pose[3] + pose[7] * pose[7]) + pose[11] * pose[11]) > 0.0)
+          ab |= 1u << j;
+      }
+      can[it] = inb;
+      abt[it] = ab;
+    }
+    __syncthreads();
+    for (int it = tid; it < kGradStates * G; it += kGradThreads)
+    {
+      const int st = it / G, gs = it - st * G;
+      unsigned alive = 0xffffffffu;
+      for (int k = g.glinks[gs].sphere_begin; k < g.glinks[gs].sphere_end; ++k)
+      {
+        const unsigned a = abt[st * S + k];
+        can[st * S + k] &= alive;
+        alive &= ~a;
+      }
+    }
+    __syncthreads();
+  }
   for (int it = tid; it < items; it += kGradThreads)
   {
     const int st = it / S, k = it - st * S;
@@ -277,6 +350,28 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
     // updateGroupStateRepresentationState :1128-1133
     double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
     int bt = B200DF_TYPE_NONE;
+    if (LF)
+    {
+      // getSelfProximityGradients: the other links' PosedDistanceFields, in link order (:388-418)
+      unsigned m = can[it];
+      while (m)
+      {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const double* pose = poses + ((size_t)st * G + j) * 12;
+        double rx, ry, rz;
+        posed_rel(pose, cx, cy, cz, rx, ry, rz);
+        double d = DBL_MAX, lx = 0.0, ly = 0.0, lz = 0.0;
+        int lt = B200DF_TYPE_NONE;
+        field_gradient_update<FT>(g.link_fields[j], rx, ry, rz, g.max_prop, B200DF_TYPE_SELF, d, lx, ly, lz, lt);
+        if (lt == B200DF_TYPE_SELF && d < best)  // dist < maximum_value && dist < distances[i]
+        {
+          best = d;
+          iso_apply(pose, lx, ly, lz, gx, gy, gz);  // pose * gradient: rotation AND translation (Q6)
+          bt = B200DF_TYPE_SELF;
+        }
+      }
+    }
     // getSelfProximityGradients: self field term (:420-422)
     if ((flags & B200DF_CHECK_SELF) && g.glinks[gs].self_enabled)
       field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
@@ -418,26 +513,39 @@ int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf,
 
 namespace
 {
-size_t gather_smem_bytes(const GroupDev& g, size_t q_elem)
+size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf)
 {
-  return ((size_t)kGradStates * g.n_spheres * 3 + (size_t)g.n_slots * 12 * kGradStates) * sizeof(double) +
-         (size_t)kGradStates * g.n_vars * q_elem;
+  size_t b = ((size_t)kGradStates * g.n_spheres * 3 + (size_t)g.n_slots * 12 * kGradStates) * sizeof(double) +
+             (size_t)kGradStates * g.n_vars * q_elem;
+  if (lf)
+    b += (size_t)kGradStates * g.n_glinks * 12 * sizeof(double) + 2 * (size_t)kGradStates * g.n_spheres * sizeof(unsigned);
+  return b;
 }
 
 template <typename QT, typename FT>
 int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n, int flags,
                          double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
 {
-  const size_t bytes = gather_smem_bytes(g, sizeof(QT));
+  const bool lf = (flags & B200DF_CHECK_LINK_FIELDS) != 0;
+  const size_t bytes = gather_smem_bytes(g, sizeof(QT), lf);
   if (bytes > 220 * 1024)
   {
     set_error("robot too large for the gradient kernel's shared-memory layout (%zu bytes)", bytes);
     return B200DF_ERR_UNSUPPORTED;
   }
-  B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT>, bytes));
   const unsigned grid = (unsigned)((n + kGradStates - 1) / kGradStates);
-  gradients_gather_kernel<QT, FT><<<grid, kGradThreads, bytes, stream>>>(g, wf, sf, static_cast<const QT*>(q), n, flags,
-                                                                         dist, grad, type, centers);
+  if (lf)
+  {
+    B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, true>, bytes));
+    gradients_gather_kernel<QT, FT, true><<<grid, kGradThreads, bytes, stream>>>(
+        g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
+  }
+  else
+  {
+    B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, false>, bytes));
+    gradients_gather_kernel<QT, FT, false><<<grid, kGradThreads, bytes, stream>>>(
+        g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
+  }
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
@@ -553,6 +661,72 @@ int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64
   return rc;
 }
 
+int b200df_group_link_count(const b200df_group* g, int32_t* n)
+{
+  B200DF_REQUIRE(g && n, "null argument");
+  *n = g->dev.n_glinks;
+  return B200DF_OK;
+}
+
+int b200df_group_set_link_fields(b200df_group* group, b200df_field* const* fields, const uint8_t* enabled)
+{
+  B200DF_REQUIRE(group, "null group");
+  DeviceGuard dg(group->device);
+  cudaFree(group->d_link_fields);
+  cudaFree(group->d_lf_enabled);
+  group->d_link_fields = group->d_lf_enabled = nullptr;
+  group->dev.link_fields = nullptr;
+  group->dev.lf_enabled = nullptr;
+  group->dev.n_link_fields = 0;
+  group->link_field_elem = 0;
+  if (!fields)
+    return B200DF_OK;
+  B200DF_REQUIRE(enabled, "null enabled matrix");
+  const int G = group->dev.n_glinks;
+  B200DF_REQUIRE(G <= 32, "the link-field term supports at most 32 links with geometry per group");
+  std::vector<FieldDev> views(std::max(G, 1));
+  std::vector<unsigned> en(std::max(G, 1), 0u);
+  std::memset(views.data(), 0, views.size() * sizeof(FieldDev));
+  for (int j = 0; j < G; ++j)
+  {
+    if (!fields[j])
+      continue;
+    B200DF_REQUIRE(fields[j]->device == group->device, "link field and group live on different devices");
+    B200DF_REQUIRE(fields[j]->desc.resolution == group->desc.resolution, "link field resolution differs from the group's");
+    int rc = field_prepare(fields[j], &views[j], nullptr);
+    if (rc)
+      return rc;
+    if (!views[j].d2)
+      continue;  // empty grid
+    B200DF_REQUIRE(group->link_field_elem == 0 || group->link_field_elem == views[j].elem_size,
+                   "link fields must share max_distance (voxel type)");
+    group->link_field_elem = views[j].elem_size;
+  }
+  for (int i = 0; i < G; ++i)
+    for (int j = 0; j < G; ++j)
+      if (i != j && enabled[(size_t)i * G + j])
+        en[i] |= 1u << j;
+  B200DF_CUDA(cudaMalloc(&group->d_link_fields, views.size() * sizeof(FieldDev)));
+  B200DF_CUDA(cudaMalloc(&group->d_lf_enabled, en.size() * sizeof(unsigned)));
+  B200DF_CUDA(cudaMemcpy(group->d_link_fields, views.data(), views.size() * sizeof(FieldDev), cudaMemcpyHostToDevice));
+  B200DF_CUDA(cudaMemcpy(group->d_lf_enabled, en.data(), en.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  group->dev.link_fields = static_cast<const FieldDev*>(group->d_link_fields);
+  group->dev.lf_enabled = static_cast<const unsigned*>(group->d_lf_enabled);
+  group->dev.n_link_fields = G;
+  return B200DF_OK;
+}
+
+// voxel type the gradient kernel is instantiated for: world / self fields and the link fields must agree
+static int resolve_elem(const b200df_group* group, int flags, int* elem)
+{
+  if (!(flags & B200DF_CHECK_LINK_FIELDS) || group->link_field_elem == 0)
+    return B200DF_OK;
+  if (flags & (B200DF_CHECK_ROBOT | B200DF_CHECK_SELF))
+    B200DF_REQUIRE(*elem == group->link_field_elem, "link fields and world/self field must share max_distance");
+  *elem = group->link_field_elem;
+  return B200DF_OK;
+}
+
 int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self,
                                   const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
                                   double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream)
@@ -564,6 +738,8 @@ int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world
   FieldDev wf, sf;
   int elem;
   int rc = prepare_fields(group, world, self, flags, &wf, &sf, &elem);
+  if (!rc)
+    rc = resolve_elem(group, flags, &elem);
   if (rc)
     return rc;
   DeviceGuard dg(group->device);
@@ -584,6 +760,8 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
   FieldDev wf, sf;
   int elem;
   int rc = prepare_fields(group, world, self, flags, &wf, &sf, &elem);
+  if (!rc)
+    rc = resolve_elem(group, flags, &elem);
   if (rc)
     return rc;
   const GroupDev& g = group->dev;

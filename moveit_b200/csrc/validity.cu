@@ -915,6 +915,8 @@ int b200df_group_destroy(b200df_group* g)
   DeviceGuard dg(g->device);
   delete g->stage;
   fast_destroy(g);
+  cudaFree(g->d_link_fields);
+  cudaFree(g->d_lf_enabled);
   for (void* p : g->allocations)
     cudaFree(p);
   delete g;

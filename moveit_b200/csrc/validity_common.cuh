@@ -93,6 +93,10 @@ struct GroupDev
   const int* sph_glink;  // [S] group-link slot of each sphere
   const int* nbr_off;    // [n_glinks + 1]
   const int2* nbr;       // {partner group-link slot, 1 if the partner is the lower-index (first) link of the pair}
+  // per-link PosedDistanceField term of getSelfProximityGradients (:395-418), set by b200df_group_set_link_fields
+  const FieldDev* link_fields;   // [n_glinks] views (d2 == nullptr: no field); all in their link's own frame
+  const unsigned* lf_enabled;    // [n_glinks] bit j: the ACM lets link j's field act on this link's spheres
+  int n_link_fields;             // 0: term off
   double tol, max_prop;
 };
 
@@ -475,6 +479,9 @@ struct b200df_group
   StagePool* stage = nullptr;
   struct FastPath;   // fp32 screening tables + scratch (validity_fast.cu); null when the model does not fit them
   FastPath* fast = nullptr;
+  void* d_link_fields = nullptr;  // device copies behind dev.link_fields / dev.lf_enabled
+  void* d_lf_enabled = nullptr;
+  int link_field_elem = 0;        // voxel type of the link fields (1 or 2)
 };
 
 namespace b200df

@@ -89,6 +89,34 @@ def resolve_acm(model_desc, group_links, acm_entry):
     return self_en, intra
 
 
+def link_distance_fields(model_desc, group_links, acm_entry, resolution=DEFAULT_RESOLUTION,
+                         max_distance=DEFAULT_MAX_PROPAGATION, signed=False):
+    """GroupStateRepresentation::link_distance_fields_ (getGroupStateRepresentation,
+    collision_env_distance_field.cpp:1187-1210) for the group's links with geometry, plus the ACM gate of
+    getSelfProximityGradients (:388-404: an entry that exists and is not NEVER switches link j's field off for link
+    i).  Returns (fields, enabled[G,G]) or (None, None) when the ACM is null / empty (the reference skips the term)."""
+    geo = [li for li in group_links if model_desc["has_geometry"][li]]
+    if acm_entry is None or not (np.asarray(acm_entry) >= 0).any():
+        return None, None
+    fields = []
+    for li in geo:
+        bs = np.asarray(model_desc["bsphere"][li], dtype=np.float64)
+        diameter = 2 * bs[3]
+        origin = bs[:3] - 0.5 * np.array([diameter, diameter, diameter])
+        f = Field((diameter, diameter, diameter), resolution, origin, max_distance, signed)
+        pts = np.asarray(model_desc["points"][li], dtype=np.float64).reshape(-1, 3)
+        if len(pts):
+            f.add_points(pts)
+        fields.append(f)
+    G = len(geo)
+    enabled = np.zeros((G, G), dtype=np.uint8)
+    for a, la in enumerate(geo):
+        for b, lb in enumerate(geo):
+            if a != b and acm_entry[la, lb] in (-1, 0):
+                enabled[a, b] = 1
+    return fields, enabled
+
+
 class Model:
     def __init__(self, model_desc):
         self.desc = model_desc
@@ -217,6 +245,20 @@ class Group:
                                                 N, flags, B.ptr(dist, C.c_double), B.ptr(grad, C.c_double),
                                                 B.ptr(typ, C.c_uint8), B.ptr(cen, C.c_double) if want_centers else None))
         return dict(dist=dist, grad=grad, type=typ, centers=cen)
+
+    def set_link_fields(self, fields, enabled):
+        """fields: one engine.Field (or None) per group link WITH geometry, in group order; enabled: [G,G] uint8."""
+        n = C.c_int32(0)
+        B.check(B.load().b200df_group_link_count(self.h, C.byref(n)))
+        if fields is None:
+            B.check(B.load().b200df_group_set_link_fields(self.h, None, None))
+            self._link_fields = None
+            return
+        assert len(fields) == n.value
+        arr = (C.c_void_p * max(n.value, 1))(*[f.h if f is not None else None for f in fields])
+        en = np.ascontiguousarray(enabled, dtype=np.uint8).reshape(n.value, n.value)
+        B.check(B.load().b200df_group_set_link_fields(self.h, arr, B.ptr(en, C.c_uint8)))
+        self._link_fields = list(fields)  # keep them alive
 
     def distance(self, q, world):
         q, dt = _q_array(q, self.model.n_vars)

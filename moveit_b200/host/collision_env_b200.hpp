@@ -272,6 +272,10 @@ public:
   {
     return entries_ == o.entries_;
   }
+  std::size_t getSize() const
+  {
+    return entries_.size();
+  }
 
 private:
   std::map<std::string, std::map<std::string, AllowedCollision::Type>> entries_;
@@ -664,7 +668,8 @@ public:
     const std::size_t S = e->sphere_radii.size();
     PinnedBuffer<double> dist(n * S), grad(n * S * 3), cen(n * S * 3);
     PinnedBuffer<std::uint8_t> type(n * S);
-    int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
+    int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0) |
+                (e->link_fields.empty() ? 0 : B200DF_CHECK_LINK_FIELDS);
     checkStatus(b200df_gradients_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
                                        dist.data(), grad.data(), type.data(), cen.data()),
                 "b200df_gradients_batch");
@@ -742,10 +747,13 @@ private:
     std::vector<std::uint8_t> geom_intra;         // intra_group_collision_enabled_ between them, [g][g]
     b200df_group* group = nullptr;
     b200df_field* self_field = nullptr;
+    std::vector<b200df_field*> link_fields;  // GroupStateRepresentation::link_distance_fields_, per geometry link
     ~CacheEntry()
     {
       b200df_group_destroy(group);
       b200df_field_destroy(self_field);
+      for (b200df_field* f : link_fields)
+        b200df_field_destroy(f);
     }
   };
 
@@ -1006,6 +1014,8 @@ private:
     gd.collision_tolerance = collision_tolerance_;
     gd.max_propagation_distance = max_propogation_distance_;
     checkStatus(b200df_group_create(model_, &gd, &e->group), "b200df_group_create");
+    if (acm && acm->getSize() > 0)
+      generateLinkDistanceFields(*e);
     if (generate_distance_field)  // :910-973: the links outside the group, posed by this state, as one point set
     {
       std::set<int> in(e->link_indices.begin(), e->link_indices.end());
@@ -1035,6 +1045,44 @@ private:
       }
     }
     return e;
+  }
+
+  // the per-link PosedDistanceFields of getGroupStateRepresentation .cpp:1187-1210 and the ACM gate of
+  // getSelfProximityGradients :388-404 (a pair whose entry exists and is not NEVER is skipped)
+  void generateLinkDistanceFields(CacheEntry& e) const
+  {
+    const std::size_t G = e.geom_model_index.size();
+    if (G == 0 || G > 32)
+      return;
+    std::vector<std::uint8_t> enabled(G * G, 0);
+    for (std::size_t a = 0; a < G; ++a)
+    {
+      const int li = e.geom_model_index[a];
+      const double diameter = 2 * link_bsphere_[4 * li + 3];
+      b200df_field_desc fd{};
+      for (int k = 0; k < 3; ++k)
+      {
+        fd.size[k] = diameter;
+        fd.origin[k] = link_bsphere_[4 * li + k] - 0.5 * diameter;
+      }
+      fd.resolution = resolution_;
+      fd.max_distance = max_propogation_distance_;
+      fd.propagate_negative = use_signed_distance_field_ ? 1 : 0;
+      b200df_field* f = nullptr;
+      checkStatus(b200df_field_create(&fd, &f), "b200df_field_create");
+      e.link_fields.push_back(f);
+      const int64_t np = link_point_offset_[li + 1] - link_point_offset_[li];
+      if (np > 0)
+        checkStatus(b200df_field_add_points(f, &link_points_[3 * link_point_offset_[li]], np), "b200df_field_add_points");
+      for (std::size_t b = 0; b < G; ++b)
+      {
+        AllowedCollision::Type t;
+        if (a != b && !(e.acm.getEntry(e.link_names[a], e.link_names[b], t) && t != AllowedCollision::NEVER))
+          enabled[a * G + b] = 1;
+      }
+    }
+    checkStatus(b200df_group_set_link_fields(e.group, e.link_fields.data(), enabled.data()),
+                "b200df_group_set_link_fields");
   }
 
   void checkSelfCollisionHelper(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,

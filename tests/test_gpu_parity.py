@@ -453,6 +453,33 @@ def test_config5_gradients_within_tolerance(gpu, oracle):
     assert (got["type"] == 3).any() and (got["type"] == 2).any()
 
 
+def test_gradients_with_link_distance_fields(gpu, oracle):
+    """getSelfProximityGradients' per-link PosedDistanceField term (:395-418), including the reference's quirks: the
+    gradient is mapped with the full pose (rotation + translation, Q6) and a link's sphere loop stops at the first
+    sphere outside the other link's field (Q7)."""
+    from moveit_b200 import engine
+    from moveit_b200.binding import CHECK_LINK_FIELDS
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    o.env.build_link_fields()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    fields, enabled = engine.link_distance_fields(e.model_desc, e.group_links, desc.acm_entry_matrix(),
+                                                  scenarios.FIELD_A["resolution"], scenarios.FIELD_A["max_distance"])
+    e.group.set_link_fields(fields, enabled)
+    traj = scenarios.chomp_trajectories(desc, 30, 100).reshape(-1, desc.nvar)
+    got = e.group.gradients(traj, e.world, flags=CHECK_ROBOT | CHECK_INTRA | CHECK_LINK_FIELDS)
+    ref = o.env.gradients_batch(traj, flags=7)
+    assert np.array_equal(got["type"], ref["type"].astype(np.uint8))
+    fin = ref["dist"] < 1e300
+    assert np.array_equal(fin, got["dist"] < 1e300)
+    assert np.max(np.abs(got["dist"][fin] - ref["dist"][fin])) < 1e-5
+    assert np.max(np.abs(got["grad"] - ref["grad"])) < 1e-5
+    # the term does change results: some spheres now carry a SELF entry that the run without link fields lacks
+    plain = e.group.gradients(traj, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+    assert (got["type"] == 1).sum() > 0 and not np.array_equal(plain["type"], got["type"])
+
+
 def test_distance_batch_definition(gpu, oracle):
     """distanceRobot is a stub in the reference (F5); the engine defines min over spheres of dist - radius."""
     desc = rd.panda()

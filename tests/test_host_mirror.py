@@ -98,9 +98,9 @@ def test_panda_arm_group_through_the_cpp_env(gpu, oracle, tmp_path):
         n_with += bool(recs)
     assert n_with > 20
 
-    # gradients (self field + intra + environment; the per-link PosedDistanceField term is not part of the engine,
-    # and the oracle only adds it after build_link_fields())
+    # gradients: per-link PosedDistanceFields + self field + intra + environment, like getCollisionGradients
     g = np.fromfile(prefix + ".grad.f64").reshape(50, -1, 8)
+    o.env.build_link_fields()
     ref = o.env.gradients_batch(q[:50], flags=7)
     assert g.shape[1] == ref["dist"].shape[1]
     assert np.max(np.abs(g[:, :, 5:8] - ref["centers"])) < 1e-12
