@@ -25,10 +25,10 @@ using namespace b200df;
 
 namespace
 {
-constexpr int kMaxLinks = 32;
-constexpr int kMaxGLinks = 32;
+constexpr int kMaxLinks = 40;
+constexpr int kMaxGLinks = 40;
 constexpr int kMaxSpheres = 128;
-constexpr int kMaxPartners = 96;
+constexpr int kMaxPartners = 512;
 constexpr int kBatch = 4;
 constexpr double kU = 5.9604644775390625e-08;  // 2^-24, unit round-off of fp32
 

@@ -396,6 +396,20 @@ def test_mobile_arm_every_joint_type_fast_exact_oracle(gpu, oracle):
     assert np.max(np.abs(T - ref)) < 1e-12
 
 
+def test_config4_pr2_like_fast_equals_exact(gpu, oracle):
+    """The PR2-like tree (33 links, 124 derived spheres, ~500 enabled link pairs) also fits the FAST tables."""
+    desc = rd.pr2_like()
+    e = EngineSetup(desc, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=31))
+    q = desc.sample_states(200_000, 12, np.float32)
+    for flags in (CHECK_ROBOT, CHECK_ROBOT | CHECK_INTRA):
+        exact = e.group.check(q, e.world, flags=flags, precision=0)
+        assert np.array_equal(exact, e.group.check(q, e.world, flags=flags, precision=1))
+        raw = e.group.check(q, e.world, flags=flags, precision=3)
+        assert np.array_equal(raw[raw != 2], exact[raw != 2])
+        print("pr2_like flags=%d undecided %.4f colliding %.3f" % (flags, (raw == 2).mean(), exact.mean()))
+        assert (raw == 2).mean() < 0.1
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine

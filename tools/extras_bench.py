@@ -94,9 +94,11 @@ def run(with_oracle=True):
     pr2 = rd.pr2_like()
     e4 = EngineSetup(pr2, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=31))
     q4 = pr2.sample_states(200_000, 12, np.float32)
-    e4.group.check(q4[:1000], e4.world, flags=fl)
-    t = best_of(lambda: e4.group.check(q4, e4.world, flags=fl), 3)
+    e4.group.check(q4[:1000], e4.world, flags=fl, precision=B.PRECISION_FAST)
+    t = best_of(lambda: e4.group.check(q4, e4.world, flags=fl, precision=B.PRECISION_FAST), 3)
+    tx = best_of(lambda: e4.group.check(q4, e4.world, flags=fl, precision=B.PRECISION_EXACT), 3)
     out["config4_pr2_like"] = {"states": len(q4), "ms": 1e3 * t, "states_per_s": len(q4) / t,
+                               "exact_states_per_s": len(q4) / tx,
                                "links": pr2.n_links, "spheres": int(e4.group.n_spheres)}
     if oracle:
         o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
