@@ -366,18 +366,68 @@ __global__ void edt_z8_from_bits_kernel(const uint32_t* __restrict__ bits, uint4
 }
 
 // Lines: line L -> first pair (L / inner) * outer_stride + (L % inner), then `stride` pairs per step along the axis.
-// The 2R+1 steps of one ring revolution are cut into three chunks; the inputs of the next chunk are loaded while
-// the current one is consumed, so a thread always has (2R+1)/3 loads in flight.
+// One ring revolution (2R+1 steps) is cut into two chunks whose inputs live in two register buffers: while one is
+// consumed the other is being loaded, so a thread always has ~R loads in flight.  Per step the fixed cost is one
+// load, one vote, one store and a few pointer adds; the 2R+1 taps are skipped for a whole warp when no lane's input
+// is finite (most rows of the y pass).
+template <int R, int U0, int CNT>
+__device__ __forceinline__ void march_chunk(const unsigned (&buf)[R + 1], unsigned (&acc)[2 * R + 1], int t_first,
+                                            int n_axis, bool live, uint32_t*& out32, uint16_t*& out16, long stride,
+                                            unsigned clamp, bool final_pass, bool out_u8)
+{
+  constexpr int W = 2 * R + 1;
+#pragma unroll
+  for (int j = 0; j < CNT; ++j)
+  {
+    const int u = U0 + j;
+    const unsigned f = buf[j];
+    if (__any_sync(0xffffffffu, f != kInfPair))
+    {
+#pragma unroll
+      for (int d = -R; d <= R; ++d)
+        acc[(u + d + W) % W] = __viaddmin_u16x2(f, (unsigned)(d * d) * 0x00010001u, acc[(u + d + W) % W]);
+    }
+    // output t-R has now seen every input within +-R of it
+    const int yo = t_first + j - R;
+    const int slot = (u + R + 1) % W;  // == (u - R) mod W
+    if (live && (unsigned)yo < (unsigned)n_axis)
+    {
+      unsigned v = acc[slot];
+      if (final_pass)
+        v = __vminu2(v, clamp);
+      if (out_u8)
+        *out16 = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));
+      else
+        *out32 = v;
+    }
+    out32 += stride;
+    out16 += stride;
+    acc[slot] = kInfPair;
+  }
+}
+
+template <int R, int CNT>
+__device__ __forceinline__ void march_load(unsigned (&buf)[R + 1], const uint32_t* p, long stride, int t_first,
+                                           int n_axis)
+{
+#pragma unroll
+  for (int j = 0; j < CNT; ++j)
+  {
+    buf[j] = (t_first + j < n_axis) ? *p : kInfPair;
+    p += stride;
+  }
+}
+
 template <int R, typename OutT, bool FINAL>
 __global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __restrict__ in, void* __restrict__ out_v,
                                                        long n_lines, long inner, long outer_stride, long stride,
                                                        int n_axis, int max_d2)
 {
   constexpr int W = 2 * R + 1;
-  constexpr int C = W / 3;
-  static_assert(C * 3 == W, "ring length must be a multiple of 3");
+  constexpr int CA = R + 1, CB = R;  // steps 0..R and R+1..2R of a revolution
   const long line0 = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long line = line0 < n_lines ? line0 : n_lines - 1;  // surplus lanes shadow the last line (keeps votes full)
+  const bool live = line0 < n_lines;
+  const long line = live ? line0 : n_lines - 1;  // surplus lanes shadow the last line (keeps the votes full)
   const long base = (line / inner) * outer_stride + (line % inner);
   const uint32_t* src = in + base;
   unsigned acc[W];
@@ -385,58 +435,17 @@ __global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __rest
   for (int j = 0; j < W; ++j)
     acc[j] = kInfPair;
   const unsigned clamp = (unsigned)max_d2 * 0x00010001u;
-  unsigned nxt[C];
-#pragma unroll
-  for (int j = 0; j < C; ++j)
-    nxt[j] = j < n_axis ? src[(long)j * stride] : kInfPair;
+  // output pointers trail the input by R steps; they start before the array and are only dereferenced in range
+  uint32_t* out32 = static_cast<uint32_t*>(out_v) + base - (long)R * stride;
+  uint16_t* out16 = static_cast<uint16_t*>(out_v) + base - (long)R * stride;
+  unsigned bufA[R + 1], bufB[R + 1];
+  march_load<R, CA>(bufA, src, stride, 0, n_axis);
   for (int t0 = 0; t0 < n_axis + R; t0 += W)
   {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-    {
-      unsigned cur[C];
-#pragma unroll
-      for (int j = 0; j < C; ++j)
-        cur[j] = nxt[j];
-#pragma unroll
-      for (int j = 0; j < C; ++j)
-      {
-        const int tn = t0 + (c + 1) * C + j;
-        nxt[j] = tn < n_axis ? src[(long)tn * stride] : kInfPair;
-      }
-#pragma unroll
-      for (int j = 0; j < C; ++j)
-      {
-        const int u = c * C + j;
-        const int t = t0 + u;
-        const unsigned f = cur[j];
-        // rows without any obstacle within reach contribute nothing: skip them warp-wide
-        if (__any_sync(0xffffffffu, f != kInfPair))
-        {
-#pragma unroll
-          for (int d = -R; d <= R; ++d)
-            acc[(u + d + W) % W] = __viaddmin_u16x2(f, (unsigned)(d * d) * 0x00010001u, acc[(u + d + W) % W]);
-        }
-        // output t-R has now seen every input within +-R of it
-        const int yo = t - R;
-        const int slot = (u + R + 1) % W;  // == (u - R) mod W
-        if (yo >= 0 && yo < n_axis && line0 < n_lines)
-        {
-          unsigned v = acc[slot];
-          if (FINAL)
-          {
-            v = __vminu2(v, clamp);
-            if (sizeof(OutT) == 1)
-              static_cast<uint16_t*>(out_v)[base + (long)yo * stride] = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));
-            else
-              static_cast<uint32_t*>(out_v)[base + (long)yo * stride] = v;
-          }
-          else
-            static_cast<uint32_t*>(out_v)[base + (long)yo * stride] = v;
-        }
-        acc[slot] = kInfPair;
-      }
-    }
+    march_load<R, CB>(bufB, src + (long)(t0 + CA) * stride, stride, t0 + CA, n_axis);
+    march_chunk<R, 0, CA>(bufA, acc, t0, n_axis, live, out32, out16, stride, clamp, FINAL, sizeof(OutT) == 1);
+    march_load<R, CA>(bufA, src + (long)(t0 + W) * stride, stride, t0 + W, n_axis);
+    march_chunk<R, CA, CB>(bufB, acc, t0 + CA, n_axis, live, out32, out16, stride, clamp, FINAL, sizeof(OutT) == 1);
   }
 }
 
