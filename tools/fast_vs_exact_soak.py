@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Soak test of the FAST precision's exactness claim: many batches of fresh random states (different seeds, two
+scenes, two robots), FAST vs EXACT verdicts compared on the device, undecided fraction of the screening pass reported.
+Prints one JSON line; the committed result lives in profiles/."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main(batches=10, n=10_000_000):
+    import torch
+    from moveit_b200 import binding as B
+    from moveit_b200 import robot_description as rd
+    from moveit_b200 import scenarios
+    from moveit_b200.rng import uniform01
+    from common import EngineSetup
+    out = {"batches": [], "states": 0, "differences": 0}
+    stream = torch.cuda.current_stream().cuda_stream
+    cases = [("panda", rd.panda(), scenarios.FIELD_A, scenarios.random_scene()),
+             ("panda_fine_field", rd.panda(),
+              dict(size=(2.0, 2.0, 2.0), resolution=0.01, center=(0.0, 0.0, 0.5), max_distance=0.25),
+              scenarios.random_scene(seed=1234)),
+             ("mobile_arm", rd.mobile_arm(), scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=57, n_boxes=3, n_cylinders=1))]
+    for name, desc, field, objs in cases:
+        e = EngineSetup(desc, field, objs)
+        lo = np.array([l[0] for l in desc.limits], dtype=np.float32)
+        hi = np.array([l[1] for l in desc.limits], dtype=np.float32)
+        lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
+        flags = B.CHECK_ROBOT | B.CHECK_INTRA
+        for b in range(batches):
+            g = torch.Generator(device="cuda")
+            g.manual_seed(1000 * (b + 1) + len(name))
+            q = lo_t + (hi_t - lo_t) * torch.rand((n, desc.nvar), generator=g, device="cuda", dtype=torch.float32)
+            for i, m in enumerate(desc.mimic):
+                if m is not None:
+                    src = desc.var_index[desc.joint_names.index(m[0])]
+                    q[:, desc.var_index[i]] = m[1] * q[:, src] + m[2]
+            q = q.contiguous()
+            v = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(3)]
+            for k, prec in enumerate((B.PRECISION_EXACT, B.PRECISION_FAST, 3)):
+                e.group.check_device(q.data_ptr(), B.Q_F32, n, v[k].data_ptr(), e.world, None, flags, prec, stream)
+            torch.cuda.synchronize()
+            diff = int((v[0] != v[1]).sum().item())
+            und = float((v[2] == 2).sum().item()) / n
+            wrong_decided = int(((v[2] != 2) & (v[2] != v[0])).sum().item())
+            out["batches"].append({"case": name, "seed": 1000 * (b + 1) + len(name), "states": n, "fast_ne_exact": diff,
+                                   "screening_undecided": und, "screening_decided_wrong": wrong_decided,
+                                   "colliding": float(v[0].float().mean().item())})
+            out["states"] += n
+            out["differences"] += diff + wrong_decided
+    print(json.dumps(out))
+    return 0 if out["differences"] == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main(int(sys.argv[1]) if len(sys.argv) > 1 else 10, int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000))
