@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200df.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 CHECK_ROBOT, CHECK_SELF, CHECK_INTRA, CHECK_LINK_FIELDS = 1, 2, 4, 8
 Q_F32, Q_F64 = 0, 1
-PRECISION_EXACT, PRECISION_FAST = 0, 1
+PRECISION_EXACT, PRECISION_FAST, PRECISION_DEBUG_SWEEP, PRECISION_DEBUG_SCREEN = 0, 1, 2, 3
 TYPE_NONE, TYPE_SELF, TYPE_INTRA, TYPE_ENVIRONMENT = 0, 1, 2, 3
 
 c_dp = C.POINTER(C.c_double)
@@ -93,6 +93,7 @@ SYMBOLS = {
     "b200df_field_import_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "b200df_check_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
     "b200df_check_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP]),
+    "b200df_check_edges": (C.c_int, [_VP, _VP, _VP, c_dp, c_dp, C.c_int64, C.c_int32, c_u8p, C.c_int, C.c_int, c_i32p]),
     "b200df_gradients_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_dp, c_dp, c_u8p, c_dp]),
     "b200df_gradients_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "b200df_distance_batch": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int64, c_dp]),

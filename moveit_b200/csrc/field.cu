@@ -449,13 +449,6 @@ __global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __rest
   }
 }
 
-__global__ void fill_kernel_u8(uint8_t* p, long n, uint8_t v)
-{
-  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i < n)
-    p[i] = v;
-}
-
 template <typename T>
 __global__ void widen_kernel(const T* __restrict__ in, int32_t* __restrict__ out, long n)
 {

@@ -367,8 +367,8 @@ int dispatch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, 
   return launch_verdict<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream, redo);
 }
 
-constexpr int kPrecisionV1 = 2;       // undocumented: the round-1 kernel, kept as an independent cross-check
-constexpr int kPrecisionFastRaw = 3;  // undocumented: FAST screening pass only, verdicts 0 / 1 / 2 = undecided (tests)
+constexpr int kPrecisionV1 = B200DF_PRECISION_DEBUG_SWEEP;        // the round-1 kernel, an independent cross-check
+constexpr int kPrecisionFastRaw = B200DF_PRECISION_DEBUG_SCREEN;  // FAST screening pass only: 0 / 1 / 2 = undecided
 
 // keeps the stream-ordered allocator from returning memory to the OS between calls (once per device)
 void keep_async_pool(int device)

@@ -246,6 +246,23 @@ class Group:
                                                 B.ptr(typ, C.c_uint8), B.ptr(cen, C.c_double) if want_centers else None))
         return dict(dist=dist, grad=grad, type=typ, centers=cen)
 
+    def check_edges(self, qa, qb, segments, world=None, self_field=None, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT,
+                    var_is_angular=None):
+        """M motions qa[i] -> qb[i] cut into `segments` pieces; returns first_invalid[M] (0 = valid)."""
+        qa = np.ascontiguousarray(qa, dtype=np.float64).reshape(-1, self.model.n_vars)
+        qb = np.ascontiguousarray(qb, dtype=np.float64).reshape(-1, self.model.n_vars)
+        assert qa.shape == qb.shape
+        out = np.zeros(len(qa), dtype=np.int32)
+        ang = None
+        if var_is_angular is not None:
+            ang = np.ascontiguousarray(var_is_angular, dtype=np.uint8)
+            assert len(ang) == self.model.n_vars
+        B.check(B.load().b200df_check_edges(self.h, world.h if world else None, self_field.h if self_field else None,
+                                            B.ptr(qa, C.c_double), B.ptr(qb, C.c_double), len(qa), int(segments),
+                                            B.ptr(ang, C.c_uint8) if ang is not None else None, flags, precision,
+                                            B.ptr(out, C.c_int32)))
+        return out
+
     def set_link_fields(self, fields, enabled):
         """fields: one engine.Field (or None) per group link WITH geometry, in group order; enabled: [G,G] uint8."""
         n = C.c_int32(0)

@@ -655,6 +655,49 @@ public:
                 "b200df_check_batch");
   }
 
+  // PlanningScene::isPathValid's waypoint loop (planning_scene.cpp:2257-2312), collision part: every waypoint in one
+  // launch; invalid_index receives the colliding waypoints like the reference (nullptr: only the verdict).
+  bool isPathValid(const CollisionRequest& req, const double* waypoints, std::int64_t n,
+                   const AllowedCollisionMatrix* acm, const core::RobotState& reference_state,
+                   std::vector<std::size_t>* invalid_index = nullptr) const
+  {
+    std::vector<std::uint8_t> v((std::size_t)n);
+    checkCollisionBatch(req, waypoints, n, acm, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT,
+                        reference_state, v.data());
+    if (invalid_index)
+      invalid_index->clear();
+    bool result = true;
+    for (std::int64_t i = 0; i < n; ++i)
+      if (v[(std::size_t)i])
+      {
+        result = false;
+        if (!invalid_index)
+          break;
+        invalid_index->push_back((std::size_t)i);
+      }
+    return result;
+  }
+
+  // m motions from[i] -> to[i], each discretised into `segments` pieces and checked on the device: the batched form
+  // of ompl::base::DiscreteMotionValidator::checkMotion over StateValidityChecker::isValid
+  // (ompl_interface/src/detail/state_validity_checker.cpp:76-121).  first_invalid[i]: 0 = valid, else the first
+  // colliding sample j (state at t = j/segments); OMPL's lastValid fraction is (j-1)/segments.
+  void checkMotionBatch(const CollisionRequest& req, const double* from, const double* to, std::int64_t m,
+                        int segments, const AllowedCollisionMatrix* acm, const core::RobotState& reference_state,
+                        std::int32_t* first_invalid, int precision = B200DF_PRECISION_EXACT) const
+  {
+    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, true);
+    int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
+    // continuous revolute joints are not modelled by the stand-in RobotModel; the planar joint's theta is angular
+    std::vector<std::uint8_t> angular((std::size_t)robot_model_->getVariableCount(), 0);
+    for (const core::LinkModel& l : robot_model_->getLinkModels())
+      if (l.joint_type == core::PLANAR)
+        angular[(std::size_t)l.first_variable + 2] = 1;
+    checkStatus(b200df_check_edges(e->group, world_field_, e->self_field, from, to, m, segments, angular.data(), flags,
+                                   precision, first_invalid),
+                "b200df_check_edges");
+  }
+
   void getCollisionGradientsBatch(const CollisionRequest& req, const double* states, std::int64_t n,
                                   const AllowedCollisionMatrix* acm, std::vector<GroupStateRepresentationPtr>& out,
                                   const core::RobotState* reference_state = nullptr) const

@@ -228,6 +228,27 @@ int main(int argc, char** argv)
       writeFile(prefix + ".grad.f64", out);
     }
 
+    // batched motion validation + isPathValid: consecutive states of the file are taken as motion end points
+    if (n >= 2)
+    {
+      const std::int64_t m = n / 2;
+      std::vector<double> from((std::size_t)m * nvar), to((std::size_t)m * nvar);
+      for (std::int64_t i = 0; i < m; ++i)
+      {
+        std::copy(&q[(std::size_t)(2 * i) * nvar], &q[(std::size_t)(2 * i) * nvar] + nvar, &from[(std::size_t)i * nvar]);
+        std::copy(&q[(std::size_t)(2 * i + 1) * nvar], &q[(std::size_t)(2 * i + 1) * nvar] + nvar,
+                  &to[(std::size_t)i * nvar]);
+      }
+      std::vector<std::int32_t> first((std::size_t)m);
+      env->checkMotionBatch(req, from.data(), to.data(), m, 8, acm_ptr, ref_state, first.data());
+      writeFile(prefix + ".motion.i32", first);
+      std::vector<std::size_t> invalid;
+      const bool ok = env->isPathValid(req, q.data(), std::min<std::int64_t>(n, 500), acm_ptr, ref_state, &invalid);
+      std::vector<std::int32_t> inv(invalid.begin(), invalid.end());
+      inv.push_back(ok ? 1 : 0);
+      writeFile(prefix + ".path.i32", inv);
+    }
+
     // world mutation through the observer: move the first object by +0.1 m in x, destroy the second
     if (mutate && object_ids.size() >= 2)
     {

@@ -410,6 +410,52 @@ def test_config4_pr2_like_fast_equals_exact(gpu, oracle):
         assert (raw == 2).mean() < 0.1
 
 
+def _interpolate_reference(qa, qb, K, angular):
+    """JointModel::interpolate in numpy doubles (revolute_joint_model.cpp:125-148, planar_joint_model.cpp:180-205)."""
+    M, nv = qa.shape
+    out = np.empty((M, K, nv))
+    for j in range(1, K + 1):
+        t = float(j) / float(K)
+        diff = qb - qa
+        lin = qa + diff * t
+        d2 = np.where(diff > 0.0, 2.0 * np.pi - diff, -2.0 * np.pi - diff)
+        r = qa - d2 * t
+        r = np.where(r > np.pi, r - 2.0 * np.pi, np.where(r < -np.pi, r + 2.0 * np.pi, r))
+        use_arc = angular[None, :].astype(bool) & (np.abs(diff) > np.pi)
+        out[:, j - 1, :] = np.where(use_arc, r, lin)
+    return out
+
+
+@pytest.mark.parametrize("robot", ["panda", "mobile_arm"])
+def test_batched_edge_check_matches_per_state_oracle(gpu, oracle, robot):
+    """b200df_check_edges: motions interpolated on the device with the reference's JointModel::interpolate arithmetic,
+    first colliding sample per motion == what checking the same interpolated states one by one with the oracle gives."""
+    desc = rd.panda() if robot == "panda" else rd.mobile_arm()
+    fd = scenarios.FIELD_A if robot == "panda" else scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene() if robot == "panda" else scenarios.random_scene(seed=57, n_boxes=3, n_cylinders=1)
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, fd, objs)
+    M, K = 3000, 12
+    qa = desc.sample_states(M, 71)
+    qb = desc.sample_states(M, 72)
+    angular = np.zeros(desc.nvar, dtype=np.uint8)
+    if robot == "mobile_arm":
+        angular[2] = 1  # planar joint's theta takes the shortest arc
+    flags = CHECK_ROBOT | CHECK_INTRA
+    got = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=0, var_is_angular=angular)
+    states = _interpolate_reference(qa, qb, K, angular)
+    ref = o.env.check_batch(states.reshape(-1, desc.nvar), mode=3, n_threads=8).reshape(M, K)
+    want = np.where(ref.any(axis=1), ref.argmax(axis=1) + 1, 0)
+    assert np.array_equal(got, want)
+    assert 0 < (got == 0).sum() < M
+    # FAST checks the interpolated states rounded to fp32
+    fast = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=1, var_is_angular=angular)
+    v32 = e.group.check(states.reshape(-1, desc.nvar).astype(np.float32), e.world, flags=flags, precision=0).reshape(M, K)
+    assert np.array_equal(fast, np.where(v32.any(axis=1), v32.argmax(axis=1) + 1, 0))
+    if robot == "mobile_arm":
+        assert (np.abs(qb[:, 2] - qa[:, 2]) > np.pi).any()  # the shortest-arc branch was exercised
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine

@@ -110,6 +110,16 @@ def test_panda_arm_group_through_the_cpp_env(gpu, oracle, tmp_path):
     assert np.max(np.abs(g[:, :, 0][fin] - ref["dist"][fin])) < 1e-5
     assert np.max(np.abs(g[:, :, 1:4] - ref["grad"])) < 1e-5
 
+    # batched motion validation (8 segments between consecutive states) and isPathValid's invalid_index
+    first = np.fromfile(prefix + ".motion.i32", dtype=np.int32)
+    qa, qb = q[0::2], q[1::2]
+    K = 8
+    inter = np.stack([qa + (qb - qa) * (float(j) / float(K)) for j in range(1, K + 1)], axis=1)
+    ref = o.env.check_batch(inter.reshape(-1, desc.nvar), mode=4, n_threads=8).reshape(len(qa), K)
+    assert np.array_equal(first, np.where(ref.any(axis=1), ref.argmax(axis=1) + 1, 0))
+    path = np.fromfile(prefix + ".path.i32", dtype=np.int32)
+    assert np.array_equal(path[:-1], np.nonzero(both[:500])[0]) and path[-1] == int(not both[:500].any())
+
     # world mutation: object 0 moved by +0.1 m in x, object 1 destroyed (removePointsFromField + addPointsToField)
     pts = [oracle_world_points(oracle, [ob], fa["resolution"]) for ob in objs]
     moved = (objs[0][0], objs[0][1], np.array(objs[0][2]) + np.array([[0, 0, 0, 0.1]] * 3) * np.array([[1], [0], [0]]))

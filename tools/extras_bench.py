@@ -90,6 +90,15 @@ def run(with_oracle=True):
     except ImportError:
         pass
 
+    # planner edge checks: 1 M random motions x 10 segments, only the end states cross PCIe
+    M, K = 1_000_000, 10
+    qa = desc.sample_states(M, 901)
+    qb = desc.sample_states(M, 902)
+    e.group.check_edges(qa[:1000], qb[:1000], K, e.world, flags=fl, precision=B.PRECISION_FAST)
+    t = best_of(lambda: e.group.check_edges(qa, qb, K, e.world, flags=fl, precision=B.PRECISION_FAST), 3)
+    out["edge_checks"] = {"motions": M, "segments": K, "ms": 1e3 * t, "motions_per_s": M / t,
+                          "states_per_s": M * K / t, "h2d_bytes": 2 * M * desc.nvar * 8, "d2h_bytes": 4 * M}
+
     # config 4: PR2-like dual-arm tree, full ACM
     pr2 = rd.pr2_like()
     e4 = EngineSetup(pr2, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=31))
