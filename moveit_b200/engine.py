@@ -41,7 +41,7 @@ def body_decomposition(shapes, resolution, padding):
 
 
 def assemble_model(desc: RobotDescription, decompose, resolution=DEFAULT_RESOLUTION, link_padding=0.0,
-                   use_sphere_overrides=True):
+                   use_sphere_overrides=True, padding_by_link=None):
     """CollisionEnvDistanceField::addLinkBodyDecompositions (collision_env_distance_field.cpp:1065-1093): one
     BodyDecomposition per link with geometry, spheres replaced by the override table when one is given.
     `decompose(shapes, resolution, padding)` is the BodyDecomposition provider (engine or oracle)."""
@@ -50,7 +50,8 @@ def assemble_model(desc: RobotDescription, decompose, resolution=DEFAULT_RESOLUT
     spheres, points, bsphere, has_geom = [], [], [], []
     for i in range(L):
         if desc.shapes[i]:
-            sph, pts, bs = decompose(desc.shapes[i], resolution, link_padding)
+            pad = (padding_by_link or {}).get(desc.link_names[i], link_padding)
+            sph, pts, bs = decompose(desc.shapes[i], resolution, pad)
             name = desc.link_names[i]
             if use_sphere_overrides and name in desc.spheres_override:
                 sph = np.array(desc.spheres_override[name], dtype=np.float64).reshape(-1, 4)

@@ -200,9 +200,49 @@ private:
 };
 using RobotModelConstPtr = std::shared_ptr<const RobotModel>;
 
-class RobotState  // the slice of moveit::core::RobotState the collision env reads: the variable vector
+struct AttachedBody  // moveit::core::AttachedBody: shapes rigidly attached to a link
+{
+  std::string name, link_name;
+  std::vector<shapes::Shape> shapes;
+  std::vector<Isometry3d> attach_trans;  // shape poses in the link frame
+  std::set<std::string> touch_links;
+};
+
+class RobotState  // the slice of moveit::core::RobotState the collision env reads: variables + attached bodies
 {
 public:
+  void attachBody(const AttachedBody& body)
+  {
+    attached_[body.name] = body;
+  }
+  bool clearAttachedBody(const std::string& name)
+  {
+    return attached_.erase(name) != 0;
+  }
+  void getAttachedBodies(std::vector<const AttachedBody*>& out) const  // name order, like RobotState's std::map
+  {
+    out.clear();
+    for (const auto& kv : attached_)
+      out.push_back(&kv.second);
+  }
+  std::string attachedSignature() const  // identifies the attached geometry (compareCacheEntryToState :1296-1338)
+  {
+    std::string s;
+    for (const auto& kv : attached_)
+    {
+      const AttachedBody& b = kv.second;
+      s += b.name + "@" + b.link_name + ":";
+      for (std::size_t i = 0; i < b.shapes.size(); ++i)
+      {
+        s.append(reinterpret_cast<const char*>(&b.shapes[i]), sizeof(shapes::Shape));
+        s.append(reinterpret_cast<const char*>(b.attach_trans[i].m), sizeof(b.attach_trans[i].m));
+      }
+      for (const std::string& t : b.touch_links)
+        s += "|" + t;
+      s += ";";
+    }
+    return s;
+  }
   explicit RobotState(const RobotModelConstPtr& model) : model_(model), position_(model->getVariableCount(), 0.0)
   {
   }
@@ -230,6 +270,7 @@ public:
 private:
   RobotModelConstPtr model_;
   std::vector<double> position_;
+  std::map<std::string, AttachedBody> attached_;
 };
 }  // namespace core
 
@@ -577,8 +618,9 @@ public:
   {
     world_->removeObserver(observer_handle_);
     dfce_.reset();
+    model_cache_.clear();
+    base_model_.reset();
     b200df_field_destroy(world_field_);
-    b200df_model_destroy(model_);
   }
 
   // ---- single-state API of CollisionEnv (each call is a batch of one) -----------------------------------
@@ -774,8 +816,30 @@ public:
   }
 
 private:
+  // The robot as the kernels see it: the RobotModel's links followed by one fixed pseudo-link per attached shape
+  // (an attached shape is posed by link_transform * attach_trans exactly like a fixed joint: robot_state.cpp
+  // updateAttachedBodies / getAttachedBodySphereDecomposition collision_common_distance_field.cpp:105-117).
+  struct ModelEntry
+  {
+    std::vector<core::LinkModel> links;
+    std::vector<int> attached_body;  // per link: -1 = robot link, else index into attached_*
+    std::vector<std::string> attached_names, attached_links;
+    std::vector<std::set<std::string>> attached_touch;
+    std::vector<double> points, spheres_flat, bsphere;
+    std::vector<int64_t> point_offset;
+    std::vector<int32_t> sphere_offset;
+    b200df_model* model = nullptr;
+    ~ModelEntry()
+    {
+      b200df_model_destroy(model);
+    }
+  };
+
   struct CacheEntry  // DistanceFieldCacheEntry, collision_common_distance_field.h:56-118
   {
+    std::shared_ptr<const ModelEntry> model;
+    std::string attached_signature;
+    std::vector<BodyTypes::Type> geom_body_type;  // ROBOT_LINK / ROBOT_ATTACHED per link with geometry
     std::string group_name;
     bool has_acm = false;
     AllowedCollisionMatrix acm;
@@ -809,7 +873,55 @@ private:
     collision_tolerance_ = collision_tolerance;
     max_propogation_distance_ = max_propogation_distance;
     link_spheres_ = link_body_decompositions;
-    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    base_model_ = buildModelEntry({});
+  }
+
+  std::shared_ptr<const ModelEntry> modelFor(const core::RobotState& state) const
+  {
+    std::vector<const core::AttachedBody*> bodies;
+    state.getAttachedBodies(bodies);
+    if (bodies.empty())
+      return base_model_;
+    const std::string sig = state.attachedSignature();
+    std::lock_guard<std::mutex> lk(model_cache_lock_);
+    auto it = model_cache_.find(sig);
+    if (it != model_cache_.end())
+      return it->second;
+    std::shared_ptr<const ModelEntry> me = buildModelEntry(bodies);
+    model_cache_[sig] = me;
+    return me;
+  }
+
+  std::shared_ptr<const ModelEntry> buildModelEntry(const std::vector<const core::AttachedBody*>& bodies) const
+  {
+    auto me = std::make_shared<ModelEntry>();
+    me->links = robot_model_->getLinkModels();
+    me->attached_body.assign(me->links.size(), -1);
+    for (const core::AttachedBody* b : bodies)
+    {
+      const int parent = robot_model_->getLinkIndex(b->link_name);
+      if (parent < 0)
+        throw B200Error("attached body " + b->name + " refers to unknown link " + b->link_name);
+      me->attached_names.push_back(b->name);
+      me->attached_links.push_back(b->link_name);
+      me->attached_touch.push_back(b->touch_links);
+      for (std::size_t s = 0; s < b->shapes.size(); ++s)
+      {
+        core::LinkModel l;
+        l.name = b->name;
+        l.joint_name = b->name + "/attach" + std::to_string(s);
+        l.parent = parent;
+        l.joint_type = core::FIXED;
+        l.joint_origin = b->attach_trans[s];
+        l.shapes.push_back(b->shapes[s]);
+        l.shape_origins.push_back(Isometry3d::Identity());
+        me->links.push_back(l);
+        me->attached_body.push_back((int)me->attached_names.size() - 1);
+      }
+    }
+    const std::vector<core::LinkModel>& links = me->links;
+    const LinkSpheres& link_body_decompositions = link_spheres_;
+
     const int L = (int)links.size();
     std::vector<int32_t> parent(L), jtype(L), ident(L), var(L), mimic_var(L, -1), has_geom(L), sph_off(L + 1, 0);
     std::vector<int64_t> pt_off(L + 1, 0);
@@ -844,20 +956,21 @@ private:
           dims.insert(dims.end(), l.shapes[s].dims, l.shapes[s].dims + 3);
           poses.insert(poses.end(), l.shape_origins[s].m, l.shape_origins[s].m + 12);
         }
+        // attached shapes: getBodyDecompositionCacheEntry -> BodyDecomposition(shape, resolution), padding 0.01
+        const double padding = me->attached_body[i] >= 0 ? 0.01 : link_padding_;
         int64_t ns = 0, np = 0;
         checkStatus(b200df_body_decomposition((int32_t)types.size(), types.data(), dims.data(), poses.data(),
-                                              resolution_, link_padding_, nullptr, 0, &ns, nullptr, 0, &np,
-                                              &bsphere[4 * i]),
+                                              resolution_, padding, nullptr, 0, &ns, nullptr, 0, &np, &bsphere[4 * i]),
                     "b200df_body_decomposition");
         std::vector<double> sph(std::max<int64_t>(ns, 1) * 4), pts(std::max<int64_t>(np, 1) * 3);
         checkStatus(b200df_body_decomposition((int32_t)types.size(), types.data(), dims.data(), poses.data(),
-                                              resolution_, link_padding_, sph.data(), ns, &ns, pts.data(), np, &np,
+                                              resolution_, padding, sph.data(), ns, &ns, pts.data(), np, &np,
                                               &bsphere[4 * i]),
                     "b200df_body_decomposition");
         sph.resize(ns * 4);
         pts.resize(np * 3);
         auto over = link_body_decompositions.find(l.name);  // replaceCollisionSpheres .cpp:1085-1088
-        if (over != link_body_decompositions.end())
+        if (me->attached_body[i] < 0 && over != link_body_decompositions.end())
         {
           sph.clear();
           for (const CollisionSphere& cs : over->second)
@@ -869,11 +982,11 @@ private:
       sph_off[i + 1] = (int32_t)(spheres.size() / 4);
       pt_off[i + 1] = (int64_t)(points.size() / 3);
     }
-    link_points_ = points;
-    link_point_offset_ = pt_off;
-    link_sphere_offset_ = sph_off;
-    link_spheres_flat_ = spheres;
-    link_bsphere_ = bsphere;
+    me->points = points;
+    me->point_offset = pt_off;
+    me->sphere_offset = sph_off;
+    me->spheres_flat = spheres;
+    me->bsphere = bsphere;
     b200df_model_desc d{};
     d.n_links = L;
     d.n_vars = robot_model_->getVariableCount();
@@ -892,7 +1005,8 @@ private:
     d.bsphere = bsphere.data();
     d.point_offset = pt_off.data();
     d.points = points.data();
-    checkStatus(b200df_model_create(&d, &model_), "b200df_model_create");
+    checkStatus(b200df_model_create(&d, &me->model), "b200df_model_create");
+    return me;
   }
 
   b200df_field* newField() const  // PropagationDistanceField(size, resolution, origin - size/2, ...) .cpp:946-948, Q14
@@ -949,7 +1063,8 @@ private:
   {
     std::lock_guard<std::mutex> lk(update_cache_lock_);
     std::shared_ptr<const CacheEntry> cur = dfce_;
-    if (cur && cur->group_name == group_name && compareCacheEntryToState(*cur, state) &&
+    if (cur && cur->group_name == group_name && cur->attached_signature == state.attachedSignature() &&
+        compareCacheEntryToState(*cur, state) &&
         compareCacheEntryToAllowedCollisionMatrix(*cur, acm) && (!generate_distance_field || cur->self_field ||
                                                                   !hasNonGroupGeometry(*cur)))
       return cur;
@@ -972,7 +1087,7 @@ private:
   }
   bool hasNonGroupGeometry(const CacheEntry& e) const
   {
-    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    const std::vector<core::LinkModel>& links = e.model->links;
     std::set<int> in(e.link_indices.begin(), e.link_indices.end());
     for (int i = 0; i < (int)links.size(); ++i)
       if (!links[i].shapes.empty() && !in.count(i))
@@ -987,12 +1102,23 @@ private:
   {
     auto e = std::make_shared<CacheEntry>();
     e->group_name = group_name;
-    const std::vector<core::LinkModel>& links = robot_model_->getLinkModels();
+    e->model = modelFor(state);
+    e->attached_signature = state.attachedSignature();
+    const ModelEntry& me = *e->model;
+    const std::vector<core::LinkModel>& links = me.links;
+    const int n_robot_links = (int)robot_model_->getLinkModels().size();
     if (group_name.empty())  // :736-739
-      for (int i = 0; i < (int)links.size(); ++i)
+      for (int i = 0; i < n_robot_links; ++i)
         e->link_indices.push_back(i);
     else
       e->link_indices = robot_model_->getUpdatedLinkModelIndices(group_name);
+    {
+      // attached bodies of the group's links follow the links (dfce->attached_body_names_, :806-812)
+      std::set<int> in_group(e->link_indices.begin(), e->link_indices.end());
+      for (int i = n_robot_links; i < (int)links.size(); ++i)
+        if (in_group.count(links[i].parent))
+          e->link_indices.push_back(i);
+    }
     if (acm)
     {
       e->has_acm = true;
@@ -1003,7 +1129,8 @@ private:
     e->sphere_begin.push_back(0);
     for (int i = 0; i < n; ++i)
     {
-      const core::LinkModel& li = links[e->link_indices[i]];
+      const int mi = e->link_indices[i];
+      const core::LinkModel& li = links[mi];
       if (li.shapes.empty())  // :846-852
       {
         self_enabled[i] = 0;
@@ -1011,18 +1138,46 @@ private:
         continue;
       }
       e->link_names.push_back(li.name);
-      e->joint_names.push_back(li.joint_name);
-      for (int s = link_sphere_offset_[e->link_indices[i]]; s < link_sphere_offset_[e->link_indices[i] + 1]; ++s)
-        e->sphere_radii.push_back(link_spheres_flat_[4 * s + 3]);
+      e->joint_names.push_back(me.attached_body[mi] >= 0 ? links[li.parent].joint_name : li.joint_name);
+      e->geom_body_type.push_back(me.attached_body[mi] >= 0 ? BodyTypes::ROBOT_ATTACHED : BodyTypes::ROBOT_LINK);
+      for (int s = me.sphere_offset[mi]; s < me.sphere_offset[mi + 1]; ++s)
+        e->sphere_radii.push_back(me.spheres_flat[4 * s + 3]);
       e->sphere_begin.push_back((int)e->sphere_radii.size());
-      if (!acm)
-        continue;  // :840-844 all enabled
-      AllowedCollision::Type t;
-      if (acm->getEntry(li.name, li.name, t) && t == AllowedCollision::ALWAYS)  // :785-790
-        self_enabled[i] = 0;
-      for (int j = i + 1; j < n; ++j)  // :793-805; only explicit ALWAYS entries disable a pair (Q12)
-        if (acm->getEntry(li.name, links[e->link_indices[j]].name, t) && t == AllowedCollision::ALWAYS)
+      for (int j = i + 1; j < n; ++j)  // the shapes of one attached body are one body: never tested against each other
+        if (me.attached_body[mi] >= 0 && me.attached_body[e->link_indices[j]] == me.attached_body[mi])
           intra[i * n + j] = 0;
+      if (!acm)
+        continue;  // :840-844 all enabled (touch links are only looked at inside the acm branch)
+      AllowedCollision::Type t;
+      if (acm->getEntry(li.name, li.name, t) && t == AllowedCollision::ALWAYS)  // :785-790, :857-861
+        self_enabled[i] = 0;
+      for (int j = i + 1; j < n; ++j)
+      {
+        const int mj = e->link_indices[j];
+        const bool i_att = me.attached_body[mi] >= 0, j_att = me.attached_body[mj] >= 0;
+        if (!i_att && !j_att)  // link / link :793-805; only explicit ALWAYS entries disable a pair (Q12)
+        {
+          if (acm->getEntry(li.name, links[mj].name, t) && t == AllowedCollision::ALWAYS)
+            intra[i * n + j] = 0;
+        }
+        else if (!i_att && j_att)
+        {
+          // link / attached body :806-834: the reference only visits the bodies attached to THIS link; the ACM entry
+          // and the touch links of a body are ignored for every other link
+          if (links[mj].parent == mi)
+          {
+            const int b = me.attached_body[mj];
+            if ((acm->getEntry(li.name, links[mj].name, t) && t == AllowedCollision::ALWAYS) ||
+                me.attached_touch[b].count(li.name))
+              intra[i * n + j] = 0;
+          }
+        }
+        else if (i_att && j_att)  // attached / attached :862-868
+        {
+          if (acm->getEntry(li.name, links[mj].name, t) && t == AllowedCollision::ALWAYS)
+            intra[i * n + j] = 0;
+        }
+      }
     }
     {
       std::vector<int> pos;  // position in the group list of each link with geometry
@@ -1056,14 +1211,14 @@ private:
     gd.resolution = resolution_;
     gd.collision_tolerance = collision_tolerance_;
     gd.max_propagation_distance = max_propogation_distance_;
-    checkStatus(b200df_group_create(model_, &gd, &e->group), "b200df_group_create");
+    checkStatus(b200df_group_create(me.model, &gd, &e->group), "b200df_group_create");
     if (acm && acm->getSize() > 0)
       generateLinkDistanceFields(*e);
     if (generate_distance_field)  // :910-973: the links outside the group, posed by this state, as one point set
     {
       std::set<int> in(e->link_indices.begin(), e->link_indices.end());
       std::vector<double> T(links.size() * 12);
-      checkStatus(b200df_model_fk(model_, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
+      checkStatus(b200df_model_fk(me.model, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
       std::vector<double> all_points;
       bool any = false;
       for (int li = 0; li < (int)links.size(); ++li)
@@ -1073,10 +1228,10 @@ private:
         any = true;
         Isometry3d pose;
         std::copy(&T[12 * li], &T[12 * li] + 12, pose.m);
-        for (int64_t p = link_point_offset_[li]; p < link_point_offset_[li + 1]; ++p)
+        for (int64_t p = me.point_offset[li]; p < me.point_offset[li + 1]; ++p)
         {
           // PosedBodyPointDecomposition::updatePose, collision_distance_field_types.cpp:368-379
-          const Vector3d w = pose * Vector3d{ link_points_[3 * p], link_points_[3 * p + 1], link_points_[3 * p + 2] };
+          const Vector3d w = pose * Vector3d{ me.points[3 * p], me.points[3 * p + 1], me.points[3 * p + 2] };
           all_points.insert(all_points.end(), { w.x, w.y, w.z });
         }
       }
@@ -1097,16 +1252,17 @@ private:
     const std::size_t G = e.geom_model_index.size();
     if (G == 0 || G > 32)
       return;
+    const ModelEntry& me = *e.model;
     std::vector<std::uint8_t> enabled(G * G, 0);
     for (std::size_t a = 0; a < G; ++a)
     {
       const int li = e.geom_model_index[a];
-      const double diameter = 2 * link_bsphere_[4 * li + 3];
+      const double diameter = 2 * me.bsphere[4 * li + 3];
       b200df_field_desc fd{};
       for (int k = 0; k < 3; ++k)
       {
         fd.size[k] = diameter;
-        fd.origin[k] = link_bsphere_[4 * li + k] - 0.5 * diameter;
+        fd.origin[k] = me.bsphere[4 * li + k] - 0.5 * diameter;
       }
       fd.resolution = resolution_;
       fd.max_distance = max_propogation_distance_;
@@ -1114,9 +1270,9 @@ private:
       b200df_field* f = nullptr;
       checkStatus(b200df_field_create(&fd, &f), "b200df_field_create");
       e.link_fields.push_back(f);
-      const int64_t np = link_point_offset_[li + 1] - link_point_offset_[li];
+      const int64_t np = me.point_offset[li + 1] - me.point_offset[li];
       if (np > 0)
-        checkStatus(b200df_field_add_points(f, &link_points_[3 * link_point_offset_[li]], np), "b200df_field_add_points");
+        checkStatus(b200df_field_add_points(f, &me.points[3 * me.point_offset[li]], np), "b200df_field_add_points");
       for (std::size_t b = 0; b < G; ++b)
       {
         AllowedCollision::Type t;
@@ -1187,7 +1343,7 @@ private:
           Contact con;
           con.pos = Vector3d{ cen[3 * s], cen[3 * s + 1], cen[3 * s + 2] };
           con.body_name_1 = e.link_names[l];
-          con.body_type_1 = BodyTypes::ROBOT_LINK;
+          con.body_type_1 = e.geom_body_type[l];
           con.body_name_2 = other;
           con.body_type_2 = other_type;
           res.contacts[std::make_pair(con.body_name_1, con.body_name_2)].push_back(con);
@@ -1223,15 +1379,16 @@ private:
                      const CacheEntry& e, const std::vector<double>& cen) const
   {
     const std::size_t n = e.link_names.size();
-    std::vector<double> T(robot_model_->getLinkModels().size() * 12);
-    checkStatus(b200df_model_fk(model_, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
+    const ModelEntry& me = *e.model;
+    std::vector<double> T(me.links.size() * 12);
+    checkStatus(b200df_model_fk(me.model, state.getVariablePositions(), B200DF_Q_F64, 1, T.data()), "b200df_model_fk");
     std::vector<Vector3d> bcen(n);
     for (std::size_t i = 0; i < n; ++i)
     {
       const int li = e.geom_model_index[i];
       Isometry3d pose;
       std::copy(&T[12 * li], &T[12 * li] + 12, pose.m);
-      bcen[i] = pose * Vector3d{ link_bsphere_[4 * li], link_bsphere_[4 * li + 1], link_bsphere_[4 * li + 2] };
+      bcen[i] = pose * Vector3d{ me.bsphere[4 * li], me.bsphere[4 * li + 1], me.bsphere[4 * li + 2] };
     }
     for (std::size_t i = 0; i < n; ++i)
       for (std::size_t j = i + 1; j < n; ++j)
@@ -1240,7 +1397,7 @@ private:
           continue;
         const double bx = bcen[i].x - bcen[j].x, by = bcen[i].y - bcen[j].y, bz = bcen[i].z - bcen[j].z;
         const double p_dist = (bx * bx + by * by) + bz * bz;  // squaredNorm vs the un-squared radius sum (Q2)
-        if (!(p_dist < link_bsphere_[4 * e.geom_model_index[i] + 3] + link_bsphere_[4 * e.geom_model_index[j] + 3]))
+        if (!(p_dist < me.bsphere[4 * e.geom_model_index[i] + 3] + me.bsphere[4 * e.geom_model_index[j] + 3]))
           continue;
         auto key = std::make_pair(e.link_names[i], e.link_names[j]);
         std::size_t num_pair = res.contacts.count(key) ? res.contacts[key].size() : 0;
@@ -1256,7 +1413,8 @@ private:
               con.pos = Vector3d{ cen[3 * k], cen[3 * k + 1], cen[3 * k + 2] };
               con.body_name_1 = e.link_names[i];
               con.body_name_2 = e.link_names[j];
-              con.body_type_1 = con.body_type_2 = BodyTypes::ROBOT_LINK;
+              con.body_type_1 = e.geom_body_type[i];
+              con.body_type_2 = e.geom_body_type[j];
               res.collision = true;
               res.contact_count++;
               res.contacts[key].push_back(con);
@@ -1279,10 +1437,9 @@ private:
   double max_propogation_distance_ = DEFAULT_MAX_PROPOGATION_DISTANCE;
   double link_padding_ = 0.0;
   LinkSpheres link_spheres_;
-  std::vector<double> link_points_, link_spheres_flat_, link_bsphere_;
-  std::vector<int64_t> link_point_offset_;
-  std::vector<int32_t> link_sphere_offset_;
-  b200df_model* model_ = nullptr;
+  std::shared_ptr<const ModelEntry> base_model_;  // the robot without attached bodies
+  mutable std::map<std::string, std::shared_ptr<const ModelEntry>> model_cache_;  // by RobotState::attachedSignature()
+  mutable std::mutex model_cache_lock_;
   b200df_field* world_field_ = nullptr;
   std::map<std::string, World::ObjectConstPtr> posed_objects_;  // posed_body_point_decompositions_ of the world entry
   World::ObserverHandle observer_handle_ = 0;

@@ -121,6 +121,32 @@ int main(int argc, char** argv)
       world->addToObject(id, sh, pose);
       object_ids.push_back(id);
     }
+    int n_attached = 0;
+    in >> tok >> n_attached;
+    std::vector<core::AttachedBody> attached;
+    for (int k = 0; k < n_attached; ++k)
+    {
+      core::AttachedBody b;
+      int ns = 0, nt = 0;
+      in >> b.name >> b.link_name >> ns;
+      for (int s = 0; s < ns; ++s)
+      {
+        shapes::Shape sh;
+        int t;
+        in >> t >> sh.dims[0] >> sh.dims[1] >> sh.dims[2];
+        sh.type = static_cast<shapes::ShapeType>(t);
+        b.shapes.push_back(sh);
+        b.attach_trans.push_back(readPose(in));
+      }
+      in >> nt;
+      for (int t = 0; t < nt; ++t)
+      {
+        std::string name;
+        in >> name;
+        b.touch_links.insert(name);
+      }
+      attached.push_back(b);
+    }
     std::string group_name;
     int n_single = 0, n_contacts = 0, n_grad = 0, mutate = 0;
     std::size_t max_contacts = 1, max_per_pair = 1;
@@ -149,6 +175,8 @@ int main(int argc, char** argv)
     CollisionRequest req;
     req.group_name = group_name;
     core::RobotState ref_state(model);  // all-zero scene state poses the non-group links
+    for (const core::AttachedBody& b : attached)
+      ref_state.attachBody(b);
     std::vector<std::uint8_t> v(n);
     env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_ROBOT, ref_state, v.data());
     writeFile(prefix + ".robot.u8", v);
@@ -162,7 +190,7 @@ int main(int argc, char** argv)
     std::vector<std::uint8_t> single;
     for (std::int64_t i = 0; i < std::min<std::int64_t>(n_single, n); ++i)
     {
-      core::RobotState st(model);
+      core::RobotState st(ref_state);
       st.setVariablePositions(&q[(std::size_t)i * nvar]);
       CollisionResult r1, r2, r3;
       if (acm_ptr)
@@ -191,7 +219,7 @@ int main(int argc, char** argv)
       creq.max_contacts_per_pair = max_per_pair;
       for (std::int64_t i = 0; i < std::min<std::int64_t>(n_contacts, n); ++i)
       {
-        core::RobotState st(model);
+        core::RobotState st(ref_state);
         st.setVariablePositions(&q[(std::size_t)i * nvar]);
         CollisionResult r;
         if (acm_ptr)
@@ -202,7 +230,7 @@ int main(int argc, char** argv)
         for (const auto& kv : r.contacts)
           for (const Contact& c : kv.second)
             cf << "contact " << c.body_name_1 << " " << c.body_name_2 << " " << c.pos.x << " " << c.pos.y << " "
-               << c.pos.z << "\n";
+               << c.pos.z << " " << (int)c.body_type_1 << " " << (int)c.body_type_2 << "\n";
       }
     }
 
@@ -211,7 +239,7 @@ int main(int argc, char** argv)
       std::vector<double> out;
       for (std::int64_t i = 0; i < std::min<std::int64_t>(n_grad, n); ++i)
       {
-        core::RobotState st(model);
+        core::RobotState st(ref_state);
         st.setVariablePositions(&q[(std::size_t)i * nvar]);
         CollisionResult r;
         GroupStateRepresentationPtr gsr;

@@ -83,7 +83,7 @@ class RobotDescription:
         self.groups = {}  # group name -> list of joint names
 
     def add_link(self, link, parent_link, joint, joint_type, xyz=(0, 0, 0), rpy=(0, 0, 0), axis=(0, 0, 1),
-                 limits=None, mimic=None):
+                 limits=None, mimic=None, origin_pose=None):
         if parent_link is None:
             p = -1
         else:
@@ -93,7 +93,7 @@ class RobotDescription:
         self.parent.append(p)
         self.joint_type.append(joint_type)
         self.axis.append(tuple(float(a) for a in axis))
-        self.origin.append(rpy_xyz_to_pose(xyz, rpy))
+        self.origin.append(np.array(origin_pose, dtype=np.float64) if origin_pose is not None else rpy_xyz_to_pose(xyz, rpy))
         nv = _NVARS[joint_type]
         if nv:
             self.var_index.append(len(self.variable_names))

@@ -8,7 +8,10 @@ def _f(v):
 
 
 def write_scenario(path, desc, field, objects, group="", use_acm=True, sphere_overrides=True, signed=False, tol=0.0,
-                   n_single=0, n_contacts=0, max_contacts=1, max_contacts_per_pair=1, n_grad=0, mutate=False):
+                   n_single=0, n_contacts=0, max_contacts=1, max_contacts_per_pair=1, n_grad=0, mutate=False,
+                   attached=(), extra_acm_always=()):
+    """attached: [(name, link_name, [(type, dims, pose3x4)], [touch link names])];
+    extra_acm_always: extra (a, b) name pairs set ALWAYS in the ACM (e.g. entries that name an attached body)."""
     lines = ["robot %s %d" % (desc.name, desc.n_links)]
     for i in range(desc.n_links):
         m = desc.mimic[i]
@@ -29,8 +32,9 @@ def write_scenario(path, desc, field, objects, group="", use_acm=True, sphere_ov
     lines.append("groups %d" % len(desc.groups))
     for g, joints in desc.groups.items():
         lines.append("%s %d %s" % (g, len(joints), " ".join(joints)))
-    lines.append("acm %d %d" % (1 if use_acm else 0, len(desc.disabled_pairs)))
-    for a, b in desc.disabled_pairs:
+    pairs = list(desc.disabled_pairs) + list(extra_acm_always)
+    lines.append("acm %d %d" % (1 if use_acm else 0, len(pairs)))
+    for a, b in pairs:
         lines.append("%s %s" % (a, b))
     lines.append("field %s %s %r %r %d %r" % (_f(field["size"]), _f(field["center"]), float(field["resolution"]),
                                               float(field["max_distance"]), 1 if signed else 0, float(tol)))
@@ -38,6 +42,13 @@ def write_scenario(path, desc, field, objects, group="", use_acm=True, sphere_ov
     for k, (t, dims, pose) in enumerate(objects):
         d = list(dims) + [0.0] * (3 - len(dims))
         lines.append("obj%d %d %s %s" % (k, t, _f(d), _f(pose)))
+    lines.append("attached %d" % len(attached))
+    for name, link, shapes, touch in attached:
+        lines.append("%s %s %d" % (name, link, len(shapes)))
+        for (t, dims, pose) in shapes:
+            d = list(dims) + [0.0] * (3 - len(dims))
+            lines.append("%d %s %s" % (t, _f(d), _f(pose)))
+        lines.append("%d %s" % (len(touch), " ".join(touch)))
     lines.append("request %s %d %d %d %d %d %d" % (group if group else "-", n_single, n_contacts, max_contacts,
                                                    max_contacts_per_pair, n_grad, 1 if mutate else 0))
     with open(path, "w") as f:

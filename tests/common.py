@@ -25,15 +25,16 @@ class OracleSetup:
     the mismatch census."""
 
     def __init__(self, oracle, desc, field, objects=(), group="", signed=False, self_state=None, use_acm=True,
-                 sphere_overrides=True, tol=0.0, exact_field=True):
+                 sphere_overrides=True, tol=0.0, exact_field=True, padding_by_link=None, acm_override=None,
+                 group_links=None):
         self.desc = desc
         self.model_desc = assemble_model(desc, oracle.body_decomposition, field["resolution"],
-                                         use_sphere_overrides=sphere_overrides)
+                                         use_sphere_overrides=sphere_overrides, padding_by_link=padding_by_link)
         self.model = oracle.Model(self.model_desc)
         self.env = oracle.Env(self.model, field["size"], field["center"], res=field["resolution"], tol=tol,
                               max_prop=field["max_distance"], signed=signed)
-        self.group_links = desc.group_links(group)
-        self.acm = desc.acm_entry_matrix() if use_acm else None
+        self.group_links = group_links if group_links is not None else desc.group_links(group)
+        self.acm = (acm_override if acm_override is not None else desc.acm_entry_matrix()) if use_acm else None
         self.env.set_group(self.group_links, self.acm, self_state)
         self.world_points = oracle_world_points(oracle, objects, field["resolution"])
         if len(self.world_points):

@@ -144,3 +144,56 @@ def test_whole_robot_no_acm_and_derived_spheres(gpu, oracle, tmp_path):
                     self_state=np.zeros(desc.nvar))
     assert np.array_equal(np.fromfile(prefix + ".robot.u8", dtype=np.uint8), o.env.check_batch(q, mode=1, n_threads=4))
     assert np.array_equal(np.fromfile(prefix + ".all.u8", dtype=np.uint8), o.env.check_batch(q, mode=4, n_threads=4))
+
+
+@pytest.mark.gpu
+def test_attached_body_through_the_cpp_env(gpu, oracle, tmp_path):
+    """A box attached to panda_hand (RobotState::attachBody).  In the reference an attached shape is posed by
+    link_transform * attach_trans and decomposed with the default 0.01 padding, i.e. it behaves like one more fixed
+    link; the ACM entry and the touch links of a body are only honoured for the link it is attached to
+    (generateDistanceFieldCacheEntry :806-834).  The oracle is given that equivalent model."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=41)
+    fa = scenarios.FIELD_A
+    q = desc.sample_states(3000, 777)
+    pose = rd.rpy_xyz_to_pose((0.0, 0.0, 0.22), (0.1, 0.2, 0.3))
+    box = (rd.SHAPE_BOX, (0.06, 0.10, 0.08), rd.rpy_xyz_to_pose())
+    attached = [("grasped_box", "panda_hand", [(box[0], box[1], pose)], ["panda_hand", "panda_leftfinger"])]
+    prefix = _run(tmp_path, desc, fa, objs, q, group="", n_single=32, n_contacts=100, max_contacts=20,
+                  max_contacts_per_pair=3, attached=attached, extra_acm_always=[("grasped_box", "panda_link7")])
+    # the equivalent model for the oracle: the box as a fixed child link of panda_hand
+    aug = rd.panda()
+    aug.add_link("grasped_box", "panda_hand", "grasped_box/attach0", rd.JOINT_FIXED, origin_pose=pose)
+    aug.add_shape("grasped_box", box[0], box[1])
+    L = aug.n_links
+    acm = np.zeros((L, L), dtype=np.int32)
+    acm[:L - 1, :L - 1] = desc.acm_entry_matrix()
+    b, hand = L - 1, aug.link_names.index("panda_hand")
+    acm[b, :] = acm[:, b] = -1          # other links: the reference never looks at their entry / touch status
+    acm[b, b] = 0                       # AllowedCollisionMatrix(names, false) has no entry for the body: not ALWAYS
+    acm[hand, b] = acm[b, hand] = 1     # touch link == the attach link
+    o = OracleSetup(oracle, aug, fa, objs, self_state=np.zeros(desc.nvar), padding_by_link={"grasped_box": 0.01},
+                    acm_override=acm, group_links=list(range(L)))
+    robot = np.fromfile(prefix + ".robot.u8", dtype=np.uint8)
+    self_ = np.fromfile(prefix + ".self.u8", dtype=np.uint8)
+    both = np.fromfile(prefix + ".all.u8", dtype=np.uint8)
+    assert np.array_equal(robot, o.env.check_batch(q, mode=1, n_threads=4))
+    assert np.array_equal(self_, o.env.check_batch(q, mode=2, n_threads=4))
+    assert np.array_equal(both, o.env.check_batch(q, mode=4, n_threads=4))
+    # the box matters: the same states without it give different verdicts
+    plain = OracleSetup(oracle, desc, fa, objs, self_state=np.zeros(desc.nvar))
+    assert (plain.env.check_batch(q, mode=1, n_threads=4) != robot).any()
+    assert (plain.env.check_batch(q, mode=2, n_threads=4) != self_).any()
+    single = np.fromfile(prefix + ".single.u8", dtype=np.uint8)
+    assert np.array_equal((single >> 2) & 1, both[:32])
+    # contacts name the body and mark it ROBOT_ATTACHED (BodyTypes::ROBOT_ATTACHED == 1)
+    seen = False
+    for line in open(prefix + ".contacts.txt"):
+        t = line.split()
+        if t[0] == "contact" and t[1] == "grasped_box":
+            assert int(t[6]) == 1
+            seen = True
+        if t[0] == "contact" and t[2] == "grasped_box":
+            assert int(t[7]) == 1
+            seen = True
+    assert seen
