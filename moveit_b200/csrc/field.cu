@@ -419,12 +419,16 @@ __device__ __forceinline__ void march_load(unsigned (&buf)[R + 1], const uint32_
 }
 
 template <int R, typename OutT, bool FINAL>
-__global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __restrict__ in, void* __restrict__ out_v,
+__global__ void __launch_bounds__(64, 9) edt_march_kernel(const uint32_t* __restrict__ in, void* __restrict__ out_v,
                                                        long n_lines, long inner, long outer_stride, long stride,
                                                        int n_axis, int max_d2)
 {
   constexpr int W = 2 * R + 1;
-  constexpr int CA = R + 1, CB = R;  // steps 0..R and R+1..2R of a revolution
+  // a revolution is cut into four chunks (13+13+13+12 steps for R = 25) that alternate between two input buffers:
+  // half the registers of a two-chunk split, which is what lets every line of a 400^3 field be resident at once
+  // (2500 warps on 148 SMs need 17 warps/SM, i.e. <= 120 registers)
+  constexpr int C0 = (W + 3) / 4, C1 = (W + 2) / 4, C2 = (W + 1) / 4, C3 = W / 4;
+  static_assert(C0 + C1 + C2 + C3 == W && C0 <= R + 1, "chunking");
   const long line0 = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const bool live = line0 < n_lines;
   const long line = live ? line0 : n_lines - 1;  // surplus lanes shadow the last line (keeps the votes full)
@@ -438,14 +442,20 @@ __global__ void __launch_bounds__(64, 6) edt_march_kernel(const uint32_t* __rest
   // output pointers trail the input by R steps; they start before the array and are only dereferenced in range
   uint32_t* out32 = static_cast<uint32_t*>(out_v) + base - (long)R * stride;
   uint16_t* out16 = static_cast<uint16_t*>(out_v) + base - (long)R * stride;
-  unsigned bufA[R + 1], bufB[R + 1];
-  march_load<R, CA>(bufA, src, stride, 0, n_axis);
+  unsigned bufA[R + 1], bufB[R + 1];  // only the first C0 entries are used
+  march_load<R, C0>(bufA, src, stride, 0, n_axis);
   for (int t0 = 0; t0 < n_axis + R; t0 += W)
   {
-    march_load<R, CB>(bufB, src + (long)(t0 + CA) * stride, stride, t0 + CA, n_axis);
-    march_chunk<R, 0, CA>(bufA, acc, t0, n_axis, live, out32, out16, stride, clamp, FINAL, sizeof(OutT) == 1);
-    march_load<R, CA>(bufA, src + (long)(t0 + W) * stride, stride, t0 + W, n_axis);
-    march_chunk<R, CA, CB>(bufB, acc, t0 + CA, n_axis, live, out32, out16, stride, clamp, FINAL, sizeof(OutT) == 1);
+    constexpr bool kU8 = sizeof(OutT) == 1;
+    march_load<R, C1>(bufB, src + (long)(t0 + C0) * stride, stride, t0 + C0, n_axis);
+    march_chunk<R, 0, C0>(bufA, acc, t0, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
+    march_load<R, C2>(bufA, src + (long)(t0 + C0 + C1) * stride, stride, t0 + C0 + C1, n_axis);
+    march_chunk<R, C0, C1>(bufB, acc, t0 + C0, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
+    march_load<R, C3>(bufB, src + (long)(t0 + C0 + C1 + C2) * stride, stride, t0 + C0 + C1 + C2, n_axis);
+    march_chunk<R, C0 + C1, C2>(bufA, acc, t0 + C0 + C1, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
+    march_load<R, C0>(bufA, src + (long)(t0 + W) * stride, stride, t0 + W, n_axis);
+    march_chunk<R, C0 + C1 + C2, C3>(bufB, acc, t0 + C0 + C1 + C2, n_axis, live, out32, out16, stride, clamp, FINAL,
+                                     kU8);
   }
 }
 
