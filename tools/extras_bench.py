@@ -42,6 +42,17 @@ def run(with_oracle=True):
     t = best_of(lambda: e.group.check(q, e.world, flags=B.CHECK_ROBOT, precision=B.PRECISION_FAST), 5)
     out["config1_10k_robot_ms"] = 1e3 * t
 
+    # one state per call, the way OMPL's StateValidityChecker::isValid drives a CollisionEnv (latency, not throughput)
+    fl1 = B.CHECK_ROBOT | B.CHECK_INTRA
+    one32, one64 = q[:1].copy(), q[:1].astype(np.float64)
+    for name, arr, prec in (("f32_fast", one32, B.PRECISION_FAST), ("f64_exact", one64, B.PRECISION_EXACT)):
+        for _ in range(20):
+            e.group.check(arr, e.world, flags=fl1, precision=prec)
+        t0 = time.perf_counter()
+        for _ in range(500):
+            e.group.check(arr, e.world, flags=fl1, precision=prec)
+        out["single_state_call_us_" + name] = 1e6 * (time.perf_counter() - t0) / 500
+
     # config 5: CHOMP gradients, 1000 trajectories x 100 waypoints
     traj = scenarios.chomp_trajectories(desc, 1000, 100).reshape(-1, desc.nvar)
     fl = B.CHECK_ROBOT | B.CHECK_INTRA
