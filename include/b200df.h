@@ -194,6 +194,9 @@ int b200df_field_dims(const b200df_field* field, int32_t* out4);
 int b200df_field_reset(b200df_field* field);                                        /* reset()                 :507-525 */
 int b200df_field_add_points(b200df_field* field, const double* xyz, int64_t n);     /* addPointsToField       :176-195 */
 int b200df_field_remove_points(b200df_field* field, const double* xyz, int64_t n);  /* removePointsFromField  :197-218 */
+/* addPointsToField for a point cloud that already lives on the GPU (fp64 [n][3] device pointer, e.g. produced by a
+ * perception pipeline); stream-ordered, no host synchronisation */
+int b200df_field_add_points_device(b200df_field* field, const double* xyz_dev, int64_t n, void* stream);
 int b200df_field_update_points(b200df_field* field, const double* old_xyz, int64_t n_old, const double* new_xyz,
                                int64_t n_new);                                      /* updatePointsInField    :120-174 */
 int b200df_field_add_voxels(b200df_field* field, const int32_t* ijk, int64_t n);    /* addNewObstacleVoxels   :220-300 */

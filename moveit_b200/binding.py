@@ -72,6 +72,7 @@ SYMBOLS = {
     "b200df_field_dims": (C.c_int, [_VP, c_i32p]),
     "b200df_field_reset": (C.c_int, [_VP]),
     "b200df_field_add_points": (C.c_int, [_VP, c_dp, C.c_int64]),
+    "b200df_field_add_points_device": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "b200df_field_remove_points": (C.c_int, [_VP, c_dp, C.c_int64]),
     "b200df_field_update_points": (C.c_int, [_VP, c_dp, C.c_int64, c_dp, C.c_int64]),
     "b200df_field_add_voxels": (C.c_int, [_VP, c_i32p, C.c_int64]),

@@ -954,6 +954,25 @@ int b200df_field_add_points(b200df_field* f, const double* xyz, int64_t n)
   return rc;
 }
 
+int b200df_field_add_points_device(b200df_field* f, const double* xyz_dev, int64_t n, void* stream)
+{
+  B200DF_REQUIRE(f && (xyz_dev || n == 0) && n >= 0, "bad arguments");
+  DeviceGuard dg(f->device);
+  std::lock_guard<std::mutex> lk(f->mu);
+  if (n > 0 && f->n_voxels > 0)
+  {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    scatter_points_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f->grid, xyz_dev, n, f->occ, 1, false);
+    B200DF_LAUNCHED();
+    B200DF_CUDA(cudaGetLastError());
+    // the rebuild runs on the field's own stream: order it after the caller's scatter
+    B200DF_CUDA(cudaEventRecord(f->ev1, st));
+    B200DF_CUDA(cudaStreamWaitEvent(f->stream, f->ev1, 0));
+  }
+  f->dirty = true;
+  return B200DF_OK;
+}
+
 int b200df_field_remove_points(b200df_field* f, const double* xyz, int64_t n)
 {
   B200DF_REQUIRE(f && (xyz || n == 0) && n >= 0, "bad arguments");

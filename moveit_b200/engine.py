@@ -329,6 +329,10 @@ class Field:
         p = B.as_f64(np.reshape(pts, (-1, 3)))
         B.check(B.load().b200df_field_add_points(self.h, B.ptr(p, C.c_double), len(p)))
 
+    def add_points_device(self, ptr, n, stream=None):
+        """pts already on the GPU: fp64 [n][3] device pointer."""
+        B.check(B.load().b200df_field_add_points_device(self.h, C.c_void_p(ptr), n, C.c_void_p(stream) if stream else None))
+
     def remove_points(self, pts):
         p = B.as_f64(np.reshape(pts, (-1, 3)))
         B.check(B.load().b200df_field_remove_points(self.h, B.ptr(p, C.c_double), len(p)))

@@ -456,6 +456,34 @@ def test_batched_edge_check_matches_per_state_oracle(gpu, oracle, robot):
         assert (np.abs(qb[:, 2] - qa[:, 2]) > np.pi).any()  # the shortest-arc branch was exercised
 
 
+def test_device_resident_cloud_and_non_finite_joint_values(gpu, oracle):
+    """b200df_field_add_points_device == add_points; NaN / inf joint values give the oracle's verdicts on every
+    precision (a NaN centre fails every range test -> free, like the reference's dead out-of-bounds branch, Q4)."""
+    import torch
+    from moveit_b200 import engine
+    fd = dict(size=(1.0, 1.0, 1.0), resolution=0.02, center=(0.0, 0.0, 0.5), max_distance=0.25)
+    pts = scenarios.synthetic_cloud(20000, field=fd)
+    a = engine.Field.centered(fd["size"], fd["resolution"], fd["center"], fd["max_distance"])
+    b = engine.Field.centered(fd["size"], fd["resolution"], fd["center"], fd["max_distance"])
+    a.add_points(pts)
+    pd = torch.from_numpy(np.ascontiguousarray(pts)).cuda()
+    b.add_points_device(pd.data_ptr(), len(pts), torch.cuda.current_stream().cuda_stream)
+    assert np.array_equal(a.d2(), b.d2()) and (a.d2() == 0).sum() > 1000
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    q = desc.sample_states(4096, 5, np.float32)
+    q[::9, 3] = np.nan
+    q[1::9, 0] = np.inf
+    q[2::9, 6] = -np.inf
+    q[3::9, 7] = np.nan  # prismatic finger
+    ref = o.env.check_batch(q.astype(np.float64), mode=3, n_threads=4)
+    for precision in (0, 1, 2):
+        got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=precision)
+        assert np.array_equal(got, ref), "precision %d: %d differences" % (precision, int((got != ref).sum()))
+
+
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
     """test_collision_distance_field.cpp:336-383 through the engine: collide, collide, free."""
     from moveit_b200 import engine
