@@ -100,7 +100,8 @@ struct b200df_field
   void* neg = nullptr;
   uint16_t* tmp_a = nullptr;
   uint16_t* tmp_b = nullptr;
-  uint32_t* bits = nullptr;    // occupancy bit rows for the fused z/y pass
+  uint32_t* bits = nullptr;    // occupancy bit rows (1 bit per voxel) of the fast EDT path
+  bool bits_valid = false;     // bits mirror occ (kept up to date by reset / add_points, else re-packed at rebuild)
   double* sqrt_table = nullptr;
   std::vector<double> sqrt_table_host;
   bool dirty = true;

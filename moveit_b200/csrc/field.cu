@@ -45,7 +45,7 @@ __device__ __forceinline__ bool world_to_grid(const GridDev& g, double x, double
 
 // addPointsToField / removePointsFromField voxelisation (propagation_distance_field.cpp:176-218)
 __global__ void scatter_points_kernel(GridDev g, const double* __restrict__ xyz, long n, uint8_t* __restrict__ vol,
-                                      uint8_t value, bool or_value)
+                                      uint8_t value, bool or_value, uint32_t* __restrict__ bits = nullptr, int wpr = 0)
 {
   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= n)
@@ -58,6 +58,8 @@ __global__ void scatter_points_kernel(GridDev g, const double* __restrict__ xyz,
     vol[r] |= value;  // only used with the same value from every thread of a launch: benign race
   else
     vol[r] = value;
+  if (bits)  // keep the bit-packed mirror of the occupancy current (only when setting voxels)
+    atomicOr(&bits[((long)ix * g.n[1] + iy) * wpr + (iz >> 5)], 1u << (iz & 31));
 }
 
 __global__ void scatter_voxels_kernel(GridDev g, const int32_t* __restrict__ ijk, long n, uint8_t* __restrict__ vol,
@@ -540,6 +542,11 @@ __global__ void unpack_occupancy_kernel(const uint8_t* __restrict__ in, uint8_t*
     occ[i] = 1;  // readFromStream ADDS the stored obstacle voxels (addNewObstacleVoxels)
 }
 
+inline size_t bits_bytes(const b200df_field* f)
+{
+  return (size_t)f->grid.n[0] * f->grid.n[1] * ((f->grid.n[2] + 31) / 32) * sizeof(uint32_t);
+}
+
 inline unsigned blocks_for(long n, int threads)
 {
   return (unsigned)((n + threads - 1) / threads);
@@ -674,6 +681,7 @@ int rasterize_into(b200df_field* f, int shape_type, const double* dims3, const d
     B200DF_CUDA(cudaStreamSynchronize(f->stream));
   }
   f->dirty = true;
+  f->bits_valid = false;
   return B200DF_OK;
 }
 
@@ -706,18 +714,24 @@ int run_edt(b200df_field* f, bool invert, T* out)
   {
     const int wpr = (nz + 31) / 32;
     const long n_rows = (long)nx * ny;
-    if (nz % 16 == 0)
+    if (!invert && f->bits_valid)
+    {
+      // the bit rows were kept current by reset / add_points: nothing to pack
+    }
+    else if (nz % 16 == 0)
     {
       pack_bits16_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
           reinterpret_cast<const uint4*>(f->occ), reinterpret_cast<uint16_t*>(f->bits), nz / 16, wpr, n_rows, invert);
+      B200DF_LAUNCHED();
     }
     else
     {
       const long n_words = n_rows * wpr;
       pack_bits_kernel<<<blocks_for(n_words * 32, threads), threads, 0, f->stream>>>(f->occ, f->bits, nz, wpr, n_words,
                                                                                     invert);
+      B200DF_LAUNCHED();
     }
-    B200DF_LAUNCHED();
+    f->bits_valid = !invert;  // the bit rows now mirror occ (or its complement, for the negative field)
     if (nz % 8 == 0)
       edt_z8_from_bits_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
           f->bits, reinterpret_cast<uint4*>(f->tmp_a), nz / 8, wpr, n_rows, f->radius);
@@ -880,6 +894,7 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out)
   B200DF_CUDA(cudaMemsetAsync(f->occ, 0, nv, f->stream));
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
   f->dirty = true;
+  f->bits_valid = false;
   *out = f.release();
   return B200DF_OK;
 }
@@ -924,8 +939,11 @@ int b200df_field_reset(b200df_field* f)
   std::lock_guard<std::mutex> lk(f->mu);
   if (f->n_voxels > 0)
     B200DF_CUDA(cudaMemsetAsync(f->occ, 0, (size_t)f->n_voxels, f->stream));
+  if (f->bits)
+    B200DF_CUDA(cudaMemsetAsync(f->bits, 0, bits_bytes(f), f->stream));
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
   f->dirty = true;
+  f->bits_valid = f->bits != nullptr;
   return B200DF_OK;
 }
 
@@ -936,8 +954,10 @@ static int scatter_host_points(b200df_field* f, const double* xyz, int64_t n, ui
   DeviceBuffer buf;
   B200DF_CUDA(cudaMalloc(&buf.p, (size_t)n * 3 * sizeof(double)));
   B200DF_CUDA(cudaMemcpyAsync(buf.p, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, f->stream));
+  const bool mirror = vol == f->occ && value == 1 && !orv && f->bits && f->bits_valid;
   scatter_points_kernel<<<blocks_for(n, 256), 256, 0, f->stream>>>(f->grid, static_cast<const double*>(buf.p), n, vol,
-                                                                   value, orv);
+                                                                   value, orv, mirror ? f->bits : nullptr,
+                                                                   (f->grid.n[2] + 31) / 32);
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
@@ -949,8 +969,10 @@ int b200df_field_add_points(b200df_field* f, const double* xyz, int64_t n)
   B200DF_REQUIRE(f && (xyz || n == 0) && n >= 0, "bad arguments");
   DeviceGuard dg(f->device);
   std::lock_guard<std::mutex> lk(f->mu);
+  const bool keep = f->bits_valid;  // scatter_host_points mirrors the new voxels into valid bit rows
   int rc = scatter_host_points(f, xyz, n, f->occ, 1, false);
   f->dirty = true;
+  f->bits_valid = keep && rc == B200DF_OK;
   return rc;
 }
 
@@ -962,14 +984,15 @@ int b200df_field_add_points_device(b200df_field* f, const double* xyz_dev, int64
   if (n > 0 && f->n_voxels > 0)
   {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    scatter_points_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f->grid, xyz_dev, n, f->occ, 1, false);
+    scatter_points_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f->grid, xyz_dev, n, f->occ, 1, false,
+                                                              f->bits_valid ? f->bits : nullptr, (f->grid.n[2] + 31) / 32);
     B200DF_LAUNCHED();
     B200DF_CUDA(cudaGetLastError());
     // the rebuild runs on the field's own stream: order it after the caller's scatter
     B200DF_CUDA(cudaEventRecord(f->ev1, st));
     B200DF_CUDA(cudaStreamWaitEvent(f->stream, f->ev1, 0));
   }
-  f->dirty = true;
+  f->dirty = true;  // bits_valid unchanged: the scatter mirrored the voxels when the bit rows were current
   return B200DF_OK;
 }
 
@@ -980,6 +1003,7 @@ int b200df_field_remove_points(b200df_field* f, const double* xyz, int64_t n)
   std::lock_guard<std::mutex> lk(f->mu);
   int rc = scatter_host_points(f, xyz, n, f->occ, 0, false);  // Q8: cleared even if another object shares the voxel
   f->dirty = true;
+  f->bits_valid = false;
   return rc;
 }
 
@@ -1005,6 +1029,7 @@ int b200df_field_update_points(b200df_field* f, const double* old_xyz, int64_t n
   B200DF_CUDA(cudaGetLastError());
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
   f->dirty = true;
+  f->bits_valid = false;
   return B200DF_OK;
 }
 
@@ -1025,6 +1050,7 @@ int b200df_field_add_voxels(b200df_field* f, const int32_t* ijk, int64_t n)
     B200DF_CUDA(cudaStreamSynchronize(f->stream));
   }
   f->dirty = true;
+  f->bits_valid = false;
   return B200DF_OK;
 }
 
@@ -1226,6 +1252,7 @@ int b200df_field_unpack_occupancy(b200df_field* f, const uint8_t* bytes, int64_t
   B200DF_CUDA(cudaGetLastError());
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
   f->dirty = true;
+  f->bits_valid = false;
   return B200DF_OK;
 }
 
@@ -1278,6 +1305,7 @@ int b200df_field_copy_from(b200df_field* dst, b200df_field* src)
     B200DF_CUDA(cudaMemcpyPeerAsync(dst->neg, dst->device, src->neg, src->device, nb, dst->stream));
   B200DF_CUDA(cudaStreamSynchronize(dst->stream));
   dst->dirty = false;
+  dst->bits_valid = false;
   return B200DF_OK;
 }
 
@@ -1318,6 +1346,8 @@ int b200df_field_import_device(b200df_field* f, const void* occ_dev, const void*
   B200DF_CUDA(cudaStreamSynchronize(st));
   if (d2_dev)
     f->dirty = false;
+  if (occ_dev)
+    f->bits_valid = false;
   return B200DF_OK;
 }
 
