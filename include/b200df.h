@@ -74,9 +74,10 @@ enum
 {
   B200DF_PRECISION_EXACT = 0, /* fp64 FK + fp64 voxel indexing, operation order of the reference */
   B200DF_PRECISION_FAST = 1,  /* fp32 fast path; states whose verdict could depend on rounding are re-run EXACT:
-                                 same verdicts as EXACT.  Needs fp32 joint values, unsigned fields and a robot that
-                                 fits the constant-bank tables (<= 40 links, 128 spheres, 512 link pairs), otherwise
-                                 the call silently runs EXACT */
+                                 same verdicts as EXACT (fp64 joint values are screened rounded to fp32 and re-run
+                                 unrounded).  Needs unsigned fields, no floating joints and a robot that fits the
+                                 constant-bank tables (<= 40 links, 128 spheres, 512 link pairs), otherwise the call
+                                 silently runs EXACT */
   /* test hooks, not for production use */
   B200DF_PRECISION_DEBUG_SWEEP = 2,  /* the independently written round-1 sweep kernel (cross-check of EXACT) */
   B200DF_PRECISION_DEBUG_SCREEN = 3, /* FAST's screening pass alone: verdict 0 / 1, or 2 = undecided */
@@ -256,8 +257,7 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
  * and checked like b200df_check_batch.  first_invalid[i] = the first j whose state collides, 0 = motion valid — what
  * ompl::base::DiscreteMotionValidator::checkMotion + StateValidityChecker::isValid
  * (moveit_planners/ompl/ompl_interface/src/detail/state_validity_checker.cpp:76-121) decide one state at a time; the
- * last valid fraction of OMPL's lastValid is (first_invalid - 1) / segments.  Only the end states cross PCIe.
- * precision FAST checks the interpolated states rounded to fp32, EXACT the fp64 states. */
+ * last valid fraction of OMPL's lastValid is (first_invalid - 1) / segments.  Only the end states cross PCIe. */
 int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_field* self, const double* qa,
                        const double* qb, int64_t m, int32_t segments, const uint8_t* var_is_angular, int flags,
                        int precision, int32_t* first_invalid);

@@ -83,10 +83,10 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
   DeviceGuard dg(group->device);
   cudaStream_t stream;
   B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  // FAST screens fp32 joint values: the interpolated state is rounded once to fp32 and that fp32 state is what both
-  // the screening pass and the exact re-run see.  EXACT checks the unrounded fp64 state, like the reference would.
-  const bool f32 = precision == B200DF_PRECISION_FAST;
-  const size_t elem = f32 ? sizeof(float) : sizeof(double);
+  // the interpolated states stay fp64 (what the reference would check); FAST screens them in fp32 and re-runs the
+  // undecided ones on the same fp64 values
+  const bool f32 = false;
+  const size_t elem = sizeof(double);
   const int64_t edges_per_chunk = std::max<int64_t>(1, (int64_t)(1 << 21) / segments);
   const int64_t chunk = std::min<int64_t>(m, edges_per_chunk);
   int rc = B200DF_OK;

@@ -415,8 +415,7 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
     amb_count = static_cast<int*>(scratch);
     amb_idx = amb_count + 1;
   }
-  int rc = fast_launch(group, wf, sf, elem, static_cast<const float*>(q_dev), n, flags, verdict_dev, amb_idx, amb_count,
-                       stream);
+  int rc = fast_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, amb_idx, amb_count, stream);
   if (!rc && !raw)
   {
     Redo redo;

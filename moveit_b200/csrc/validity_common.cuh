@@ -489,12 +489,12 @@ namespace b200df
 // FAST path (validity_fast.cu)
 int fast_create(b200df_group* group);   // builds the fp32 tables; leaves group->fast null when unsupported
 void fast_destroy(b200df_group* group);
-// true when the FAST kernel can serve this call (fp32 joint values, unsigned fields, model fits the tables)
+// true when the FAST kernel can serve this call (unsigned fields, model fits the tables)
 bool fast_supported(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int q_dtype, int flags);
 // fp32 screening pass: verdict[i] in {0, 1} or 2 = "rounding could matter"; the indices of the 2s are appended to
 // amb_idx (capacity n) and counted in *amb_count, both device memory, *amb_count zeroed by this call
-int fast_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const float* q,
-                long n, int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream);
+int fast_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                int q_dtype, long n, int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream);
 
 // fills wf / sf for the requested flags (rebuilding dirty fields) and checks they fit the group
 int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field* self, int flags, FieldDev* wf,

@@ -293,10 +293,10 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
   maybe |= any;
 }
 
-template <typename FT, int B, bool PAIR_SMEM>
+template <typename QT, typename FT, int B, bool PAIR_SMEM>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
                                                           FastLookup sf, const float2* __restrict__ pair_T_global,
-                                                          const float* __restrict__ q, long n, int flags,
+                                                          const QT* __restrict__ q, long n, int flags,
                                                           uint8_t* __restrict__ verdict, int* __restrict__ amb_idx,
                                                           int* __restrict__ amb_count, int n_pair_smem)
 {
@@ -311,9 +311,9 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   {
     const int total = B * T.n_vars;
     const long limit = (n - base) * T.n_vars;
-    const float* src = q + base * T.n_vars;
+    const QT* src = q + base * T.n_vars;
     for (int e = tid; e < total; e += B)
-      qs[e] = (e < limit) ? src[e] : 0.f;
+      qs[e] = (e < limit) ? (float)src[e] : 0.f;  // fp64 joint values are rounded once (covered by the margins)
   }
   // the pair thresholds are read once per sphere-pair test by every warp: keep them in shared memory when they fit
   // (L1 is nearly all shared-memory carve-out here and what is left is thrashed by the voxel gathers)
@@ -475,7 +475,7 @@ double norm3(const double* v)
 
 // Travel assumed for translational joint variables and the angle range assumed for rotational ones; values
 // outside are detected at run time and sent to the exact kernel.
-constexpr double kPrismaticTravel = 2.0, kPlanarTravel = 16.0, kAngleRange = 64.0;
+constexpr double kPrismaticTravel = 2.0, kPlanarTravel = 16.0, kAngleRange = 8.0;
 
 struct LinkErr
 {
@@ -576,8 +576,9 @@ int fast_create(b200df_group* g)
     {
       const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
       f.vmax = (float)(planar ? kPlanarTravel : kAngleRange);  // planar: x, y and theta share the bound
-      // mimic: the fp64 value is rounded once to fp32 -> angle error <= u*|v|
-      const double dv = l.is_mimic ? u * (planar ? kPlanarTravel : kAngleRange) : 0.0;
+      // the joint value reaches the fp32 FK rounded once (fp64 inputs, mimic joints evaluated in fp64 from the
+      // rounded source value): angle error <= u*|v| (1 + |mimic factor|)
+      const double dv = u * (planar ? kPlanarTravel : kAngleRange) * (1.0 + (l.is_mimic ? std::fabs(l.mimic_mult) : 0.0));
       const double dsc = sc + dv;
       // axis-aligned: entries are c, +-s (error dsc) and one ~1; general Rodrigues: every entry within 4*dsc + 4u
       const double eJ = (planar || l.jkind != 0) ? std::sqrt(4.0 * dsc * dsc + 4.0 * u * u) : 3.0 * (4.0 * dsc + 4.0 * u);
@@ -585,7 +586,7 @@ int fast_create(b200df_group* g)
       if (planar)
       {
         const double tr = kPlanarTravel * std::sqrt(2.0);
-        e.et = b.et + b.eR * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
+        e.et = b.et + b.eR * tr + 2.0 * u * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
         e.reach = b.reach + tr;
       }
     }
@@ -593,8 +594,9 @@ int fast_create(b200df_group* g)
     {
       f.vmax = (float)kPrismaticTravel;
       const double tr = kPrismaticTravel;
-      // axis rounded to fp32 (u*tr), axis*v rounded (u*tr), mimic value rounded (u*tr), then R*t + t0
-      e.et = b.et + b.eR * tr + 3.0 * u * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
+      // axis rounded to fp32 (u*tr), axis*v rounded (u*tr), joint value rounded (u*tr (1 + |mimic factor|)), R*t + t0
+      e.et = b.et + b.eR * tr + (3.0 + (l.is_mimic ? std::fabs(l.mimic_mult) : 0.0)) * u * tr +
+             4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
       e.reach = b.reach + tr;
     }
     E[i] = e;
@@ -698,7 +700,7 @@ void fast_destroy(b200df_group* g)
 
 bool fast_supported(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int q_dtype, int flags)
 {
-  if (!g->fast || !g->fast->ok || q_dtype != B200DF_Q_F32)
+  if (!g->fast || !g->fast->ok || (q_dtype != B200DF_Q_F32 && q_dtype != B200DF_Q_F64))
     return false;
   if ((flags & B200DF_CHECK_ROBOT) && wf.neg)
     return false;  // signed fields: the predicate needs the fp64 distances
@@ -734,8 +736,8 @@ FastLookup make_fast_lookup(const FieldDev& f)
 
 constexpr long kPairSmemMax = 1024;  // sphere pairs whose thresholds are staged in shared memory (8 KB)
 
-template <typename FT, int B>
-int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const float* q, long n, int flags,
+template <typename QT, typename FT, int B>
+int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const QT* q, long n, int flags,
                 uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream)
 {
   const bool pairs = (flags & B200DF_CHECK_INTRA) && g->fast->tables.n_partners > 0;
@@ -744,15 +746,15 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
   const unsigned grid = (unsigned)((n + B - 1) / B);
   if (n_pair_smem > 0)
   {
-    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B, true>, bytes));
-    validity_fast_kernel<FT, B, true><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
+    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<QT, FT, B, true>, bytes));
+    validity_fast_kernel<QT, FT, B, true><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
                                                                   make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
                                                                   verdict, amb_idx, amb_count, n_pair_smem);
   }
   else
   {
-    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<FT, B, false>, bytes));
-    validity_fast_kernel<FT, B, false><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
+    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<QT, FT, B, false>, bytes));
+    validity_fast_kernel<QT, FT, B, false><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
                                                                    make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
                                                                    verdict, amb_idx, amb_count, 0);
   }
@@ -762,10 +764,11 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
 }
 }  // namespace
 
-namespace b200df
+namespace
 {
-int fast_launch(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const float* q, long n,
-                int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream)
+template <typename QT>
+int fast_launch_typed(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const QT* q, long n,
+                      int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream)
 {
   const FastTables& T = g->fast->tables;
   const bool pairs = (flags & B200DF_CHECK_INTRA) && T.n_partners > 0;
@@ -780,13 +783,26 @@ int fast_launch(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, i
   if (b128 <= 100 * 1024)
   {
     if (field_elem == 1)
-      return launch_fast<uint8_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
-    return launch_fast<uint16_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
+      return launch_fast<QT, uint8_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
+    return launch_fast<QT, uint16_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
   }
   const size_t b32 = smem(32);
   B200DF_REQUIRE(b32 <= 220 * 1024, "robot too large for the per-state shared-memory layout");
   if (field_elem == 1)
-    return launch_fast<uint8_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
-  return launch_fast<uint16_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+    return launch_fast<QT, uint8_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+  return launch_fast<QT, uint16_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+}
+}  // namespace
+
+namespace b200df
+{
+int fast_launch(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q, int q_dtype,
+                long n, int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream)
+{
+  if (q_dtype == B200DF_Q_F32)
+    return fast_launch_typed(g, wf, sf, field_elem, static_cast<const float*>(q), n, flags, verdict, amb_idx, amb_count,
+                             stream);
+  return fast_launch_typed(g, wf, sf, field_elem, static_cast<const double*>(q), n, flags, verdict, amb_idx, amb_count,
+                           stream);
 }
 }  // namespace b200df

@@ -448,10 +448,8 @@ def test_batched_edge_check_matches_per_state_oracle(gpu, oracle, robot):
     want = np.where(ref.any(axis=1), ref.argmax(axis=1) + 1, 0)
     assert np.array_equal(got, want)
     assert 0 < (got == 0).sum() < M
-    # FAST checks the interpolated states rounded to fp32
     fast = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=1, var_is_angular=angular)
-    v32 = e.group.check(states.reshape(-1, desc.nvar).astype(np.float32), e.world, flags=flags, precision=0).reshape(M, K)
-    assert np.array_equal(fast, np.where(v32.any(axis=1), v32.argmax(axis=1) + 1, 0))
+    assert np.array_equal(fast, got)  # FAST screens the fp64 states in fp32 and re-runs the undecided ones unrounded
     if robot == "mobile_arm":
         assert (np.abs(qb[:, 2] - qa[:, 2]) > np.pi).any()  # the shortest-arc branch was exercised
 
@@ -482,6 +480,12 @@ def test_device_resident_cloud_and_non_finite_joint_values(gpu, oracle):
     for precision in (0, 1, 2):
         got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=precision)
         assert np.array_equal(got, ref), "precision %d: %d differences" % (precision, int((got != ref).sum()))
+    # fp64 joint values through FAST: screened rounded to fp32, undecided states re-run on the fp64 values
+    q64 = desc.sample_states(300_000, 88, np.float64)
+    a = e.group.check(q64, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=1)
+    b = e.group.check(q64, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0)
+    raw = e.group.check(q64, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=3)
+    assert np.array_equal(a, b) and np.array_equal(raw[raw != 2], b[raw != 2]) and (raw == 2).mean() < 0.01
 
 
 def test_padding_sphere_known_answer_on_gpu(gpu, oracle):
