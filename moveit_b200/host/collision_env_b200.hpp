@@ -677,6 +677,26 @@ public:
     gsr = one[0];
   }
 
+  // getAllCollisions .cpp:1559-1578: self field, intra group and environment are all visited (each stops on its own
+  // at max_contacts); with req.contacts == false this is the logical OR the verdict kernel computes
+  void getAllCollisions(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                        const AllowedCollisionMatrix* acm) const
+  {
+    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, state, acm, true);
+    const int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
+    if (!req.contacts)
+    {
+      std::uint8_t v = 0;
+      checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, state.getVariablePositions(), B200DF_Q_F64,
+                                     1, flags, B200DF_PRECISION_EXACT, &v),
+                  "b200df_check_batch");
+      if (v)
+        res.collision = true;
+      return;
+    }
+    contactsFromSpheres(req, res, state, *e, flags, /*stop_when_done=*/false);
+  }
+
   // ---- batched entry points (new): N states, row-major [n][variable count] -------------------------------
   // verdict[i] = res.collision of the corresponding single-state call with req.contacts == false.
   // which: B200DF_CHECK_ROBOT = checkRobotCollision, SELF|INTRA = checkSelfCollision, all three = checkCollision.
@@ -1317,7 +1337,7 @@ private:
   }
 
   void contactsFromSpheres(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
-                           const CacheEntry& e, int flags) const
+                           const CacheEntry& e, int flags, bool stop_when_done = true) const
   {
     const std::size_t S = e.sphere_radii.size();
     std::vector<double> cen(S * 3), dist(S), grad(S * 3);
@@ -1365,9 +1385,9 @@ private:
     }
     else
       field_pass(0, nullptr, nullptr);  // posed centres only
-    if (!done && (flags & B200DF_CHECK_INTRA))
+    if (!(done && stop_when_done) && (flags & B200DF_CHECK_INTRA))
       done = intraContacts(req, res, state, e, cen);
-    if (!done && (flags & B200DF_CHECK_ROBOT))
+    if (!(done && stop_when_done) && (flags & B200DF_CHECK_ROBOT))
     {
       field_pass(B200DF_CHECK_ROBOT, world_field_, nullptr);
       field_contacts("environment", BodyTypes::WORLD_OBJECT, nullptr);
