@@ -1357,6 +1357,13 @@ private:
           continue;
         const std::size_t allowed = std::min(req.max_contacts_per_pair, req.max_contacts - res.contact_count);
         std::size_t found = 0;
+        if (allowed == 0)  // getCollisionSphereCollision with num_coll == 0 reports the collision without a contact
+          for (int s = e.sphere_begin[l]; s < e.sphere_begin[l + 1]; ++s)
+            if (sphere_hits(s))
+            {
+              res.collision = true;
+              break;
+            }
         for (int s = e.sphere_begin[l]; s < e.sphere_begin[l + 1] && found < allowed; ++s)
         {
           if (!sphere_hits(s))
