@@ -81,6 +81,8 @@ enum
   /* test hooks, not for production use */
   B200DF_PRECISION_DEBUG_SWEEP = 2,  /* the independently written round-1 sweep kernel (cross-check of EXACT) */
   B200DF_PRECISION_DEBUG_SCREEN = 3, /* FAST's screening pass alone: verdict 0 / 1, or 2 = undecided */
+  B200DF_PRECISION_DEBUG_SMALL = 4,  /* the one-CTA-per-state kernel that EXACT and FAST pick for small batches, at
+                                        any batch size (same verdicts as EXACT) */
 };
 
 /* CollisionType of a gradient entry (collision_distance_field_types.h:57-63) */

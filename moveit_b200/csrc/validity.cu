@@ -39,60 +39,6 @@ int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf,
 
 namespace
 {
-// what the verdict kernel reads of a field: the fp64 world->grid mapping plus integer bounds
-struct LookupDev
-{
-  double om[3];      // origin_minus_
-  double oo;         // oo_resolution_
-  unsigned lim[3];   // n-2 (0 when n < 2): cell c is inside the 1-cell inset box iff (unsigned)(c-1) < lim
-  int stride1, stride2;
-  const void* d2;
-  const void* neg;
-  const double* sqrt_table;
-};
-
-LookupDev make_lookup(const FieldDev& f)
-{
-  LookupDev l{};
-  for (int i = 0; i < 3; ++i)
-  {
-    l.om[i] = f.g.om[i];
-    l.lim[i] = f.g.n[i] >= 2 ? (unsigned)(f.g.n[i] - 2) : 0u;
-  }
-  l.oo = f.g.oo;
-  l.stride1 = (int)f.g.stride1;
-  l.stride2 = (int)f.g.stride2;
-  l.d2 = f.d2;
-  l.neg = f.neg;
-  l.sqrt_table = f.sqrt_table;
-  return l;
-}
-
-// getCollisionSphereCollision's per-sphere predicate (collision_distance_field_types.cpp:213-227) on top of
-// getDistanceGradient's cell lookup (distance_field.cpp:62-86, voxel_grid.h:515-532).
-// floor((p - origin_minus) * oo) is evaluated in fp64 exactly like the reference; cvt.rmi.s32.f64 IS that floor for
-// every value inside the grid and saturates outside (NaN -> 0), where the unsigned range test fails anyway.
-// A centre outside the 1-cell inset box reads as "max distance" in the reference => never a collision (Q4).
-// world->grid cell of a sphere centre: flat voxel index (0 when outside) + "inside the 1-cell inset box"
-__device__ __forceinline__ unsigned cell_index(const LookupDev& f, double x, double y, double z, bool& in)
-{
-  const int ix = __double2int_rd((x - f.om[0]) * f.oo);
-  const int iy = __double2int_rd((y - f.om[1]) * f.oo);
-  const int iz = __double2int_rd((z - f.om[2]) * f.oo);
-  in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
-  return in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
-}
-
-template <typename FT>
-__device__ __forceinline__ bool voxel_hits(const LookupDev& f, unsigned idx, bool in, int d2, double radius, int thr,
-                                           double tol, double max_prop)
-{
-  if (!f.neg)
-    return in & (d2 < thr);  // host-resolved threshold, exactly equivalent to the fp64 predicate
-  const double dist = f.sqrt_table[d2] - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
-  return in && (max_prop > dist) && (radius - dist > tol);
-}
-
 constexpr int kBatch = 4;  // spheres posed / looked up / pair-tested together (independent chains for the fp64 pipe)
 
 // redo_idx / redo_count: when set, the kernel re-evaluates the listed states only (the FAST path's ambiguous set); it is
@@ -369,6 +315,17 @@ int dispatch_verdict(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, 
 
 constexpr int kPrecisionV1 = B200DF_PRECISION_DEBUG_SWEEP;        // the round-1 kernel, an independent cross-check
 constexpr int kPrecisionFastRaw = B200DF_PRECISION_DEBUG_SCREEN;  // FAST screening pass only: 0 / 1 / 2 = undecided
+constexpr int kPrecisionSmall = B200DF_PRECISION_DEBUG_SMALL;     // the one-CTA-per-state kernel at any batch size
+
+// Batches up to this many states run on the one-CTA-per-state kernel (validity_small.cu): below it the batched
+// kernels leave most of the GPU idle and the call time is one thread's walk through a whole state.
+// B200DF_SMALL_MAX_STATES overrides it (0 switches the small-batch kernel off); read on every call so that a test
+// can flip it.
+int64_t small_max_states()
+{
+  const char* e = getenv("B200DF_SMALL_MAX_STATES");
+  return e ? (int64_t)atoll(e) : (int64_t)16384;
+}
 
 // keeps the stream-ordered allocator from returning memory to the OS between calls (once per device)
 void keep_async_pool(int device)
@@ -396,6 +353,10 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
 {
   if (precision == kPrecisionV1)
     return launch_verdict_v1(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+  if (precision == kPrecisionSmall ||
+      ((precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST) && n <= small_max_states() &&
+       small_supported(group)))
+    return small_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
   const bool raw = precision == kPrecisionFastRaw;
   if (raw && !fast_supported(group, wf, sf, q_dtype, flags))
   {
@@ -445,6 +406,7 @@ struct b200df_group::StagePool
     uint8_t* v[kSlots] = {};
     int* amb[kSlots] = {};  // [0] = count, [1..] = indices (FAST path scratch)
     size_t q_bytes = 0, v_bytes = 0;
+    void* pin = nullptr;  // mapped pinned staging of the small-batch path: joint values, then verdicts
   };
   std::mutex mu;
   std::vector<Ctx*> free_list;
@@ -463,6 +425,8 @@ struct b200df_group::StagePool
       if (c->stream[i])
         cudaStreamDestroy(c->stream[i]);
     }
+    if (c->pin)
+      cudaFreeHost(c->pin);
     delete c;
   }
   Ctx* acquire()
@@ -496,6 +460,19 @@ int64_t chunk_states()
     return x >= 1024 ? (int64_t)x : kChunkStates;
   }();
   return v;
+}
+
+// Small batches (the per-state isValid() callers of the reference: OMPL's StateValidityChecker, checkCollision on one
+// RobotState) are latency-bound, not bandwidth-bound: two staged copies and their driver calls cost more than the
+// kernel.  Up to kSmallStates states travel through one mapped pinned buffer instead: the kernel reads the joint
+// values and writes the verdicts across PCIe itself, so the call is one launch and one stream synchronise.
+constexpr int64_t kSmallStates = 2048;
+constexpr size_t kSmallQBytes = 256 * 1024;
+
+bool small_batch_enabled()
+{
+  const char* e = getenv("B200DF_SMALL_BATCH");
+  return !(e && e[0] == '0');
 }
 
 int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
@@ -896,6 +873,8 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
   if ((rc = upload(g.get(), pair_T, &dev.pair_T)))
     return rc;
   g->stage = new b200df_group::StagePool;
+  if ((rc = small_create(g.get())))
+    return rc;
   if ((rc = fast_create(g.get())))
   {
     delete g->stage;
@@ -914,6 +893,7 @@ int b200df_group_destroy(b200df_group* g)
   DeviceGuard dg(g->device);
   delete g->stage;
   fast_destroy(g);
+  small_destroy(g);
   cudaFree(g->d_link_fields);
   cudaFree(g->d_lf_enabled);
   for (void* p : g->allocations)
@@ -935,7 +915,7 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q_dev && verdict_dev)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
   B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1 ||
-                     precision == kPrecisionFastRaw,
+                     precision == kPrecisionFastRaw || precision == kPrecisionSmall,
                  "unknown precision");
   if (n == 0)
     return B200DF_OK;
@@ -955,7 +935,7 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && verdict)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
   B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST || precision == kPrecisionV1 ||
-                     precision == kPrecisionFastRaw,
+                     precision == kPrecisionFastRaw || precision == kPrecisionSmall,
                  "unknown precision");
   if (n == 0)
     return B200DF_OK;
@@ -968,8 +948,40 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
   const size_t row = (size_t)group->dev.n_vars * q_elem_size(q_dtype);
   const int64_t chunk = std::min<int64_t>(n, chunk_states());
   b200df_group::StagePool::Ctx* ctx = group->stage->acquire();
-  rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
   cudaError_t e = cudaSuccess;
+  if (n <= kSmallStates && (size_t)n * row <= kSmallQBytes && small_batch_enabled() &&
+      (precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST))
+  {
+    // one launch of the small-batch exact kernel (FAST returns the same verdicts by construction; its screening pass
+    // only pays off on batches that fill the GPU)
+    if (!ctx->stream[0])
+      e = cudaStreamCreateWithFlags(&ctx->stream[0], cudaStreamNonBlocking);
+    if (e == cudaSuccess && !ctx->pin)
+      e = cudaHostAlloc(&ctx->pin, kSmallQBytes + (size_t)kSmallStates, cudaHostAllocMapped);
+    void* dpin = nullptr;
+    if (e == cudaSuccess)
+      e = cudaHostGetDevicePointer(&dpin, ctx->pin, 0);
+    if (e == cudaSuccess)
+    {
+      std::memcpy(ctx->pin, q, (size_t)n * row);
+      uint8_t* hv = static_cast<uint8_t*>(ctx->pin) + kSmallQBytes;
+      uint8_t* dv = static_cast<uint8_t*>(dpin) + kSmallQBytes;
+      rc = small_supported(group)
+               ? small_launch(group, wf, sf, elem, dpin, q_dtype, n, flags, dv, ctx->stream[0])
+               : dispatch_verdict(group->dev, wf, sf, elem, dpin, q_dtype, n, flags, dv, ctx->stream[0]);
+      e = cudaStreamSynchronize(ctx->stream[0]);
+      if (!rc && e == cudaSuccess)
+        std::memcpy(verdict, hv, (size_t)n);
+    }
+    group->stage->give_back(ctx);
+    if (!rc && e != cudaSuccess)
+    {
+      set_error("small-batch check failed: %s", cudaGetErrorString(e));
+      rc = B200DF_ERR_CUDA;
+    }
+    return rc;
+  }
+  rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
   int k = 0;
   for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k = (k + 1) % kSlots)
   {

@@ -431,6 +431,60 @@ __device__ __forceinline__ bool sphere_collides(const FieldDev& f, double x, dou
   return (max_prop > dist) && (radius - dist > tol);
 }
 
+// what the verdict kernel reads of a field: the fp64 world->grid mapping plus integer bounds
+struct LookupDev
+{
+  double om[3];      // origin_minus_
+  double oo;         // oo_resolution_
+  unsigned lim[3];   // n-2 (0 when n < 2): cell c is inside the 1-cell inset box iff (unsigned)(c-1) < lim
+  int stride1, stride2;
+  const void* d2;
+  const void* neg;
+  const double* sqrt_table;
+};
+
+inline LookupDev make_lookup(const FieldDev& f)
+{
+  LookupDev l{};
+  for (int i = 0; i < 3; ++i)
+  {
+    l.om[i] = f.g.om[i];
+    l.lim[i] = f.g.n[i] >= 2 ? (unsigned)(f.g.n[i] - 2) : 0u;
+  }
+  l.oo = f.g.oo;
+  l.stride1 = (int)f.g.stride1;
+  l.stride2 = (int)f.g.stride2;
+  l.d2 = f.d2;
+  l.neg = f.neg;
+  l.sqrt_table = f.sqrt_table;
+  return l;
+}
+
+// getCollisionSphereCollision's per-sphere predicate (collision_distance_field_types.cpp:213-227) on top of
+// getDistanceGradient's cell lookup (distance_field.cpp:62-86, voxel_grid.h:515-532).
+// floor((p - origin_minus) * oo) is evaluated in fp64 exactly like the reference; cvt.rmi.s32.f64 IS that floor for
+// every value inside the grid and saturates outside (NaN -> 0), where the unsigned range test fails anyway.
+// A centre outside the 1-cell inset box reads as "max distance" in the reference => never a collision (Q4).
+// world->grid cell of a sphere centre: flat voxel index (0 when outside) + "inside the 1-cell inset box"
+__device__ __forceinline__ unsigned cell_index(const LookupDev& f, double x, double y, double z, bool& in)
+{
+  const int ix = __double2int_rd((x - f.om[0]) * f.oo);
+  const int iy = __double2int_rd((y - f.om[1]) * f.oo);
+  const int iz = __double2int_rd((z - f.om[2]) * f.oo);
+  in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
+  return in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
+}
+
+template <typename FT>
+__device__ __forceinline__ bool voxel_hits(const LookupDev& f, unsigned idx, bool in, int d2, double radius, int thr,
+                                           double tol, double max_prop)
+{
+  if (!f.neg)
+    return in & (d2 < thr);  // host-resolved threshold, exactly equivalent to the fp64 predicate
+  const double dist = f.sqrt_table[d2] - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
+  return in && (max_prop > dist) && (radius - dist > tol);
+}
+
 // stage one tile of joint values into shared memory as [var][thread] (coalesced global read)
 template <typename QT>
 __device__ __forceinline__ void stage_q(const QT* __restrict__ q, long base, long n, int n_vars, int B, int tid,
@@ -479,6 +533,8 @@ struct b200df_group
   StagePool* stage = nullptr;
   struct FastPath;   // fp32 screening tables + scratch (validity_fast.cu); null when the model does not fit them
   FastPath* fast = nullptr;
+  struct SmallPath;  // one-CTA-per-state kernel for latency-bound small batches (validity_small.cu)
+  SmallPath* small = nullptr;
   void* d_link_fields = nullptr;  // device copies behind dev.link_fields / dev.lf_enabled
   void* d_lf_enabled = nullptr;
   int link_field_elem = 0;        // voxel type of the link fields (1 or 2)
@@ -495,6 +551,13 @@ bool fast_supported(const b200df_group* group, const FieldDev& wf, const FieldDe
 // amb_idx (capacity n) and counted in *amb_count, both device memory, *amb_count zeroed by this call
 int fast_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
                 int q_dtype, long n, int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream);
+
+// small-batch path (validity_small.cu): one CTA per state, same verdicts as the batched exact kernel
+int small_create(b200df_group* group);  // leaves group->small null when the robot does not fit shared memory
+void small_destroy(b200df_group* group);
+bool small_supported(const b200df_group* group);
+int small_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
+                 int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream);
 
 // fills wf / sf for the requested flags (rebuilding dirty fields) and checks they fit the group
 int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field* self, int flags, FieldDev* wf,

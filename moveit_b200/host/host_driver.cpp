@@ -6,6 +6,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "collision_env_b200.hpp"
 
@@ -208,6 +209,35 @@ int main(int argc, char** argv)
       single.push_back((r1.collision ? 1 : 0) | (r2.collision ? 2 : 0) | (r3.collision ? 4 : 0));
     }
     writeFile(prefix + ".single.u8", single);
+
+    // concurrent callers on one shared env (planning_scene/test/test_multi_threaded.cpp: every thread repeats
+    // checkCollision on its own state and must keep getting the answer a lone caller got)
+    {
+      const int n_threads = (int)std::min<std::int64_t>(4, (std::int64_t)single.size());
+      const int trials = 200;
+      std::vector<int> bad(n_threads > 0 ? n_threads : 1, 0);
+      std::vector<std::thread> threads;
+      for (int t = 0; t < n_threads; ++t)
+        threads.emplace_back([&, t] {
+          core::RobotState st(ref_state);
+          st.setVariablePositions(&q[(std::size_t)t * nvar]);
+          for (int k = 0; k < trials; ++k)
+          {
+            CollisionResult r;
+            if (acm_ptr)
+              env->checkCollision(req, r, st, acm);
+            else
+              env->checkCollision(req, r, st);
+            if (r.collision != ((single[t] & 4) != 0))
+              ++bad[t];
+          }
+        });
+      for (std::thread& th : threads)
+        th.join();
+      for (int t = 0; t < n_threads; ++t)
+        if (bad[t])
+          throw std::runtime_error("concurrent checkCollision disagrees with the single-threaded answer");
+    }
 
     // contacts
     {

@@ -634,3 +634,140 @@ def test_config3_field_b_cloud(gpu, oracle):
     want = np.minimum(np.rint(dist * dist).astype(np.int64), 625)
     assert np.array_equal(d2[sample[:, 0], sample[:, 1], sample[:, 2]], want)
     print("field B rebuild: %.3f ms" % ms)
+
+
+def test_concurrent_callers_share_one_group(gpu, oracle):
+    """planning_scene/test/test_multi_threaded.cpp, batched: several host threads call the C ABI on the same model,
+    group and field at once (verdicts in both precisions, gradients, edges) and every one must get the answer a lone
+    caller gets."""
+    import threading
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    flags = CHECK_ROBOT | CHECK_INTRA
+    n_threads, rounds = 6, 12
+    batches = [desc.sample_states(20_000 + 3_000 * t, 900 + t, np.float32) for t in range(n_threads)]
+    want = [e.group.check(b, e.world, flags=flags, precision=0) for b in batches]
+    want_grad = [e.group.gradients(b[:500], e.world) for b in batches]
+    want_edge = [e.group.check_edges(b[:2000].astype(np.float64), b[2000:4000].astype(np.float64), 8, e.world,
+                                     flags=flags) for b in batches]
+    errors = []
+
+    def worker(t):
+        try:
+            for k in range(rounds):
+                got = e.group.check(batches[t], e.world, flags=flags, precision=k % 2)
+                if not np.array_equal(got, want[t]):
+                    errors.append("thread %d round %d: %d verdicts differ" % (t, k, int((got != want[t]).sum())))
+                if k % 4 == 0:
+                    g = e.group.gradients(batches[t][:500], e.world)
+                    for key in ("dist", "grad", "type", "centers"):
+                        if not np.array_equal(g[key], want_grad[t][key]):
+                            errors.append("thread %d round %d: gradients[%s] differ" % (t, k, key))
+                            break
+                if k % 4 == 2:
+                    ed = e.group.check_edges(batches[t][:2000].astype(np.float64),
+                                             batches[t][2000:4000].astype(np.float64), 8, e.world, flags=flags)
+                    if not np.array_equal(ed, want_edge[t]):
+                        errors.append("thread %d round %d: edge results differ" % (t, k))
+        except Exception as ex:  # noqa: BLE001 - reported through the assertion below
+            errors.append("thread %d: %r" % (t, ex))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]
+
+
+# ------------------------------------------------------------------------------- small-batch (one CTA per state) kernel
+SMALL = 4  # B200DF_PRECISION_DEBUG_SMALL: the kernel EXACT / FAST pick for small batches, forced at any batch size
+
+
+@pytest.mark.parametrize("robot", ["panda", "mobile_arm", "pr2_like"])
+def test_small_batch_kernel_equals_batched_exact_and_oracle(gpu, oracle, robot):
+    """validity_small.cu spreads one state over a CTA; the transforms and predicates are the same arithmetic, so the
+    verdicts equal the one-thread-per-state kernel's (and the oracle's) on every robot, flag set and joint dtype."""
+    desc = {"panda": rd.panda, "mobile_arm": rd.mobile_arm, "pr2_like": rd.pr2_like}[robot]()
+    fd = scenarios.FIELD_A if robot == "panda" else scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene() if robot == "panda" else scenarios.random_scene(seed=31)
+    e = EngineSetup(desc, fd, objs)
+    n = 60_000 if robot != "pr2_like" else 30_000
+    for dtype in (np.float32, np.float64):
+        q = desc.sample_states(n, 17, dtype)
+        for flags in (CHECK_ROBOT, CHECK_INTRA, CHECK_ROBOT | CHECK_INTRA):
+            batched = e.group.check(q, e.world, flags=flags, precision=0)  # n > small-batch limit: batched kernel
+            small = e.group.check(q, e.world, flags=flags, precision=SMALL)
+            assert np.array_equal(small, batched), (robot, dtype, flags, int((small != batched).sum()))
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    q = desc.sample_states(3000, 18)
+    got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL)
+    assert np.array_equal(got, o.env.check_batch(q, mode=3, n_threads=8))
+
+
+def test_small_batch_kernel_self_field_signed_fine_and_non_finite(gpu, oracle):
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=77)
+    q0 = np.zeros(desc.nvar)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, group="panda_arm", self_state=q0)
+    sp = self_field_points(o.model_desc, desc, o.group_links, o.model.fk(q0))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, group="panda_arm", self_points=sp)
+    q = desc.sample_states(20_000, 99)
+    flags = CHECK_ROBOT | CHECK_SELF | CHECK_INTRA
+    got = e.group.check(q, e.world, e.self_field, flags=flags, precision=SMALL)
+    assert np.array_equal(got, e.group.check(q, e.world, e.self_field, flags=flags, precision=0))
+    assert np.array_equal(got[:4000], o.env.check_batch(q[:4000], mode=3, n_threads=8))
+    # signed world field (fp64 predicate instead of the integer threshold)
+    es = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene(seed=5), signed=True)
+    assert np.array_equal(es.group.check(q, es.world, flags=CHECK_ROBOT, precision=SMALL),
+                          es.group.check(q, es.world, flags=CHECK_ROBOT, precision=0))
+    # 1 cm / u16 field
+    fine = dict(size=(2.0, 2.0, 2.0), resolution=0.01, center=(0.0, 0.0, 0.5), max_distance=0.25)
+    ef = EngineSetup(desc, fine, objs)
+    a = ef.group.check(q, ef.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL)
+    assert np.array_equal(a, ef.group.check(q, ef.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0))
+    assert 0 < a.sum() < len(a)
+    # NaN / inf joint values
+    qn = desc.sample_states(12_000, 5, np.float32)
+    qn[::9, 3] = np.nan
+    qn[1::9, 0] = np.inf
+    qn[2::9, 6] = -np.inf
+    qn[3::9, 7] = np.nan
+    ew = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
+    assert np.array_equal(ew.group.check(qn, ew.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL),
+                          ew.group.check(qn, ew.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0))
+
+
+def test_small_batches_take_the_low_latency_path_and_agree(gpu, oracle, monkeypatch):
+    """n = 1 ... a few thousand states: EXACT and FAST route to the small-batch kernel (host entry: through one mapped
+    pinned buffer).  Same verdicts with the route switched off, and the oracle's."""
+    import torch
+    from moveit_b200.binding import Q_F32
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    flags = CHECK_ROBOT | CHECK_INTRA
+    q = desc.sample_states(6000, 41, np.float32)
+    ref = o.env.check_batch(q.astype(np.float64), mode=3, n_threads=8)
+    for n in (1, 2, 31, 32, 33, 500, 2048, 2049, 6000):
+        for precision in (0, 1):
+            assert np.array_equal(e.group.check(q[:n], e.world, flags=flags, precision=precision), ref[:n]), (n, precision)
+        assert np.array_equal(e.group.check(q[:n].astype(np.float64), e.world, flags=flags), ref[:n])
+    # one state at a time, the way isValid() is called
+    single = np.array([e.group.check(q[i:i + 1], e.world, flags=flags)[0] for i in range(300)], dtype=np.uint8)
+    assert np.array_equal(single, ref[:300])
+    # device-resident entry
+    qd = torch.from_numpy(q).cuda()
+    vd = torch.empty(len(q), dtype=torch.uint8, device="cuda")
+    e.group.check_device(qd.data_ptr(), Q_F32, 777, vd.data_ptr(), e.world, flags=flags, precision=1,
+                         stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(vd[:777].cpu().numpy(), ref[:777])
+    # the batched kernels still serve small batches when the small-batch route is off
+    monkeypatch.setenv("B200DF_SMALL_MAX_STATES", "0")
+    monkeypatch.setenv("B200DF_SMALL_BATCH", "0")
+    for n in (1, 33, 2048):
+        for precision in (0, 1):
+            assert np.array_equal(e.group.check(q[:n], e.world, flags=flags, precision=precision), ref[:n])
