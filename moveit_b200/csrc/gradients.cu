@@ -239,8 +239,10 @@ __device__ __forceinline__ void posed_rel(const double* pose, double x, double y
   iso_apply(inv, x, y, z, rx, ry, rz);
 }
 
-template <typename QT, typename FT, bool LF>
-__global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
+// COOP (small batches): GS = 4 states per CTA and one warp walks one state (warp_fk), so a 100-waypoint trajectory
+// spreads over 25 SMs and phase 1 costs one FK chain; otherwise 32 states per CTA, one thread per state's FK.
+template <typename QT, typename FT, bool LF, int GS, int NT, bool COOP>
+__global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
                                                                         const QT* __restrict__ q, long n, int flags,
                                                                         double* __restrict__ out_dist,
                                                                         double* __restrict__ out_grad,
@@ -249,30 +251,48 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
 {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
-  const long base = (long)blockIdx.x * kGradStates;
+  const long base = (long)blockIdx.x * GS;
   const int S = g.n_spheres;
   const int G = g.n_glinks;
-  double* cen = smem;                                          // [state][S][3]
-  double* slots = cen + (size_t)kGradStates * S * 3;           // [n_slots][12][state]
-  double* poses = slots + (size_t)g.n_slots * 12 * kGradStates;  // LF: [state][G][12] link poses
-  unsigned* can = reinterpret_cast<unsigned*>(poses + (LF ? (size_t)kGradStates * G * 12 : 0));  // LF: [state][S]
-  unsigned* abt = can + (LF ? (size_t)kGradStates * S : 0);                                       // LF: [state][S]
-  QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)kGradStates * S : 0));  // [state][n_vars]
+  const int L = g.n_links;
+  double* cen = smem;                        // [state][S][3]
+  double* slots = cen + (size_t)GS * S * 3;  // !COOP: [n_slots][12][state]   COOP: T [state][L][12]
+  double* poses = slots + (COOP ? (size_t)GS * L * 12 : (size_t)g.n_slots * 12 * GS);  // !COOP && LF: [state][G][12]
+  double* staging = poses + ((LF && !COOP) ? (size_t)GS * G * 12 : 0);                 // COOP: warp_fk staging per warp
+  unsigned* can = reinterpret_cast<unsigned*>(staging + (COOP ? (NT / 32) * warp_fk_staging_doubles(L) : 0));
+  unsigned* abt = can + (LF ? (size_t)GS * S : 0);                        // LF: [state][S] (can likewise)
+  QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)GS * S : 0));        // [state][n_vars]
   {
-    const int total = kGradStates * g.n_vars;
+    const int total = GS * g.n_vars;
     const long limit = (n - base) * g.n_vars;
     const QT* src = q + base * g.n_vars;
-    for (int e = tid; e < total; e += kGradThreads)
+    for (int e = tid; e < total; e += NT)
       qs[e] = (e < limit) ? src[e] : QT(0);
   }
   __syncthreads();
-  if (tid < kGradStates)
+  if (COOP)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int st = warp; st < GS; st += NT / 32)
+    {
+      double* T = slots + (size_t)st * L * 12;
+      warp_fk(g.links, L, qs + (size_t)st * g.n_vars, lane, staging + warp * warp_fk_staging_doubles(L), T);
+      double* my_cen = cen + (size_t)st * S * 3;
+      for (int s = lane; s < S; s += 32)
+      {
+        const double* rel = g.sph + 4 * s;
+        const double* Tl = T + (size_t)g.glinks[g.sph_glink[s]].link * 12;
+        iso_apply(Tl, rel[0], rel[1], rel[2], my_cen[3 * s], my_cen[3 * s + 1], my_cen[3 * s + 2]);
+      }
+    }
+  }
+  else if (tid < GS)
   {
     double cur[12];
     double* my_cen = cen + (size_t)tid * S * 3;
     for (int i = 0; i < g.n_links; ++i)
     {
-      fk_step(g.links[i], qs + (size_t)tid * g.n_vars, slots + tid, 1, kGradStates, cur);
+      fk_step(g.links[i], qs + (size_t)tid * g.n_vars, slots + tid, 1, GS, cur);
       const int gs = g.link_gslot[i];
       if (gs < 0)
         continue;
@@ -291,14 +311,18 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
     }
   }
   __syncthreads();
-  const int items = kGradStates * S;
+  // pose of group link j in state st (PosedDistanceField::updatePose)
+  auto link_pose = [&](int st, int j) -> const double* {
+    return COOP ? slots + ((size_t)st * L + g.glinks[j].link) * 12 : poses + ((size_t)st * G + j) * 12;
+  };
+  const int items = GS * S;
   if (LF)
   {
     // Which link fields may act on which sphere.  PosedDistanceField::getCollisionSphereGradients
     // (collision_distance_field_types.cpp:81-141) walks a link's spheres in order and RETURNS at the first sphere
     // that is outside the other link's field (Q7; the "gradient norm > 0" guard is the norm of pose * 0 = the
     // pose's translation, Q6), so sphere k sees field j only if it is inside AND no earlier sphere of its link aborted.
-    for (int it = tid; it < items; it += kGradThreads)
+    for (int it = tid; it < items; it += NT)
     {
       const int st = it / S, k = it - st * S;
       const double* sc = cen + (size_t)st * S * 3;
@@ -312,7 +336,7 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
         const FieldDev& f = g.link_fields[j];
         if (!f.d2)
           continue;
-        const double* pose = poses + ((size_t)st * G + j) * 12;
+        const double* pose = link_pose(st, j);
         double rx, ry, rz;
         posed_rel(pose, sc[3 * k], sc[3 * k + 1], sc[3 * k + 2], rx, ry, rz);
         long idx;
@@ -325,7 +349,7 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
       abt[it] = ab;
     }
     __syncthreads();
-    for (int it = tid; it < kGradStates * G; it += kGradThreads)
+    for (int it = tid; it < GS * G; it += NT)
     {
       const int st = it / G, gs = it - st * G;
       unsigned alive = 0xffffffffu;
@@ -338,7 +362,7 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
     }
     __syncthreads();
   }
-  for (int it = tid; it < items; it += kGradThreads)
+  for (int it = tid; it < items; it += NT)
   {
     const int st = it / S, k = it - st * S;
     const long state = base + st;
@@ -358,7 +382,7 @@ __global__ void __launch_bounds__(kGradThreads) gradients_gather_kernel(GroupDev
       {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        const double* pose = poses + ((size_t)st * G + j) * 12;
+        const double* pose = link_pose(st, j);
         double rx, ry, rz;
         posed_rel(pose, cx, cy, cz, rx, ry, rz);
         double d = DBL_MAX, lx = 0.0, ly = 0.0, lz = 0.0;
@@ -513,42 +537,62 @@ int launch_verdict_v1(const GroupDev& g, const FieldDev& wf, const FieldDev& sf,
 
 namespace
 {
-size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf)
+constexpr int kCoopStates = 4, kCoopThreads = 128;  // small-batch variant
+constexpr size_t kSmallGradBytes = 1 << 20;         // host-buffer calls up to this size use the mapped pinned staging
+constexpr int64_t kCoopMaxStates = 4096;            // above this the 32-states-per-CTA variant has the GPU filled
+
+size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf, int gs, int nt, bool coop)
 {
-  size_t b = ((size_t)kGradStates * g.n_spheres * 3 + (size_t)g.n_slots * 12 * kGradStates) * sizeof(double) +
-             (size_t)kGradStates * g.n_vars * q_elem;
+  size_t d = (size_t)gs * g.n_spheres * 3;
+  if (coop)
+    d += (size_t)gs * g.n_links * 12 + (size_t)(nt / 32) * warp_fk_staging_doubles(g.n_links);
+  else
+    d += (size_t)g.n_slots * 12 * gs + (lf ? (size_t)gs * g.n_glinks * 12 : 0);
+  size_t b = d * sizeof(double) + (size_t)gs * g.n_vars * q_elem;
   if (lf)
-    b += (size_t)kGradStates * g.n_glinks * 12 * sizeof(double) + 2 * (size_t)kGradStates * g.n_spheres * sizeof(unsigned);
+    b += 2 * (size_t)gs * g.n_spheres * sizeof(unsigned);
   return b;
+}
+
+template <typename QT, typename FT, bool LF, int GS, int NT, bool COOP>
+int launch_gather_variant(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n,
+                          int flags, double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream,
+                          size_t bytes)
+{
+  B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, LF, GS, NT, COOP>, bytes));
+  const unsigned grid = (unsigned)((n + GS - 1) / GS);
+  gradients_gather_kernel<QT, FT, LF, GS, NT, COOP><<<grid, NT, bytes, stream>>>(
+      g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  return B200DF_OK;
 }
 
 template <typename QT, typename FT>
 int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n, int flags,
-                         double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
+                  double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
 {
   const bool lf = (flags & B200DF_CHECK_LINK_FIELDS) != 0;
-  const size_t bytes = gather_smem_bytes(g, sizeof(QT), lf);
+  const size_t coop_bytes = gather_smem_bytes(g, sizeof(QT), lf, kCoopStates, kCoopThreads, true);
+  if (n <= kCoopMaxStates && coop_bytes <= 200 * 1024)
+  {
+    if (lf)
+      return launch_gather_variant<QT, FT, true, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
+                                                                                  type, centers, stream, coop_bytes);
+    return launch_gather_variant<QT, FT, false, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
+                                                                                 type, centers, stream, coop_bytes);
+  }
+  const size_t bytes = gather_smem_bytes(g, sizeof(QT), lf, kGradStates, kGradThreads, false);
   if (bytes > 220 * 1024)
   {
     set_error("robot too large for the gradient kernel's shared-memory layout (%zu bytes)", bytes);
     return B200DF_ERR_UNSUPPORTED;
   }
-  const unsigned grid = (unsigned)((n + kGradStates - 1) / kGradStates);
   if (lf)
-  {
-    B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, true>, bytes));
-    gradients_gather_kernel<QT, FT, true><<<grid, kGradThreads, bytes, stream>>>(
-        g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
-  }
-  else
-  {
-    B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, false>, bytes));
-    gradients_gather_kernel<QT, FT, false><<<grid, kGradThreads, bytes, stream>>>(
-        g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
-  }
-  B200DF_LAUNCHED();
-  B200DF_CUDA(cudaGetLastError());
-  return B200DF_OK;
+    return launch_gather_variant<QT, FT, true, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
+                                                                                 type, centers, stream, bytes);
+  return launch_gather_variant<QT, FT, false, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
+                                                                                type, centers, stream, bytes);
 }
 
 int dispatch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int elem, const void* q,
@@ -587,48 +631,61 @@ static int run_f64_output(const b200df_group* group, b200df_field* world, const 
       return rc;
   }
   DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const size_t qbytes = (size_t)n * group->dev.n_vars * q_elem_size(q_dtype);
   const size_t obytes = (size_t)n * out_per_state * sizeof(double);
+  typedef b200df_group::StagePool Pool;
+  Pool::Ctx* ctx = group->stage->acquire();
+  cudaError_t e = Pool::ensure_stream(ctx, 0);
   int rc = B200DF_OK;
+  // small calls: joint values in and results out through the context's mapped pinned buffer (one launch, one sync)
+  const size_t o_out = (qbytes + 255) & ~(size_t)255;
+  const bool mapped = o_out + obytes <= kSmallGradBytes && small_batch_enabled();
+  void *dq = nullptr, *dout = nullptr;
+  if (e == cudaSuccess && mapped)
   {
-    ScratchBuffer dq, dout;
-    dq.stream = dout.stream = stream;
-    cudaError_t e = cudaMallocAsync(&dq.p, std::max<size_t>(qbytes, 1), stream);
+    void* dpin = nullptr;
+    e = Pool::ensure_pin(ctx, o_out + obytes, &dpin);
     if (e == cudaSuccess)
-      e = cudaMallocAsync(&dout.p, std::max<size_t>(obytes, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(dq.p, q, qbytes, cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
     {
-      set_error("staging the batch failed: %s", cudaGetErrorString(e));
-      rc = B200DF_ERR_CUDA;
-    }
-    if (!rc)
-    {
-      double* o = static_cast<double*>(dout.p);
-      if (mode == OUT_CENTERS)
-        rc = dispatch_exact<OUT_CENTERS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-      else if (mode == OUT_TRANSFORMS)
-        rc = dispatch_exact<OUT_TRANSFORMS>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-      else
-        rc = dispatch_exact<OUT_CLEARANCE>(group->dev, wf, sf, elem, dq.p, q_dtype, n, 0, nullptr, o, stream);
-    }
-    if (!rc)
-    {
-      e = cudaMemcpyAsync(out, dout.p, obytes, cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);
-      if (e != cudaSuccess)
-      {
-        set_error("reading results back failed: %s", cudaGetErrorString(e));
-        rc = B200DF_ERR_CUDA;
-      }
+      std::memcpy(ctx->pin, q, qbytes);
+      dq = dpin;
+      dout = static_cast<char*>(dpin) + o_out;
     }
   }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
+  else if (e == cudaSuccess)
+  {
+    e = Pool::ensure_scratch(ctx, 0, std::max<size_t>(qbytes, 1));
+    if (e == cudaSuccess)
+      e = Pool::ensure_scratch(ctx, 1, std::max<size_t>(obytes, 1));
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->scratch[0], q, qbytes, cudaMemcpyHostToDevice, ctx->stream[0]);
+    dq = ctx->scratch[0];
+    dout = ctx->scratch[1];
+  }
+  if (e == cudaSuccess)
+  {
+    double* o = static_cast<double*>(dout);
+    cudaStream_t stream = ctx->stream[0];
+    if (mode == OUT_CENTERS)
+      rc = dispatch_exact<OUT_CENTERS>(group->dev, wf, sf, elem, dq, q_dtype, n, 0, nullptr, o, stream);
+    else if (mode == OUT_TRANSFORMS)
+      rc = dispatch_exact<OUT_TRANSFORMS>(group->dev, wf, sf, elem, dq, q_dtype, n, 0, nullptr, o, stream);
+    else
+      rc = dispatch_exact<OUT_CLEARANCE>(group->dev, wf, sf, elem, dq, q_dtype, n, 0, nullptr, o, stream);
+    if (!rc && !mapped)
+      e = cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, stream);
+    const cudaError_t es = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess)
+      e = es;
+    if (!rc && e == cudaSuccess && mapped)
+      std::memcpy(out, static_cast<char*>(ctx->pin) + o_out, obytes);
+  }
+  group->stage->give_back(ctx);
+  if (!rc && e != cudaSuccess)
+  {
+    set_error("staging / running / reading back the batch failed: %s", cudaGetErrorString(e));
+    rc = B200DF_ERR_CUDA;
+  }
   return rc;
 }
 
@@ -768,81 +825,110 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
   const size_t S = (size_t)g.n_spheres;
   DeviceGuard dg(group->device);
   const size_t row = (size_t)g.n_vars * q_elem_size(q_dtype);
-  const int64_t chunk = std::min<int64_t>(n, 16384);
-  struct Slot
-  {
-    cudaStream_t stream = nullptr;
-    ScratchBuffer q, d, gr, t, c;
-  } slot[2];
+  typedef b200df_group::StagePool Pool;
+  Pool::Ctx* ctx = group->stage->acquire();
   cudaError_t e = cudaSuccess;
+  auto finish = [&](int status) {
+    group->stage->give_back(ctx);
+    if (!status && e != cudaSuccess)
+    {
+      set_error("gradient batch failed while staging / running / reading back: %s", cudaGetErrorString(e));
+      status = B200DF_ERR_CUDA;
+    }
+    return status;
+  };
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+
+  // Small calls (CHOMP evaluates one trajectory, ~100 waypoints, per iteration): one mapped pinned buffer carries the
+  // joint values in and the results out, so the call is one launch and one synchronise instead of five staged copies.
+  const size_t o_q = 0, o_d = up((size_t)n * row), o_g = o_d + up(n * S * sizeof(double)),
+               o_t = o_g + up(n * S * 3 * sizeof(double)), o_c = o_t + up(n * S),
+               total = o_c + (centers ? up(n * S * 3 * sizeof(double)) : 0);
+  if (total <= kSmallGradBytes && small_batch_enabled())
+  {
+    void* dpin = nullptr;
+    e = Pool::ensure_stream(ctx, 0);
+    if (e == cudaSuccess)
+      e = Pool::ensure_pin(ctx, total, &dpin);
+    if (e != cudaSuccess)
+      return finish(B200DF_OK);
+    char* hp = static_cast<char*>(ctx->pin);
+    char* dp = static_cast<char*>(dpin);
+    std::memcpy(hp + o_q, q, (size_t)n * row);
+    // result arrays the caller already keeps in pinned memory (b200df_host_alloc) are written in place
+    auto pinned_alias = [](void* host) -> void* {
+      cudaPointerAttributes a;
+      if (host && cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost)
+        return a.devicePointer;
+      cudaGetLastError();
+      return nullptr;
+    };
+    void* a_d = pinned_alias(dist);
+    void* a_g = pinned_alias(grad);
+    void* a_t = pinned_alias(type);
+    void* a_c = pinned_alias(centers);
+    rc = dispatch_gather(g, wf, sf, elem, dp + o_q, q_dtype, n, flags, static_cast<double*>(a_d ? a_d : dp + o_d),
+                         static_cast<double*>(a_g ? a_g : dp + o_g), static_cast<uint8_t*>(a_t ? a_t : dp + o_t),
+                         centers ? static_cast<double*>(a_c ? a_c : dp + o_c) : nullptr, ctx->stream[0]);
+    e = cudaStreamSynchronize(ctx->stream[0]);
+    if (!rc && e == cudaSuccess)
+    {
+      if (!a_d)
+        std::memcpy(dist, hp + o_d, n * S * sizeof(double));
+      if (!a_g)
+        std::memcpy(grad, hp + o_g, n * S * 3 * sizeof(double));
+      if (!a_t)
+        std::memcpy(type, hp + o_t, n * S);
+      if (centers && !a_c)
+        std::memcpy(centers, hp + o_c, n * S * 3 * sizeof(double));
+    }
+    return finish(rc);
+  }
+
+  // Large calls: chunks of states travel H2D -> kernel -> D2H on two streams of the cached context, so the (large)
+  // result copies of one chunk overlap the kernel of the next.
+  const int64_t chunk = std::min<int64_t>(n, 16384);
+  const size_t want[5] = { std::max<size_t>(chunk * row, 1), chunk * S * sizeof(double), chunk * S * 3 * sizeof(double),
+                           chunk * S, centers ? chunk * S * 3 * sizeof(double) : 0 };
   for (int k = 0; k < 2 && e == cudaSuccess; ++k)
   {
-    e = cudaStreamCreateWithFlags(&slot[k].stream, cudaStreamNonBlocking);
-    Slot& sl = slot[k];
-    sl.q.stream = sl.d.stream = sl.gr.stream = sl.t.stream = sl.c.stream = sl.stream;
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&sl.q.p, std::max<size_t>(chunk * row, 1), sl.stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&sl.d.p, std::max<size_t>(chunk * S * sizeof(double), 1), sl.stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&sl.gr.p, std::max<size_t>(chunk * S * 3 * sizeof(double), 1), sl.stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&sl.t.p, std::max<size_t>(chunk * S, 1), sl.stream);
-    if (e == cudaSuccess && centers)
-      e = cudaMallocAsync(&sl.c.p, std::max<size_t>(chunk * S * 3 * sizeof(double), 1), sl.stream);
+    e = Pool::ensure_stream(ctx, k);
+    for (int b = 0; b < 5 && e == cudaSuccess; ++b)
+      if (want[b])
+        e = Pool::ensure_scratch(ctx, 5 * k + b, want[b]);
   }
   int k = 0;
   for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k ^= 1)
   {
     const int64_t m = std::min<int64_t>(chunk, n - s);
-    Slot& sl = slot[k];
-    e = cudaMemcpyAsync(sl.q.p, static_cast<const char*>(q) + (size_t)s * row, (size_t)m * row, cudaMemcpyHostToDevice,
-                        sl.stream);
+    void** buf = ctx->scratch + 5 * k;
+    cudaStream_t st = ctx->stream[k];
+    e = cudaMemcpyAsync(buf[0], static_cast<const char*>(q) + (size_t)s * row, (size_t)m * row, cudaMemcpyHostToDevice,
+                        st);
     if (e != cudaSuccess)
       break;
-    rc = dispatch_gather(g, wf, sf, elem, sl.q.p, q_dtype, m, flags, static_cast<double*>(sl.d.p),
-                         static_cast<double*>(sl.gr.p), static_cast<uint8_t*>(sl.t.p), static_cast<double*>(sl.c.p),
-                         sl.stream);
+    rc = dispatch_gather(g, wf, sf, elem, buf[0], q_dtype, m, flags, static_cast<double*>(buf[1]),
+                         static_cast<double*>(buf[2]), static_cast<uint8_t*>(buf[3]),
+                         centers ? static_cast<double*>(buf[4]) : nullptr, st);
     if (rc)
       break;
-    e = cudaMemcpyAsync(dist + s * S, sl.d.p, m * S * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+    e = cudaMemcpyAsync(dist + s * S, buf[1], m * S * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(grad + s * S * 3, sl.gr.p, m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+      e = cudaMemcpyAsync(grad + s * S * 3, buf[2], m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(type + s * S, sl.t.p, m * S, cudaMemcpyDeviceToHost, sl.stream);
+      e = cudaMemcpyAsync(type + s * S, buf[3], m * S, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && centers)
-      e = cudaMemcpyAsync(centers + s * S * 3, sl.c.p, m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, sl.stream);
+      e = cudaMemcpyAsync(centers + s * S * 3, buf[4], m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
   }
   for (int i = 0; i < 2; ++i)
   {
-    if (!slot[i].stream)
+    if (!ctx->stream[i])
       continue;
-    const cudaError_t es = cudaStreamSynchronize(slot[i].stream);
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream[i]);
     if (e == cudaSuccess)
       e = es;
   }
-  if (!rc && e != cudaSuccess)
-  {
-    set_error("gradient batch failed while staging / running / reading back: %s", cudaGetErrorString(e));
-    rc = B200DF_ERR_CUDA;
-  }
-  // the scratch buffers are freed stream-ordered by their destructors before the streams go away
-  for (int i = 0; i < 2; ++i)
-  {
-    Slot& sl = slot[i];
-    for (ScratchBuffer* b : { &sl.q, &sl.d, &sl.gr, &sl.t, &sl.c })
-    {
-      if (b->p)
-        cudaFreeAsync(b->p, sl.stream);
-      b->p = nullptr;
-    }
-    if (sl.stream)
-    {
-      cudaStreamSynchronize(sl.stream);
-      cudaStreamDestroy(sl.stream);
-    }
-  }
-  return rc;
+  return finish(rc);
 }
 
 }  // extern "C"

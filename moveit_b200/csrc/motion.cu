@@ -10,6 +10,7 @@
 //   PlanarJointModel::interpolate     robot_model/src/planar_joint_model.cpp:180-205    (holonomic: x, y linear, theta shortest arc)
 // Compiled with --fmad=false: the interpolation rounds like the reference's double arithmetic.
 #include <algorithm>
+#include <cstring>
 
 #include "validity_common.cuh"
 
@@ -70,6 +71,8 @@ __global__ void first_invalid_kernel(const uint8_t* __restrict__ verdict, long m
 }
 }  // namespace
 
+constexpr size_t kSmallEdgeBytes = 256 * 1024;  // end points + results of a call that takes the mapped pinned staging
+
 extern "C" {
 
 int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_field* self, const double* qa,
@@ -81,75 +84,109 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
     return B200DF_OK;
   const int nv = group->dev.n_vars;
   DeviceGuard dg(group->device);
-  cudaStream_t stream;
-  B200DF_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  typedef b200df_group::StagePool Pool;
   // the interpolated states stay fp64 (what the reference would check); FAST screens them in fp32 and re-runs the
   // undecided ones on the same fp64 values
-  const bool f32 = false;
-  const size_t elem = sizeof(double);
   const int64_t edges_per_chunk = std::max<int64_t>(1, (int64_t)(1 << 21) / segments);
   const int64_t chunk = std::min<int64_t>(m, edges_per_chunk);
+  const size_t end_bytes = (size_t)chunk * nv * sizeof(double);
+  std::vector<uint8_t> ang(std::max(nv, 1), 0);
+  if (var_is_angular)
+    std::copy(var_is_angular, var_is_angular + nv, ang.begin());
+  Pool::Ctx* ctx = group->stage->acquire();
+  cudaError_t e = Pool::ensure_stream(ctx, 0);
   int rc = B200DF_OK;
-  {
-    ScratchBuffer da, db, dang, dq, dv, dout;
-    da.stream = db.stream = dang.stream = dq.stream = dv.stream = dout.stream = stream;
-    std::vector<uint8_t> ang(nv, 0);
-    if (var_is_angular)
-      ang.assign(var_is_angular, var_is_angular + nv);
-    cudaError_t e = cudaMallocAsync(&da.p, (size_t)chunk * nv * sizeof(double), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&db.p, (size_t)chunk * nv * sizeof(double), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dang.p, std::max(nv, 1), stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dq.p, (size_t)chunk * segments * nv * elem, stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dv.p, (size_t)chunk * segments, stream);
-    if (e == cudaSuccess)
-      e = cudaMallocAsync(&dout.p, (size_t)chunk * sizeof(int32_t), stream);
-    if (e == cudaSuccess && nv > 0)
-      e = cudaMemcpyAsync(dang.p, ang.data(), nv, cudaMemcpyHostToDevice, stream);
-    for (int64_t s = 0; s < m && !rc && e == cudaSuccess; s += chunk)
-    {
-      const int64_t mc = std::min<int64_t>(chunk, m - s);
-      e = cudaMemcpyAsync(da.p, qa + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, stream);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(db.p, qb + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, stream);
-      if (e != cudaSuccess)
-        break;
-      const long total = mc * segments * nv;
-      const unsigned blocks = (unsigned)((total + 255) / 256);
-      if (f32)
-        interpolate_edges_kernel<float><<<blocks, 256, 0, stream>>>(
-            static_cast<const double*>(da.p), static_cast<const double*>(db.p), mc, segments, nv,
-            static_cast<const uint8_t*>(dang.p), static_cast<float*>(dq.p));
-      else
-        interpolate_edges_kernel<double><<<blocks, 256, 0, stream>>>(
-            static_cast<const double*>(da.p), static_cast<const double*>(db.p), mc, segments, nv,
-            static_cast<const uint8_t*>(dang.p), static_cast<double*>(dq.p));
-      B200DF_LAUNCHED();
-      rc = b200df_check_batch_device(group, world, self, dq.p, f32 ? B200DF_Q_F32 : B200DF_Q_F64, mc * segments, flags,
-                                     precision, static_cast<uint8_t*>(dv.p), stream);
-      if (rc)
-        break;
-      first_invalid_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(static_cast<const uint8_t*>(dv.p), mc,
-                                                                             segments, static_cast<int32_t*>(dout.p));
-      B200DF_LAUNCHED();
-      e = cudaGetLastError();
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(first_invalid + s, dout.p, (size_t)mc * sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
-      if (e == cudaSuccess)
-        e = cudaStreamSynchronize(stream);  // the next chunk reuses the buffers
-    }
+  auto finish = [&]() {
+    group->stage->give_back(ctx);
     if (!rc && e != cudaSuccess)
     {
       set_error("edge check failed while staging / running / reading back: %s", cudaGetErrorString(e));
       rc = B200DF_ERR_CUDA;
     }
+    return rc;
+  };
+  if (e != cudaSuccess)
+    return finish();
+  cudaStream_t stream = ctx->stream[0];
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  enum { kStates = 0, kVerdict = 1, kA = 2, kB = 3, kAng = 4, kOut = 5 };  // scratch slots
+  e = Pool::ensure_scratch(ctx, kStates, (size_t)chunk * segments * nv * sizeof(double));
+  if (e == cudaSuccess)
+    e = Pool::ensure_scratch(ctx, kVerdict, (size_t)chunk * segments);
+  if (e != cudaSuccess)
+    return finish();
+  double* dq = static_cast<double*>(ctx->scratch[kStates]);
+  uint8_t* dv = static_cast<uint8_t*>(ctx->scratch[kVerdict]);
+
+  auto run_chunk = [&](const double* da, const double* db, const uint8_t* dang, int64_t mc, int32_t* dout) {
+    const long total = mc * segments * nv;
+    interpolate_edges_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(da, db, mc, segments, nv,
+                                                                                          dang, dq);
+    B200DF_LAUNCHED();
+    rc = b200df_check_batch_device(group, world, self, dq, B200DF_Q_F64, mc * segments, flags, precision, dv, stream);
+    if (rc)
+      return;
+    first_invalid_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(dv, mc, segments, dout);
+    B200DF_LAUNCHED();
+    e = cudaGetLastError();
+  };
+
+  // Small calls (a MotionValidator checks one edge at a time): end points in, first-invalid indices out through one
+  // mapped pinned buffer - three launches and one synchronise, no staged copies.
+  const size_t o_b = up(end_bytes), o_ang = 2 * o_b, o_out = o_ang + up(ang.size()),
+               total_pin = o_out + up((size_t)m * sizeof(int32_t));
+  if (m == chunk && total_pin <= kSmallEdgeBytes && small_batch_enabled())
+  {
+    void* dpin = nullptr;
+    e = Pool::ensure_pin(ctx, total_pin, &dpin);
+    if (e != cudaSuccess)
+      return finish();
+    char* hp = static_cast<char*>(ctx->pin);
+    char* dp = static_cast<char*>(dpin);
+    std::memcpy(hp, qa, end_bytes);
+    std::memcpy(hp + o_b, qb, end_bytes);
+    std::memcpy(hp + o_ang, ang.data(), ang.size());
+    run_chunk(reinterpret_cast<const double*>(dp), reinterpret_cast<const double*>(dp + o_b),
+              reinterpret_cast<const uint8_t*>(dp + o_ang), m, reinterpret_cast<int32_t*>(dp + o_out));
+    const cudaError_t es = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess)
+      e = es;
+    if (!rc && e == cudaSuccess)
+      std::memcpy(first_invalid, hp + o_out, (size_t)m * sizeof(int32_t));
+    return finish();
   }
-  cudaStreamSynchronize(stream);
-  cudaStreamDestroy(stream);
-  return rc;
+
+  e = Pool::ensure_scratch(ctx, kA, end_bytes);
+  if (e == cudaSuccess)
+    e = Pool::ensure_scratch(ctx, kB, end_bytes);
+  if (e == cudaSuccess)
+    e = Pool::ensure_scratch(ctx, kAng, ang.size());
+  if (e == cudaSuccess)
+    e = Pool::ensure_scratch(ctx, kOut, (size_t)chunk * sizeof(int32_t));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(ctx->scratch[kAng], ang.data(), ang.size(), cudaMemcpyHostToDevice, stream);
+  for (int64_t s = 0; s < m && !rc && e == cudaSuccess; s += chunk)
+  {
+    const int64_t mc = std::min<int64_t>(chunk, m - s);
+    e = cudaMemcpyAsync(ctx->scratch[kA], qa + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->scratch[kB], qb + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice,
+                          stream);
+    if (e != cudaSuccess)
+      break;
+    run_chunk(static_cast<const double*>(ctx->scratch[kA]), static_cast<const double*>(ctx->scratch[kB]),
+              static_cast<const uint8_t*>(ctx->scratch[kAng]), mc, static_cast<int32_t*>(ctx->scratch[kOut]));
+    if (rc || e != cudaSuccess)
+      break;
+    e = cudaMemcpyAsync(first_invalid + s, ctx->scratch[kOut], (size_t)mc * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                        stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(stream);  // the next chunk reuses the buffers
+  }
+  const cudaError_t es = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess)
+    e = es;
+  return finish();
 }
 
 }  // extern "C"

@@ -390,63 +390,6 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
 }
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------------------
-// Staging contexts of the host-buffer entry point: a batch is cut into 2^20-state chunks that travel H2D -> kernel ->
-// D2H on three streams, so the PCIe copies of one chunk overlap the kernel of another.  Contexts are cached per group
-// (checks may run concurrently from several threads: each call takes its own context).
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kSlots = 3;  // chunks in flight: H2D of one overlaps the kernel of another and the D2H of a third
-
-struct b200df_group::StagePool
-{
-  struct Ctx
-  {
-    cudaStream_t stream[kSlots] = {};
-    void* q[kSlots] = {};
-    uint8_t* v[kSlots] = {};
-    int* amb[kSlots] = {};  // [0] = count, [1..] = indices (FAST path scratch)
-    size_t q_bytes = 0, v_bytes = 0;
-    void* pin = nullptr;  // mapped pinned staging of the small-batch path: joint values, then verdicts
-  };
-  std::mutex mu;
-  std::vector<Ctx*> free_list;
-  ~StagePool()
-  {
-    for (Ctx* c : free_list)
-      release(c);
-  }
-  static void release(Ctx* c)
-  {
-    for (int i = 0; i < kSlots; ++i)
-    {
-      cudaFree(c->q[i]);
-      cudaFree(c->v[i]);
-      cudaFree(c->amb[i]);
-      if (c->stream[i])
-        cudaStreamDestroy(c->stream[i]);
-    }
-    if (c->pin)
-      cudaFreeHost(c->pin);
-    delete c;
-  }
-  Ctx* acquire()
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!free_list.empty())
-    {
-      Ctx* c = free_list.back();
-      free_list.pop_back();
-      return c;
-    }
-    return new Ctx;
-  }
-  void give_back(Ctx* c)
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    free_list.push_back(c);
-  }
-};
-
 namespace
 {
 constexpr int64_t kChunkStates = 1 << 20;
@@ -468,12 +411,6 @@ int64_t chunk_states()
 // values and writes the verdicts across PCIe itself, so the call is one launch and one stream synchronise.
 constexpr int64_t kSmallStates = 2048;
 constexpr size_t kSmallQBytes = 256 * 1024;
-
-bool small_batch_enabled()
-{
-  const char* e = getenv("B200DF_SMALL_BATCH");
-  return !(e && e[0] == '0');
-}
 
 int ensure_ctx(b200df_group::StagePool::Ctx* c, size_t q_bytes, size_t v_bytes)
 {
@@ -954,13 +891,10 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
   {
     // one launch of the small-batch exact kernel (FAST returns the same verdicts by construction; its screening pass
     // only pays off on batches that fill the GPU)
-    if (!ctx->stream[0])
-      e = cudaStreamCreateWithFlags(&ctx->stream[0], cudaStreamNonBlocking);
-    if (e == cudaSuccess && !ctx->pin)
-      e = cudaHostAlloc(&ctx->pin, kSmallQBytes + (size_t)kSmallStates, cudaHostAllocMapped);
+    e = b200df_group::StagePool::ensure_stream(ctx, 0);
     void* dpin = nullptr;
     if (e == cudaSuccess)
-      e = cudaHostGetDevicePointer(&dpin, ctx->pin, 0);
+      e = b200df_group::StagePool::ensure_pin(ctx, kSmallQBytes + (size_t)kSmallStates, &dpin);
     if (e == cudaSuccess)
     {
       std::memcpy(ctx->pin, q, (size_t)n * row);

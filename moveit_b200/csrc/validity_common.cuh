@@ -9,9 +9,11 @@
 // Everything here is fp64 in the reference's operation order; the including translation units are compiled with
 // --fmad=false so mul/add round like the reference's non-FMA x86-64 build.
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <map>
 #include <utility>
+#include <vector>
 
 #include "b200df_internal.cuh"
 
@@ -393,6 +395,85 @@ __device__ __forceinline__ void fk_step(const DevLink& l, const QT* qs, double* 
   fk_step(l, qs, slots, stride, stride, cur);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Cooperative FK: ONE state walked by ONE warp (the latency-bound small-batch kernels).  Lane i first evaluates the
+// joint transform of link i (all sincos in parallel), then the chain T_link = (T_parent * T_origin) * T_joint runs in
+// link order with one matrix entry per lane.  Every entry is the same left-to-right sum of products iso_mul / fk_step
+// evaluate on a single thread, so the transforms are bit-identical to the batched kernels'.
+// Shared-memory staging owned by the calling warp: J, O [n_links][12], par_flag [2 * n_links], TMP [16].
+// Output: T [n_links][12] (global link transforms).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kCoopFixed = 1, kCoopOriginIdentity = 2;
+
+// entry (r, c) of a.affine() * b.matrix(), the sums in iso_mul's order
+__device__ __forceinline__ double iso_mul_entry(const double* a, const double* b, int r, int c)
+{
+  const double a0 = a[4 * r], a1 = a[4 * r + 1], a2 = a[4 * r + 2];
+  const double v = (a0 * b[c] + a1 * b[4 + c]) + a2 * b[8 + c];
+  return c == 3 ? v + a[4 * r + 3] : v;
+}
+
+__host__ __device__ inline size_t warp_fk_staging_doubles(int n_links)
+{
+  return (size_t)n_links * 24 + 16 + (size_t)(n_links + 1) / 2 * 2;  // J, O, TMP, parent + flags as ints
+}
+
+template <typename QT>
+__device__ __forceinline__ void warp_fk(const DevLink* __restrict__ links, int L, const QT* my_q, int lane,
+                                        double* staging, double* T)
+{
+  double* J = staging;
+  double* O = J + (size_t)L * 12;
+  double* TMP = O + (size_t)L * 12;
+  int* parent = reinterpret_cast<int*>(TMP + 16);
+  int* lflags = parent + L;
+  for (int i = lane; i < L; i += 32)
+  {
+    const DevLink& l = links[i];
+    double j[12];
+    joint_transform(l, my_q, 1, j);
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+    {
+      J[i * 12 + k] = j[k];
+      O[i * 12 + k] = l.origin[k];
+    }
+    parent[i] = l.parent;
+    lflags[i] = (l.joint_type == B200DF_JOINT_FIXED ? kCoopFixed : 0) | (l.origin_is_identity ? kCoopOriginIdentity : 0);
+  }
+  __syncwarp();
+  const int e = lane < 12 ? lane : 0;  // lanes 12..31 shadow lane 0 and do not store
+  const int r = e >> 2, c = e & 3;
+  for (int i = 0; i < L; ++i)
+  {
+    const int p = parent[i], f = lflags[i];
+    const double* par = T + p * 12;
+    const double* Ji = J + i * 12;
+    const double* Oi = O + i * 12;
+    double out;
+    if (p >= 0 && (f & kCoopFixed))
+      out = iso_mul_entry(par, Oi, r, c);  // robot_state.cpp:727-729
+    else if (p >= 0)
+    {
+      if (f & kCoopOriginIdentity)
+        out = iso_mul_entry(par, Ji, r, c);  // :732-734
+      else
+      {
+        const double tmp = iso_mul_entry(par, Oi, r, c);  // :735-738, left to right
+        if (lane < 12)
+          TMP[e] = tmp;
+        __syncwarp();
+        out = iso_mul_entry(TMP, Ji, r, c);
+      }
+    }
+    else
+      out = (f & kCoopOriginIdentity) ? Ji[e] : iso_mul_entry(Oi, Ji, r, c);  // :743-747
+    if (lane < 12)
+      T[i * 12 + e] = out;
+    __syncwarp();
+  }
+}
+
 // getDistanceGradient's cell lookup without the gradient: false when the centre is outside the 1-cell-inset
 // box (the reference then reports max_distance => never a collision, Q4).  NaN fails every comparison.
 __device__ __forceinline__ bool inset_cell(const GridDev& g, double x, double y, double z, long& idx)
@@ -540,6 +621,107 @@ struct b200df_group
   int link_field_elem = 0;        // voxel type of the link fields (1 or 2)
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Staging contexts of the host-buffer entry point: a batch is cut into 2^20-state chunks that travel H2D -> kernel ->
+// D2H on three streams, so the PCIe copies of one chunk overlap the kernel of another.  Contexts are cached per group
+// (checks may run concurrently from several threads: each call takes its own context).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSlots = 3;  // chunks in flight: H2D of one overlaps the kernel of another and the D2H of a third
+
+struct b200df_group::StagePool
+{
+  struct Ctx
+  {
+    cudaStream_t stream[kSlots] = {};
+    void* q[kSlots] = {};
+    uint8_t* v[kSlots] = {};
+    int* amb[kSlots] = {};  // [0] = count, [1..] = indices (FAST path scratch)
+    size_t q_bytes = 0, v_bytes = 0;
+    // small-call staging shared by every entry point (grow-only): one mapped pinned buffer the kernels read their
+    // inputs from and write their results to across PCIe, plus device scratch
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    static constexpr int kScratch = 10;
+    void* scratch[kScratch] = {};
+    size_t scratch_bytes[kScratch] = {};
+  };
+  std::mutex mu;
+  std::vector<Ctx*> free_list;
+  ~StagePool()
+  {
+    for (Ctx* c : free_list)
+      release(c);
+  }
+  static void release(Ctx* c)
+  {
+    for (int i = 0; i < kSlots; ++i)
+    {
+      cudaFree(c->q[i]);
+      cudaFree(c->v[i]);
+      cudaFree(c->amb[i]);
+      if (c->stream[i])
+        cudaStreamDestroy(c->stream[i]);
+    }
+    if (c->pin)
+      cudaFreeHost(c->pin);
+    for (void* p : c->scratch)
+      cudaFree(p);
+    delete c;
+  }
+  Ctx* acquire()
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!free_list.empty())
+    {
+      Ctx* c = free_list.back();
+      free_list.pop_back();
+      return c;
+    }
+    return new Ctx;
+  }
+  void give_back(Ctx* c)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    free_list.push_back(c);
+  }
+  static cudaError_t ensure_stream(Ctx* c, int i)
+  {
+    return c->stream[i] ? cudaSuccess : cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking);
+  }
+  // mapped pinned buffer of at least `bytes`; *dev = the address kernels use for it
+  static cudaError_t ensure_pin(Ctx* c, size_t bytes, void** dev)
+  {
+    cudaError_t e = cudaSuccess;
+    if (bytes > c->pin_bytes)
+    {
+      if (c->pin)
+        cudaFreeHost(c->pin);
+      c->pin = nullptr;
+      c->pin_bytes = 0;
+      const size_t want = std::max<size_t>(bytes, 64 * 1024);
+      e = cudaHostAlloc(&c->pin, want, cudaHostAllocMapped);
+      if (e != cudaSuccess)
+        return e;
+      c->pin_bytes = want;
+    }
+    return cudaHostGetDevicePointer(dev, c->pin, 0);
+  }
+  static cudaError_t ensure_scratch(Ctx* c, int i, size_t bytes)
+  {
+    if (bytes <= c->scratch_bytes[i])
+      return cudaSuccess;
+    cudaFree(c->scratch[i]);
+    c->scratch[i] = nullptr;
+    c->scratch_bytes[i] = 0;
+    const cudaError_t e = cudaMalloc(&c->scratch[i], bytes);
+    if (e == cudaSuccess)
+      c->scratch_bytes[i] = bytes;
+    return e;
+  }
+};
+
+
+
 namespace b200df
 {
 // FAST path (validity_fast.cu)
@@ -558,6 +740,13 @@ void small_destroy(b200df_group* group);
 bool small_supported(const b200df_group* group);
 int small_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
                  int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream);
+
+// B200DF_SMALL_BATCH=0 switches the mapped-pinned small-call staging of the host-buffer entry points off
+inline bool small_batch_enabled()
+{
+  const char* e = getenv("B200DF_SMALL_BATCH");
+  return !(e && e[0] == '0');
+}
 
 // fills wf / sf for the requested flags (rebuilding dirty fields) and checks they fit the group
 int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field* self, int flags, FieldDev* wf,

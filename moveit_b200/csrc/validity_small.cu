@@ -53,16 +53,6 @@ struct SmallDev
   int n_items;
 };
 
-constexpr int kFlagFixed = 1, kFlagOriginIdentity = 2;
-
-// entry (r, c) of a.affine() * b.matrix(), the sums in iso_mul's order
-__device__ __forceinline__ double mul_entry(const double* a, const double* b, int r, int c)
-{
-  const double a0 = a[4 * r], a1 = a[4 * r + 1], a2 = a[4 * r + 2];
-  const double v = (a0 * b[c] + a1 * b[4 + c]) + a2 * b[8 + c];
-  return c == 3 ? v + a[4 * r + 3] : v;
-}
-
 template <typename QT, typename FT>
 __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDev t, LookupDev wf, LookupDev sf,
                                                              const QT* __restrict__ q, long n, int flags,
@@ -70,14 +60,10 @@ __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDe
 {
   extern __shared__ double sm[];
   const int L = g.n_links, S = g.n_spheres, G = g.n_glinks;
-  double* J = sm;               // [L][12] joint transforms
-  double* O = J + L * 12;       // [L][12] joint origins
-  double* T = O + L * 12;       // [L][12] global link transforms
-  double* TMP = T + L * 12;     // [12] (T_parent * T_origin) of the link being chained
-  double* C = TMP + 16;         // [S][3] posed sphere centres
-  double* BC = C + S * 3;       // [G][3] posed bounding-sphere centres
-  int* parent = reinterpret_cast<int*>(BC + G * 3);  // [L]
-  int* lflags = parent + L;                          // [L]
+  double* T = sm;                                      // [L][12] global link transforms
+  double* C = T + L * 12;                              // [S][3] posed sphere centres
+  double* BC = C + S * 3;                              // [G][3] posed bounding-sphere centres
+  double* staging = BC + G * 3;                        // warp_fk's joint transforms / origins / parents
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool do_robot = (flags & B200DF_CHECK_ROBOT) != 0;
   const bool do_self = (flags & B200DF_CHECK_SELF) != 0;
@@ -85,55 +71,8 @@ __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDe
 
   for (long state = blockIdx.x; state < n; state += gridDim.x)
   {
-    const QT* my_q = q + state * g.n_vars;
-    for (int i = tid; i < L; i += nt)
-    {
-      const DevLink& l = g.links[i];
-      double j[12];
-      joint_transform(l, my_q, 1, j);
-#pragma unroll
-      for (int k = 0; k < 12; ++k)
-      {
-        J[i * 12 + k] = j[k];
-        O[i * 12 + k] = l.origin[k];
-      }
-      parent[i] = l.parent;
-      lflags[i] = (l.joint_type == B200DF_JOINT_FIXED ? kFlagFixed : 0) | (l.origin_is_identity ? kFlagOriginIdentity : 0);
-    }
-    __syncthreads();
     if (tid < 32)
-    {
-      const int lane = tid < 12 ? tid : 0;  // lanes 12..31 shadow lane 0 and do not store
-      const int r = lane >> 2, c = lane & 3;
-      for (int i = 0; i < L; ++i)
-      {
-        const int p = parent[i], f = lflags[i];
-        const double* par = T + p * 12;
-        const double* Ji = J + i * 12;
-        const double* Oi = O + i * 12;
-        double out;
-        if (p >= 0 && (f & kFlagFixed))
-          out = mul_entry(par, Oi, r, c);  // robot_state.cpp:727-729
-        else if (p >= 0)
-        {
-          if (f & kFlagOriginIdentity)
-            out = mul_entry(par, Ji, r, c);  // :732-734
-          else
-          {
-            const double tmp = mul_entry(par, Oi, r, c);  // :735-738, left to right
-            if (tid < 12)
-              TMP[lane] = tmp;
-            __syncwarp();
-            out = mul_entry(TMP, Ji, r, c);
-          }
-        }
-        else
-          out = (f & kFlagOriginIdentity) ? Ji[lane] : mul_entry(Oi, Ji, r, c);  // :743-747
-        if (tid < 12)
-          T[i * 12 + lane] = out;
-        __syncwarp();
-      }
-    }
+      warp_fk(g.links, L, q + state * g.n_vars, tid, staging, T);
     __syncthreads();
 
     bool hit = false;
@@ -288,7 +227,7 @@ int small_create(b200df_group* g)
   sp->dev.n_items = (int)items.size();
   const int want = std::max(std::max(S, L), ((int)items.size() + 1) / 2);
   sp->threads = std::min(256, std::max(32, (want + 31) / 32 * 32));
-  sp->smem = ((size_t)L * 36 + 16 + (size_t)S * 3 + (size_t)G * 3) * sizeof(double) + (size_t)L * 2 * sizeof(int);
+  sp->smem = ((size_t)L * 12 + (size_t)S * 3 + (size_t)G * 3 + warp_fk_staging_doubles(L)) * sizeof(double);
   if (sp->smem > 200 * 1024)
     return B200DF_OK;  // no small-batch kernel for this robot: callers fall back to the batched kernel
   g->small = sp.release();

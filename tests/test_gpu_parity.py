@@ -682,7 +682,7 @@ def test_concurrent_callers_share_one_group(gpu, oracle):
 
 
 # ------------------------------------------------------------------------------- small-batch (one CTA per state) kernel
-SMALL = 4  # B200DF_PRECISION_DEBUG_SMALL: the kernel EXACT / FAST pick for small batches, forced at any batch size
+PREC_SMALL = 4  # B200DF_PRECISION_DEBUG_SMALL: the kernel EXACT / FAST pick for small batches, forced at any batch size
 
 
 @pytest.mark.parametrize("robot", ["panda", "mobile_arm", "pr2_like"])
@@ -698,11 +698,11 @@ def test_small_batch_kernel_equals_batched_exact_and_oracle(gpu, oracle, robot):
         q = desc.sample_states(n, 17, dtype)
         for flags in (CHECK_ROBOT, CHECK_INTRA, CHECK_ROBOT | CHECK_INTRA):
             batched = e.group.check(q, e.world, flags=flags, precision=0)  # n > small-batch limit: batched kernel
-            small = e.group.check(q, e.world, flags=flags, precision=SMALL)
+            small = e.group.check(q, e.world, flags=flags, precision=PREC_SMALL)
             assert np.array_equal(small, batched), (robot, dtype, flags, int((small != batched).sum()))
     o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
     q = desc.sample_states(3000, 18)
-    got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL)
+    got = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=PREC_SMALL)
     assert np.array_equal(got, o.env.check_batch(q, mode=3, n_threads=8))
 
 
@@ -715,17 +715,17 @@ def test_small_batch_kernel_self_field_signed_fine_and_non_finite(gpu, oracle):
     e = EngineSetup(desc, scenarios.FIELD_A, objs, group="panda_arm", self_points=sp)
     q = desc.sample_states(20_000, 99)
     flags = CHECK_ROBOT | CHECK_SELF | CHECK_INTRA
-    got = e.group.check(q, e.world, e.self_field, flags=flags, precision=SMALL)
+    got = e.group.check(q, e.world, e.self_field, flags=flags, precision=PREC_SMALL)
     assert np.array_equal(got, e.group.check(q, e.world, e.self_field, flags=flags, precision=0))
     assert np.array_equal(got[:4000], o.env.check_batch(q[:4000], mode=3, n_threads=8))
     # signed world field (fp64 predicate instead of the integer threshold)
     es = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene(seed=5), signed=True)
-    assert np.array_equal(es.group.check(q, es.world, flags=CHECK_ROBOT, precision=SMALL),
+    assert np.array_equal(es.group.check(q, es.world, flags=CHECK_ROBOT, precision=PREC_SMALL),
                           es.group.check(q, es.world, flags=CHECK_ROBOT, precision=0))
     # 1 cm / u16 field
     fine = dict(size=(2.0, 2.0, 2.0), resolution=0.01, center=(0.0, 0.0, 0.5), max_distance=0.25)
     ef = EngineSetup(desc, fine, objs)
-    a = ef.group.check(q, ef.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL)
+    a = ef.group.check(q, ef.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=PREC_SMALL)
     assert np.array_equal(a, ef.group.check(q, ef.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0))
     assert 0 < a.sum() < len(a)
     # NaN / inf joint values
@@ -735,7 +735,7 @@ def test_small_batch_kernel_self_field_signed_fine_and_non_finite(gpu, oracle):
     qn[2::9, 6] = -np.inf
     qn[3::9, 7] = np.nan
     ew = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
-    assert np.array_equal(ew.group.check(qn, ew.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=SMALL),
+    assert np.array_equal(ew.group.check(qn, ew.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=PREC_SMALL),
                           ew.group.check(qn, ew.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=0))
 
 
@@ -771,3 +771,39 @@ def test_small_batches_take_the_low_latency_path_and_agree(gpu, oracle, monkeypa
     for n in (1, 33, 2048):
         for precision in (0, 1):
             assert np.array_equal(e.group.check(q[:n], e.world, flags=flags, precision=precision), ref[:n])
+
+
+def test_gradient_call_sizes_and_pinned_outputs_agree(gpu, oracle):
+    """One CHOMP iteration hands over one trajectory (~100 waypoints): such calls take the warp-per-state FK variant
+    of the gradient kernel and the mapped pinned staging; results must be bit-identical to one big call (32 states
+    per CTA, staged copies), with pageable or pinned result arrays, with and without the per-link fields."""
+    import torch
+    from moveit_b200 import engine
+    from moveit_b200.binding import CHECK_LINK_FIELDS
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    fields, enabled = engine.link_distance_fields(e.model_desc, e.group_links, desc.acm_entry_matrix(),
+                                                  scenarios.FIELD_A["resolution"], scenarios.FIELD_A["max_distance"])
+    e.group.set_link_fields(fields, enabled)
+    traj = scenarios.chomp_trajectories(desc, 60, 100).reshape(-1, desc.nvar)  # 6000 states: the big-call variant
+    S = e.group.n_spheres
+    for flags in (CHECK_ROBOT | CHECK_INTRA, CHECK_ROBOT | CHECK_INTRA | CHECK_LINK_FIELDS):
+        big = e.group.gradients(traj, e.world, flags=flags)
+        for lo, n in ((0, 100), (100, 100), (1234, 1), (2000, 37), (3000, 1500)):
+            part = e.group.gradients(traj[lo:lo + n], e.world, flags=flags)
+            for key in ("dist", "grad", "type", "centers"):
+                assert np.array_equal(part[key], big[key][lo:lo + n]), (flags, lo, n, key)
+        n = 100
+        pin = dict(dist=torch.empty((n, S), dtype=torch.float64).pin_memory().numpy(),
+                   grad=torch.empty((n, S, 3), dtype=torch.float64).pin_memory().numpy(),
+                   type=torch.empty((n, S), dtype=torch.uint8).pin_memory().numpy(),
+                   centers=torch.empty((n, S, 3), dtype=torch.float64).pin_memory().numpy())
+        got = e.group.gradients(traj[500:600], e.world, flags=flags, out=pin)
+        for key in ("dist", "grad", "type", "centers"):
+            assert np.array_equal(got[key], big[key][500:600]), (flags, "pinned", key)
+    # sphere centres / clearance / FK through the same small-call staging
+    c_big = e.group.sphere_centers(traj)
+    assert np.array_equal(e.group.sphere_centers(traj[77:78]), c_big[77:78])
+    d_big = e.group.distance(traj, e.world)
+    assert np.array_equal(e.group.distance(traj[300:420], e.world), d_big[300:420])

@@ -66,6 +66,51 @@ def main():
             b.record()
             torch.cuda.synchronize()
             out["kernel_us"]["%s_n%d" % (name, n)] = round(1e3 * a.elapsed_time(b) / reps, 2)
+
+    # the other per-call entry points a planner drives with small inputs: CHOMP evaluates the gradients of one
+    # trajectory (~100 waypoints) per iteration, OMPL's MotionValidator checks one edge per call
+    os.environ.pop("B200DF_SMALL_MAX_STATES")
+    os.environ.pop("B200DF_SMALL_BATCH")
+    out["gradients_host_call_us"], out["gradients_kernel_us"], out["edges_host_call_us"] = {}, {}, {}
+    S = int(e.group.n_spheres)
+    for n in (1, 100, 1000):
+        qn = q_all[:n].astype(np.float64)
+        bufs = dict(dist=np.empty((n, S)), grad=np.empty((n, S, 3)), type=np.empty((n, S), dtype=np.uint8),
+                    centers=np.empty((n, S, 3)))
+        call = lambda: e.group.gradients(qn, e.world, flags=flags, out=bufs)
+        for _ in range(20):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            call()
+        out["gradients_host_call_us"]["n%d" % n] = round(1e6 * (time.perf_counter() - t0) / 300, 2)
+        qd = torch.from_numpy(qn).cuda()
+        dd = torch.empty((n, S), dtype=torch.float64, device="cuda")
+        gd = torch.empty((n, S, 3), dtype=torch.float64, device="cuda")
+        td = torch.empty((n, S), dtype=torch.uint8, device="cuda")
+        cd = torch.empty((n, S, 3), dtype=torch.float64, device="cuda")
+        run = lambda: B.check(lib.b200df_gradients_batch_device(
+            e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F64, n, flags, C.c_void_p(dd.data_ptr()),
+            C.c_void_p(gd.data_ptr()), C.c_void_p(td.data_ptr()), C.c_void_p(cd.data_ptr()), C.c_void_p(st)))
+        for _ in range(20):
+            run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(200):
+            run()
+        b.record()
+        torch.cuda.synchronize()
+        out["gradients_kernel_us"]["n%d" % n] = round(1e3 * a.elapsed_time(b) / 200, 2)
+    for m, seg in ((1, 16), (1, 64), (64, 16)):
+        qa, qb = q_all[:m].astype(np.float64), q_all[m:2 * m].astype(np.float64)
+        call = lambda: e.group.check_edges(qa, qb, seg, e.world, flags=flags, precision=B.PRECISION_FAST)
+        for _ in range(20):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            call()
+        out["edges_host_call_us"]["m%d_seg%d" % (m, seg)] = round(1e6 * (time.perf_counter() - t0) / 300, 2)
     print(json.dumps(out))
 
 
