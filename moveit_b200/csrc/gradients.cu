@@ -705,17 +705,22 @@ int b200df_distance_batch(const b200df_group* group, b200df_field* world, const 
 int b200df_model_fk(const b200df_model* model, const void* q, int q_dtype, int64_t n, double* link_transforms)
 {
   B200DF_REQUIRE(model, "null model");
-  // an empty group over the model gives the kernel its link table
-  b200df_group_desc gd{};
-  gd.n_group_links = 0;
-  gd.resolution = 1.0;
+  // an empty group over the model gives the kernel its link table (built once per model)
   b200df_group* g = nullptr;
-  int rc = b200df_group_create(model, &gd, &g);
-  if (rc)
-    return rc;
-  rc = run_f64_output(g, nullptr, q, q_dtype, n, OUT_TRANSFORMS, (size_t)model->n_links * 12, link_transforms);
-  b200df_group_destroy(g);
-  return rc;
+  {
+    std::lock_guard<std::mutex> lk(model->fk_mu);
+    if (!model->fk_group)
+    {
+      b200df_group_desc gd{};
+      gd.n_group_links = 0;
+      gd.resolution = 1.0;
+      const int rc = b200df_group_create(model, &gd, &model->fk_group);
+      if (rc)
+        return rc;
+    }
+    g = model->fk_group;
+  }
+  return run_f64_output(g, nullptr, q, q_dtype, n, OUT_TRANSFORMS, (size_t)model->n_links * 12, link_transforms);
 }
 
 int b200df_group_link_count(const b200df_group* g, int32_t* n)

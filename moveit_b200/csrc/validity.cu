@@ -593,6 +593,8 @@ int b200df_model_destroy(b200df_model* m)
   if (!m)
     return B200DF_OK;
   DeviceGuard dg(m->device);
+  if (m->fk_group)
+    b200df_group_destroy(m->fk_group);
   cudaFree(m->d_links);
   delete m;
   return B200DF_OK;

@@ -595,6 +595,9 @@ struct b200df_model
   std::vector<double> points;
   int n_slots = 0;
   b200df::DevLink* d_links = nullptr;
+  // b200df_model_fk's link table: an empty group over the model, built on first use and kept
+  mutable std::mutex fk_mu;
+  mutable b200df_group* fk_group = nullptr;
 };
 
 struct b200df_group

@@ -657,6 +657,11 @@ public:
   {
     run(req, res, state, &acm, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT, true);  // .cpp:1441-1464
   }
+  std::size_t cacheGenerations() const
+  {
+    std::lock_guard<std::mutex> lk(update_cache_lock_);
+    return cache_generations_;
+  }
   // distanceRobot / distanceSelf are stubs in the reference (.h:108-123,178-198); defined here as the minimum over
   // the group's spheres of (world-field distance - radius)
   double distanceRobot(const core::RobotState& state, const std::string& group_name = "") const
@@ -1089,6 +1094,7 @@ private:
         compareCacheEntryToAllowedCollisionMatrix(*cur, acm) && (!generate_distance_field || cur->self_field ||
                                                                   !hasNonGroupGeometry(*cur)))
       return cur;
+    ++cache_generations_;
     dfce_ = generateDistanceFieldCacheEntry(group_name, state, acm, generate_distance_field);
     return dfce_;
   }
@@ -1473,6 +1479,7 @@ private:
   World::ObserverHandle observer_handle_ = 0;
   mutable std::mutex update_cache_lock_, update_cache_lock_world_;  // .h:295,302
   mutable std::shared_ptr<const CacheEntry> dfce_;
+  mutable std::size_t cache_generations_ = 0;  // how often the entry had to be regenerated (guarded by update_cache_lock_)
   mutable std::string last_error_;
 };
 using CollisionEnvB200Ptr = std::shared_ptr<CollisionEnvB200>;

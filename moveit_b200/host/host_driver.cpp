@@ -2,6 +2,7 @@
 // moveit_b200/scenario_io.py, builds RobotModel + World + AllowedCollisionMatrix through the reference-shaped API,
 // allocates the env through CollisionDetectorAllocatorB200 and writes verdicts / contacts / gradients that
 // tests/test_host_mirror.py compares with the CPU oracle.  Everything numeric happens on the GPU via libb200df.so.
+#include <chrono>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -239,6 +240,38 @@ int main(int argc, char** argv)
           throw std::runtime_error("concurrent checkCollision disagrees with the single-threaded answer");
     }
 
+    // per-call cost of the single-state CollisionEnv API (what an OMPL StateValidityChecker pays per isValid())
+    // (one fixed state: a planner keeps the joints outside the group still, so the cached group entry stays valid)
+    double us_plain = 0.0, us_contacts = 0.0;
+    std::size_t regenerated = 0;
+    if (!single.empty())
+    {
+      const int reps = 300;
+      const std::size_t gen0 = env->cacheGenerations();
+      CollisionRequest creq = req;
+      creq.contacts = true;
+      creq.max_contacts = 10;
+      creq.max_contacts_per_pair = 2;
+      for (int pass = 0; pass < 2; ++pass)
+      {
+        const CollisionRequest& r = pass ? creq : req;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int k = 0; k < reps; ++k)
+        {
+          core::RobotState st(ref_state);
+          st.setVariablePositions(&q[0]);
+          CollisionResult res;
+          if (acm_ptr)
+            env->checkCollision(r, res, st, acm);
+          else
+            env->checkCollision(r, res, st);
+        }
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+        (pass ? us_contacts : us_plain) = us;
+      }
+      regenerated = env->cacheGenerations() - gen0;
+    }
+
     // contacts
     {
       std::ofstream cf(prefix + ".contacts.txt");
@@ -324,8 +357,10 @@ int main(int argc, char** argv)
       if (v2 != v)
         throw std::runtime_error("env copied onto the same world disagrees with the original");
     }
-    std::printf("host_driver ok: %s, %lld states, detector %s, %lld kernel launches\n", robot_name.c_str(),
-                (long long)n, alloc->getName().c_str(), (long long)b200df_launch_count());
+    std::printf("host_driver ok: %s, %lld states, detector %s, %lld kernel launches, checkCollision %.1f us/call "
+                "(%.1f us with contacts; %zu cache regenerations in the timed calls)\n",
+                robot_name.c_str(), (long long)n, alloc->getName().c_str(), (long long)b200df_launch_count(), us_plain,
+                us_contacts, regenerated);
     return 0;
   }
   catch (const std::exception& ex)

@@ -46,6 +46,7 @@ def _run(tmp_path, desc, field, objs, q, **kw):
     r = subprocess.run([exe, scen, states, prefix], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "B200DistanceField" in r.stdout
+    print(r.stdout.strip())
     return prefix
 
 

@@ -101,6 +101,23 @@ def run(with_oracle=True):
     except ImportError:
         pass
 
+    # small calls, the granularity the reference's callers use (tools/latency_probe.py has the full sweep)
+    small = {}
+    q256 = q[:256].copy()
+    t100 = traj[:100].copy()
+    qa1, qb1 = q[:1].astype(np.float64), q[1:2].astype(np.float64)
+    for name, fn in (("check_256_states", lambda: e.group.check(q256, e.world, flags=fl1, precision=B.PRECISION_FAST)),
+                     ("gradients_100_waypoints", lambda: e.group.gradients(t100, e.world, flags=fl)),
+                     ("edge_1_motion_16_segments",
+                      lambda: e.group.check_edges(qa1, qb1, 16, e.world, flags=fl, precision=B.PRECISION_FAST))):
+        for _ in range(20):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            fn()
+        small[name + "_us"] = 1e6 * (time.perf_counter() - t0) / 300
+    out["small_call_latency_incl_python_binding"] = small
+
     # planner edge checks: 1 M random motions x 10 segments, only the end states cross PCIe
     M, K = 1_000_000, 10
     qa = desc.sample_states(M, 901)
