@@ -107,18 +107,26 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
   };
   if (e != cudaSuccess)
     return finish();
-  cudaStream_t stream = ctx->stream[0];
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  enum { kStates = 0, kVerdict = 1, kA = 2, kB = 3, kAng = 4, kOut = 5 };  // scratch slots
-  e = Pool::ensure_scratch(ctx, kStates, (size_t)chunk * segments * nv * sizeof(double));
-  if (e == cudaSuccess)
-    e = Pool::ensure_scratch(ctx, kVerdict, (size_t)chunk * segments);
+  // scratch slots: two pipeline slots of {states, verdicts, A, B, out}, then the angular flags
+  enum { kStates = 0, kVerdict = 1, kA = 2, kB = 3, kOut = 4, kPerSlot = 5, kAng = 10 };
+  auto ensure_slot = [&](int k) {
+    cudaError_t r = Pool::ensure_stream(ctx, k);
+    if (r == cudaSuccess)
+      r = Pool::ensure_scratch(ctx, kPerSlot * k + kStates, (size_t)chunk * segments * nv * sizeof(double));
+    if (r == cudaSuccess)
+      r = Pool::ensure_scratch(ctx, kPerSlot * k + kVerdict, (size_t)chunk * segments);
+    return r;
+  };
+  e = ensure_slot(0);
   if (e != cudaSuccess)
     return finish();
-  double* dq = static_cast<double*>(ctx->scratch[kStates]);
-  uint8_t* dv = static_cast<uint8_t*>(ctx->scratch[kVerdict]);
 
-  auto run_chunk = [&](const double* da, const double* db, const uint8_t* dang, int64_t mc, int32_t* dout) {
+  // interpolate -> verdicts -> first invalid sample, all on slot k's stream
+  auto run_chunk = [&](int k, const double* da, const double* db, const uint8_t* dang, int64_t mc, int32_t* dout) {
+    cudaStream_t stream = ctx->stream[k];
+    double* dq = static_cast<double*>(ctx->scratch[kPerSlot * k + kStates]);
+    uint8_t* dv = static_cast<uint8_t*>(ctx->scratch[kPerSlot * k + kVerdict]);
     const long total = mc * segments * nv;
     interpolate_edges_kernel<double><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(da, db, mc, segments, nv,
                                                                                           dang, dq);
@@ -146,9 +154,9 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
     std::memcpy(hp, qa, end_bytes);
     std::memcpy(hp + o_b, qb, end_bytes);
     std::memcpy(hp + o_ang, ang.data(), ang.size());
-    run_chunk(reinterpret_cast<const double*>(dp), reinterpret_cast<const double*>(dp + o_b),
+    run_chunk(0, reinterpret_cast<const double*>(dp), reinterpret_cast<const double*>(dp + o_b),
               reinterpret_cast<const uint8_t*>(dp + o_ang), m, reinterpret_cast<int32_t*>(dp + o_out));
-    const cudaError_t es = cudaStreamSynchronize(stream);
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream[0]);
     if (e == cudaSuccess)
       e = es;
     if (!rc && e == cudaSuccess)
@@ -156,36 +164,58 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
     return finish();
   }
 
-  e = Pool::ensure_scratch(ctx, kA, end_bytes);
-  if (e == cudaSuccess)
-    e = Pool::ensure_scratch(ctx, kB, end_bytes);
+  // Large calls: two slots on two streams, software-pipelined so that the end points of chunk i+1 are staged and its
+  // kernels queued while chunk i computes; only then is chunk i's result read back (a copy into pageable memory
+  // holds the host until that chunk is done).
+  const int64_t n_chunks = (m + chunk - 1) / chunk;
+  const int n_slots = n_chunks > 1 ? 2 : 1;
+  for (int k = 0; k < n_slots && e == cudaSuccess; ++k)
+  {
+    e = ensure_slot(k);
+    if (e == cudaSuccess)
+      e = Pool::ensure_scratch(ctx, kPerSlot * k + kA, end_bytes);
+    if (e == cudaSuccess)
+      e = Pool::ensure_scratch(ctx, kPerSlot * k + kB, end_bytes);
+    if (e == cudaSuccess)
+      e = Pool::ensure_scratch(ctx, kPerSlot * k + kOut, (size_t)chunk * sizeof(int32_t));
+  }
   if (e == cudaSuccess)
     e = Pool::ensure_scratch(ctx, kAng, ang.size());
   if (e == cudaSuccess)
-    e = Pool::ensure_scratch(ctx, kOut, (size_t)chunk * sizeof(int32_t));
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(ctx->scratch[kAng], ang.data(), ang.size(), cudaMemcpyHostToDevice, stream);
-  for (int64_t s = 0; s < m && !rc && e == cudaSuccess; s += chunk)
-  {
-    const int64_t mc = std::min<int64_t>(chunk, m - s);
-    e = cudaMemcpyAsync(ctx->scratch[kA], qa + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, stream);
+    e = cudaMemcpy(ctx->scratch[kAng], ang.data(), ang.size(), cudaMemcpyHostToDevice);
+  auto issue = [&](int64_t i) {  // stage + queue chunk i on slot i % 2
+    const int k = (int)(i % 2);
+    const int64_t s0 = i * chunk, mc = std::min<int64_t>(chunk, m - s0);
+    void** buf = ctx->scratch + kPerSlot * k;
+    e = cudaMemcpyAsync(buf[kA], qa + s0 * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream[k]);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(ctx->scratch[kB], qb + s * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice,
-                          stream);
-    if (e != cudaSuccess)
-      break;
-    run_chunk(static_cast<const double*>(ctx->scratch[kA]), static_cast<const double*>(ctx->scratch[kB]),
-              static_cast<const uint8_t*>(ctx->scratch[kAng]), mc, static_cast<int32_t*>(ctx->scratch[kOut]));
+      e = cudaMemcpyAsync(buf[kB], qb + s0 * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice,
+                          ctx->stream[k]);
+    if (e == cudaSuccess)
+      run_chunk(k, static_cast<const double*>(buf[kA]), static_cast<const double*>(buf[kB]),
+                static_cast<const uint8_t*>(ctx->scratch[kAng]), mc, static_cast<int32_t*>(buf[kOut]));
+  };
+  if (e == cudaSuccess)
+    issue(0);
+  for (int64_t i = 0; i < n_chunks && !rc && e == cudaSuccess; ++i)
+  {
+    if (i + 1 < n_chunks)
+      issue(i + 1);  // slot (i+1) % 2 was drained when chunk i-1 was read back
     if (rc || e != cudaSuccess)
       break;
-    e = cudaMemcpyAsync(first_invalid + s, ctx->scratch[kOut], (size_t)mc * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                        stream);
+    const int k = (int)(i % 2);
+    const int64_t s0 = i * chunk, mc = std::min<int64_t>(chunk, m - s0);
+    e = cudaMemcpyAsync(first_invalid + s0, ctx->scratch[kPerSlot * k + kOut], (size_t)mc * sizeof(int32_t),
+                        cudaMemcpyDeviceToHost, ctx->stream[k]);
     if (e == cudaSuccess)
-      e = cudaStreamSynchronize(stream);  // the next chunk reuses the buffers
+      e = cudaStreamSynchronize(ctx->stream[k]);
   }
-  const cudaError_t es = cudaStreamSynchronize(stream);
-  if (e == cudaSuccess)
-    e = es;
+  for (int k = 0; k < n_slots; ++k)
+  {
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream[k]);
+    if (e == cudaSuccess)
+      e = es;
+  }
   return finish();
 }
 

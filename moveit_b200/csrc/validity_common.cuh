@@ -644,7 +644,7 @@ struct b200df_group::StagePool
     // inputs from and write their results to across PCIe, plus device scratch
     void* pin = nullptr;
     size_t pin_bytes = 0;
-    static constexpr int kScratch = 10;
+    static constexpr int kScratch = 12;
     void* scratch[kScratch] = {};
     size_t scratch_bytes[kScratch] = {};
   };

@@ -449,7 +449,12 @@ def test_batched_edge_check_matches_per_state_oracle(gpu, oracle, robot):
     assert np.array_equal(got, want)
     assert 0 < (got == 0).sum() < M
     fast = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=1, var_is_angular=angular)
-    assert np.array_equal(fast, got)  # FAST screens the fp64 states in fp32 and re-runs the undecided ones unrounded
+    assert np.array_equal(fast, got)
+    # enough states for the FAST screening pass to be taken (>= 64 k): it screens the fp64 states in fp32 and re-runs
+    # the undecided ones unrounded
+    qa2, qb2 = desc.sample_states(20_000, 73), desc.sample_states(20_000, 74)
+    assert np.array_equal(e.group.check_edges(qa2, qb2, K, e.world, flags=flags, precision=1, var_is_angular=angular),
+                          e.group.check_edges(qa2, qb2, K, e.world, flags=flags, precision=0, var_is_angular=angular))
     if robot == "mobile_arm":
         assert (np.abs(qb[:, 2] - qa[:, 2]) > np.pi).any()  # the shortest-arc branch was exercised
 
