@@ -310,6 +310,8 @@ class Field:
         self.dims = (dims[0], dims[1], dims[2])
         self.max_d2 = dims[3]
         self.resolution = resolution
+        self.size = tuple(float(v) for v in size)
+        self.origin = tuple(float(v) for v in origin)
 
     @classmethod
     def centered(cls, size, resolution, center, max_distance, signed=False):
@@ -403,6 +405,27 @@ class Field:
     def unpack_occupancy(self, payload):
         b = np.ascontiguousarray(payload, dtype=np.uint8)
         B.check(B.load().b200df_field_unpack_occupancy(self.h, B.ptr(b, C.c_uint8), len(b)))
+
+    def write_stream(self, fileobj):
+        """PropagationDistanceField::writeToStream (propagation_distance_field.cpp:636-673)."""
+        from . import field_stream
+        return field_stream.write_stream(fileobj, self.resolution, self.size, self.origin, self.pack_occupancy().tobytes())
+
+    @classmethod
+    def from_stream(cls, fileobj, max_distance, signed=False):
+        """PropagationDistanceField(std::istream&, max_distance, propagate_negative) (:64-74, 675-761); None when the
+        stream does not hold a field."""
+        from . import field_stream
+        got = field_stream.read_stream(fileobj)
+        if got is None:
+            return None
+        h, payload = got
+        f = cls((h["size_x"], h["size_y"], h["size_z"]), h["resolution"], (h["origin_x"], h["origin_y"], h["origin_z"]),
+                max_distance, signed)
+        if len(payload) < field_stream.payload_size(f.dims):
+            return None
+        f.unpack_occupancy(np.frombuffer(payload, dtype=np.uint8)[:field_stream.payload_size(f.dims)])
+        return f
 
     def device_arrays(self):
         d2, neg = C.c_void_p(), C.c_void_p()

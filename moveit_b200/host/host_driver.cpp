@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "collision_env_b200.hpp"
+#include "distance_field_b200.hpp"
 
 using namespace collision_detection_b200;
 
@@ -31,8 +32,92 @@ void writeFile(const std::string& path, const std::vector<T>& v)
 }
 }  // namespace
 
+// distance_field/test/test_distance_field.cpp:882-928 (TestReadWrite) through PropagationDistanceFieldB200, plus the
+// files the Python-side test cross-reads: host_driver --field-stream <prefix> [<stream written elsewhere>]
+static int fieldStreamTest(const std::string& prefix, const char* foreign)
+{
+  using distance_field_b200::PropagationDistanceFieldB200;
+  auto require = [](bool ok, const char* what) {
+    if (!ok)
+      throw std::runtime_error(std::string("field stream test: ") + what);
+  };
+  auto dump = [](const std::string& path, const std::vector<std::int32_t>& v) {
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)(v.size() * sizeof(std::int32_t)));
+  };
+  PropagationDistanceFieldB200 small_df(1.0, 1.0, 1.0, 0.1, 0.0, 0.0, 0.0, 0.3);
+  small_df.addPointsToField({ Vector3d{ 0.1, 0.0, 0.0 }, Vector3d{ 0.0, 0.1, 0.2 }, Vector3d{ 0.4, 0.0, 0.0 } });
+  {
+    std::ofstream sf(prefix + ".small.df", std::ios::out | std::ios::binary);
+    require(small_df.writeToStream(sf), "writeToStream(small)");
+  }
+  {
+    std::ifstream si(prefix + ".small.df", std::ios::in | std::ios::binary);
+    PropagationDistanceFieldB200 small_df2(si, 0.25, false);
+    require(small_df2.valid() && small_df2.getXNumCells() == 10, "small field read back");
+    require(small_df.distanceSquares() == small_df2.distanceSquares(), "small field distances differ after the round trip");
+    // cell and world queries agree with the gradient query's distance
+    double gx, gy, gz;
+    bool inb;
+    require(small_df2.getDistance(1, 0, 0) == 0.0 && small_df2.getDistance(0.1, 0.0, 0.0) == 0.0, "obstacle cell");
+    require(small_df2.getDistance(5, 5, 5) == small_df2.getDistanceGradient(0.5, 0.5, 0.5, gx, gy, gz, inb) && inb,
+            "cell vs gradient query");
+    require(small_df2.getDistance(1000.0, 0.0, 0.0) == small_df2.getUninitializedDistance(), "out of bounds distance");
+  }
+  dump(prefix + ".small.d2.i32", small_df.distanceSquares());
+
+  PropagationDistanceFieldB200 df(3.0, 3.0, 4.0, 0.02, 0.0, 0.0, 0.0, 0.25, false);
+  shapes::Shape sphere;
+  sphere.type = shapes::SPHERE;
+  sphere.dims[0] = 0.5;
+  Isometry3d pose;
+  pose.m[3] = pose.m[7] = pose.m[11] = 0.5;
+  df.addShapeToField(&sphere, pose);
+  {
+    std::ofstream f(prefix + ".big.df", std::ios::out | std::ios::binary);
+    require(df.writeToStream(f), "writeToStream(big)");
+  }
+  std::ifstream i(prefix + ".big.df", std::ios::in | std::ios::binary);
+  PropagationDistanceFieldB200 df2(i, 0.25, false);
+  require(df2.valid() && df.distanceSquares() == df2.distanceSquares(), "big field distances differ after the round trip");
+  PropagationDistanceFieldB200 dfx(i, 0.25, false);  // "we shouldn't segfault if we start with an old ifstream"
+  require(!dfx.valid(), "an exhausted stream must not yield a field");
+  std::ifstream i2(prefix + ".big.df", std::ios::in | std::ios::binary);
+  PropagationDistanceFieldB200 df3(i2, 0.25 + 0.02, false);
+  require(df3.valid() && df.distanceSquares() != df3.distanceSquares(), "a larger max distance must change the field");
+  dump(prefix + ".big.d2.i32", df.distanceSquares());
+  // moveShapeInField == remove + add (test_distance_field.cpp:601-649)
+  Isometry3d moved = pose;
+  moved.m[3] = moved.m[7] = moved.m[11] = 0.7;
+  df.moveShapeInField(&sphere, pose, moved);
+  PropagationDistanceFieldB200 fresh(3.0, 3.0, 4.0, 0.02, 0.0, 0.0, 0.0, 0.25, false);
+  fresh.addShapeToField(&sphere, moved);
+  require(df.distanceSquares() == fresh.distanceSquares(), "moved shape differs from a fresh add");
+  if (foreign)
+  {
+    std::ifstream fi(foreign, std::ios::in | std::ios::binary);
+    PropagationDistanceFieldB200 other(fi, 0.25, false);
+    require(other.valid(), "could not read the foreign stream");
+    dump(prefix + ".foreign.d2.i32", other.distanceSquares());
+  }
+  std::printf("field stream test ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc >= 3 && std::string(argv[1]) == "--field-stream")
+  {
+    try
+    {
+      return fieldStreamTest(argv[2], argc > 3 ? argv[3] : nullptr);
+    }
+    catch (const std::exception& ex)
+    {
+      std::fprintf(stderr, "host_driver failed: %s\n", ex.what());
+      return 1;
+    }
+  }
   if (argc < 4)
   {
     std::fprintf(stderr, "usage: host_driver <scenario.txt> <states.f64> <out_prefix>\n");

@@ -26,6 +26,11 @@
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference/moveit_core unless stated otherwise).
 #pragma once
+#include <zlib.h>
+
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -648,6 +653,75 @@ public:
               obs_points.push_back(I3{ x, y, z + zi });
         }
     addNewObstacleVoxels(obs_points);
+  }
+
+  // writeToStream (propagation_distance_field.cpp:636-673): seven "key: value" lines with the default ostream
+  // formatting of a double (operator<<(double) == printf("%g"), six significant digits), then the occupancy bits
+  // through boost::iostreams::zlib_compressor (default parameters: a plain zlib stream, restated with zlib's own
+  // compress2 at the default level).  Written into a byte vector: this library carries a static libstdc++, whose
+  // iostreams must not be mixed with the host process's.
+  bool writeToStream(std::vector<uint8_t>& os) const
+  {
+    const char* keys[7] = { "resolution", "size_x", "size_y", "size_z", "origin_x", "origin_y", "origin_z" };
+    const double vals[7] = { resolution_, size_[0], size_[1], size_[2], origin_[0], origin_[1], origin_[2] };
+    for (int i = 0; i < 7; ++i)
+    {
+      char line[96];
+      const int n = std::snprintf(line, sizeof(line), "%s: %g\n", keys[i], vals[i]);
+      os.insert(os.end(), line, line + n);
+    }
+    const std::vector<uint8_t> bits = packOccupancy();
+    uLongf n = compressBound((uLong)bits.size());
+    std::vector<uint8_t> z(n);
+    if (compress2(z.data(), &n, bits.data(), (uLong)bits.size(), Z_DEFAULT_COMPRESSION) != Z_OK)
+      return false;
+    os.insert(os.end(), z.begin(), z.begin() + n);
+    return true;
+  }
+
+  // readFromStream (propagation_distance_field.cpp:675-761); max_distance_ and propagate_negative_ keep the values
+  // the field was constructed with (:712).  operator>>(std::string) / operator>>(double) read whitespace-separated
+  // tokens.
+  bool readFromStream(const uint8_t* data, size_t size)
+  {
+    if (size == 0)
+      return false;  // !is.good()
+    size_t pos = 0;
+    auto token = [&](std::string& out) {
+      while (pos < size && std::isspace(data[pos]))
+        ++pos;
+      const size_t b = pos;
+      while (pos < size && !std::isspace(data[pos]))
+        ++pos;
+      out.assign(reinterpret_cast<const char*>(data) + b, pos - b);
+      return !out.empty();
+    };
+    const char* keys[7] = { "resolution:", "size_x:", "size_y:", "size_z:", "origin_x:", "origin_y:", "origin_z:" };
+    double* dst[7] = { &resolution_, &size_[0], &size_[1], &size_[2], &origin_[0], &origin_[1], &origin_[2] };
+    for (int i = 0; i < 7; ++i)
+    {
+      std::string temp;
+      if (!token(temp) || temp != keys[i])
+        return false;
+      if (!token(temp))
+        return false;
+      char* end = nullptr;
+      *dst[i] = std::strtod(temp.c_str(), &end);
+      if (end == temp.c_str())
+        return false;
+    }
+    inv_twice_resolution_ = 1.0 / (2.0 * resolution_);
+    initialize();
+    if (pos < size)
+      ++pos;  // "this should be newline" (:717-719)
+    const size_t want = (size_t)g_.num_cells[0] * g_.num_cells[1] * ((g_.num_cells[2] + 7) / 8);
+    std::vector<uint8_t> bits(want);
+    uLongf got = (uLongf)want;
+    const int rc = uncompress(bits.data(), &got, data + pos, (uLong)(size - pos));
+    if ((rc != Z_OK && rc != Z_BUF_ERROR) || got < want)
+      return false;  // the reference stops with false when the decompressor runs dry (:739-742)
+    unpackOccupancy(bits.data(), want);
+    return true;
   }
 
   Voxel& cell(int x, int y, int z)

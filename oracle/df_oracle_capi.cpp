@@ -130,6 +130,37 @@ void orc_field_unpack_occupancy(void* f, const uint8_t* bytes, long n)
 {
   static_cast<PropagationDistanceField*>(f)->unpackOccupancy(bytes, (size_t)n);
 }
+// writeToStream into a caller buffer (two-pass: returns the byte count; copies when it fits)
+long orc_field_write_stream(void* f, uint8_t* out, long cap)
+{
+  std::vector<uint8_t> s;
+  if (!static_cast<PropagationDistanceField*>(f)->writeToStream(s))
+    return -1;
+  if ((long)s.size() <= cap)
+    std::memcpy(out, s.data(), s.size());
+  return (long)s.size();
+}
+// PropagationDistanceField(std::istream&, max_distance, propagate_negative) (:64-74); NULL when readFromStream fails
+void* orc_field_from_stream(const uint8_t* bytes, long n, double max_distance, int propagate_negative)
+{
+  auto* df = new PropagationDistanceField(1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, max_distance, propagate_negative != 0);
+  if (!df->readFromStream(bytes, (size_t)n))
+  {
+    delete df;
+    return nullptr;
+  }
+  return df;
+}
+void orc_field_geometry(void* f, double* out7)
+{
+  auto* df = static_cast<PropagationDistanceField*>(f);
+  out7[0] = df->resolution_;
+  for (int i = 0; i < 3; ++i)
+  {
+    out7[1 + i] = df->size_[i];
+    out7[4 + i] = df->origin_[i];
+  }
+}
 void orc_field_add_voxels(void* f, const int32_t* ijk, long n)
 {
   auto* df = static_cast<PropagationDistanceField*>(f);

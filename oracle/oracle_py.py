@@ -60,6 +60,11 @@ def lib():
         L.orc_field_pack_occupancy.restype = C.c_long
         L.orc_field_pack_occupancy.argtypes = [C.c_void_p, c_u8p, C.c_long]
         L.orc_field_unpack_occupancy.argtypes = [C.c_void_p, c_u8p, C.c_long]
+        L.orc_field_write_stream.restype = C.c_long
+        L.orc_field_write_stream.argtypes = [C.c_void_p, c_u8p, C.c_long]
+        L.orc_field_from_stream.restype = C.c_void_p
+        L.orc_field_from_stream.argtypes = [c_u8p, C.c_long, C.c_double, C.c_int]
+        L.orc_field_geometry.argtypes = [C.c_void_p, c_dp]
         L.orc_field_add_voxels.argtypes = [C.c_void_p, c_i32p, C.c_long]
         L.orc_field_make_exact.argtypes = [C.c_void_p]
         for n in ("orc_edt_exact", "orc_edt_brute"):
@@ -203,6 +208,36 @@ class Field:
         out = np.empty(n, dtype=np.uint8)
         lib().orc_field_pack_occupancy(self.h, out.ctypes.data_as(c_u8p), n)
         return out
+
+    def write_stream(self):
+        """writeToStream (propagation_distance_field.cpp:636-673) -> bytes."""
+        n = lib().orc_field_write_stream(self.h, None, 0)
+        assert n > 0
+        out = np.empty(n, dtype=np.uint8)
+        lib().orc_field_write_stream(self.h, out.ctypes.data_as(c_u8p), n)
+        return out.tobytes()
+
+    @classmethod
+    def from_stream(cls, data, max_dist, signed=False):
+        """PropagationDistanceField(std::istream&, max_distance, propagate_negative); None when readFromStream fails."""
+        b = np.frombuffer(bytes(data), dtype=np.uint8).copy()
+        h = lib().orc_field_from_stream(b.ctypes.data_as(c_u8p), len(b), max_dist, int(signed))
+        if not h:
+            return None
+        f = cls.__new__(cls)
+        f._own = True
+        f.h = h
+        d = (C.c_int * 4)()
+        lib().orc_field_dims(h, d)
+        f.dims = (d[0], d[1], d[2])
+        f.max_d2 = d[3]
+        return f
+
+    def geometry(self):
+        """(resolution, size xyz, origin xyz)"""
+        g = np.empty(7)
+        lib().orc_field_geometry(self.h, g.ctypes.data_as(c_dp))
+        return g[0], tuple(g[1:4]), tuple(g[4:7])
 
     def unpack_occupancy(self, b):
         b = np.ascontiguousarray(b, dtype=np.uint8)

@@ -198,3 +198,42 @@ def test_attached_body_through_the_cpp_env(gpu, oracle, tmp_path):
             assert int(t[7]) == 1
             seen = True
     assert seen
+
+
+@pytest.mark.gpu
+def test_distance_field_class_and_stream_format(gpu, oracle, tmp_path):
+    """PropagationDistanceFieldB200 (the C++ mirror of the reference's DistanceField API) runs the reference's
+    TestReadWrite (test_distance_field.cpp:882-928) and its moved-shape test; the streams it writes are read by the
+    Python engine and by the oracle's restatement of readFromStream, and it reads a stream the Python engine wrote."""
+    from moveit_b200 import engine
+    exe = _build_driver()
+    prefix = str(tmp_path / "fs")
+    pts = [(0.1, 0.0, 0.0), (0.0, 0.1, 0.2), (0.4, 0.0, 0.0)]
+    f = engine.Field((1.0, 1.0, 1.0), 0.1, (0.0, 0.0, 0.0), 0.3)
+    f.add_points(pts)
+    py_stream = str(tmp_path / "py.df")
+    with open(py_stream, "wb") as fo:
+        assert f.write_stream(fo)
+    r = subprocess.run([exe, "--field-stream", prefix, py_stream], capture_output=True, text=True)
+    assert r.returncode == 0 and "field stream test ok" in r.stdout, r.stderr + r.stdout
+    # C++ read the Python-written stream
+    assert np.array_equal(np.fromfile(prefix + ".foreign.d2.i32", dtype=np.int32).reshape(f.dims), f.d2())
+    # the C++-written small stream: same bytes up to the zlib payload, same field through every reader
+    small = open(prefix + ".small.df", "rb").read()
+    assert small == open(py_stream, "rb").read()
+    g = engine.Field.from_stream(open(prefix + ".small.df", "rb"), 0.25)
+    want = np.fromfile(prefix + ".small.d2.i32", dtype=np.int32).reshape(g.dims)
+    assert np.array_equal(g.d2(), want) and np.array_equal(want, f.d2())
+    o = oracle.Field.from_stream(small, 0.25)
+    assert o is not None and np.array_equal(o.d2(), want)  # three isolated points: propagation is exact here
+    # the big one (150 x 150 x 200, a sphere of radius 0.5): Python engine and oracle read what C++ wrote
+    big = open(prefix + ".big.df", "rb").read()
+    gb = engine.Field.from_stream(open(prefix + ".big.df", "rb"), 0.25)
+    assert gb.dims == (150, 150, 200)
+    wb = np.fromfile(prefix + ".big.d2.i32", dtype=np.int32).reshape(gb.dims)
+    assert np.array_equal(gb.d2(), wb) and (wb == 0).sum() > 10000
+    ob = oracle.Field.from_stream(big, 0.25)
+    assert ob is not None and np.array_equal(ob.d2() == 0, wb == 0)
+    ob.make_exact()
+    assert np.array_equal(ob.d2(), wb)
+    assert engine.Field.from_stream(open(prefix + ".small.d2.i32", "rb"), 0.25) is None  # not a field stream

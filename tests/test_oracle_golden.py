@@ -200,6 +200,46 @@ def test_read_write_round_trip(oracle):
     assert not np.array_equal(big.d2(), big3.d2())
 
 
+def test_read_write_stream_format(oracle):
+    """The same test through the complete on-disk format (writeToStream :636-673 / readFromStream :675-761): text
+    header + one zlib stream, and the product's host-side framing (moveit_b200/field_stream.py) against it."""
+    import io
+    from moveit_b200 import field_stream
+    f = small_field(oracle)
+    f.add_points([POINT1, POINT2, POINT3])
+    blob = f.write_stream()
+    head = blob[:blob.index(b"origin_z")].decode()
+    assert head == "resolution: 0.1\nsize_x: 1\nsize_y: 1\nsize_z: 1\norigin_x: 0\norigin_y: 0\n"
+    g = oracle.Field.from_stream(blob, 0.25)  # small_df2(si, PERF_MAX_DIST, false)
+    assert g is not None and g.dims == f.dims and np.array_equal(f.d2(), g.d2())
+    # the product's framing reads what the oracle wrote ...
+    hdr, payload = field_stream.read_stream(io.BytesIO(blob))
+    assert hdr == dict(resolution=0.1, size_x=1.0, size_y=1.0, size_z=1.0, origin_x=0.0, origin_y=0.0, origin_z=0.0)
+    assert payload == f.pack_occupancy().tobytes() and len(payload) == field_stream.payload_size(f.dims)
+    # ... and writes what the oracle reads, byte for byte the same header
+    out = io.BytesIO()
+    field_stream.write_stream(out, 0.1, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), payload)
+    assert out.getvalue()[:len(head)] == head.encode()
+    h = oracle.Field.from_stream(out.getvalue(), 0.3)
+    assert h is not None and np.array_equal(h.d2(), f.d2())
+    # non-trivial numbers take the default six-digit formatting of operator<<(double)
+    odd = oracle.Field((0.7, 0.35, 0.21), 0.07, (-0.123456789, 1e-7, 12345678.0), 0.2)
+    odd.add_points([(0.0, 0.1, 12345678.1)])
+    oblob = odd.write_stream()
+    otext = oblob[:oblob.index(b"\n", oblob.index(b"origin_z")) + 1].decode()
+    assert otext == ("resolution: 0.07\nsize_x: 0.7\nsize_y: 0.35\nsize_z: 0.21\norigin_x: -0.123457\n"
+                     "origin_y: 1e-07\norigin_z: 1.23457e+07\n")
+    out = io.BytesIO()
+    field_stream.write_stream(out, 0.07, (0.7, 0.35, 0.21), (-0.123456789, 1e-7, 12345678.0), odd.pack_occupancy())
+    assert out.getvalue()[:len(otext)] == otext.encode()
+    # a stream that is not a field, an exhausted stream and a truncated payload are refused (returns false, no crash)
+    assert oracle.Field.from_stream(b"", 0.25) is None and field_stream.read_stream(io.BytesIO(b"")) is None
+    assert oracle.Field.from_stream(b"resolution 0.1\n", 0.25) is None
+    assert field_stream.read_stream(io.BytesIO(b"resolution 0.1\n")) is None
+    cut = blob[:len(blob) - 6]
+    assert oracle.Field.from_stream(cut, 0.25) is None and field_stream.read_stream(io.BytesIO(cut)) is None
+
+
 # ---- test_collision_distance_field.cpp:336-383 DistanceFieldCollisionDetectionPadding.Sphere ------------------
 def _padding_sphere_env(oracle):
     r = rd.RobotDescription("test")
