@@ -220,7 +220,7 @@ __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double 
 // by consecutive threads to consecutive spheres of a state: coalesced, no read-modify-write of global memory.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGradStates = 32;    // states per CTA
-constexpr int kGradThreads = 256;
+constexpr int kGradThreads = 128;
 
 // PosedDistanceField::getDistanceGradient's point mapping (collision_distance_field_types.h:156-160):
 // rel = pose.inverse() * p with Eigen's isometry inverse (R^T, -(R^T t))
@@ -255,13 +255,19 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
   const int S = g.n_spheres;
   const int G = g.n_glinks;
   const int L = g.n_links;
-  double* cen = smem;                        // [state][S][3]
-  double* slots = cen + (size_t)GS * S * 3;  // !COOP: [n_slots][12][state]   COOP: T [state][L][12]
+  // XPOSE (the 32-states-per-CTA variant): lane = state, a warp works on ONE sphere index for 32 states, so the
+  // partner loops have the same trip count on every lane (the per-sphere mapping left 12 of 32 lanes active on
+  // average).  The per-state strides are odd so that 32 lanes reading the same element of 32 states hit different banks.
+  constexpr bool XPOSE = !COOP && GS == 32;
+  const int CS = (S * 3) | 1;  // doubles per state in cen
+  const int US = S | 1;        // words per state in can / abt
+  double* cen = smem;                        // [state][CS]: posed sphere centres, [k][3] inside a state
+  double* slots = cen + (size_t)GS * CS;     // !COOP: [n_slots][12][state]   COOP: T [state][L][12]
   double* poses = slots + (COOP ? (size_t)GS * L * 12 : (size_t)g.n_slots * 12 * GS);  // !COOP && LF: [state][G][12]
   double* staging = poses + ((LF && !COOP) ? (size_t)GS * G * 12 : 0);                 // COOP: warp_fk staging per warp
   unsigned* can = reinterpret_cast<unsigned*>(staging + (COOP ? (NT / 32) * warp_fk_staging_doubles(L) : 0));
-  unsigned* abt = can + (LF ? (size_t)GS * S : 0);                        // LF: [state][S] (can likewise)
-  QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)GS * S : 0));        // [state][n_vars]
+  unsigned* abt = can + (LF ? (size_t)GS * US : 0);                       // LF: [state][US] (can likewise)
+  QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)GS * US : 0));  // [state][n_vars]
   {
     const int total = GS * g.n_vars;
     const long limit = (n - base) * g.n_vars;
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     {
       double* T = slots + (size_t)st * L * 12;
       warp_fk(g.links, L, qs + (size_t)st * g.n_vars, lane, staging + warp * warp_fk_staging_doubles(L), T);
-      double* my_cen = cen + (size_t)st * S * 3;
+      double* my_cen = cen + (size_t)st * CS;
       for (int s = lane; s < S; s += 32)
       {
         const double* rel = g.sph + 4 * s;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
   else if (tid < GS)
   {
     double cur[12];
-    double* my_cen = cen + (size_t)tid * S * 3;
+    double* my_cen = cen + (size_t)tid * CS;
     for (int i = 0; i < g.n_links; ++i)
     {
       fk_step(g.links[i], qs + (size_t)tid * g.n_vars, slots + tid, 1, GS, cur);
@@ -324,8 +330,8 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     // pose's translation, Q6), so sphere k sees field j only if it is inside AND no earlier sphere of its link aborted.
     for (int it = tid; it < items; it += NT)
     {
-      const int st = it / S, k = it - st * S;
-      const double* sc = cen + (size_t)st * S * 3;
+      const int st = XPOSE ? it % GS : it / S, k = XPOSE ? it / GS : it - st * S;
+      const double* sc = cen + (size_t)st * CS;
       const int gs = g.sph_glink[k];
       unsigned allowed = g.glinks[gs].self_enabled ? (g.lf_enabled[gs] & ~(1u << gs)) : 0u;
       unsigned inb = 0u, ab = 0u;
@@ -345,8 +351,8 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
         else if (sqrt((pose[3] * pose[3] + pose[7] * pose[7]) + pose[11] * pose[11]) > 0.0)
           ab |= 1u << j;
       }
-      can[it] = inb;
-      abt[it] = ab;
+      can[st * US + k] = inb;
+      abt[st * US + k] = ab;
     }
     __syncthreads();
     for (int it = tid; it < GS * G; it += NT)
@@ -355,8 +361,8 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
       unsigned alive = 0xffffffffu;
       for (int k = g.glinks[gs].sphere_begin; k < g.glinks[gs].sphere_end; ++k)
       {
-        const unsigned a = abt[st * S + k];
-        can[st * S + k] &= alive;
+        const unsigned a = abt[st * US + k];
+        can[st * US + k] &= alive;
         alive &= ~a;
       }
     }
@@ -364,11 +370,15 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
   }
   for (int it = tid; it < items; it += NT)
   {
-    const int st = it / S, k = it - st * S;
+    const int st = XPOSE ? it % GS : it / S, k = XPOSE ? it / GS : it - st * S;
     const long state = base + st;
     if (state >= n)
+    {
+      if (XPOSE)
+        continue;
       break;
-    const double* sc = cen + (size_t)st * S * 3;
+    }
+    const double* sc = cen + (size_t)st * CS;
     const double cx = sc[3 * k], cy = sc[3 * k + 1], cz = sc[3 * k + 2];
     const int gs = g.sph_glink[k];
     // updateGroupStateRepresentationState :1128-1133
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     if (LF)
     {
       // getSelfProximityGradients: the other links' PosedDistanceFields, in link order (:388-418)
-      unsigned m = can[it];
+      unsigned m = can[st * US + k];
       while (m)
       {
         const int j = __ffs(m) - 1;
@@ -401,35 +411,51 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
       field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
     if (flags & B200DF_CHECK_INTRA)
     {
-      // sqrt is only taken for candidates that can still win: e2 > bound  =>  sqrt(e2) > best
+      // sqrt is only taken for candidates that can still win: e2 > bound  =>  sqrt(e2) > best.
+      // The reference's gradient is centre(first link) - centre(second link), negated for the second link's sphere;
+      // both cases come out as -(other - own) bit for bit, and the squared norm does not see the sign.
       double bound = best * best * 1.000000000000001;
+      auto consider = [&](double dx, double dy, double dz, double e2) {
+        if (e2 > bound)
+          return;
+        const double d = sqrt(e2);
+        if (d < best)
+        {
+          best = d;
+          bound = d * d * 1.000000000000001;
+          gx = -dx;
+          gy = -dy;
+          gz = -dz;
+          bt = B200DF_TYPE_INTRA;
+        }
+      };
       for (int nb = g.nbr_off[gs]; nb < g.nbr_off[gs + 1]; ++nb)
       {
-        const int2 o = g.nbr[nb];
-        const DevGroupLink& ol = g.glinks[o.x];
-        for (int m = ol.sphere_begin; m < ol.sphere_end; ++m)
+        const int4 o = g.nbr[nb];  // partner link: its sphere range is [z, w)
+        int m = o.z;
+        // four candidates at a time: independent loads and distance chains, then the reference's sequential
+        // comparison (a candidate above the current bound stays above every later, smaller bound)
+        for (; m + 4 <= o.w; m += 4)
         {
-          // gradient = centre(first link of the pair) - centre(second link); the second link's sphere gets -gradient
-          double ex = sc[3 * m] - cx, ey = sc[3 * m + 1] - cy, ez = sc[3 * m + 2] - cz;
-          if (!o.y)
+          double dx[4], dy[4], dz[4], e2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
           {
-            ex = -ex;  // this sphere is on the first link: (cx - other), computed as the reference does
-            ey = -ey;
-            ez = -ez;
+            dx[j] = sc[3 * (m + j)] - cx;
+            dy[j] = sc[3 * (m + j) + 1] - cy;
+            dz[j] = sc[3 * (m + j) + 2] - cz;
+            e2[j] = (dx[j] * dx[j] + dy[j] * dy[j]) + dz[j] * dz[j];
           }
-          const double e2 = (ex * ex + ey * ey) + ez * ez;
-          if (e2 > bound)
+          if ((e2[0] > bound) & (e2[1] > bound) & (e2[2] > bound) & (e2[3] > bound))
             continue;
-          const double d = sqrt(e2);
-          if (d < best)
-          {
-            best = d;
-            bound = d * d * 1.000000000000001;
-            gx = o.y ? -ex : ex;
-            gy = o.y ? -ey : ey;
-            gz = o.y ? -ez : ez;
-            bt = B200DF_TYPE_INTRA;
-          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            consider(dx[j], dy[j], dz[j], e2[j]);
+        }
+        for (; m < o.w; ++m)
+        {
+          const double dx = sc[3 * m] - cx, dy = sc[3 * m + 1] - cy, dz = sc[3 * m + 2] - cz;
+          consider(dx, dy, dz, (dx * dx + dy * dy) + dz * dz);
         }
       }
     }
@@ -543,14 +569,14 @@ constexpr int64_t kCoopMaxStates = 4096;            // above this the 32-states-
 
 size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf, int gs, int nt, bool coop)
 {
-  size_t d = (size_t)gs * g.n_spheres * 3;
+  size_t d = (size_t)gs * ((g.n_spheres * 3) | 1);
   if (coop)
     d += (size_t)gs * g.n_links * 12 + (size_t)(nt / 32) * warp_fk_staging_doubles(g.n_links);
   else
     d += (size_t)g.n_slots * 12 * gs + (lf ? (size_t)gs * g.n_glinks * 12 : 0);
   size_t b = d * sizeof(double) + (size_t)gs * g.n_vars * q_elem;
   if (lf)
-    b += 2 * (size_t)gs * g.n_spheres * sizeof(unsigned);
+    b += 2 * (size_t)gs * (g.n_spheres | 1) * sizeof(unsigned);
   return b;
 }
 
@@ -591,6 +617,9 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
   if (lf)
     return launch_gather_variant<QT, FT, true, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
                                                                                  type, centers, stream, bytes);
+  if (getenv("B200DF_GRAD_NT256"))  // experiment
+    return launch_gather_variant<QT, FT, false, kGradStates, 256, false>(g, wf, sf, q, n, flags, dist, grad, type,
+                                                                         centers, stream, bytes);
   return launch_gather_variant<QT, FT, false, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
                                                                                 type, centers, stream, bytes);
 }

@@ -792,17 +792,17 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
   g->sph_thr = sph_thr;
   // gather form of the pair list for the gradient kernel
   std::vector<int> sph_glink(g->sph.size() / 4, 0), nbr_off(G + 1, 0);
-  std::vector<int2> nbr;
+  std::vector<int4> nbr;
   for (int gs = 0; gs < G; ++gs)
   {
     for (int s2 = g->glinks[gs].sphere_begin; s2 < g->glinks[gs].sphere_end; ++s2)
       sph_glink[s2] = gs;
     for (const DevPair& pr : g->pairs)  // already in (i asc, j asc) order
       if (pr.gj == gs)
-        nbr.push_back(make_int2(pr.gi, 1));
+        nbr.push_back(make_int4(pr.gi, 1, g->glinks[pr.gi].sphere_begin, g->glinks[pr.gi].sphere_end));
     for (const DevPair& pr : g->pairs)
       if (pr.gi == gs)
-        nbr.push_back(make_int2(pr.gj, 0));
+        nbr.push_back(make_int4(pr.gj, 0, g->glinks[pr.gj].sphere_begin, g->glinks[pr.gj].sphere_end));
     nbr_off[gs + 1] = (int)nbr.size();
   }
   if ((rc = upload(g.get(), partners, &dev.partners)))

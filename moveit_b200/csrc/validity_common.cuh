@@ -94,7 +94,8 @@ struct GroupDev
   // in the order the reference's pair loop touches gs (lower-index partners ascending, then higher-index ascending)
   const int* sph_glink;  // [S] group-link slot of each sphere
   const int* nbr_off;    // [n_glinks + 1]
-  const int2* nbr;       // {partner group-link slot, 1 if the partner is the lower-index (first) link of the pair}
+  const int4* nbr;       // {partner group-link slot, 1 if the partner is the lower-index (first) link of the pair,
+                         //  the partner's sphere range [begin, end)}
   // per-link PosedDistanceField term of getSelfProximityGradients (:395-418), set by b200df_group_set_link_fields
   const FieldDev* link_fields;   // [n_glinks] views (d2 == nullptr: no field); all in their link's own frame
   const unsigned* lf_enabled;    // [n_glinks] bit j: the ACM lets link j's field act on this link's spheres
