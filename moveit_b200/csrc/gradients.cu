@@ -216,11 +216,14 @@ __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double 
 // Phase 2: one thread per (state, sphere) replays, for ITS sphere only, the candidate sequence the reference's loops
 // produce for it — self field, then every sphere of every enabled partner link (lower-index partners ascending, then
 // higher-index partners ascending: exactly the order in which getIntraGroupProximityGradients :662-727 touches this
-// sphere), then the environment field — keeping the minimum with strict '<' like the reference.  Outputs are written
-// by consecutive threads to consecutive spheres of a state: coalesced, no read-modify-write of global memory.
+// sphere), then the environment field — keeping the minimum with strict '<' like the reference.  No read-modify-write
+// of global memory.  In the 32-states-per-CTA variant a warp holds ONE sphere index for 32 states (lane = state), so
+// the partner loops run the same trip count on every lane; the small-call variant (4 states per CTA) keeps
+// consecutive threads on consecutive spheres of a state.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGradStates = 32;    // states per CTA
 constexpr int kGradThreads = 128;
+constexpr int kMaxStagedNbr = 1024;  // neighbour-table entries staged in shared memory (16 KB)
 
 // PosedDistanceField::getDistanceGradient's point mapping (collision_distance_field_types.h:156-160):
 // rel = pose.inverse() * p with Eigen's isometry inverse (R^T, -(R^T t))
@@ -268,6 +271,41 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
   unsigned* can = reinterpret_cast<unsigned*>(staging + (COOP ? (NT / 32) * warp_fk_staging_doubles(L) : 0));
   unsigned* abt = can + (LF ? (size_t)GS * US : 0);                       // LF: [state][US] (can likewise)
   QT* qs = reinterpret_cast<QT*>(abt + (LF ? (size_t)GS * US : 0));  // [state][n_vars]
+  // the pair tables of the gather phase, staged once per CTA (a global load per partner link in the inner loop was
+  // the top stall): neighbour list (16-byte aligned), its offsets, the link slot of every sphere
+  const bool stage_tables = g.n_nbr <= kMaxStagedNbr;
+  int4* s_nbr = reinterpret_cast<int4*>(
+      (reinterpret_cast<uintptr_t>(qs + (size_t)GS * g.n_vars) + 15) & ~static_cast<uintptr_t>(15));
+  int* s_nbr_off = reinterpret_cast<int*>(s_nbr + (stage_tables ? g.n_nbr : 0));
+  int* s_sph_glink = s_nbr_off + (G + 1);
+  if (stage_tables)
+  {
+    for (int e = tid; e < g.n_nbr; e += NT)
+      s_nbr[e] = g.nbr[e];
+    for (int e = tid; e <= G; e += NT)
+      s_nbr_off[e] = g.nbr_off[e];
+    for (int e = tid; e < S; e += NT)
+      s_sph_glink[e] = g.sph_glink[e];
+  }
+  // the fields' sqrt tables (<= 626 doubles each): 7 dependent lookups per sphere and field otherwise go to L1 / L2
+  double* s_sqrt_w = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(s_sph_glink + S) + 7) & ~static_cast<uintptr_t>(7));
+  double* s_sqrt_s = s_sqrt_w + (wf.d2 ? wf.max_d2 + 1 : 0);
+  if (wf.d2)
+  {
+    for (int e = tid; e <= wf.max_d2; e += NT)
+      s_sqrt_w[e] = wf.sqrt_table[e];
+    wf.sqrt_table = s_sqrt_w;
+  }
+  if (sf.d2)
+  {
+    for (int e = tid; e <= sf.max_d2; e += NT)
+      s_sqrt_s[e] = sf.sqrt_table[e];
+    sf.sqrt_table = s_sqrt_s;
+  }
+  const int4* nbr = stage_tables ? s_nbr : g.nbr;
+  const int* nbr_off = stage_tables ? s_nbr_off : g.nbr_off;
+  const int* sph_glink = stage_tables ? s_sph_glink : g.sph_glink;
   {
     const int total = GS * g.n_vars;
     const long limit = (n - base) * g.n_vars;
@@ -332,7 +370,7 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     {
       const int st = XPOSE ? it % GS : it / S, k = XPOSE ? it / GS : it - st * S;
       const double* sc = cen + (size_t)st * CS;
-      const int gs = g.sph_glink[k];
+      const int gs = sph_glink[k];
       unsigned allowed = g.glinks[gs].self_enabled ? (g.lf_enabled[gs] & ~(1u << gs)) : 0u;
       unsigned inb = 0u, ab = 0u;
       while (allowed)
@@ -380,7 +418,7 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     }
     const double* sc = cen + (size_t)st * CS;
     const double cx = sc[3 * k], cy = sc[3 * k + 1], cz = sc[3 * k + 2];
-    const int gs = g.sph_glink[k];
+    const int gs = sph_glink[k];
     // updateGroupStateRepresentationState :1128-1133
     double best = DBL_MAX, gx = 0.0, gy = 0.0, gz = 0.0;
     int bt = B200DF_TYPE_NONE;
@@ -429,9 +467,9 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
           bt = B200DF_TYPE_INTRA;
         }
       };
-      for (int nb = g.nbr_off[gs]; nb < g.nbr_off[gs + 1]; ++nb)
+      for (int nb = nbr_off[gs]; nb < nbr_off[gs + 1]; ++nb)
       {
-        const int4 o = g.nbr[nb];  // partner link: its sphere range is [z, w)
+        const int4 o = nbr[nb];  // partner link: its sphere range is [z, w)
         int m = o.z;
         // four candidates at a time: independent loads and distance chains, then the reference's sequential
         // comparison (a candidate above the current bound stays above every later, smaller bound)
@@ -567,7 +605,8 @@ constexpr int kCoopStates = 4, kCoopThreads = 128;  // small-batch variant
 constexpr size_t kSmallGradBytes = 1 << 20;         // host-buffer calls up to this size use the mapped pinned staging
 constexpr int64_t kCoopMaxStates = 4096;            // above this the 32-states-per-CTA variant has the GPU filled
 
-size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf, int gs, int nt, bool coop)
+size_t gather_smem_bytes(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, size_t q_elem, bool lf, int gs,
+                         int nt, bool coop)
 {
   size_t d = (size_t)gs * ((g.n_spheres * 3) | 1);
   if (coop)
@@ -577,6 +616,9 @@ size_t gather_smem_bytes(const GroupDev& g, size_t q_elem, bool lf, int gs, int 
   size_t b = d * sizeof(double) + (size_t)gs * g.n_vars * q_elem;
   if (lf)
     b += 2 * (size_t)gs * (g.n_spheres | 1) * sizeof(unsigned);
+  b += 16 + (g.n_nbr <= kMaxStagedNbr ? (size_t)g.n_nbr * sizeof(int4) : 0) +
+       (size_t)(g.n_glinks + 1 + g.n_spheres) * sizeof(int);
+  b += 8 + (size_t)((wf.d2 ? wf.max_d2 + 1 : 0) + (sf.d2 ? sf.max_d2 + 1 : 0)) * sizeof(double);
   return b;
 }
 
@@ -599,7 +641,7 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
                   double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
 {
   const bool lf = (flags & B200DF_CHECK_LINK_FIELDS) != 0;
-  const size_t coop_bytes = gather_smem_bytes(g, sizeof(QT), lf, kCoopStates, kCoopThreads, true);
+  const size_t coop_bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kCoopStates, kCoopThreads, true);
   if (n <= kCoopMaxStates && coop_bytes <= 200 * 1024)
   {
     if (lf)
@@ -608,7 +650,7 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
     return launch_gather_variant<QT, FT, false, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
                                                                                  type, centers, stream, coop_bytes);
   }
-  const size_t bytes = gather_smem_bytes(g, sizeof(QT), lf, kGradStates, kGradThreads, false);
+  const size_t bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kGradStates, kGradThreads, false);
   if (bytes > 220 * 1024)
   {
     set_error("robot too large for the gradient kernel's shared-memory layout (%zu bytes)", bytes);
@@ -617,9 +659,6 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
   if (lf)
     return launch_gather_variant<QT, FT, true, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
                                                                                  type, centers, stream, bytes);
-  if (getenv("B200DF_GRAD_NT256"))  // experiment
-    return launch_gather_variant<QT, FT, false, kGradStates, 256, false>(g, wf, sf, q, n, flags, dist, grad, type,
-                                                                         centers, stream, bytes);
   return launch_gather_variant<QT, FT, false, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
                                                                                 type, centers, stream, bytes);
 }

@@ -811,6 +811,7 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     return rc;
   if ((rc = upload(g.get(), nbr_off, &dev.nbr_off)))
     return rc;
+  dev.n_nbr = (int)nbr.size();
   if ((rc = upload(g.get(), nbr, &dev.nbr)))
     return rc;
   if ((rc = upload(g.get(), pair_T, &dev.pair_T)))

@@ -94,6 +94,7 @@ struct GroupDev
   // in the order the reference's pair loop touches gs (lower-index partners ascending, then higher-index ascending)
   const int* sph_glink;  // [S] group-link slot of each sphere
   const int* nbr_off;    // [n_glinks + 1]
+  int n_nbr;             // nbr_off[n_glinks]
   const int4* nbr;       // {partner group-link slot, 1 if the partner is the lower-index (first) link of the pair,
                          //  the partner's sphere range [begin, end)}
   // per-link PosedDistanceField term of getSelfProximityGradients (:395-418), set by b200df_group_set_link_fields
@@ -494,8 +495,7 @@ __device__ __forceinline__ double cell_dist(const FieldDev& f, long idx)
   double d = f.sqrt_table[static_cast<const FT*>(f.d2)[idx]];
   if (f.neg)
     d = d - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
-  else
-    d = d - f.sqrt_table[0];
+  // unsigned field: the reference subtracts sqrt_table_[0] = sqrt(0) * resolution = +0.0, and d - 0.0 == d bit for bit
   return d;
 }
 
