@@ -838,7 +838,14 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out)
   int ndev = 0;
   B200DF_CUDA(cudaGetDeviceCount(&ndev));
   B200DF_REQUIRE(ndev > 0, "no CUDA device");
-  std::unique_ptr<b200df_field> f(new b200df_field);
+  struct Destroy  // an early return (e.g. out of device memory half way) releases what was allocated so far
+  {
+    void operator()(b200df_field* p) const
+    {
+      b200df_field_destroy(p);
+    }
+  };
+  std::unique_ptr<b200df_field, Destroy> f(new b200df_field);
   f->device = current_device();
   f->desc = *desc;
   // VoxelGrid::resize (voxel_grid.h:367-399)

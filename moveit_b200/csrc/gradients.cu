@@ -642,7 +642,9 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
 {
   const bool lf = (flags & B200DF_CHECK_LINK_FIELDS) != 0;
   const size_t coop_bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kCoopStates, kCoopThreads, true);
-  if (n <= kCoopMaxStates && coop_bytes <= 200 * 1024)
+  const size_t big_bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kGradStates, kGradThreads, false);
+  // small calls, and robots whose 32-state tile does not fit an SM's shared memory at any size
+  if ((n <= kCoopMaxStates || big_bytes > 220 * 1024) && coop_bytes <= 200 * 1024)
   {
     if (lf)
       return launch_gather_variant<QT, FT, true, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
@@ -650,7 +652,7 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
     return launch_gather_variant<QT, FT, false, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
                                                                                  type, centers, stream, coop_bytes);
   }
-  const size_t bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kGradStates, kGradThreads, false);
+  const size_t bytes = big_bytes;
   if (bytes > 220 * 1024)
   {
     set_error("robot too large for the gradient kernel's shared-memory layout (%zu bytes)", bytes);

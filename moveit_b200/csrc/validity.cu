@@ -359,6 +359,13 @@ int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& s
        small_supported(group)))
     return small_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
   const bool raw = precision == kPrecisionFastRaw;
+  // Robots whose per-state shared-memory column does not fit an SM even at 32 states per CTA (hundreds of stored
+  // spheres) cannot use the one-thread-per-state kernels at all; the one-CTA-per-state kernel keeps one state's
+  // transforms and centres only and serves them at any batch size.
+  if (!raw && small_supported(group) &&
+      verdict_smem_bytes(group->dev, 32, (flags & B200DF_CHECK_INTRA) && group->dev.n_partners > 0,
+                         q_elem_size(q_dtype)) > 220 * 1024)
+    return small_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
   if (raw && !fast_supported(group, wf, sf, q_dtype, flags))
   {
     set_error("the FAST screening pass does not support this call (needs fp32 joint values, unsigned fields, a model "
@@ -503,7 +510,14 @@ int b200df_model_create(const b200df_model_desc* d, b200df_model** out)
   int ndev = 0;
   B200DF_CUDA(cudaGetDeviceCount(&ndev));
   B200DF_REQUIRE(ndev > 0, "no CUDA device");
-  std::unique_ptr<b200df_model> m(new b200df_model);
+  struct DestroyModel
+  {
+    void operator()(b200df_model* p) const
+    {
+      b200df_model_destroy(p);
+    }
+  };
+  std::unique_ptr<b200df_model, DestroyModel> m(new b200df_model);
   m->device = current_device();
   const int L = d->n_links;
   m->n_links = L;
@@ -610,7 +624,15 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
   B200DF_REQUIRE(d->n_group_links >= 0 && (d->n_group_links == 0 || (d->group_links && d->self_enabled)),
                  "bad group arrays");
   B200DF_REQUIRE(d->resolution > 0.0, "resolution must be > 0");
-  std::unique_ptr<b200df_group> g(new b200df_group);
+  // every early return below releases what was built so far (device tables, staging pool, FAST / small-batch paths)
+  struct Destroy
+  {
+    void operator()(b200df_group* p) const
+    {
+      b200df_group_destroy(p);
+    }
+  };
+  std::unique_ptr<b200df_group, Destroy> g(new b200df_group);
   g->model = model;
   g->device = model->device;
   g->desc = *d;

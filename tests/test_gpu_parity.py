@@ -812,3 +812,41 @@ def test_gradient_call_sizes_and_pinned_outputs_agree(gpu, oracle):
     assert np.array_equal(e.group.sphere_centers(traj[77:78]), c_big[77:78])
     d_big = e.group.distance(traj, e.world)
     assert np.array_equal(e.group.distance(traj[300:420], e.world), d_big[300:420])
+
+
+def test_robot_too_large_for_the_batched_kernels_runs_on_the_cta_per_state_kernel(gpu, oracle):
+    """378 collision spheres on the PR2-like tree: a state's shared-memory column of the one-thread-per-state kernels
+    no longer fits an SM (and FAST's tables overflow), so every batch size is served by the one-CTA-per-state
+    kernel.  Verdicts against the oracle."""
+    desc = rd.pr2_like()
+    n_sph = 0
+    for li, (name, shapes) in enumerate(zip(desc.link_names, desc.shapes)):
+        if not shapes:
+            continue
+        rng = np.random.default_rng(1000 + li)  # irregular positions: a regular lattice makes exact distance ties
+        desc.set_spheres(name, [(rng.uniform(-0.2, 0.2), rng.uniform(-0.03, 0.03), rng.uniform(-0.03, 0.03),
+                                 rng.uniform(0.03, 0.045)) for _ in range(14)])
+        n_sph += 14
+    assert n_sph > 300
+    fd = scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene(seed=31)
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, fd, objs)
+    assert e.group.n_spheres == n_sph
+    q = desc.sample_states(40_000, 77, np.float32)  # above the small-batch limit: the fallback, not the routing
+    flags = CHECK_ROBOT | CHECK_INTRA
+    got = e.group.check(q, e.world, flags=flags, precision=0)
+    assert np.array_equal(got, e.group.check(q, e.world, flags=flags, precision=1))
+    ref = o.env.check_batch(q[:3000].astype(np.float64), mode=3, n_threads=8)
+    assert np.array_equal(got[:3000], ref)
+    robot_only = e.group.check(q, e.world, flags=CHECK_ROBOT, precision=0)
+    assert np.array_equal(robot_only[:3000], o.env.check_batch(q[:3000].astype(np.float64), mode=1, n_threads=8))
+    assert 0 < robot_only.sum() < len(q)
+    # the gradient kernel likewise: its 32-state tile does not fit, the 4-state variant serves any batch size
+    qg = desc.sample_states(5000, 78)
+    got = e.group.gradients(qg, e.world, flags=flags)
+    ref = o.env.gradients_batch(qg[:300], flags=2 | 4)
+    assert np.array_equal(got["type"][:300], ref["type"].astype(np.uint8))
+    fin = ref["dist"] < 1e300
+    assert np.max(np.abs(got["dist"][:300][fin] - ref["dist"][fin])) < 1e-5
+    assert np.max(np.abs(got["grad"][:300] - ref["grad"])) < 1e-5
