@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Soak test of the FAST precision's exactness claim: many batches of fresh random states (different seeds, two
-scenes, two robots), FAST vs EXACT verdicts compared on the device, undecided fraction of the screening pass reported.
+"""Soak test of the FAST precision's exactness claim (and of the small-batch kernel's): many batches of fresh random
+states (different seeds, two scenes, two robots), FAST and the one-CTA-per-state kernel vs EXACT verdicts compared on
+the device, undecided fraction of the screening pass reported.
 Prints one JSON line; the committed result lives in profiles/."""
 import json
 import os
@@ -43,14 +44,15 @@ def main(batches=10, n=10_000_000):
                     src = desc.var_index[desc.joint_names.index(m[0])]
                     q[:, desc.var_index[i]] = m[1] * q[:, src] + m[2]
             q = q.contiguous()
-            v = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(3)]
-            for k, prec in enumerate((B.PRECISION_EXACT, B.PRECISION_FAST, 3)):
+            v = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(4)]
+            # 4 = the one-CTA-per-state kernel (what small batches run on), forced at this batch size
+            for k, prec in enumerate((B.PRECISION_EXACT, B.PRECISION_FAST, 3, 4)):
                 e.group.check_device(q.data_ptr(), B.Q_F32, n, v[k].data_ptr(), e.world, None, flags, prec, stream)
             torch.cuda.synchronize()
-            diff = int((v[0] != v[1]).sum().item())
+            diff = int((v[0] != v[1]).sum().item()) + int((v[0] != v[3]).sum().item())
             und = float((v[2] == 2).sum().item()) / n
             wrong_decided = int(((v[2] != 2) & (v[2] != v[0])).sum().item())
-            out["batches"].append({"case": name, "seed": 1000 * (b + 1) + len(name), "states": n, "fast_ne_exact": diff,
+            out["batches"].append({"case": name, "seed": 1000 * (b + 1) + len(name), "states": n, "fast_or_small_ne_exact": diff,
                                    "screening_undecided": und, "screening_decided_wrong": wrong_decided,
                                    "colliding": float(v[0].float().mean().item())})
             out["states"] += n
