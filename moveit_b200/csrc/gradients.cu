@@ -211,6 +211,67 @@ __device__ __forceinline__ void field_gradient_update(const FieldDev& f, double 
   }
 }
 
+// The same query split in two, so that a caller can issue the seven voxel loads early and consume them after other
+// work (the gather kernel puts its partner-sphere loop between the two halves: the L2 round trip hides behind it).
+struct FieldTaps
+{
+  bool in;
+  int v[7];  // d2 at the centre cell, +x, -x, +y, -y, +z, -z
+  int n[7];  // negative_distance_square at the same cells (signed fields)
+};
+
+template <typename FT>
+__device__ __forceinline__ void field_taps_load(const FieldDev& f, double x, double y, double z, FieldTaps& t)
+{
+  long idx;
+  t.in = inset_cell(f.g, x, y, z, idx);
+  if (!t.in)
+    return;
+  const long off[7] = { 0, f.g.stride1, -f.g.stride1, f.g.stride2, -f.g.stride2, 1, -1 };
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+    t.v[k] = (int)static_cast<const FT*>(f.d2)[idx + off[k]];
+  if (f.neg)
+  {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      t.n[k] = (int)static_cast<const FT*>(f.neg)[idx + off[k]];
+  }
+}
+
+__device__ __forceinline__ void field_taps_finish(const FieldDev& f, const double* sqrt_table, const FieldTaps& t,
+                                                  double max_value, int type, double& best, double& gx, double& gy,
+                                                  double& gz, int& btype)
+{
+  double dist, dgx = 0.0, dgy = 0.0, dgz = 0.0;
+  if (!t.in)
+    dist = f.max_distance;
+  else
+  {
+    double d[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+    {
+      d[k] = sqrt_table[t.v[k]];  // cell_dist: sqrt_table_[d2] - sqrt_table_[neg d2]
+      if (f.neg)
+        d[k] = d[k] - sqrt_table[t.n[k]];
+    }
+    const double itr = (double)f.inv_twice_res;
+    dgx = (d[1] - d[2]) * itr;
+    dgy = (d[3] - d[4]) * itr;
+    dgz = (d[5] - d[6]) * itr;
+    dist = d[0];
+  }
+  if (dist < max_value && dist < best)
+  {
+    best = dist;
+    gx = dgx;
+    gy = dgy;
+    gz = dgz;
+    btype = type;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Gradient kernel, gather form.  Phase 1: one thread per state runs FK and poses every sphere into shared memory.
 // Phase 2: one thread per (state, sphere) replays, for ITS sphere only, the candidate sequence the reference's loops
@@ -274,8 +335,10 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
   // the pair tables of the gather phase, staged once per CTA (a global load per partner link in the inner loop was
   // the top stall): neighbour list (16-byte aligned), its offsets, the link slot of every sphere
   const bool stage_tables = g.n_nbr <= kMaxStagedNbr;
-  int4* s_nbr = reinterpret_cast<int4*>(
-      (reinterpret_cast<uintptr_t>(qs + (size_t)GS * g.n_vars) + 15) & ~static_cast<uintptr_t>(15));
+  // (offsets are taken relative to the shared-memory base so that the compiler keeps these in the shared address space)
+  char* const sm_bytes = reinterpret_cast<char*>(smem);
+  const size_t nbr_at = ((size_t)(reinterpret_cast<char*>(qs + (size_t)GS * g.n_vars) - sm_bytes) + 15) & ~(size_t)15;
+  int4* s_nbr = reinterpret_cast<int4*>(sm_bytes + nbr_at);
   int* s_nbr_off = reinterpret_cast<int*>(s_nbr + (stage_tables ? g.n_nbr : 0));
   int* s_sph_glink = s_nbr_off + (G + 1);
   if (stage_tables)
@@ -288,8 +351,8 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
       s_sph_glink[e] = g.sph_glink[e];
   }
   // the fields' sqrt tables (<= 626 doubles each): 7 dependent lookups per sphere and field otherwise go to L1 / L2
-  double* s_sqrt_w = reinterpret_cast<double*>(
-      (reinterpret_cast<uintptr_t>(s_sph_glink + S) + 7) & ~static_cast<uintptr_t>(7));
+  const size_t sqrt_at = ((size_t)(reinterpret_cast<char*>(s_sph_glink + S) - sm_bytes) + 7) & ~(size_t)7;
+  double* s_sqrt_w = reinterpret_cast<double*>(sm_bytes + sqrt_at);
   double* s_sqrt_s = s_sqrt_w + (wf.d2 ? wf.max_d2 + 1 : 0);
   if (wf.d2)
   {
@@ -303,8 +366,6 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
       s_sqrt_s[e] = sf.sqrt_table[e];
     sf.sqrt_table = s_sqrt_s;
   }
-  const int4* nbr = stage_tables ? s_nbr : g.nbr;
-  const int* nbr_off = stage_tables ? s_nbr_off : g.nbr_off;
   const int* sph_glink = stage_tables ? s_sph_glink : g.sph_glink;
   {
     const int total = GS * g.n_vars;
@@ -447,6 +508,9 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     // getSelfProximityGradients: self field term (:420-422)
     if ((flags & B200DF_CHECK_SELF) && g.glinks[gs].self_enabled)
       field_gradient_update<FT>(sf, cx, cy, cz, g.max_prop, B200DF_TYPE_SELF, best, gx, gy, gz, bt);
+    FieldTaps wt;
+    if (flags & B200DF_CHECK_ROBOT)
+      field_taps_load<FT>(wf, cx, cy, cz, wt);  // consumed after the partner loop
     if (flags & B200DF_CHECK_INTRA)
     {
       // sqrt is only taken for candidates that can still win: e2 > bound  =>  sqrt(e2) > best.
@@ -467,7 +531,9 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
           bt = B200DF_TYPE_INTRA;
         }
       };
-      for (int nb = nbr_off[gs]; nb < nbr_off[gs + 1]; ++nb)
+      // (a lambda instantiated once per table location, so that the staged copy is read with shared-memory loads)
+      auto partner_loop = [&](const int4* nbr, int nb0, int nb1) {
+      for (int nb = nb0; nb < nb1; ++nb)
       {
         const int4 o = nbr[nb];  // partner link: its sphere range is [z, w)
         int m = o.z;
@@ -496,10 +562,15 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
           consider(dx, dy, dz, (dx * dx + dy * dy) + dz * dz);
         }
       }
+      };
+      if (stage_tables)
+        partner_loop(s_nbr, s_nbr_off[gs], s_nbr_off[gs + 1]);
+      else
+        partner_loop(g.nbr, g.nbr_off[gs], g.nbr_off[gs + 1]);
     }
     // getEnvironmentProximityGradients :1664-1700
     if (flags & B200DF_CHECK_ROBOT)
-      field_gradient_update<FT>(wf, cx, cy, cz, g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
+      field_taps_finish(wf, s_sqrt_w, wt, g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
     const long o = state * S + k;
     out_dist[o] = best;
     out_grad[3 * o] = gx;
