@@ -194,6 +194,8 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out);
 int b200df_field_destroy(b200df_field* field);
 /* out4 = nx, ny, nz, max_distance_sq_ (propagation_distance_field.cpp:78, voxel_grid.h:387) */
 int b200df_field_dims(const b200df_field* field, int32_t* out4);
+/* the geometry the field was created with (getSizeX/Y/Z, getOriginX/Y/Z, getResolution, getUninitializedDistance) */
+int b200df_field_get_desc(const b200df_field* field, b200df_field_desc* out);
 int b200df_field_reset(b200df_field* field);                                        /* reset()                 :507-525 */
 int b200df_field_add_points(b200df_field* field, const double* xyz, int64_t n);     /* addPointsToField       :176-195 */
 int b200df_field_remove_points(b200df_field* field, const double* xyz, int64_t n);  /* removePointsFromField  :197-218 */

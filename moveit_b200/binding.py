@@ -70,6 +70,7 @@ SYMBOLS = {
     "b200df_field_create": (C.c_int, [C.POINTER(FieldDesc), _VPP]),
     "b200df_field_destroy": (C.c_int, [_VP]),
     "b200df_field_dims": (C.c_int, [_VP, c_i32p]),
+    "b200df_field_get_desc": (C.c_int, [_VP, C.POINTER(FieldDesc)]),
     "b200df_field_reset": (C.c_int, [_VP]),
     "b200df_field_add_points": (C.c_int, [_VP, c_dp, C.c_int64]),
     "b200df_field_add_points_device": (C.c_int, [_VP, _VP, C.c_int64, _VP]),

@@ -939,6 +939,13 @@ int b200df_field_dims(const b200df_field* f, int32_t* out4)
   return B200DF_OK;
 }
 
+int b200df_field_get_desc(const b200df_field* f, b200df_field_desc* out)
+{
+  B200DF_REQUIRE(f && out, "null argument");
+  *out = f->desc;
+  return B200DF_OK;
+}
+
 int b200df_field_reset(b200df_field* f)
 {
   B200DF_REQUIRE(f, "null field");

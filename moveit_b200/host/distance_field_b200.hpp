@@ -49,12 +49,41 @@ public:
     readFromStream(is);
   }
 
+  // a non-owning view of a field that lives elsewhere (CollisionEnvB200::getDistanceField(), a cache entry's self
+  // field): queries and edits go to that field, the handle is not destroyed with the view
+  explicit PropagationDistanceFieldB200(b200df_field* borrowed) : max_distance_(0.0), propagate_negative_(false), owns_(false)
+  {
+    b200df_field_desc d{};
+    check(b200df_field_get_desc(borrowed, &d), "b200df_field_get_desc");
+    field_ = borrowed;
+    for (int i = 0; i < 3; ++i)
+    {
+      size_[i] = d.size[i];
+      origin_[i] = d.origin[i];
+    }
+    resolution_ = d.resolution;
+    max_distance_ = d.max_distance;
+    propagate_negative_ = d.propagate_negative != 0;
+    std::int32_t dims[4];
+    check(b200df_field_dims(field_, dims), "b200df_field_dims");
+    n_[0] = dims[0];
+    n_[1] = dims[1];
+    n_[2] = dims[2];
+    max_distance_sq_ = dims[3];
+  }
+  // the view's cached host copy is refreshed on the next per-cell query (call after the owner changed the field)
+  void invalidateHostCopy()
+  {
+    host_d2_valid_ = false;
+  }
+
   PropagationDistanceFieldB200(const PropagationDistanceFieldB200&) = delete;
   PropagationDistanceFieldB200& operator=(const PropagationDistanceFieldB200&) = delete;
 
   ~PropagationDistanceFieldB200()
   {
-    b200df_field_destroy(field_);
+    if (owns_)
+      b200df_field_destroy(field_);
   }
 
   bool valid() const  // false after a stream constructor that could not read a field
@@ -321,9 +350,10 @@ private:
   }
   void create(double sx, double sy, double sz, double resolution, double ox, double oy, double oz)
   {
-    if (field_)
+    if (field_ && owns_)
       b200df_field_destroy(field_);
     field_ = nullptr;
+    owns_ = true;
     size_[0] = sx;
     size_[1] = sy;
     size_[2] = sz;
@@ -367,6 +397,7 @@ private:
   b200df_field* field_ = nullptr;
   double size_[3] = { 0, 0, 0 }, origin_[3] = { 0, 0, 0 }, resolution_ = 1.0, max_distance_;
   bool propagate_negative_;
+  bool owns_ = true;
   int n_[3] = { 0, 0, 0 }, max_distance_sq_ = 0;
   mutable std::vector<std::int32_t> host_d2_, host_neg_;  // per-cell queries read a lazily refreshed host copy
   mutable bool host_d2_valid_ = false;

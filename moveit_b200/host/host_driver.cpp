@@ -442,6 +442,17 @@ int main(int argc, char** argv)
       if (v2 != v)
         throw std::runtime_error("env copied onto the same world disagrees with the original");
     }
+    // getDistanceField() (.h:200-203) through the DistanceField API mirror: the world field as a non-owning view
+    {
+      distance_field_b200::PropagationDistanceFieldB200 view(env->getDistanceField());
+      if (view.getXNumCells() <= 0 || view.getResolution() != res || view.getUninitializedDistance() != max_dist)
+        throw std::runtime_error("getDistanceField view reports the wrong geometry");
+      double gx, gy, gz;
+      bool inb;
+      const double dc = view.getDistanceGradient(center[0], center[1], center[2], gx, gy, gz, inb);
+      if (!inb || dc != view.getDistance(center[0], center[1], center[2]))
+        throw std::runtime_error("getDistanceField view: cell query and gradient query disagree");
+    }
     std::printf("host_driver ok: %s, %lld states, detector %s, %lld kernel launches, checkCollision %.1f us/call "
                 "(%.1f us with contacts; %zu cache regenerations in the timed calls)\n",
                 robot_name.c_str(), (long long)n, alloc->getName().c_str(), (long long)b200df_launch_count(), us_plain,
