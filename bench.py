@@ -34,6 +34,22 @@ ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out (
 # dram__bytes_read.sum + dram__bytes_write.sum per state from the committed ncu --set full captures (2 000 000 states):
 # profiles/r01_validity_fast_full.txt (72.80 MB + 1.00 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
 NCU_DRAM_BYTES_PER_STATE = {"fast": (72.800768e6 + 0.996352e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
+# smsp__inst_executed.sum of the same captures / 2 000 000 states: warp instructions the kernel issues per state
+NCU_WARP_INSTR_PER_STATE = {"fast": 1029132483 / 2.0e6}
+
+
+def issue_roofline(precision, states_per_s_per_gpu, clocks):
+    """The resource that actually binds the validity kernel: warp-instruction issue slots.  achieved = (warp
+    instructions per state, counted by ncu on the committed capture) x (states/s measured in this run on one GPU);
+    peak = 148 SMs x 4 schedulers x the SM clock sampled during the timed region."""
+    per_state = NCU_WARP_INSTR_PER_STATE.get(precision)
+    mhz = (clocks or {}).get("sm_mhz")
+    if not per_state or not mhz:
+        return None
+    peak = 148 * 4 * mhz * 1e6
+    achieved = per_state * states_per_s_per_gpu
+    return {"achieved": achieved, "peak": peak, "unit": "warp-instructions/s", "frac": achieved / peak,
+            "warp_instructions_per_state": per_state, "source": "profiles/r01_validity_fast_full.txt x live rate"}
 
 
 def parse():
@@ -406,11 +422,12 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_STATE.get(args.precision, NCU_DRAM_BYTES_PER_STATE["exact"]) * n,
                          "peak_source": peak_src,
+                         "issue": issue_roofline(args.precision, n * args.steps / (ms_total * 1e-3), clocks),
                          "kernel": ("validity_fast_kernel<unsigned char, 128> (+ validity_kernel on the undecided "
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
                          "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
                                  "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
-                                 "The fused FK+lookup+pair kernel executes ~18 k warp instructions per 32 states and "
+                                 "The fused FK+lookup+pair kernel executes ~16.5 k warp instructions per 32 states and "
                                  "is issue/latency bound by construction (DESIGN.md section 4); the HBM-bound "
                                  "kernel of this path is the EDT, see edt_ms.field_b_roofline"},
             "colliding_fraction": colliding / n,
