@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(64, 9) edt_march_kernel(const uint32_t* __rest
                                                        int n_axis, int max_d2)
 {
   constexpr int W = 2 * R + 1;
-  // a revolution is cut into four chunks (13+13+13+12 steps for R = 25) that alternate between two input buffers:
+  // a revolution is cut into four chunks (13+12+12+12 steps for R = 24) that alternate between two input buffers:
   // half the registers of a two-chunk split, which is what lets every line of a 400^3 field be resident at once
   // (2500 warps on 148 SMs need 17 warps/SM, i.e. <= 120 registers)
   constexpr int C0 = (W + 3) / 4, C1 = (W + 2) / 4, C2 = (W + 1) / 4, C3 = W / 4;
@@ -739,11 +739,15 @@ int run_edt(b200df_field* f, bool invert, T* out)
       edt_z_from_bits_kernel<<<blocks_for(n_rows, 4), dim3(64, 4), 0, f->stream>>>(
           f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), nz / 2, wpr, n_rows, f->radius);
     B200DF_LAUNCHED();
-    if (f->radius <= 13)
-      return run_edt_march<13, T>(f, out);
-    if (f->radius <= 25)
-      return run_edt_march<25, T>(f, out);
-    return run_edt_march<31, T>(f, out);
+    // a tap at offset d adds d*d >= radius^2 >= max_d2 once |d| reaches the radius: such a candidate is clamped away
+    // by the final pass (and can never be the minimiser of a later pass below max_d2), so the marching window only
+    // needs +-(radius - 1)
+    const int reach = f->radius - 1;
+    if (reach <= 12)
+      return run_edt_march<12, T>(f, out);
+    if (reach <= 24)
+      return run_edt_march<24, T>(f, out);
+    return run_edt_march<30, T>(f, out);
   }
   if (invert)
     edt_pass_z_kernel<true><<<blocks, threads, 0, f->stream>>>(f->occ, f->tmp_a, nz, n, f->radius);
