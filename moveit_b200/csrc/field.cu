@@ -732,12 +732,13 @@ int run_edt(b200df_field* f, bool invert, T* out)
       B200DF_LAUNCHED();
     }
     f->bits_valid = !invert;  // the bit rows now mirror occ (or its complement, for the negative field)
+    // z distances of radius cells or more square to >= max_d2 and are written as INF right away (see `reach` below)
     if (nz % 8 == 0)
       edt_z8_from_bits_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
-          f->bits, reinterpret_cast<uint4*>(f->tmp_a), nz / 8, wpr, n_rows, f->radius);
+          f->bits, reinterpret_cast<uint4*>(f->tmp_a), nz / 8, wpr, n_rows, f->radius - 1);
     else
       edt_z_from_bits_kernel<<<blocks_for(n_rows, 4), dim3(64, 4), 0, f->stream>>>(
-          f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), nz / 2, wpr, n_rows, f->radius);
+          f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), nz / 2, wpr, n_rows, f->radius - 1);
     B200DF_LAUNCHED();
     // a tap at offset d adds d*d >= radius^2 >= max_d2 once |d| reaches the radius: such a candidate is clamped away
     // by the final pass (and can never be the minimiser of a later pass below max_d2), so the marching window only
