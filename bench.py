@@ -221,6 +221,27 @@ def workload_config(states_per_gpu):
             "parallelism": "states sharded across ranks, field replicated once by NCCL broadcast"}
 
 
+def edt_cpu_baseline(scenarios):
+    """The reference's own (single-threaded) propagation on Field A through the oracle's restatement:
+    part of the cpu_baseline leg.  Field B takes ~20 s the same way and is left out of the default
+    run."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py as oracle
+    from common import oracle_world_points
+    fa = scenarios.FIELD_A
+    corner = [fa["center"][i] - 0.5 * fa["size"][i] for i in range(3)]
+    pts = oracle_world_points(oracle, scenarios.random_scene(), fa["resolution"])
+    best = 1e9
+    for _ in range(3):
+        f = oracle.Field(fa["size"], fa["resolution"], corner, fa["max_distance"])
+        t0 = time.perf_counter()
+        f.add_points(pts)
+        best = min(best, time.perf_counter() - t0)
+    return {"field_a_reference_propagation_ms": 1e3 * best, "cores": 1, "kind": "port",
+            "sample": "Field A, the bench scene's 12 objects in one addPointsToField call (one propagatePositive sweep)"}
+
+
 def edt_timings(engine, scenarios, B):
     """EDT rebuild ms (BASELINE metric's second half): Field A from the bench scene, Field B from the 1 M-point cloud."""
     out = {}
@@ -439,6 +460,8 @@ def main():
         if not args.no_edt:
             try:
                 line["edt_ms"] = edt_timings(engine, scenarios, B)
+                if world == 1 and not args.no_cpu_baseline:
+                    line["edt_ms"]["cpu_baseline"] = edt_cpu_baseline(scenarios)
             except Exception as ex:  # keep the headline line even if the big field does not fit
                 line["edt_ms"] = {"error": str(ex)}
         if world == 1 and not args.no_extras:

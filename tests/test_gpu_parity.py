@@ -617,8 +617,9 @@ def test_full_size_properties_10m_states(gpu, oracle):
 
 
 def test_config3_field_b_cloud(gpu, oracle):
-    """Config 3: 1M-point cloud into the 400^3 field; exactness checked by a KD-tree on a voxel sample and by the
-    oracle's exact EDT on a sub-block; mismatch census against the reference propagation on the sub-block."""
+    """Config 3: 1M-point cloud into the 400^3 field; exactness checked against a KD-tree on 300 000 sampled voxels.
+    (The mismatch census against the reference's propagation on this field is a 30 s CPU job: 30 761 of 64 M voxels,
+    always reference > exact, at most 8 in d^2 - DESIGN.md F4 table.)"""
     from scipy.spatial import cKDTree
     from moveit_b200 import engine
     fb = scenarios.FIELD_B
