@@ -520,15 +520,26 @@ template <typename T>
 class PinnedBuffer
 {
 public:
-  explicit PinnedBuffer(std::size_t n) : n_(n)
+  // Page-locked above kPinThreshold bytes (large result copies then run at PCIe speed); plain heap memory below it:
+  // the C ABI stages small calls through its own mapped buffer, and cudaHostAlloc costs more than such a call.
+  static constexpr std::size_t kPinThreshold = 1 << 20;
+  explicit PinnedBuffer(std::size_t n) : n_(n), pinned_(n * sizeof(T) > kPinThreshold)
   {
-    void* p = nullptr;
-    checkStatus(b200df_host_alloc(n * sizeof(T), &p), "b200df_host_alloc");
-    p_ = static_cast<T*>(p);
+    if (pinned_)
+    {
+      void* p = nullptr;
+      checkStatus(b200df_host_alloc(n * sizeof(T), &p), "b200df_host_alloc");
+      p_ = static_cast<T*>(p);
+    }
+    else
+      p_ = static_cast<T*>(::operator new(std::max<std::size_t>(n, 1) * sizeof(T)));
   }
   ~PinnedBuffer()
   {
-    b200df_host_free(p_);
+    if (pinned_)
+      b200df_host_free(p_);
+    else
+      ::operator delete(p_);
   }
   PinnedBuffer(const PinnedBuffer&) = delete;
   PinnedBuffer& operator=(const PinnedBuffer&) = delete;
@@ -548,6 +559,7 @@ public:
 private:
   T* p_ = nullptr;
   std::size_t n_ = 0;
+  bool pinned_ = false;
 };
 
 // ------------------------------------------------------------------------------------------------------------

@@ -327,7 +327,7 @@ int main(int argc, char** argv)
 
     // per-call cost of the single-state CollisionEnv API (what an OMPL StateValidityChecker pays per isValid())
     // (one fixed state: a planner keeps the joints outside the group still, so the cached group entry stays valid)
-    double us_plain = 0.0, us_contacts = 0.0;
+    double us_plain = 0.0, us_contacts = 0.0, us_grad = 0.0;
     std::size_t regenerated = 0;
     if (!single.empty())
     {
@@ -353,6 +353,19 @@ int main(int argc, char** argv)
         }
         const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
         (pass ? us_contacts : us_plain) = us;
+      }
+      {
+        // one waypoint's getCollisionGradients, the call CHOMP makes per trajectory point (chomp_optimizer.cpp:924)
+        core::RobotState st(ref_state);
+        st.setVariablePositions(&q[0]);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int k = 0; k < reps; ++k)
+        {
+          CollisionResult res;
+          GroupStateRepresentationPtr gsr;
+          env->getCollisionGradients(req, res, st, acm_ptr, gsr);
+        }
+        us_grad = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
       }
       regenerated = env->cacheGenerations() - gen0;
     }
@@ -454,9 +467,9 @@ int main(int argc, char** argv)
         throw std::runtime_error("getDistanceField view: cell query and gradient query disagree");
     }
     std::printf("host_driver ok: %s, %lld states, detector %s, %lld kernel launches, checkCollision %.1f us/call "
-                "(%.1f us with contacts; %zu cache regenerations in the timed calls)\n",
+                "(%.1f us with contacts), getCollisionGradients %.1f us/call; %zu cache regenerations in the timed calls\n",
                 robot_name.c_str(), (long long)n, alloc->getName().c_str(), (long long)b200df_launch_count(), us_plain,
-                us_contacts, regenerated);
+                us_contacts, us_grad, regenerated);
     return 0;
   }
   catch (const std::exception& ex)
