@@ -126,6 +126,15 @@ def run(with_oracle=True):
     t = best_of(lambda: e.group.check_edges(qa, qb, K, e.world, flags=fl, precision=B.PRECISION_FAST), 3)
     out["edge_checks"] = {"motions": M, "segments": K, "ms": 1e3 * t, "motions_per_s": M / t,
                           "states_per_s": M * K / t, "h2d_bytes": 2 * M * desc.nvar * 8, "d2h_bytes": 4 * M}
+    try:  # the same with the end points in page-locked memory (the 144 MB H2D then runs at PCIe speed)
+        import torch
+        pa = torch.from_numpy(qa).pin_memory().numpy()
+        pb = torch.from_numpy(qb).pin_memory().numpy()
+        tp = best_of(lambda: e.group.check_edges(pa, pb, K, e.world, flags=fl, precision=B.PRECISION_FAST), 3)
+        out["edge_checks"]["pinned_ms"] = 1e3 * tp
+        out["edge_checks"]["pinned_states_per_s"] = M * K / tp
+    except ImportError:
+        pass
 
     # config 4: PR2-like dual-arm tree, full ACM
     pr2 = rd.pr2_like()
