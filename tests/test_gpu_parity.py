@@ -851,3 +851,45 @@ def test_robot_too_large_for_the_batched_kernels_runs_on_the_cta_per_state_kerne
     fin = ref["dist"] < 1e300
     assert np.max(np.abs(got["dist"][:300][fin] - ref["dist"][fin])) < 1e-5
     assert np.max(np.abs(got["grad"][:300] - ref["grad"])) < 1e-5
+
+
+def test_c_abi_error_behaviour(gpu, oracle):
+    """The reference never throws across its API; the C ABI likewise answers every misuse with a status + message and
+    stays usable: null pointers, unknown dtype / precision, a flag without its field, fields that do not fit the
+    group, the screening-only hook on a call it cannot serve."""
+    import ctypes as C
+    from moveit_b200 import binding as B
+    from moveit_b200 import engine
+    lib = B.load()
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    q = desc.sample_states(64, 3, np.float32)
+    v = np.zeros(64, dtype=np.uint8)
+    qp, vp = q.ctypes.data_as(C.c_void_p), B.ptr(v, C.c_uint8)
+    good = e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA)
+
+    def expect(code, rc):
+        assert rc == code, (rc, lib.b200df_last_error())
+        assert len(lib.b200df_last_error()) > 0
+
+    expect(B.ERR_INVALID, lib.b200df_check_batch(None, e.world.h, None, qp, B.Q_F32, 64, CHECK_ROBOT, 0, vp))
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, e.world.h, None, None, B.Q_F32, 64, CHECK_ROBOT, 0, vp))
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, e.world.h, None, qp, 7, 64, CHECK_ROBOT, 0, vp))
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, e.world.h, None, qp, B.Q_F32, 64, CHECK_ROBOT, 99, vp))
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, e.world.h, None, qp, B.Q_F32, -1, CHECK_ROBOT, 0, vp))
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, None, None, qp, B.Q_F32, 64, CHECK_ROBOT, 0, vp))  # no world
+    coarse = engine.Field.centered((1.0, 1.0, 1.0), 0.05, (0.0, 0.0, 0.5), 0.25)  # other resolution than the group's
+    expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, coarse.h, None, qp, B.Q_F32, 64, CHECK_ROBOT, 0, vp))
+    signed = engine.Field.centered(scenarios.FIELD_A["size"], 0.02, scenarios.FIELD_A["center"], 0.25, True)
+    q64 = q.astype(np.float64)
+    expect(B.ERR_UNSUPPORTED, lib.b200df_check_batch(e.group.h, signed.h, None, q64.ctypes.data_as(C.c_void_p), B.Q_F64,
+                                                     64, CHECK_ROBOT, 3, vp))  # screening hook: needs an unsigned field
+    expect(B.ERR_INVALID, lib.b200df_field_add_points(None, None, 5))
+    expect(B.ERR_INVALID, lib.b200df_gradients_batch(e.group.h, e.world.h, None, qp, B.Q_F32, 4, CHECK_ROBOT, None,
+                                                     None, None, None))
+    assert lib.b200df_check_batch(e.group.h, e.world.h, None, qp, B.Q_F32, 0, CHECK_ROBOT, 0, None) == B.OK  # n = 0
+    # none of the above left the engine in a bad state
+    assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT | CHECK_INTRA), good)
+    with pytest.raises(B.B200dfError):
+        e.group.check(q, None, flags=CHECK_ROBOT)
