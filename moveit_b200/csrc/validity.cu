@@ -348,12 +348,23 @@ void keep_async_pool(int device)
 }
 
 // amb_idx (n ints) / amb_count (1 int): device scratch of the FAST path; allocated stream-ordered when null
-int run_verdict(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int elem, const void* q_dev,
+int run_verdict(const b200df_group* group, const FieldDev& wf_in, const FieldDev& sf_in, int elem, const void* q_dev,
                 int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, cudaStream_t stream,
                 int* amb_idx = nullptr, int* amb_count = nullptr)
 {
   if (precision == kPrecisionV1)
-    return launch_verdict_v1(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+    return launch_verdict_v1(group->dev, wf_in, sf_in, elem, q_dev, q_dtype, n, flags, verdict_dev, stream);
+  // Signed fields.  A sphere centre in a free cell has negative_distance_square 0, so the signed distance there IS the
+  // unsigned one; in an occupied cell (d2 == 0) the signed distance is negative and the sphere collides whenever
+  // max_propagation_distance > 0 and radius > tolerance - which is also what the unsigned integer test "0 < threshold"
+  // says.  When every sphere of the group meets that condition the verdict kernels therefore ignore the negative
+  // field (same verdicts, integer test, FAST usable); the debug sweep above keeps the full fp64 predicate.
+  FieldDev wf = wf_in, sf = sf_in;
+  if (group->neg_irrelevant)
+  {
+    wf.neg = nullptr;
+    sf.neg = nullptr;
+  }
   if (precision == kPrecisionSmall ||
       ((precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST) && n <= small_max_states() &&
        small_supported(group)))
@@ -812,6 +823,10 @@ int b200df_group_create(const b200df_model* model, const b200df_group_desc* d, b
     return rc;
   g->partners = partners;
   g->sph_thr = sph_thr;
+  g->neg_irrelevant = d->max_propagation_distance > 0.0;
+  for (size_t i = 3; i < g->sph.size(); i += 4)
+    if (!(g->sph[i] > d->collision_tolerance))
+      g->neg_irrelevant = false;
   // gather form of the pair list for the gradient kernel
   std::vector<int> sph_glink(g->sph.size() / 4, 0), nbr_off(G + 1, 0);
   std::vector<int4> nbr;
@@ -929,9 +944,7 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
       std::memcpy(ctx->pin, q, (size_t)n * row);
       uint8_t* hv = static_cast<uint8_t*>(ctx->pin) + kSmallQBytes;
       uint8_t* dv = static_cast<uint8_t*>(dpin) + kSmallQBytes;
-      rc = small_supported(group)
-               ? small_launch(group, wf, sf, elem, dpin, q_dtype, n, flags, dv, ctx->stream[0])
-               : dispatch_verdict(group->dev, wf, sf, elem, dpin, q_dtype, n, flags, dv, ctx->stream[0]);
+      rc = run_verdict(group, wf, sf, elem, dpin, q_dtype, n, flags, precision, dv, ctx->stream[0]);
       e = cudaStreamSynchronize(ctx->stream[0]);
       if (!rc && e == cudaSuccess)
         std::memcpy(verdict, hv, (size_t)n);

@@ -614,6 +614,7 @@ struct b200df_group
   std::vector<void*> allocations;
   std::vector<b200df::DevPartner> partners;  // host copies the FAST tables are derived from
   std::vector<int> sph_thr;
+  bool neg_irrelevant = false;  // verdicts of this group never depend on a field's negative distances (validity.cu)
   struct StagePool;  // host<->device staging contexts of the pipelined host-buffer entry points (validity.cu)
   StagePool* stage = nullptr;
   struct FastPath;   // fp32 screening tables + scratch (validity_fast.cu); null when the model does not fit them

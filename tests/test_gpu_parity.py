@@ -246,6 +246,10 @@ def test_group_with_self_field(gpu, oracle):
 
 
 def test_signed_world_field_verdicts(gpu, oracle):
+    """use_signed_distance_field: the verdict kernels skip the negative field when it cannot matter (radius >
+    tolerance: in an occupied cell both predicates collide, in a free cell the negative distance is 0) - every kernel
+    against the oracle's full signed predicate and against the debug sweep, which keeps the fp64 signed evaluation;
+    with a tolerance above the radii the negative field does matter and the fp64 path is taken."""
     desc = rd.panda()
     objs = scenarios.random_scene(seed=5)
     o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, signed=True)
@@ -254,6 +258,21 @@ def test_signed_world_field_verdicts(gpu, oracle):
     assert np.array_equal(e.world.d2(True), o.env.world.d2(True))
     q = desc.sample_states(5000, 3)
     assert np.array_equal(e.group.check(q, e.world, flags=CHECK_ROBOT), o.env.check_batch(q, mode=1))
+    big = desc.sample_states(200_000, 4, np.float32)
+    ref = o.env.check_batch(big[:20000].astype(np.float64), mode=1, n_threads=8)
+    sweep = e.group.check(big, e.world, flags=CHECK_ROBOT, precision=2)
+    assert np.array_equal(sweep[:20000], ref) and 0 < ref.sum() < len(ref)
+    for precision in (0, 1, 4):
+        assert np.array_equal(e.group.check(big, e.world, flags=CHECK_ROBOT, precision=precision), sweep), precision
+    raw = e.group.check(big, e.world, flags=CHECK_ROBOT, precision=3)  # FAST now serves signed fields
+    assert np.array_equal(raw[raw != 2], sweep[raw != 2]) and (raw == 2).mean() < 0.05
+    # tolerance 0.08 > every radius... the spheres inside obstacles still collide through the negative distance
+    ot = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, signed=True, tol=0.08)
+    et = EngineSetup(desc, scenarios.FIELD_A, objs, signed=True, tol=0.08)
+    reft = ot.env.check_batch(big[:20000].astype(np.float64), mode=1, n_threads=8)
+    for precision in (0, 1, 2, 4):
+        got = et.group.check(big[:20000], et.world, flags=CHECK_ROBOT, precision=precision)
+        assert np.array_equal(got, reft), precision
 
 
 def test_tolerance_and_no_acm(gpu, oracle):
@@ -883,8 +902,10 @@ def test_c_abi_error_behaviour(gpu, oracle):
     expect(B.ERR_INVALID, lib.b200df_check_batch(e.group.h, coarse.h, None, qp, B.Q_F32, 64, CHECK_ROBOT, 0, vp))
     signed = engine.Field.centered(scenarios.FIELD_A["size"], 0.02, scenarios.FIELD_A["center"], 0.25, True)
     q64 = q.astype(np.float64)
-    expect(B.ERR_UNSUPPORTED, lib.b200df_check_batch(e.group.h, signed.h, None, q64.ctypes.data_as(C.c_void_p), B.Q_F64,
-                                                     64, CHECK_ROBOT, 3, vp))  # screening hook: needs an unsigned field
+    # screening hook on a call it cannot serve: a signed field whose negative distances matter (tolerance >= radius)
+    et = EngineSetup(desc, scenarios.FIELD_A, objs, tol=1.0)
+    expect(B.ERR_UNSUPPORTED, lib.b200df_check_batch(et.group.h, signed.h, None, q64.ctypes.data_as(C.c_void_p), B.Q_F64,
+                                                     64, CHECK_ROBOT, 3, vp))
     expect(B.ERR_INVALID, lib.b200df_field_add_points(None, None, 5))
     expect(B.ERR_INVALID, lib.b200df_gradients_batch(e.group.h, e.world.h, None, qp, B.Q_F32, 4, CHECK_ROBOT, None,
                                                      None, None, None))
