@@ -1023,3 +1023,47 @@ def test_random_robots_every_kernel_against_the_oracle(gpu, oracle, seed, n_link
     fin = refg["dist"] < 1e300
     assert np.max(np.abs(got["dist"][fin] - refg["dist"][fin])) < 1e-5
     assert np.max(np.abs(got["grad"] - refg["grad"])) < 1e-5
+
+
+# radius = ceil(max_distance / resolution); the EDT dispatch depends on it and on nz:
+#   nz odd -> windowed fallback kernels; nz % 8 != 0 -> pair-wise z pass; nz % 16 != 0 -> word-wise bit packing;
+#   radius <= 13 / 25 / 31 -> marching instantiations 12 / 24 / 30; radius > 31 -> windowed fallback
+_EDT_CASES = [
+    ((31, 29, 27), 0.02, 0.10, False),   # nz odd, radius 5, u8
+    ((20, 22, 30), 0.02, 0.26, False),   # nz even, not % 8, radius 13 (march<12>), u8 (169)
+    ((18, 20, 40), 0.02, 0.27, False),   # nz % 8 == 0, not % 16, radius 14 -> march<24>, u8 (196)
+    ((24, 18, 48), 0.01, 0.25, False),   # nz % 16 == 0, radius 25 (march<24>), u16 (625)
+    ((30, 26, 32), 0.01, 0.255, False),  # radius 26 -> march<30>, u16
+    ((40, 36, 64), 0.01, 0.31, False),   # radius 31 (march<30>), u16 (961)
+    ((40, 36, 64), 0.01, 0.33, False),   # radius 33 -> windowed fallback
+    ((22, 24, 32), 0.02, 0.26, True),    # signed: the negative field runs the same passes on the complement
+    ((17, 19, 26), 0.05, 0.02, False),   # radius 1: max_d2 = 1
+    ((9, 70, 8), 0.02, 0.25, False),     # a thin grid
+]
+
+
+@pytest.mark.parametrize("shape,res,max_dist,signed", _EDT_CASES)
+def test_edt_dispatch_variants_bit_exact(gpu, oracle, shape, res, max_dist, signed):
+    """Every branch of the EDT dispatch against brute force (sparse random voxels plus a solid blob, so that both the
+    INF-skip and the dense paths run), after an incremental sequence of edits as well."""
+    from moveit_b200 import engine
+    size = [s * res + 1e-9 for s in shape]
+    g = engine.Field(size, res, (0, 0, 0), max_dist, signed)
+    assert g.dims == shape
+    rng = np.random.default_rng(sum(shape))
+    n_pts = max(4, int(np.prod(shape)) // 400)
+    ijk = np.stack([rng.integers(0, s, n_pts) for s in shape], axis=1)
+    c = [s // 2 for s in shape]
+    blob = np.array([(c[0] + a, c[1] + b, c[2] + d) for a in range(-2, 3) for b in range(-2, 3) for d in range(-2, 3)
+                     if 0 <= c[0] + a < shape[0] and 0 <= c[1] + b < shape[1] and 0 <= c[2] + d < shape[2]])
+    occ = np.zeros(shape, dtype=np.uint8)
+    for batch in (ijk[: n_pts // 2], blob, ijk[n_pts // 2:]):  # a rebuild after every edit
+        g.add_voxels(batch)
+        occ[batch[:, 0], batch[:, 1], batch[:, 2]] = 1
+        assert np.array_equal(g.occupancy(), occ)
+        want = oracle.edt_exact(occ, g.max_d2, brute=max(shape) <= 48)
+        assert np.array_equal(g.d2(), want), shape
+        if signed:
+            assert np.array_equal(g.d2(True), oracle.edt_exact(1 - occ, g.max_d2, brute=max(shape) <= 48))
+    g.reset()
+    assert (g.d2() == g.max_d2).all()
