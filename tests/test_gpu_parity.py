@@ -1023,6 +1023,21 @@ def test_random_robots_every_kernel_against_the_oracle(gpu, oracle, seed, n_link
     fin = refg["dist"] < 1e300
     assert np.max(np.abs(got["dist"][fin] - refg["dist"][fin])) < 1e-5
     assert np.max(np.abs(got["grad"] - refg["grad"])) < 1e-5
+    # ... and with the per-link PosedDistanceFields of getSelfProximityGradients (Q6 / Q7), which take at most 32 links
+    if len(desc.links_with_geometry()) <= 32:
+        from moveit_b200 import engine
+        from moveit_b200.binding import CHECK_LINK_FIELDS
+        o.env.build_link_fields()
+        fields, enabled = engine.link_distance_fields(e.model_desc, e.group_links, desc.acm_entry_matrix(),
+                                                      fd["resolution"], fd["max_distance"])
+        e.group.set_link_fields(fields, enabled)
+        got = e.group.gradients(q[:300], e.world, flags=CHECK_ROBOT | CHECK_INTRA | CHECK_LINK_FIELDS)
+        refg = o.env.gradients_batch(q[:300], flags=7)
+        assert np.array_equal(got["type"], refg["type"].astype(np.uint8))
+        fin = refg["dist"] < 1e300
+        assert np.array_equal(fin, got["dist"] < 1e300)
+        assert np.max(np.abs(got["dist"][fin] - refg["dist"][fin])) < 1e-5
+        assert np.max(np.abs(got["grad"] - refg["grad"])) < 1e-5
 
 
 # radius = ceil(max_distance / resolution); the EDT dispatch depends on it and on nz:
