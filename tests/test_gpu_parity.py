@@ -917,69 +917,7 @@ def test_c_abi_error_behaviour(gpu, oracle):
 
 
 # ----------------------------------------------------------------------------------------------- random robots (fuzz)
-def _random_robot(seed, n_links, floating_root=False, pair_off=0.5, spread=(0.12, 0.3), radius=(0.012, 0.03),
-                  p_identity=0.25, max_spheres=9, dense_tail=0, p_geometry=0.85):
-    """A random kinematic tree: every joint type, oblique axes, identity and general origins, branches, links without
-    geometry, 1-9 spheres per link (batch-of-4 boundaries), mimic joints, a random ACM."""
-    import math
-    rng = np.random.default_rng(seed)
-    r = rd.RobotDescription("fuzz%d" % seed)
-    one_var = []  # (joint name, type) of earlier one-variable joints, candidates for mimicking
-    for i in range(n_links):
-        name, jname = "l%d" % i, "j%d" % i
-        parent = None if i == 0 else "l%d" % (i - 1 if rng.random() < 0.6 else rng.integers(0, i))
-        u = rng.random()
-        if i == 0:
-            jt = rd.JOINT_FLOATING if floating_root else (rd.JOINT_PLANAR if u < 0.5 else rd.JOINT_FIXED)
-        else:
-            jt = rd.JOINT_FIXED if u < 0.2 else rd.JOINT_REVOLUTE if u < 0.75 else rd.JOINT_PRISMATIC if u < 0.93 \
-                else rd.JOINT_PLANAR
-        axis = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (0, 0, -1), (0, -1, 0),
-                tuple(rng.normal(size=3))][rng.integers(0, 6)]
-        ident = rng.random() < p_identity
-        xyz = (0, 0, 0) if ident else tuple(rng.uniform(spread[0], spread[1], 3) * rng.choice([-1.0, 1.0], 3))
-        rpy = (0, 0, 0) if ident else tuple(rng.uniform(-math.pi, math.pi, 3))
-        limits, mimic = None, None
-        if jt == rd.JOINT_REVOLUTE:
-            limits = (-2.5, 2.5)
-        elif jt == rd.JOINT_PRISMATIC:
-            limits = (-0.2, 0.3)
-        elif jt == rd.JOINT_PLANAR:
-            limits = [(-0.4, 0.4), (-0.4, 0.4), (-math.pi, math.pi)]
-        if jt in (rd.JOINT_REVOLUTE, rd.JOINT_PRISMATIC):
-            same = [j for j, t in one_var if t == jt]
-            if same and rng.random() < 0.12:
-                mimic = (same[rng.integers(0, len(same))], float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-0.1, 0.1)))
-            else:
-                one_var.append((jname, jt))
-        r.add_link(name, parent, jname, jt, xyz, rpy, axis=axis, limits=limits, mimic=mimic)
-        if rng.random() < p_geometry:
-            r.add_shape(name, rd.SHAPE_BOX, (0.1, 0.08, 0.06))
-            k = int(rng.integers(1, max_spheres + 1))
-            r.set_spheres(name, [(rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05),
-                                  rng.uniform(radius[0], radius[1])) for _ in range(k)])
-    geom = [r.link_names[i] for i in range(n_links) if r.shapes[i]]
-    for i in range(n_links):  # parent-child pairs never collide; some random extra pairs are allowed to as well
-        if r.parent[i] >= 0:
-            r.disabled_pairs.append((r.link_names[r.parent[i]], r.link_names[i]))
-    for a in range(len(geom)):
-        for b in range(a + 1, len(geom)):
-            if b < len(geom) - dense_tail and rng.random() < pair_off:  # the last dense_tail links keep every pair
-                r.disabled_pairs.append((geom[a], geom[b]))
-    return r
-
-
-_FUZZ = [  # seed, links, floating root, generator settings (tuned so that each check has both outcomes)
-    (1, 12, False, dict(pair_off=0.6, p_identity=0.1)),
-    (2, 25, False, dict(pair_off=0.8, p_identity=0.1)),
-    (3, 40, False, dict(pair_off=0.8)),
-    (4, 40, False, dict(pair_off=0.0, spread=(0.35, 0.7), radius=(0.01, 0.022), p_identity=0.0)),  # > 32 partners
-    (5, 18, True, dict(pair_off=0.7, p_identity=0.1)),
-    (6, 33, True, dict(pair_off=0.8)),
-    # fits FAST's tables (<= 128 spheres, <= 512 link pairs) AND has links with more than 32 partners
-    (7, 40, False, dict(pair_off=0.85, max_spheres=3, dense_tail=3, spread=(0.25, 0.5), radius=(0.02, 0.04),
-                        p_geometry=0.97)),
-]
+from common import FUZZ_CASES as _FUZZ, random_robot as _random_robot  # noqa: E402
 
 
 @pytest.mark.parametrize("seed,n_links,floating,kw", _FUZZ)

@@ -237,3 +237,26 @@ def test_distance_field_class_and_stream_format(gpu, oracle, tmp_path):
     ob.make_exact()
     assert np.array_equal(ob.d2(), wb)
     assert engine.Field.from_stream(open(prefix + ".small.d2.i32", "rb"), 0.25) is None  # not a field stream
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [1, 5])  # a planar-root tree with mimic joints, a floating-root tree
+def test_random_robots_through_the_cpp_env(gpu, oracle, tmp_path, case):
+    """The C++ mirror builds its own kinematic model from RobotModel-shaped input (variable indexing, mimic joints by
+    name, planar / floating variable blocks, ACM by link names): the fuzz robots of test_gpu_parity.py through it."""
+    from common import FUZZ_CASES, random_robot
+    seed, n_links, floating, kw = FUZZ_CASES[case]
+    desc = random_robot(100 + seed, n_links, floating, **kw)
+    fd = scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene(seed=200 + seed, n_boxes=6, n_cylinders=3)
+    q = desc.sample_states(3000, 300 + seed)
+    prefix = _run(tmp_path, desc, fd, objs, q, group="", n_single=16, n_grad=20)
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    robot = np.fromfile(prefix + ".robot.u8", dtype=np.uint8)
+    both = np.fromfile(prefix + ".all.u8", dtype=np.uint8)
+    assert np.array_equal(robot, o.env.check_batch(q, mode=1, n_threads=8))
+    assert np.array_equal(np.fromfile(prefix + ".self.u8", dtype=np.uint8), o.env.check_batch(q, mode=2, n_threads=8))
+    assert np.array_equal(both, o.env.check_batch(q, mode=4, n_threads=8))
+    assert 0 < both.sum() < len(q)
+    single = np.fromfile(prefix + ".single.u8", dtype=np.uint8)
+    assert np.array_equal(single & 1, robot[:16]) and np.array_equal((single >> 2) & 1, both[:16])
