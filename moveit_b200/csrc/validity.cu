@@ -401,10 +401,17 @@ int run_verdict(const b200df_group* group, const FieldDev& wf_in, const FieldDev
   int rc = fast_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, amb_idx, amb_count, stream);
   if (!rc && !raw)
   {
-    Redo redo;
-    redo.idx = amb_idx;
-    redo.count = amb_count;
-    rc = dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream, redo);
+    // the undecided states (a few hundred per million) go to the one-CTA-per-state kernel: the one-thread-per-state
+    // kernel would spend a full ~85 us warp latency on a handful of warps
+    if (small_supported(group))
+      rc = small_launch(group, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream, amb_idx, amb_count);
+    else
+    {
+      Redo redo;
+      redo.idx = amb_idx;
+      redo.count = amb_count;
+      rc = dispatch_verdict(group->dev, wf, sf, elem, q_dev, q_dtype, n, flags, verdict_dev, stream, redo);
+    }
   }
   if (scratch)
     cudaFreeAsync(scratch, stream);

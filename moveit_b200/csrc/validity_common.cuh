@@ -743,8 +743,10 @@ int fast_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& s
 int small_create(b200df_group* group);  // leaves group->small null when the robot does not fit shared memory
 void small_destroy(b200df_group* group);
 bool small_supported(const b200df_group* group);
+// redo_idx / redo_count (device): evaluate only the listed states (the FAST path's undecided set)
 int small_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
-                 int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream);
+                 int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream, const int* redo_idx = nullptr,
+                 const int* redo_count = nullptr);
 
 // B200DF_SMALL_BATCH=0 switches the mapped-pinned small-call staging of the host-buffer entry points off
 inline bool small_batch_enabled()

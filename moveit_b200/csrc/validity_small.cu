@@ -56,7 +56,9 @@ struct SmallDev
 template <typename QT, typename FT>
 __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDev t, LookupDev wf, LookupDev sf,
                                                              const QT* __restrict__ q, long n, int flags,
-                                                             uint8_t* __restrict__ verdict)
+                                                             uint8_t* __restrict__ verdict,
+                                                             const int* __restrict__ redo_idx,
+                                                             const int* __restrict__ redo_count)
 {
   extern __shared__ double sm[];
   const int L = g.n_links, S = g.n_spheres, G = g.n_glinks;
@@ -69,8 +71,12 @@ __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDe
   const bool do_self = (flags & B200DF_CHECK_SELF) != 0;
   const bool do_pairs = (flags & B200DF_CHECK_INTRA) != 0 && t.n_items > 0;
 
-  for (long state = blockIdx.x; state < n; state += gridDim.x)
+  // redo_idx / redo_count: when set, only the listed states are evaluated (the FAST path's undecided set, whose length
+  // lives in device memory; a few hundred states per million - far too few for the one-thread-per-state kernel)
+  const long total = redo_idx ? (long)*redo_count : n;
+  for (long item = blockIdx.x; item < total; item += gridDim.x)
   {
+    const long state = redo_idx ? (long)redo_idx[item] : item;
     if (tid < 32)
       warp_fk(g.links, L, q + state * g.n_vars, tid, staging, T);
     __syncthreads();
@@ -166,13 +172,14 @@ namespace
 {
 template <typename QT, typename FT>
 int launch_small(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const void* q, long n, int flags,
-                 uint8_t* verdict, cudaStream_t stream)
+                 uint8_t* verdict, cudaStream_t stream, const int* redo_idx, const int* redo_count)
 {
   const b200df_group::SmallPath& sp = *g->small;
   B200DF_CUDA(allow_dynamic_smem(validity_small_kernel<QT, FT>, sp.smem));
-  const unsigned grid = (unsigned)std::min<long>(n, 148L * 64);
+  const unsigned grid = (unsigned)std::min<long>(n, redo_idx ? 148L * 32 : 148L * 64);
   validity_small_kernel<QT, FT><<<grid, sp.threads, sp.smem, stream>>>(g->dev, sp.dev, make_lookup(wf), make_lookup(sf),
-                                                                      static_cast<const QT*>(q), n, flags, verdict);
+                                                                      static_cast<const QT*>(q), n, flags, verdict,
+                                                                      redo_idx, redo_count);
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
@@ -250,13 +257,16 @@ bool small_supported(const b200df_group* g)
 }
 
 int small_launch(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
-                 int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream)
+                 int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream, const int* redo_idx,
+                 const int* redo_count)
 {
   B200DF_REQUIRE(g->small, "this group has no small-batch kernel");
   if (q_dtype == B200DF_Q_F32)
-    return field_elem == 1 ? launch_small<float, uint8_t>(g, wf, sf, q, n, flags, verdict, stream)
-                           : launch_small<float, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
-  return field_elem == 1 ? launch_small<double, uint8_t>(g, wf, sf, q, n, flags, verdict, stream)
-                         : launch_small<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream);
+    return field_elem == 1
+               ? launch_small<float, uint8_t>(g, wf, sf, q, n, flags, verdict, stream, redo_idx, redo_count)
+               : launch_small<float, uint16_t>(g, wf, sf, q, n, flags, verdict, stream, redo_idx, redo_count);
+  return field_elem == 1
+             ? launch_small<double, uint8_t>(g, wf, sf, q, n, flags, verdict, stream, redo_idx, redo_count)
+             : launch_small<double, uint16_t>(g, wf, sf, q, n, flags, verdict, stream, redo_idx, redo_count);
 }
 }  // namespace b200df
