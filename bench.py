@@ -444,7 +444,7 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_STATE.get(args.precision, NCU_DRAM_BYTES_PER_STATE["exact"]) * n,
                          "peak_source": peak_src,
                          "issue": issue_roofline(args.precision, n * args.steps / (ms_total * 1e-3), clocks),
-                         "kernel": ("validity_fast_kernel<unsigned char, 128> (+ validity_kernel on the undecided "
+                         "kernel": ("validity_fast_kernel<unsigned char, 128> (+ validity_small_kernel on the undecided "
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
                          "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
                                  "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
