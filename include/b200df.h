@@ -75,7 +75,7 @@ enum
   B200DF_PRECISION_EXACT = 0, /* fp64 FK + fp64 voxel indexing, operation order of the reference */
   B200DF_PRECISION_FAST = 1,  /* fp32 fast path; states whose verdict could depend on rounding are re-run EXACT:
                                  same verdicts as EXACT (fp64 joint values are screened rounded to fp32 and re-run
-                                 unrounded).  Needs no floating joints, a robot that fits the constant-bank tables
+                                 unrounded).  Needs a robot that fits the constant-bank tables
                                  (<= 40 links, 128 spheres, 512 link pairs) and, with signed fields, every sphere
                                  radius above the collision tolerance (the negative distances then cannot change a
                                  verdict); otherwise the call silently runs EXACT */

@@ -169,6 +169,36 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
       cur[4 * i + 3] = fmaf(base[4 * i + 2], tz, fmaf(base[4 * i + 1], ty, fmaf(base[4 * i], tx, base[4 * i + 3])));
     }
   }
+  else if (l.joint_type == B200DF_JOINT_FLOATING)  // translation + normalised quaternion (floating_joint_model.cpp:224-229)
+  {
+    float j[12];
+    j[3] = jointf(l, q, 0, out_of_range);
+    j[7] = jointf(l, q, 1, out_of_range);
+    j[11] = jointf(l, q, 2, out_of_range);
+    float qx = jointf(l, q, 3, out_of_range), qy = jointf(l, q, 4, out_of_range), qz = jointf(l, q, 5, out_of_range),
+          qw = jointf(l, q, 6, out_of_range);
+    const float n2 = fmaf(qw, qw, fmaf(qz, qz, fmaf(qy, qy, qx * qx)));
+    out_of_range |= !(n2 > 1e-6f && n2 < 1e6f);  // the error analysis assumes a quaternion that can be normalised in fp32
+    const float inv = 1.f / sqrtf(n2);
+    qx *= inv;
+    qy *= inv;
+    qz *= inv;
+    qw *= inv;
+    const float tx = 2.f * qx, ty = 2.f * qy, tz = 2.f * qz;
+    const float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    const float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+    const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    j[0] = 1.f - (tyy + tzz);
+    j[1] = txy - twz;
+    j[2] = txz + twy;
+    j[4] = txy + twz;
+    j[5] = 1.f - (txx + tzz);
+    j[6] = tyz - twx;
+    j[8] = txz - twy;
+    j[9] = tyz + twx;
+    j[10] = 1.f - (txx + tyy);
+    mulf(base, j, cur);
+  }
   else  // revolute, or planar = translation (x, y) followed by a rotation about z
   {
     const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
@@ -475,7 +505,7 @@ double norm3(const double* v)
 
 // Travel assumed for translational joint variables and the angle range assumed for rotational ones; values
 // outside are detected at run time and sent to the exact kernel.
-constexpr double kPrismaticTravel = 2.0, kPlanarTravel = 16.0, kAngleRange = 8.0;
+constexpr double kPrismaticTravel = 2.0, kPlanarTravel = 16.0, kAngleRange = 8.0, kFloatingTravel = 4.0;
 
 struct LinkErr
 {
@@ -501,9 +531,6 @@ int fast_create(b200df_group* g)
   const int P = (int)g->partners.size();
   if (L > kMaxLinks || G > kMaxGLinks || S > kMaxSpheres || P > kMaxPartners)
     return B200DF_OK;  // FAST silently degrades to EXACT for robots that do not fit the constant-bank tables
-  for (const DevLink& l : m->links)
-    if (l.joint_type == B200DF_JOINT_FLOATING)
-      return B200DF_OK;
   std::unique_ptr<b200df_group::FastPath> fp(new b200df_group::FastPath);
   FastTables& T = fp->tables;
   std::memset(&T, 0, sizeof(T));
@@ -589,6 +616,19 @@ int fast_create(b200df_group* g)
         e.et = b.et + b.eR * tr + 2.0 * u * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
         e.reach = b.reach + tr;
       }
+    }
+    else if (l.joint_type == B200DF_JOINT_FLOATING)
+    {
+      // The seven variables reach the kernel rounded to fp32 (relative u each).  Normalised quaternion: input
+      // rounding moves it by <= 2u, the fp32 normalisation (squared norm, sqrt, reciprocal, product) by <= 5u more.
+      // Every entry of R(q) is quadratic in q with gradient norm <= 4 on the unit sphere, plus ~6u of rounding while
+      // forming it: <= 34u per entry, 102u in Frobenius norm.
+      f.vmax = (float)kFloatingTravel;
+      const double eJ = 102.0 * u;
+      const double tr = kFloatingTravel * std::sqrt(3.0);
+      e.eR = b.eR * (1.0 + eJ) + eJ + 9.1 * u;
+      e.et = b.et + b.eR * tr + 2.0 * u * tr + 4.0 * u * std::sqrt(3.0) * (std::sqrt(3.0) * tr + b.reach);
+      e.reach = b.reach + tr;
     }
     else if (l.joint_type == B200DF_JOINT_PRISMATIC)
     {

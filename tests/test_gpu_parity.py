@@ -953,7 +953,16 @@ def test_random_robots_every_kernel_against_the_oracle(gpu, oracle, seed, n_link
             raw = e.group.check(q32, e.world, flags=flags, precision=3)
             assert np.array_equal(raw[raw != 2], e32[raw != 2]) and (raw == 2).mean() < 0.2
         except B.B200dfError as ex:
-            assert ex.code == B.ERR_UNSUPPORTED and seed != 7  # case 7 is built to fit
+            assert ex.code == B.ERR_UNSUPPORTED and seed not in (5, 7)  # those two are built to fit FAST's tables
+    if seed in (5, 7):  # a floating-root tree / a tree with two partner chunks: FAST at a size where margins get hit
+        big = desc.sample_states(1_000_000, 400 + seed, np.float32)
+        fl = CHECK_ROBOT | CHECK_INTRA
+        ex_big = e.group.check(big, e.world, flags=fl, precision=0)
+        assert np.array_equal(e.group.check(big, e.world, flags=fl, precision=1), ex_big)
+        raw = e.group.check(big, e.world, flags=fl, precision=3)
+        assert np.array_equal(raw[raw != 2], ex_big[raw != 2])
+        print("fuzz %d: FAST undecided %.4f" % (seed, (raw == 2).mean()))
+        assert (raw == 2).mean() < 0.2
     # gradients (random geometry: no exact distance ties)
     got = e.group.gradients(q[:300], e.world, flags=CHECK_ROBOT | CHECK_INTRA)
     refg = o.env.gradients_batch(q[:300], flags=2 | 4)

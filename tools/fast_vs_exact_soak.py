@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Soak test of the FAST precision's exactness claim (and of the small-batch kernel's): many batches of fresh random
-states (different seeds, two scenes, two robots), FAST and the one-CTA-per-state kernel vs EXACT verdicts compared on
+states (different seeds, three scenes, three robots incl. a floating-root tree), FAST and the one-CTA-per-state kernel vs EXACT verdicts compared on
 the device, undecided fraction of the screening pass reported.
 Prints one JSON line; the committed result lives in profiles/."""
 import json
@@ -29,6 +29,10 @@ def main(batches=10, n=10_000_000):
               dict(size=(2.0, 2.0, 2.0), resolution=0.01, center=(0.0, 0.0, 0.5), max_distance=0.25),
               scenarios.random_scene(seed=1234)),
              ("mobile_arm", rd.mobile_arm(), scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=57, n_boxes=3, n_cylinders=1))]
+    from common import FUZZ_CASES, random_robot
+    seed, n_links, floating, kw = FUZZ_CASES[4]  # the floating-root tree of the fuzz tests (quaternion joint in FAST)
+    cases.append(("fuzz_floating_root", random_robot(100 + seed, n_links, floating, **kw), scenarios.FIELD_DEFAULT,
+                  scenarios.random_scene(seed=200 + seed, n_boxes=6, n_cylinders=3)))
     for name, desc, field, objs in cases:
         e = EngineSetup(desc, field, objs)
         lo = np.array([l[0] for l in desc.limits], dtype=np.float32)
