@@ -1029,3 +1029,78 @@ def test_edt_dispatch_variants_bit_exact(gpu, oracle, shape, res, max_dist, sign
             assert np.array_equal(g.d2(True), oracle.edt_exact(1 - occ, g.max_d2, brute=max(shape) <= 48))
     g.reset()
     assert (g.d2() == g.max_d2).all()
+
+
+@pytest.mark.parametrize("seed,signed", [(1, False), (2, False), (3, True)])
+def test_random_field_edit_sequences(gpu, oracle, seed, signed):
+    """Forty random edits (points in and out of bounds, removals of present and absent points, updatePointsInField,
+    shapes added / removed / moved with random poses, octree leaves, voxel lists, resets): after every edit the
+    occupancy equals the oracle's zero set and d^2 (and the negative field) equal the exact EDT of it."""
+    from moveit_b200 import engine
+    rng = np.random.default_rng(700 + seed)
+    size, res, corner, maxd = (0.64, 0.56, 0.48), 0.02, (-0.3, -0.2, 0.1), 0.17
+    g = engine.Field(size, res, corner, maxd, signed)
+    o = oracle.Field(size, res, corner, maxd, signed)
+    lo, hi = np.array(corner) - 0.1, np.array(corner) + np.array(size) + 0.1  # some points fall outside the grid
+    held = np.zeros((0, 3))
+
+    def rand_pose():
+        qv = rng.normal(size=4)
+        qv /= np.linalg.norm(qv)
+        x, y, z, w = qv
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        return oracle.pose12(rng.uniform(lo + 0.15, hi - 0.15), R)
+
+    shapes = []
+    for step in range(40):
+        op = rng.integers(0, 8)
+        if op == 0 or len(held) == 0:
+            pts = rng.uniform(lo, hi, size=(int(rng.integers(1, 60)), 3))
+            g.add_points(pts)
+            o.add_points(pts)
+            held = np.concatenate([held, pts])
+        elif op == 1:
+            pick = held[rng.random(len(held)) < 0.3]
+            extra = rng.uniform(lo, hi, size=(5, 3))  # points that were never added
+            pts = np.concatenate([pick, extra])
+            g.remove_points(pts)
+            o.remove_points(pts)
+        elif op == 2:
+            old = held[rng.random(len(held)) < 0.5]
+            new = np.concatenate([old[: len(old) // 2], rng.uniform(lo, hi, size=(int(rng.integers(1, 30)), 3))])
+            g.update_points(old, new)
+            o.update_points(old, new)
+            held = new
+        elif op == 3:
+            t = [rd.SHAPE_SPHERE, rd.SHAPE_BOX, rd.SHAPE_CYLINDER][rng.integers(0, 3)]
+            dims = {rd.SHAPE_SPHERE: (rng.uniform(0.03, 0.1),), rd.SHAPE_BOX: tuple(rng.uniform(0.04, 0.2, 3)),
+                    rd.SHAPE_CYLINDER: (rng.uniform(0.03, 0.08), rng.uniform(0.05, 0.25))}[t]
+            pose = rand_pose()
+            g.add_shape(t, dims, pose)
+            o.add_points(oracle.shape_points(t, dims, pose, res))
+            shapes.append((t, dims, pose))
+        elif op == 4 and shapes:
+            t, dims, pose = shapes.pop(int(rng.integers(0, len(shapes))))
+            g.remove_shape(t, dims, pose)
+            o.remove_points(oracle.shape_points(t, dims, pose, res))
+        elif op == 5:
+            leaves = np.concatenate([rng.uniform(lo + 0.1, hi - 0.1, size=(4, 3)), rng.choice([0.01, 0.02, 0.05], (4, 1))],
+                                    axis=1)
+            g.add_octree_leaves(leaves)
+            o.add_points(oracle.octree_points(res, [tuple(l) for l in leaves]))
+        elif op == 6:
+            ijk = np.stack([rng.integers(-2, n + 2, 20) for n in g.dims], axis=1)  # some outside the grid
+            g.add_voxels(ijk)
+            o.add_voxels(ijk)
+        elif op == 7 and rng.random() < 0.3:
+            g.reset()
+            o.reset()
+            held = np.zeros((0, 3))
+            shapes = []
+        occ = (o.d2() == 0).astype(np.uint8)
+        assert np.array_equal(g.occupancy(), occ), (seed, step, int(op))
+        assert np.array_equal(g.d2(), oracle.edt_exact(occ, g.max_d2)), (seed, step, int(op))
+        if signed:
+            assert np.array_equal(g.d2(True), oracle.edt_exact(1 - occ, g.max_d2)), (seed, step, int(op))
