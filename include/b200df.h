@@ -258,7 +258,9 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
 /* Batched motion validation: M straight joint-space motions qa[i] -> qb[i] (host, fp64 [m][n_vars]), each cut into
  * `segments` pieces; the states at t = j/segments, j = 1..segments, are interpolated on the device with the
  * reference's JointModel::interpolate arithmetic (revolute_joint_model.cpp:125-148, planar_joint_model.cpp:180-205;
- * var_is_angular[v] != 0 marks continuous-revolute / planar-theta variables that take the shortest arc; NULL = none)
+ * var_is_angular[v] == 1 marks continuous-revolute / planar-theta variables that take the shortest arc, 2 the first and
+ * 3 the other three quaternion variables (x, y, z, w) of a floating joint, which are slerped like
+ * FloatingJointModel::interpolate, floating_joint_model.cpp:130-158; NULL = all linear)
  * and checked like b200df_check_batch.  first_invalid[i] = the first j whose state collides, 0 = motion valid — what
  * ompl::base::DiscreteMotionValidator::checkMotion + StateValidityChecker::isValid
  * (moveit_planners/ompl/ompl_interface/src/detail/state_validity_checker.cpp:76-121) decide one state at a time; the

@@ -10,6 +10,7 @@
 //   PlanarJointModel::interpolate     robot_model/src/planar_joint_model.cpp:180-205    (holonomic: x, y linear, theta shortest arc)
 // Compiled with --fmad=false: the interpolation rounds like the reference's double arithmetic.
 #include <algorithm>
+#include <cfloat>
 #include <cstring>
 
 #include "validity_common.cuh"
@@ -34,10 +35,38 @@ __global__ void interpolate_edges_kernel(const double* __restrict__ qa, const do
   const long e = s / K;
   const int j = (int)(s - e * K) + 1;
   const double t = (double)j / (double)K;
+  const uint8_t kind = angular[v];
+  if (kind == 3)
+    return;  // a quaternion component: written by the thread of the quaternion's first variable
+  if (kind == 2)
+  {
+    // FloatingJointModel::interpolate, rotation part (floating_joint_model.cpp:137-157): slerp on |dot| (the
+    // reference's long-angle branch tests the absolute value for < 0 and is dead; reproduced by leaving it out)
+    const double* f = qa + e * n_vars + v;
+    const double* g = qb + e * n_vars + v;
+    const double dq = fabs(((f[0] * g[0] + f[1] * g[1]) + f[2] * g[2]) + f[3] * g[3]);
+    const double theta = (dq + DBL_EPSILON >= 1.0) ? 0.0 : acos(dq);
+    if (theta > DBL_EPSILON)
+    {
+      const double d = 1.0 / sin(theta);
+      const double s0 = sin((1.0 - t) * theta);
+      const double s1 = sin(t * theta);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        out[i + c] = (QT)((f[c] * s0 + g[c] * s1) * d);
+    }
+    else
+    {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        out[i + c] = (QT)f[c];
+    }
+    return;
+  }
   const double from = qa[e * n_vars + v], to = qb[e * n_vars + v];
   double r;
   double diff = to - from;
-  if (!angular[v] || fabs(diff) <= kPi)
+  if (kind != 1 || fabs(diff) <= kPi)
     r = from + diff * t;
   else
   {

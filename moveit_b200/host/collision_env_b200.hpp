@@ -768,11 +768,20 @@ public:
   {
     std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, true);
     int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
-    // continuous revolute joints are not modelled by the stand-in RobotModel; the planar joint's theta is angular
+    // continuous revolute joints are not modelled by the stand-in RobotModel; the planar joint's theta is angular,
+    // a floating joint's quaternion (variables 3..6) is slerped
     std::vector<std::uint8_t> angular((std::size_t)robot_model_->getVariableCount(), 0);
     for (const core::LinkModel& l : robot_model_->getLinkModels())
+    {
       if (l.joint_type == core::PLANAR)
         angular[(std::size_t)l.first_variable + 2] = 1;
+      if (l.joint_type == core::FLOATING)
+      {
+        angular[(std::size_t)l.first_variable + 3] = 2;
+        for (int k = 4; k < 7; ++k)
+          angular[(std::size_t)l.first_variable + k] = 3;
+      }
+    }
     checkStatus(b200df_check_edges(e->group, world_field_, e->self_field, from, to, m, segments, angular.data(), flags,
                                    precision, first_invalid),
                 "b200df_check_edges");

@@ -440,8 +440,18 @@ def _interpolate_reference(qa, qb, K, angular):
         d2 = np.where(diff > 0.0, 2.0 * np.pi - diff, -2.0 * np.pi - diff)
         r = qa - d2 * t
         r = np.where(r > np.pi, r - 2.0 * np.pi, np.where(r < -np.pi, r + 2.0 * np.pi, r))
-        use_arc = angular[None, :].astype(bool) & (np.abs(diff) > np.pi)
+        use_arc = (angular[None, :] == 1) & (np.abs(diff) > np.pi)
         out[:, j - 1, :] = np.where(use_arc, r, lin)
+        for v in np.nonzero(angular == 2)[0]:  # FloatingJointModel::interpolate (floating_joint_model.cpp:137-157)
+            f, g = qa[:, v:v + 4], qb[:, v:v + 4]
+            dq = np.abs(((f[:, 0] * g[:, 0] + f[:, 1] * g[:, 1]) + f[:, 2] * g[:, 2]) + f[:, 3] * g[:, 3])
+            theta = np.where(dq + np.finfo(np.float64).eps >= 1.0, 0.0, np.arccos(np.minimum(dq, 1.0)))
+            big = theta > np.finfo(np.float64).eps
+            with np.errstate(divide="ignore", invalid="ignore"):
+                d = 1.0 / np.sin(theta)
+                s0, s1 = np.sin((1.0 - t) * theta), np.sin(t * theta)
+                sl = (f * s0[:, None] + g * s1[:, None]) * d[:, None]
+            out[:, j - 1, v:v + 4] = np.where(big[:, None], sl, f)
     return out
 
 
@@ -1104,3 +1114,28 @@ def test_random_field_edit_sequences(gpu, oracle, seed, signed):
         assert np.array_equal(g.d2(), oracle.edt_exact(occ, g.max_d2)), (seed, step, int(op))
         if signed:
             assert np.array_equal(g.d2(True), oracle.edt_exact(1 - occ, g.max_d2)), (seed, step, int(op))
+
+
+def test_edge_check_slerps_floating_joints(gpu, oracle):
+    """b200df_check_edges on a floating-root tree: the quaternion block is interpolated like
+    FloatingJointModel::interpolate (slerp on |dot|, translation linear)."""
+    seed, n_links, floating, kw = _FUZZ[4]
+    desc = _random_robot(100 + seed, n_links, floating, **kw)
+    assert desc.joint_type[0] == rd.JOINT_FLOATING
+    fd = scenarios.FIELD_DEFAULT
+    objs = scenarios.random_scene(seed=200 + seed, n_boxes=6, n_cylinders=3)
+    o = OracleSetup(oracle, desc, fd, objs, self_state=np.zeros(desc.nvar))
+    e = EngineSetup(desc, fd, objs)
+    M, K = 2500, 10
+    qa, qb = desc.sample_states(M, 81), desc.sample_states(M, 82)
+    qb[:50, 3:7] = qa[:50, 3:7]  # identical orientations: the theta <= eps branch
+    angular = np.zeros(desc.nvar, dtype=np.uint8)
+    angular[3], angular[4:7] = 2, 3
+    flags = CHECK_ROBOT | CHECK_INTRA
+    got = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=0, var_is_angular=angular)
+    states = _interpolate_reference(qa, qb, K, angular)
+    ref = o.env.check_batch(states.reshape(-1, desc.nvar), mode=3, n_threads=8).reshape(M, K)
+    assert np.array_equal(got, np.where(ref.any(axis=1), ref.argmax(axis=1) + 1, 0))
+    assert 0 < (got == 0).sum() < M
+    lin = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=0)  # plain lerp of the quaternion: not the same
+    assert not np.array_equal(lin, got)
