@@ -249,7 +249,9 @@ class Group:
 
     def check_edges(self, qa, qb, segments, world=None, self_field=None, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT,
                     var_is_angular=None):
-        """M motions qa[i] -> qb[i] cut into `segments` pieces; returns first_invalid[M] (0 = valid)."""
+        """M motions qa[i] -> qb[i] cut into `segments` pieces; returns first_invalid[M] (0 = valid).
+        var_is_angular[v]: 0 linear, 1 shortest-arc angle (continuous revolute, planar theta), 2 / 3 the first / the
+        other three quaternion variables of a floating joint (slerp)."""
         qa = np.ascontiguousarray(qa, dtype=np.float64).reshape(-1, self.model.n_vars)
         qb = np.ascontiguousarray(qb, dtype=np.float64).reshape(-1, self.model.n_vars)
         assert qa.shape == qb.shape
