@@ -98,6 +98,7 @@ struct LinkModel  // a link together with its parent joint, as RobotModel stores
   std::string name, joint_name;
   int parent = -1;
   JointType joint_type = FIXED;
+  bool continuous = false;  // RevoluteJointModel::isContinuous(): interpolation takes the shortest arc
   double axis[3] = { 0, 0, 1 };
   Isometry3d joint_origin;
   std::string mimic_joint;  // empty: none
@@ -768,11 +769,13 @@ public:
   {
     std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, true);
     int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
-    // continuous revolute joints are not modelled by the stand-in RobotModel; the planar joint's theta is angular,
-    // a floating joint's quaternion (variables 3..6) is slerped
+    // JointModel::interpolate per joint type: continuous revolute joints and the planar joint's theta take the
+    // shortest arc, a floating joint's quaternion (variables 3..6) is slerped
     std::vector<std::uint8_t> angular((std::size_t)robot_model_->getVariableCount(), 0);
     for (const core::LinkModel& l : robot_model_->getLinkModels())
     {
+      if (l.joint_type == core::REVOLUTE && l.continuous)
+        angular[(std::size_t)l.first_variable] = 1;
       if (l.joint_type == core::PLANAR)
         angular[(std::size_t)l.first_variable + 2] = 1;
       if (l.joint_type == core::FLOATING)
