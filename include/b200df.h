@@ -249,7 +249,11 @@ int b200df_field_import_device(b200df_field* field, const void* occ_dev, const v
 /* ---- batched checks ----------------------------------------------------------------------------------------
  * N joint vectors -> N verdicts.  Replaces, per state, checkRobotCollision (:1500-1519), checkSelfCollision
  * (:254-261 -> :182-204) and checkCollision (:1441-1464) with req.contacts == false.
- * world / self may be NULL when the corresponding flag is not set. */
+ * world / self may be NULL when the corresponding flag is not set.
+ * Any batch size is served: up to 16 384 states run on a one-CTA-per-state kernel (a single state answers in ~20 us
+ * through the host-buffer entry, which stages small inputs in a mapped page-locked buffer of a cached per-call
+ * context), larger batches on the one-thread-per-state kernels, pipelined over PCIe in 2^20-state chunks.  The entry
+ * points are re-entrant: concurrent calls on the same handles each take their own context. */
 int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
                        int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict);
 int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q_dev,
