@@ -964,6 +964,65 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
     }
     return rc;
   }
+  // Pageable caller memory: a cudaMemcpyAsync on it goes through the driver's own staging at a few GB/s and holds this
+  // thread (the D2H even until the chunk's kernel is done, which serialises the pipeline).  Such batches are staged
+  // through page-locked buffers of the context instead: a few host threads fill slot k while the GPU works on the
+  // other slots, and the verdicts of a chunk are handed over when its slot comes round again.
+  if ((size_t)n * row >= (size_t(4) << 20) && (is_pageable_host(q) || is_pageable_host(verdict)))
+  {
+    const int64_t cs = std::min<int64_t>(n, 1 << 18);
+    const size_t q_at = 0, v_at = ((size_t)cs * row + 255) & ~size_t(255);
+    rc = ensure_ctx(ctx, (size_t)cs * row, (size_t)cs);
+    for (int i = 0; i < kSlots && !rc && e == cudaSuccess; ++i)
+      e = b200df_group::StagePool::ensure_hstage(ctx, i, v_at + (size_t)cs);
+    const int64_t n_chunks = (n + cs - 1) / cs;
+    auto drain = [&](int64_t i) {  // chunk i is done: its verdicts leave the staging buffer
+      const int slot = (int)(i % kSlots);
+      const cudaError_t es = cudaStreamSynchronize(ctx->stream[slot]);
+      if (e == cudaSuccess)
+        e = es;
+      if (e == cudaSuccess)
+        std::memcpy(verdict + i * cs, static_cast<const char*>(ctx->hstage[slot]) + v_at,
+                    (size_t)std::min<int64_t>(cs, n - i * cs));
+    };
+    int64_t drained = 0;
+    for (int64_t i = 0; i < n_chunks && !rc && e == cudaSuccess; ++i)
+    {
+      const int slot = (int)(i % kSlots);
+      if (i >= kSlots)
+        drain(drained++);  // == i - kSlots: frees this slot's staging buffer
+      if (e != cudaSuccess)
+        break;
+      const int64_t s0 = i * cs, m = std::min<int64_t>(cs, n - s0);
+      char* hs = static_cast<char*>(ctx->hstage[slot]);
+      parallel_memcpy(hs + q_at, static_cast<const char*>(q) + (size_t)s0 * row, (size_t)m * row);
+      cudaStream_t st = ctx->stream[slot];
+      e = cudaMemcpyAsync(ctx->q[slot], hs + q_at, (size_t)m * row, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess)
+        break;
+      rc = run_verdict(group, wf, sf, elem, ctx->q[slot], q_dtype, m, flags, precision, ctx->v[slot], st,
+                       ctx->amb[slot] + 1, ctx->amb[slot]);
+      if (rc)
+        break;
+      e = cudaMemcpyAsync(hs + v_at, ctx->v[slot], (size_t)m, cudaMemcpyDeviceToHost, st);
+    }
+    while (!rc && e == cudaSuccess && drained < n_chunks)
+      drain(drained++);
+    for (int i = 0; i < kSlots; ++i)
+      if (ctx->stream[i])
+      {
+        const cudaError_t es = cudaStreamSynchronize(ctx->stream[i]);
+        if (e == cudaSuccess)
+          e = es;
+      }
+    group->stage->give_back(ctx);
+    if (!rc && e != cudaSuccess)
+    {
+      set_error("batched check failed while staging / running / reading back: %s", cudaGetErrorString(e));
+      rc = B200DF_ERR_CUDA;
+    }
+    return rc;
+  }
   rc = ensure_ctx(ctx, std::max<size_t>(1, (size_t)chunk * row), (size_t)chunk);
   int k = 0;
   for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k = (k + 1) % kSlots)

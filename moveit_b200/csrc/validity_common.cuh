@@ -11,7 +11,10 @@
 #pragma once
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 #include <map>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -649,6 +652,9 @@ struct b200df_group::StagePool
     static constexpr int kScratch = 12;
     void* scratch[kScratch] = {};
     size_t scratch_bytes[kScratch] = {};
+    // page-locked staging of large transfers from / to pageable caller memory, one per pipeline slot (grow-only)
+    void* hstage[kSlots] = {};
+    size_t hstage_bytes[kSlots] = {};
   };
   std::mutex mu;
   std::vector<Ctx*> free_list;
@@ -671,6 +677,9 @@ struct b200df_group::StagePool
       cudaFreeHost(c->pin);
     for (void* p : c->scratch)
       cudaFree(p);
+    for (void* p : c->hstage)
+      if (p)
+        cudaFreeHost(p);
     delete c;
   }
   Ctx* acquire()
@@ -711,6 +720,19 @@ struct b200df_group::StagePool
     }
     return cudaHostGetDevicePointer(dev, c->pin, 0);
   }
+  static cudaError_t ensure_hstage(Ctx* c, int i, size_t bytes)
+  {
+    if (bytes <= c->hstage_bytes[i])
+      return cudaSuccess;
+    if (c->hstage[i])
+      cudaFreeHost(c->hstage[i]);
+    c->hstage[i] = nullptr;
+    c->hstage_bytes[i] = 0;
+    const cudaError_t e = cudaHostAlloc(&c->hstage[i], bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess)
+      c->hstage_bytes[i] = bytes;
+    return e;
+  }
   static cudaError_t ensure_scratch(Ctx* c, int i, size_t bytes)
   {
     if (bytes <= c->scratch_bytes[i])
@@ -747,6 +769,48 @@ bool small_supported(const b200df_group* group);
 int small_launch(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int field_elem, const void* q,
                  int q_dtype, long n, int flags, uint8_t* verdict, cudaStream_t stream, const int* redo_idx = nullptr,
                  const int* redo_count = nullptr);
+
+// true when p is ordinary pageable host memory (a cudaMemcpyAsync on it goes through the driver's own small staging
+// buffer at a few GB/s and holds the calling thread)
+inline bool is_pageable_host(const void* p)
+{
+  const char* off = getenv("B200DF_STAGE_PAGEABLE");  // "0": leave pageable memory to the driver (for A/B measurements)
+  if (off && off[0] == '0')
+    return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy split over a few host threads: one core moves ~10 GB/s, PCIe Gen5 five times that
+inline void parallel_memcpy(void* dst, const void* src, size_t bytes)
+{
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t max_threads = std::min<size_t>(8, std::max<unsigned>(1, hw / 2));
+  const size_t n = std::min(max_threads, bytes / (size_t(2) << 20));  // at least 2 MB per thread
+  if (n <= 1)
+  {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t piece = ((bytes / n) + 4095) & ~size_t(4095);
+  std::vector<std::thread> workers;
+  for (size_t i = 1; i < n; ++i)
+  {
+    const size_t off = i * piece;
+    if (off >= bytes)
+      break;
+    const size_t len = std::min(piece, bytes - off);
+    workers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+  }
+  std::memcpy(dst, src, std::min(piece, bytes));
+  for (std::thread& w : workers)
+    w.join();
+}
 
 // B200DF_SMALL_BATCH=0 switches the mapped-pinned small-call staging of the host-buffer entry points off
 inline bool small_batch_enabled()

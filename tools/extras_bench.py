@@ -42,6 +42,13 @@ def run(with_oracle=True):
     t = best_of(lambda: e.group.check(q, e.world, flags=B.CHECK_ROBOT, precision=B.PRECISION_FAST), 5)
     out["config1_10k_robot_ms"] = 1e3 * t
 
+    # what a C++ caller with RobotState doubles in ordinary (pageable) vectors sees: 2 M states, fp64, FAST
+    qp = desc.sample_states(2_000_000, 4242, np.float64)
+    flp = B.CHECK_ROBOT | B.CHECK_INTRA
+    e.group.check(qp[:100000], e.world, flags=flp, precision=B.PRECISION_FAST)
+    tpg = best_of(lambda: e.group.check(qp, e.world, flags=flp, precision=B.PRECISION_FAST), 3)
+    out["check_2M_f64_pageable"] = {"ms": 1e3 * tpg, "states_per_s": len(qp) / tpg, "h2d_bytes": int(qp.nbytes)}
+
     # one state per call, the way OMPL's StateValidityChecker::isValid drives a CollisionEnv (latency, not throughput)
     fl1 = B.CHECK_ROBOT | B.CHECK_INTRA
     one32, one64 = q[:1].copy(), q[:1].astype(np.float64)
@@ -57,7 +64,11 @@ def run(with_oracle=True):
     traj = scenarios.chomp_trajectories(desc, 1000, 100).reshape(-1, desc.nvar)
     fl = B.CHECK_ROBOT | B.CHECK_INTRA
     e.group.gradients(traj[:1000], e.world, flags=fl)
-    t = best_of(lambda: e.group.gradients(traj, e.world, flags=fl), 3)
+    Sg = int(e.group.n_spheres)
+    # result arrays in ordinary (pageable) memory, allocated and touched once like a caller's reused buffers
+    pg = dict(dist=np.zeros((len(traj), Sg)), grad=np.zeros((len(traj), Sg, 3)),
+              type=np.zeros((len(traj), Sg), dtype=np.uint8), centers=np.zeros((len(traj), Sg, 3)))
+    t = best_of(lambda: e.group.gradients(traj, e.world, flags=fl, out=pg), 3)
     out["config5_chomp_gradients"] = {"states": len(traj), "ms": 1e3 * t, "states_per_s": len(traj) / t,
                                       "spheres": int(e.group.n_spheres),
                                       "d2h_bytes": len(traj) * int(e.group.n_spheres) * (8 + 24 + 1 + 24)}
