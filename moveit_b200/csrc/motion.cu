@@ -212,14 +212,28 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
     e = Pool::ensure_scratch(ctx, kAng, ang.size());
   if (e == cudaSuccess)
     e = cudaMemcpy(ctx->scratch[kAng], ang.data(), ang.size(), cudaMemcpyHostToDevice);
+  // end points in pageable memory are staged through page-locked buffers of the context by a few host threads (the
+  // driver's own staging of a pageable H2D moves ~10 GB/s and holds this thread)
+  const bool stage_in = end_bytes >= (size_t(2) << 20) && (is_pageable_host(qa) || is_pageable_host(qb));
+  for (int k = 0; k < n_slots && stage_in && e == cudaSuccess; ++k)
+    e = Pool::ensure_hstage(ctx, k, 2 * up(end_bytes));
   auto issue = [&](int64_t i) {  // stage + queue chunk i on slot i % 2
     const int k = (int)(i % 2);
     const int64_t s0 = i * chunk, mc = std::min<int64_t>(chunk, m - s0);
     void** buf = ctx->scratch + kPerSlot * k;
-    e = cudaMemcpyAsync(buf[kA], qa + s0 * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream[k]);
+    const size_t bytes = (size_t)mc * nv * sizeof(double);
+    const void *src_a = qa + s0 * nv, *src_b = qb + s0 * nv;
+    if (stage_in)
+    {
+      char* hs = static_cast<char*>(ctx->hstage[k]);  // free: chunk i - 2 was drained before this call
+      parallel_memcpy(hs, src_a, bytes);
+      parallel_memcpy(hs + up(end_bytes), src_b, bytes);
+      src_a = hs;
+      src_b = hs + up(end_bytes);
+    }
+    e = cudaMemcpyAsync(buf[kA], src_a, bytes, cudaMemcpyHostToDevice, ctx->stream[k]);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(buf[kB], qb + s0 * nv, (size_t)mc * nv * sizeof(double), cudaMemcpyHostToDevice,
-                          ctx->stream[k]);
+      e = cudaMemcpyAsync(buf[kB], src_b, bytes, cudaMemcpyHostToDevice, ctx->stream[k]);
     if (e == cudaSuccess)
       run_chunk(k, static_cast<const double*>(buf[kA]), static_cast<const double*>(buf[kB]),
                 static_cast<const uint8_t*>(ctx->scratch[kAng]), mc, static_cast<int32_t*>(buf[kOut]));
