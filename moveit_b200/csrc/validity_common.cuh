@@ -791,7 +791,7 @@ inline void parallel_memcpy(void* dst, const void* src, size_t bytes)
 {
   const unsigned hw = std::thread::hardware_concurrency();
   const size_t max_threads = std::min<size_t>(8, std::max<unsigned>(1, hw / 2));
-  const size_t n = std::min(max_threads, bytes / (size_t(2) << 20));  // at least 2 MB per thread
+  const size_t n = std::min(max_threads, bytes / (size_t(4) << 20));  // at least 4 MB per thread (a spawn costs ~20 us)
   if (n <= 1)
   {
     std::memcpy(dst, src, bytes);
