@@ -116,6 +116,9 @@ __device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, b
   return v;
 }
 
+// FLOATING: compiled only into the kernel variant for robots that have a floating joint (the hot kernel is sensitive
+// to code size: the extra branch alone cost 6 % on a Panda)
+template <bool FLOATING>
 __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float* slots, int B, float* cur,
                                           bool& out_of_range)
 {
@@ -169,7 +172,7 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
       cur[4 * i + 3] = fmaf(base[4 * i + 2], tz, fmaf(base[4 * i + 1], ty, fmaf(base[4 * i], tx, base[4 * i + 3])));
     }
   }
-  else if (l.joint_type == B200DF_JOINT_FLOATING)  // translation + normalised quaternion (floating_joint_model.cpp:224-229)
+  else if (FLOATING && l.joint_type == B200DF_JOINT_FLOATING)  // translation + normalised quaternion (floating_joint_model.cpp:224-229)
   {
     float j[12];
     j[3] = jointf(l, q, 0, out_of_range);
@@ -323,7 +326,7 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
   maybe |= any;
 }
 
-template <typename QT, typename FT, int B, bool PAIR_SMEM>
+template <typename QT, typename FT, int B, bool PAIR_SMEM, bool FLOATING>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
                                                           FastLookup sf, const float2* __restrict__ pair_T_global,
                                                           const QT* __restrict__ q, long n, int flags,
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   for (int i = 0; i < T.n_links; ++i)
   {
     const FLink& l = T.links[i];
-    fk_step_f(l, my_q, my_slots, B, cur, oor);
+    fk_step_f<FLOATING>(l, my_q, my_slots, B, cur, oor);
     const int gs = l.gslot;
     if (gs < 0)
       continue;
@@ -520,6 +523,7 @@ struct b200df_group::FastPath
   FastTables tables;
   float2* pair_T = nullptr;  // device
   bool ok = false;
+  bool has_floating = false;  // picks the kernel variant that knows the quaternion joint
 };
 
 namespace b200df
@@ -619,6 +623,7 @@ int fast_create(b200df_group* g)
     }
     else if (l.joint_type == B200DF_JOINT_FLOATING)
     {
+      fp->has_floating = true;
       // The seven variables reach the kernel rounded to fp32 (relative u each).  Normalised quaternion: input
       // rounding moves it by <= 2u, the fp32 normalisation (squared norm, sqrt, reciprocal, product) by <= 5u more.
       // Every entry of R(q) is quadratic in q with gradient norm <= 4 on the unit sphere, plus ~6u of rounding while
@@ -784,20 +789,19 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
   const int n_pair_smem = (pairs && g->dev.n_pair_consts <= kPairSmemMax) ? (int)g->dev.n_pair_consts : 0;
   bytes += (size_t)n_pair_smem * sizeof(float2);
   const unsigned grid = (unsigned)((n + B - 1) / B);
+  auto go = [&](auto kernel) -> cudaError_t {
+    const cudaError_t e = allow_dynamic_smem(kernel, bytes);
+    if (e != cudaSuccess)
+      return e;
+    kernel<<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf), make_fast_lookup(sf), g->fast->pair_T, q, n,
+                                       flags, verdict, amb_idx, amb_count, n_pair_smem);
+    return cudaSuccess;
+  };
+  const bool fl = g->fast->has_floating;
   if (n_pair_smem > 0)
-  {
-    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<QT, FT, B, true>, bytes));
-    validity_fast_kernel<QT, FT, B, true><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
-                                                                  make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
-                                                                  verdict, amb_idx, amb_count, n_pair_smem);
-  }
+    B200DF_CUDA(fl ? go(validity_fast_kernel<QT, FT, B, true, true>) : go(validity_fast_kernel<QT, FT, B, true, false>));
   else
-  {
-    B200DF_CUDA(allow_dynamic_smem(validity_fast_kernel<QT, FT, B, false>, bytes));
-    validity_fast_kernel<QT, FT, B, false><<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf),
-                                                                   make_fast_lookup(sf), g->fast->pair_T, q, n, flags,
-                                                                   verdict, amb_idx, amb_count, 0);
-  }
+    B200DF_CUDA(fl ? go(validity_fast_kernel<QT, FT, B, false, true>) : go(validity_fast_kernel<QT, FT, B, false, false>));
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
