@@ -116,9 +116,10 @@ __device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, b
   return v;
 }
 
-// FLOATING: compiled only into the kernel variant for robots that have a floating joint (the hot kernel is sensitive
-// to code size: the extra branch alone cost 6 % on a Panda)
-template <bool FLOATING>
+// FULL: floating joints, planar joints and revolute joints about an oblique axis are compiled only into the kernel
+// variant for robots that have one (the hot kernel is sensitive to code size: the quaternion branch alone cost 6 % on a
+// Panda, whose joints are all fixed, prismatic or revolute about a coordinate axis)
+template <bool FULL>
 __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float* slots, int B, float* cur,
                                           bool& out_of_range)
 {
@@ -172,7 +173,7 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
       cur[4 * i + 3] = fmaf(base[4 * i + 2], tz, fmaf(base[4 * i + 1], ty, fmaf(base[4 * i], tx, base[4 * i + 3])));
     }
   }
-  else if (FLOATING && l.joint_type == B200DF_JOINT_FLOATING)  // translation + normalised quaternion (floating_joint_model.cpp:224-229)
+  else if (FULL && l.joint_type == B200DF_JOINT_FLOATING)  // translation + normalised quaternion (floating_joint_model.cpp:224-229)
   {
     float j[12];
     j[3] = jointf(l, q, 0, out_of_range);
@@ -204,7 +205,7 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
   }
   else  // revolute, or planar = translation (x, y) followed by a rotation about z
   {
-    const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
+    const bool planar = FULL && l.joint_type == B200DF_JOINT_PLANAR;
     float px = 0.f, py = 0.f;
     if (planar)
     {
@@ -215,7 +216,7 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
     float s, c;
     sincosf(v, &s, &c);
     const int kind = planar ? 3 : l.jkind;
-    if (kind == 0)
+    if (FULL && kind == 0)
     {
       const float tt = 1.f - c;
       float j[12];
@@ -326,7 +327,7 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
   maybe |= any;
 }
 
-template <typename QT, typename FT, int B, bool PAIR_SMEM, bool FLOATING>
+template <typename QT, typename FT, int B, bool PAIR_SMEM, bool FULL>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
                                                           FastLookup sf, const float2* __restrict__ pair_T_global,
                                                           const QT* __restrict__ q, long n, int flags,
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   for (int i = 0; i < T.n_links; ++i)
   {
     const FLink& l = T.links[i];
-    fk_step_f<FLOATING>(l, my_q, my_slots, B, cur, oor);
+    fk_step_f<FULL>(l, my_q, my_slots, B, cur, oor);
     const int gs = l.gslot;
     if (gs < 0)
       continue;
@@ -523,7 +524,7 @@ struct b200df_group::FastPath
   FastTables tables;
   float2* pair_T = nullptr;  // device
   bool ok = false;
-  bool has_floating = false;  // picks the kernel variant that knows the quaternion joint
+  bool needs_full = false;  // a floating / planar / oblique-axis revolute joint: the kernel variant that knows them
 };
 
 namespace b200df
@@ -606,6 +607,8 @@ int fast_create(b200df_group* g)
     if (l.joint_type == B200DF_JOINT_REVOLUTE || l.joint_type == B200DF_JOINT_PLANAR)
     {
       const bool planar = l.joint_type == B200DF_JOINT_PLANAR;
+      if (planar || l.jkind == 0)
+        fp->needs_full = true;
       f.vmax = (float)(planar ? kPlanarTravel : kAngleRange);  // planar: x, y and theta share the bound
       // the joint value reaches the fp32 FK rounded once (fp64 inputs, mimic joints evaluated in fp64 from the
       // rounded source value): angle error <= u*|v| (1 + |mimic factor|)
@@ -623,7 +626,7 @@ int fast_create(b200df_group* g)
     }
     else if (l.joint_type == B200DF_JOINT_FLOATING)
     {
-      fp->has_floating = true;
+      fp->needs_full = true;
       // The seven variables reach the kernel rounded to fp32 (relative u each).  Normalised quaternion: input
       // rounding moves it by <= 2u, the fp32 normalisation (squared norm, sqrt, reciprocal, product) by <= 5u more.
       // Every entry of R(q) is quadratic in q with gradient norm <= 4 on the unit sphere, plus ~6u of rounding while
@@ -797,7 +800,7 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
                                        flags, verdict, amb_idx, amb_count, n_pair_smem);
     return cudaSuccess;
   };
-  const bool fl = g->fast->has_floating;
+  const bool fl = g->fast->needs_full;
   if (n_pair_smem > 0)
     B200DF_CUDA(fl ? go(validity_fast_kernel<QT, FT, B, true, true>) : go(validity_fast_kernel<QT, FT, B, true, false>));
   else
