@@ -15,6 +15,7 @@
 // This translation unit is compiled WITH fused multiply-add (no --fmad=false): nothing here has to round like the
 // reference, it only has to stay inside the margins.
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -327,7 +328,8 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
   maybe |= any;
 }
 
-template <typename QT, typename FT, int B, bool PAIR_SMEM, bool FULL>
+// SELF: the self-field lookups are compiled in only when the call asks for them (code size again)
+template <typename QT, typename FT, int B, bool PAIR_SMEM, bool FULL, bool SELF>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
                                                           FastLookup sf, const float2* __restrict__ pair_T_global,
                                                           const QT* __restrict__ q, long n, int flags,
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   float* my_stc = stc + tid;
   float* my_stb = stb + tid;
   const bool do_robot = (flags & B200DF_CHECK_ROBOT) != 0;
-  const bool do_self = (flags & B200DF_CHECK_SELF) != 0;
+  constexpr bool do_self = SELF;
 
   bool hit = !active;  // certain collision (padding lanes: no work)
   bool amb = false;    // some test fell inside its margin
@@ -801,10 +803,17 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
     return cudaSuccess;
   };
   const bool fl = g->fast->needs_full;
+  const bool self = (flags & B200DF_CHECK_SELF) != 0;
+  auto pick = [&](auto pair_smem, auto full) -> cudaError_t {
+    constexpr bool P = decltype(pair_smem)::value, F = decltype(full)::value;
+    return self ? go(validity_fast_kernel<QT, FT, B, P, F, true>) : go(validity_fast_kernel<QT, FT, B, P, F, false>);
+  };
+  using T_ = std::true_type;
+  using F_ = std::false_type;
   if (n_pair_smem > 0)
-    B200DF_CUDA(fl ? go(validity_fast_kernel<QT, FT, B, true, true>) : go(validity_fast_kernel<QT, FT, B, true, false>));
+    B200DF_CUDA(fl ? pick(T_(), T_()) : pick(T_(), F_()));
   else
-    B200DF_CUDA(fl ? go(validity_fast_kernel<QT, FT, B, false, true>) : go(validity_fast_kernel<QT, FT, B, false, false>));
+    B200DF_CUDA(fl ? pick(F_(), T_()) : pick(F_(), F_()));
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
