@@ -32,10 +32,10 @@ sys.path.insert(0, ROOT)
 STATES_PER_GPU = 10_000_000
 ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out
 # dram__bytes_read.sum + dram__bytes_write.sum per state from the committed ncu --set full captures (2 000 000 states):
-# profiles/r01_validity_fast_full.txt (72.80 MB + 1.00 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
-NCU_DRAM_BYTES_PER_STATE = {"fast": (72.800768e6 + 0.996352e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
+# profiles/r01_validity_fast_full.txt (72.79 MB + 1.01 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
+NCU_DRAM_BYTES_PER_STATE = {"fast": (72.787200e6 + 1.014272e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
 # smsp__inst_executed.sum of the same captures / 2 000 000 states: warp instructions the kernel issues per state
-NCU_WARP_INSTR_PER_STATE = {"fast": 1029132483 / 2.0e6}
+NCU_WARP_INSTR_PER_STATE = {"fast": 1017828236 / 2.0e6}
 
 
 def issue_roofline(precision, states_per_s_per_gpu, clocks):
@@ -444,7 +444,8 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_STATE.get(args.precision, NCU_DRAM_BYTES_PER_STATE["exact"]) * n,
                          "peak_source": peak_src,
                          "issue": issue_roofline(args.precision, n * args.steps / (ms_total * 1e-3), clocks),
-                         "kernel": ("validity_fast_kernel<unsigned char, 128> (+ validity_small_kernel on the undecided "
+                         "kernel": ("validity_fast_kernel<float, unsigned char, 128, pair thresholds in smem, simple joints, no self field> "
+                                    "(+ validity_small_kernel on the undecided "
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
                          "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
                                  "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
