@@ -42,6 +42,30 @@ def run(with_oracle=True):
     t = best_of(lambda: e.group.check(q, e.world, flags=B.CHECK_ROBOT, precision=B.PRECISION_FAST), 5)
     out["config1_10k_robot_ms"] = 1e3 * t
 
+    # checkRobotCollision alone (no intra-group pairs) on device-resident states: the kernel variant without the pair code
+    try:
+        import torch
+        nq = 4_000_000
+        qd = torch.from_numpy(desc.sample_states(nq, 777, np.float32)).cuda()
+        vd = torch.empty(nq, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        res = {}
+        for name, fl_ in (("robot_only", B.CHECK_ROBOT), ("robot_and_intra", B.CHECK_ROBOT | B.CHECK_INTRA)):
+            run = lambda: e.group.check_device(qd.data_ptr(), B.Q_F32, nq, vd.data_ptr(), e.world, flags=fl_,
+                                               precision=B.PRECISION_FAST, stream=st)
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name + "_states_per_s"] = nq * 5 / (e0.elapsed_time(e1) * 1e-3)
+        out["fast_device_resident_4M"] = res
+    except ImportError:
+        pass
+
     # what a C++ caller with RobotState doubles in ordinary (pageable) vectors sees: 2 M states, fp64, FAST
     qp = desc.sample_states(2_000_000, 4242, np.float64)
     flp = B.CHECK_ROBOT | B.CHECK_INTRA
