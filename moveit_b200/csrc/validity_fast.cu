@@ -20,6 +20,7 @@
 #include <cstring>
 #include <memory>
 
+#include "sincos_small.cuh"
 #include "validity_common.cuh"
 
 using namespace b200df;
@@ -215,7 +216,10 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
     }
     const float v = jointf(l, q, planar ? 2 : 0, out_of_range);
     float s, c;
-    sincosf(v, &s, &c);
+    if (FULL)
+      sincosf(v, &s, &c);  // planar theta is analysed up to 16 rad
+    else
+      sincos_small(v, &s, &c);  // |v| <= kAngleRange or the state is flagged; no large-argument path to carry around
     const int kind = planar ? 3 : l.jkind;
     if (FULL && kind == 0)
     {
@@ -556,7 +560,9 @@ int fast_create(b200df_group* g)
   // of multiplying; every product of fp32 3x3 blocks adds at most 9u in Frobenius norm: 3 terms per entry,
   // |row| |col| <= 1 by Cauchy-Schwarz)
   const double u = kU;
-  const double sc = 2.0 * 2.0 * u;  // sincosf: <= 2 ulp, ulp(1) = 2^-23 = 2u
+  // sincosf: <= 2 ulp, ulp(1) = 2^-23 = 2u; sincos_small (the SIMPLE variant, |x| <= 8): 0.78 ulp over every fp32 value in
+  // range (tools/sincos_check.cu)
+  const double sc = 2.0 * 2.0 * u;
   std::vector<LinkErr> E(L);
   for (int i = 0; i < L; ++i)
   {
