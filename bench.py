@@ -315,10 +315,9 @@ def main():
     torch.cuda.set_device(local_rank)
     B.check(B.load().b200df_set_device(local_rank))
     if world > 1:
-        # stdout carries the one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) goes to stdout
-        # too, so it is turned down unless somebody asked for more detail on purpose
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the one JSON line: NCCL's own messages (the GPU boxes set NCCL_DEBUG=VERSION, whose banner
+        # goes to stdout) are sent to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
