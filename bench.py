@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(states_per_gpu):
@@ -295,8 +295,32 @@ def edt_timings(engine, scenarios, B):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Native libraries print there too (the GPU boxes set NCCL_DEBUG=VERSION,
+    whose banner goes to stdout), so file descriptor 1 is pointed at stderr for the rest of the process and the JSON
+    line is written to the original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -315,9 +339,6 @@ def main():
     torch.cuda.set_device(local_rank)
     B.check(B.load().b200df_set_device(local_rank))
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own messages (the GPU boxes set NCCL_DEBUG=VERSION, whose banner
-        # goes to stdout) are sent to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -479,7 +500,7 @@ def main():
                                               "%.1f s), CPU oracle, one thread per host core; omits MoveIt's per-call "
                                               "GSR copies / string-map ACM look-ups, i.e. faster than stock MoveIt"
                                               % (ns, ts)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
