@@ -336,7 +336,7 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
 // PAIRS: likewise the whole intra-group pair machinery (a checkRobotCollision batch does not need it)
 template <typename QT, typename FT, int B, bool PAIRS, bool PAIR_SMEM, bool FULL, bool SELF>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
-                                                          FastLookup sf, const float2* __restrict__ pair_T_global,
+                                                          FastLookup sf, const int2* __restrict__ pair_T_global,
                                                           const QT* __restrict__ q, long n, int flags,
                                                           uint8_t* __restrict__ verdict, int* __restrict__ amb_idx,
                                                           int* __restrict__ amb_count, int n_pair_smem)
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   }
   // the pair thresholds are read once per sphere-pair test by every warp: keep them in shared memory when they fit
   // (L1 is nearly all shared-memory carve-out here and what is left is thrashed by the voxel gathers)
-  float2* pair_T_shared = reinterpret_cast<float2*>(qs + B * T.n_vars);
+  int2* pair_T_shared = reinterpret_cast<int2*>(qs + B * T.n_vars);
   if (PAIR_SMEM)
   {
     for (int e = tid; e < n_pair_smem; e += B)
@@ -462,17 +462,21 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
           }
         }
         unsigned mm = warp_mask;
-        const float2* t_row = (PAIR_SMEM ? pair_T_shared : pair_T_global) + gl.pair_const_begin +
+        const int2* t_row = (PAIR_SMEM ? pair_T_shared : pair_T_global) + gl.pair_const_begin +
                               (long)(s0 - gl.sphere_begin) * gl.pair_const_stride;
         while (mm)
         {
           const int b = __ffs(mm) - 1;
           mm &= mm - 1;
           const FPartner& pr = T.partners[p0 + b];
-          const float2* t = t_row + pr.const_offset;
+          const int2* t = t_row + pr.const_offset;
           const float* pc = my_stc + pr.store_sphere * 3 * B;
           const int stride = gl.pair_const_stride;
-          bool h_sure = false, h_maybe = false;
+          // A squared distance is a non-negative float, so its bit pattern orders like the value.  The thresholds are
+          // stored as the negated patterns {-bits(lo2), -(bits(hi2) + 1)}: "e2 < lo2" and "e2 <= hi2" become "the sum
+          // is negative", and a running minimum of the sums (one VIADDMNMX each) replaces compare + select + or.
+          // NaN and +inf have patterns above every finite threshold and never count, like the float comparison.
+          int a_sure = 0x7fffffff, a_maybe = 0x7fffffff;
           for (int m = 0; m < pr.count; ++m)
           {
             const float px = pc[(m * 3 + 0) * B], py = pc[(m * 3 + 1) * B], pz = pc[(m * 3 + 2) * B];
@@ -482,13 +486,14 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
               if (k < cnt)
               {
                 const float ex = cx[k] - px, ey = cy[k] - py, ez = cz[k] - pz;
-                const float e2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                const float2 th = t[k * stride + m];  // {certainly touching below, certainly apart above}
-                h_sure |= e2 < th.x;
-                h_maybe |= e2 <= th.y;
+                const int e2 = __float_as_int(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                const int2 th = t[k * stride + m];  // {certainly touching below, certainly apart above}, encoded
+                a_sure = __viaddmin_s32(e2, th.x, a_sure);
+                a_maybe = __viaddmin_s32(e2, th.y, a_maybe);
               }
             }
           }
+          const bool h_sure = a_sure < 0, h_maybe = a_maybe < 0;
           const bool p_sure = (sure_mask >> b) & 1u, p_maybe = (maybe_mask >> b) & 1u;
           hit |= h_sure && p_sure;
           amb |= h_maybe && p_maybe;
@@ -530,7 +535,7 @@ struct LinkErr
 struct b200df_group::FastPath
 {
   FastTables tables;
-  float2* pair_T = nullptr;  // device
+  int2* pair_T = nullptr;  // device: {-bits(lo2), -(bits(hi2) + 1)} per sphere pair, see the pair loop
   bool ok = false;
   bool needs_full = false;  // a floating / planar / oblique-axis revolute joint: the kernel variant that knows them
 };
@@ -704,7 +709,12 @@ int fast_create(b200df_group* g)
     const double d = R + Esum;
     return std::nextafter((float)(d * d * (1.0 + 16.0 * u)), INFINITY);
   };
-  std::vector<float2> pair_T((size_t)std::max<long>(1, g->dev.n_pair_consts));
+  std::vector<int2> pair_T((size_t)std::max<long>(1, g->dev.n_pair_consts), make_int2(0, 0));
+  auto bits = [](float v) {
+    int i;
+    std::memcpy(&i, &v, sizeof(i));
+    return i;
+  };
   for (int gs = 0; gs < G; ++gs)
   {
     const DevGroupLink& gl = g->glinks[gs];
@@ -735,13 +745,13 @@ int fast_create(b200df_group* g)
           const double Es = sph_eps[s] + sph_eps[ps];
           const size_t at = (size_t)gl.pair_const_begin + (size_t)(s - gl.sphere_begin) * gl.pair_const_stride +
                             pr.const_offset + mm;
-          pair_T[at] = make_float2(lo2(R, Es), hi2(R, Es));
+          pair_T[at] = make_int2(-bits(lo2(R, Es)), -(bits(hi2(R, Es)) + 1));
         }
     }
   }
   DeviceGuard dg(g->device);
-  B200DF_CUDA(cudaMalloc(&fp->pair_T, pair_T.size() * sizeof(float2)));
-  B200DF_CUDA(cudaMemcpy(fp->pair_T, pair_T.data(), pair_T.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  B200DF_CUDA(cudaMalloc(&fp->pair_T, pair_T.size() * sizeof(int2)));
+  B200DF_CUDA(cudaMemcpy(fp->pair_T, pair_T.data(), pair_T.size() * sizeof(int2), cudaMemcpyHostToDevice));
   fp->ok = true;
   g->fast = fp.release();
   return B200DF_OK;
@@ -800,7 +810,7 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
 {
   const bool pairs = (flags & B200DF_CHECK_INTRA) && g->fast->tables.n_partners > 0;
   const int n_pair_smem = (pairs && g->dev.n_pair_consts <= kPairSmemMax) ? (int)g->dev.n_pair_consts : 0;
-  bytes += (size_t)n_pair_smem * sizeof(float2);
+  bytes += (size_t)n_pair_smem * sizeof(int2);
   const unsigned grid = (unsigned)((n + B - 1) / B);
   auto go = [&](auto kernel) -> cudaError_t {
     const cudaError_t e = allow_dynamic_smem(kernel, bytes);
