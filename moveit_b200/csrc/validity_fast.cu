@@ -293,43 +293,47 @@ __device__ __forceinline__ int axis_cell(float p, float oo, float k, float delta
   return c;
 }
 
+// Flags are carried as signed margins and combined with integer min / max (one instruction each) instead of bools
+// (compare + select + and/or chains): a margin < 0 means "collides".
+// margin of one cell: d2 - thr inside the inset box, a large positive number outside it (never a collision, Q4)
 template <typename FT>
-__device__ __forceinline__ bool cell_status(const FastLookup& f, int ix, int iy, int iz, int thr)
+__device__ __forceinline__ int cell_margin(const FastLookup& f, int ix, int iy, int iz, int thr)
 {
   const bool in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
   const unsigned idx = in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
-  return in & ((int)static_cast<const FT*>(f.d2)[idx] < thr);
+  const int v = (int)static_cast<const FT*>(f.d2)[idx] - thr;
+  return in ? v : 0x3fffffff;
 }
 
-// Sphere vs field.  sure: the exact evaluation certainly reports this sphere colliding; maybe: it could.
+// Sphere vs field.  sure (< 0): the exact evaluation certainly reports this sphere colliding; maybe (< 0): it could.
 template <typename FT>
 __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float y, float z, float eps, int thr,
-                                             bool& sure, bool& maybe)
+                                             int& sure, int& maybe)
 {
   const float delta = fmaf(eps, f.oo, f.gerr);
   int ax, ay, az;
   const int ix = axis_cell(x, f.oo, f.k[0], delta, ax);
   const int iy = axis_cell(y, f.oo, f.k[1], delta, ay);
   const int iz = axis_cell(z, f.oo, f.k[2], delta, az);
-  const bool s0 = cell_status<FT>(f, ix, iy, iz, thr);
+  const int s0 = cell_margin<FT>(f, ix, iy, iz, thr);
   if ((ax | ay | az) == 0)  // the common case: the centre is clear of every voxel face
   {
-    sure |= s0;
-    maybe |= s0;
+    sure = min(sure, s0);
+    maybe = min(maybe, s0);
     return;
   }
   // near a face: the exact cell is one of up to 8 candidates; the verdict is settled only if they all agree
-  bool all = s0, any = s0;
+  int worst = s0, best = s0;  // all collide <=> the largest margin is negative; any collides <=> the smallest is
   for (int m = 1; m < 8; ++m)
   {
     if (((m & 1) && !ax) || ((m & 2) && !ay) || ((m & 4) && !az))
       continue;
-    const bool sm = cell_status<FT>(f, ix + ((m & 1) ? ax : 0), iy + ((m & 2) ? ay : 0), iz + ((m & 4) ? az : 0), thr);
-    all &= sm;
-    any |= sm;
+    const int sm = cell_margin<FT>(f, ix + ((m & 1) ? ax : 0), iy + ((m & 2) ? ay : 0), iz + ((m & 4) ? az : 0), thr);
+    worst = max(worst, sm);
+    best = min(best, sm);
   }
-  sure |= all;
-  maybe |= any;
+  sure = min(sure, worst);
+  maybe = min(maybe, best);
 }
 
 // SELF: the self-field lookups are compiled in only when the call asks for them (code size again)
@@ -375,8 +379,10 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   const bool do_robot = (flags & B200DF_CHECK_ROBOT) != 0;
   constexpr bool do_self = SELF;
 
-  bool hit = !active;  // certain collision (padding lanes: no work)
-  bool amb = false;    // some test fell inside its margin
+  // running minima of signed margins: negative = a certain collision (padding lanes start there: no work) / some test
+  // fell inside its error margin
+  int hit_m = active ? 0x3fffffff : -1;
+  int amb_m = 0x3fffffff;
   bool oor = false;    // a joint value outside the analysed range: nothing computed here can be trusted
   float cur[12];
   for (int i = 0; i < T.n_links; ++i)
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
           const float dy = my_stb[(pr.store_link * 3 + 1) * B] - by;
           const float dz = my_stb[(pr.store_link * 3 + 2) * B] - bz;
           const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          const bool open = !hit && d2 < pr.tight_hi;
+          const bool open = hit_m >= 0 && d2 < pr.tight_hi;
           sure_mask |= ((open && d2 < pr.rs_lo) ? 1u : 0u) << b;
           maybe_mask |= ((open && d2 < pr.rs_hi) ? 1u : 0u) << b;
         }
@@ -451,13 +457,11 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
             if (k < cnt)
             {
               const FSphere& sp = T.sph[s0 + k];
-              bool sure = false, maybe = false;
+              // (maybe && !sure) is what matters; a certain hit overrides it at the end
               if (do_robot)
-                sphere_field<FT>(wf, cx[k], cy[k], cz[k], sp.eps, sp.thr, sure, maybe);
+                sphere_field<FT>(wf, cx[k], cy[k], cz[k], sp.eps, sp.thr, hit_m, amb_m);
               if (self_here)
-                sphere_field<FT>(sf, cx[k], cy[k], cz[k], sp.eps, sp.thr, sure, maybe);
-              hit |= sure;
-              amb |= maybe;  // (maybe && !sure) is what matters; a certain hit overrides it at the end
+                sphere_field<FT>(sf, cx[k], cy[k], cz[k], sp.eps, sp.thr, hit_m, amb_m);
             }
           }
         }
@@ -493,19 +497,18 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
               }
             }
           }
-          const bool h_sure = a_sure < 0, h_maybe = a_maybe < 0;
-          const bool p_sure = (sure_mask >> b) & 1u, p_maybe = (maybe_mask >> b) & 1u;
-          hit |= h_sure && p_sure;
-          amb |= h_maybe && p_maybe;
+          // the sphere-pair result counts for the lanes whose own bounding-sphere prune passed
+          hit_m = min(hit_m, ((sure_mask >> b) & 1u) ? a_sure : 0x3fffffff);
+          amb_m = min(amb_m, ((maybe_mask >> b) & 1u) ? a_maybe : 0x3fffffff);
         }
       }
     }
-    if (__all_sync(0xffffffffu, hit))
+    if (__all_sync(0xffffffffu, hit_m < 0))
       break;
   }
   if (active)
   {
-    const int v = oor ? 2 : (hit ? 1 : (amb ? 2 : 0));
+    const int v = oor ? 2 : (hit_m < 0 ? 1 : (amb_m < 0 ? 2 : 0));
     verdict[state] = (uint8_t)v;
     if (v == 2)
       amb_idx[atomicAdd(amb_count, 1)] = (int)state;
