@@ -61,9 +61,10 @@ struct FSphere
 struct FPartner
 {
   int store_link, store_sphere, count, const_offset;
-  float rs_lo, rs_hi;  // doBoundingSpheresIntersect threshold (on the squared distance, Q2) minus / plus its margin
-  float tight_hi;      // exact-cull threshold plus margin
-  float pad;
+  // negated bit patterns of the squared-distance thresholds below which the prune certainly / possibly passes:
+  // min(exact-cull threshold + margin, doBoundingSpheresIntersect threshold (Q2) - / + its margin)
+  int n_sure, n_maybe;
+  int pad[2];
 };
 
 struct FastTables  // passed by value: lives in the constant bank, read with warp-uniform indices
@@ -415,18 +416,21 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
       if (np > 0)
       {
         const int pc = min(32, gl.partner_end - p0);
+        // highest partner first, so that shifting the masks left by one per partner leaves partner b in bit b;
+        // "d2 < threshold" is the sign of bits(d2) + (negated threshold bits), see the pair loop
 #pragma unroll 2
-        for (int b = 0; b < pc; ++b)
+        for (int b = pc - 1; b >= 0; --b)
         {
           const FPartner& pr = T.partners[p0 + b];
           const float dx = my_stb[(pr.store_link * 3 + 0) * B] - bx;
           const float dy = my_stb[(pr.store_link * 3 + 1) * B] - by;
           const float dz = my_stb[(pr.store_link * 3 + 2) * B] - bz;
-          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          const bool open = hit_m >= 0 && d2 < pr.tight_hi;
-          sure_mask |= ((open && d2 < pr.rs_lo) ? 1u : 0u) << b;
-          maybe_mask |= ((open && d2 < pr.rs_hi) ? 1u : 0u) << b;
+          const int d2 = __float_as_int(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+          sure_mask = (sure_mask << 1) + ((unsigned)(d2 + pr.n_sure) >> 31);
+          maybe_mask = (maybe_mask << 1) + ((unsigned)(d2 + pr.n_maybe) >> 31);
         }
+        if (hit_m < 0)  // a state that already collides opens no more pair work
+          sure_mask = maybe_mask = 0u;
       }
       const unsigned warp_mask = __reduce_or_sync(0xffffffffu, maybe_mask);
       for (int s0 = gl.sphere_begin; s0 < gl.sphere_end; s0 += kBatch)
@@ -737,9 +741,14 @@ int fast_create(b200df_group* g)
       const double Eb = bs_eps[gs] + bs_eps[lo];
       // the reference compares the SQUARED distance with radius_sum (Q2): distance threshold sqrt(radius_sum)
       const double rs = std::sqrt(std::max(0.0, pr.radius_sum));
-      f.rs_lo = lo2(rs, Eb);
-      f.rs_hi = hi2(rs, Eb);
-      f.tight_hi = hi2(std::sqrt(pr.tight2), Eb);
+      const float tight_hi = hi2(std::sqrt(pr.tight2), Eb);
+      auto fbits = [](float v) {
+        int i;
+        std::memcpy(&i, &v, sizeof(i));
+        return i;
+      };
+      f.n_sure = -fbits(std::min(tight_hi, lo2(rs, Eb)));
+      f.n_maybe = -fbits(std::min(tight_hi, hi2(rs, Eb)));
       for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
         for (int mm = 0; mm < pr.count; ++mm)
         {
