@@ -33,9 +33,9 @@ STATES_PER_GPU = 10_000_000
 ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out
 # dram__bytes_read.sum + dram__bytes_write.sum per state from the committed ncu --set full captures (2 000 000 states):
 # profiles/r01_validity_fast_full.txt (72.79 MB + 1.01 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
-NCU_DRAM_BYTES_PER_STATE = {"fast": (72.790016e6 + 1.127424e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
+NCU_DRAM_BYTES_PER_STATE = {"fast": (72.788992e6 + 1.494784e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
 # smsp__inst_executed.sum of the same captures / 2 000 000 states: warp instructions the kernel issues per state
-NCU_WARP_INSTR_PER_STATE = {"fast": 891241813 / 2.0e6}
+NCU_WARP_INSTR_PER_STATE = {"fast": 844093209 / 2.0e6}
 
 
 def issue_roofline(precision, states_per_s_per_gpu, clocks):
@@ -469,7 +469,7 @@ def main():
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
                          "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
                                  "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
-                                 "The fused FK+lookup+pair kernel executes ~14.3 k warp instructions per 32 states and "
+                                 "The fused FK+lookup+pair kernel executes ~13.5 k warp instructions per 32 states and "
                                  "is issue/latency bound by construction (DESIGN.md section 4); the HBM-bound "
                                  "kernel of this path is the EDT, see edt_ms.field_b_roofline"},
             "colliding_fraction": colliding / n,
