@@ -238,13 +238,33 @@ int b200df_field_pack_occupancy(b200df_field* field, uint8_t* out, int64_t cap, 
 int b200df_field_unpack_occupancy(b200df_field* field, const uint8_t* bytes, int64_t n_bytes);
 /* device view for replication across GPUs (NCCL broadcast / peer copy of the built arrays) */
 int b200df_field_device_arrays(b200df_field* field, void** d2, void** neg_d2, int64_t* n_bytes, int32_t* elem_size);
-int b200df_field_mark_built(b200df_field* field); /* after the arrays were overwritten by a broadcast */
+/* after the arrays behind b200df_field_device_arrays were overwritten in place (e.g. by a broadcast): the distances
+ * are served as they are.  The occupancy is NOT touched by this route: replicate it as well
+ * (b200df_field_import_device / b200df_field_copy_from do) before editing the replica, or the next edit rebuilds
+ * from the replica's own (stale) occupancy. */
+int b200df_field_mark_built(b200df_field* field);
 int b200df_field_copy_from(b200df_field* dst, b200df_field* src); /* same geometry; peer copy when on two GPUs */
 /* copies of the built arrays to / from caller-owned device buffers (occupancy: n voxels bytes; d2 / neg_d2:
  * n_bytes each), e.g. the tensor an NCCL broadcast runs on.  NULL pointers are skipped. */
 int b200df_field_export_device(b200df_field* field, void* occ_dev, void* d2_dev, void* neg_d2_dev, void* stream);
 int b200df_field_import_device(b200df_field* field, const void* occ_dev, const void* d2_dev, const void* neg_d2_dev,
                                void* stream);
+/* Reference-field mode.  The engine's own distances are the EXACT clamped squared EDT; the reference's
+ * PropagationDistanceField::propagatePositive (propagation_distance_field.cpp:389-444) is a wavefront that
+ * over-estimates d^2 on a few voxels in 10^4 and depends on the insertion order.  A caller that holds
+ * the reference's own distance_square_ / negative_distance_square_ arrays (int per voxel, z fastest) uploads them
+ * here; occupancy becomes (d2 == 0) and every query, verdict and gradient is then served from exactly these values
+ * until the next occupancy edit (add / remove / reset / unpack), which rebuilds the exact EDT.  Values outside
+ * [0, max_distance_sq_] are refused (B200DF_ERR_INVALID, field unchanged).  neg_d2 is required for signed fields. */
+int b200df_field_upload_d2(b200df_field* field, const int32_t* d2, const int32_t* neg_d2);
+int b200df_field_values_uploaded(const b200df_field* field, int32_t* uploaded); /* 1 while uploaded values are served */
+/* PropagationDistanceField::getNearestCell (propagation_distance_field.h:411-431) for n cells ijk[n][3]:
+ * dist[n] (negative inside obstacles of a signed field), pos[n][3], found[n].  The engine keeps no closest_point_
+ * per voxel; pos is the first voxel (x-major scan of offsets) of the other kind at exactly the cell's squared
+ * distance - one of the equidistant nearest cells, not necessarily the one the reference's wavefront recorded.
+ * found = 0 (pos = the cell itself) for obstacle cells of unsigned fields, clamped cells and out-of-range cells. */
+int b200df_field_nearest_cells(b200df_field* field, const int32_t* ijk, int64_t n, double* dist, int32_t* pos,
+                               uint8_t* found);
 
 /* ---- batched checks ----------------------------------------------------------------------------------------
  * N joint vectors -> N verdicts.  Replaces, per state, checkRobotCollision (:1500-1519), checkSelfCollision

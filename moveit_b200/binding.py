@@ -93,6 +93,9 @@ SYMBOLS = {
     "b200df_field_copy_from": (C.c_int, [_VP, _VP]),
     "b200df_field_export_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "b200df_field_import_device": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "b200df_field_upload_d2": (C.c_int, [_VP, c_i32p, c_i32p]),
+    "b200df_field_values_uploaded": (C.c_int, [_VP, c_i32p]),
+    "b200df_field_nearest_cells": (C.c_int, [_VP, c_i32p, C.c_int64, c_dp, c_i32p, c_u8p]),
     "b200df_check_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
     "b200df_check_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP]),
     "b200df_check_edges": (C.c_int, [_VP, _VP, _VP, c_dp, c_dp, C.c_int64, C.c_int32, c_u8p, C.c_int, C.c_int, c_i32p]),

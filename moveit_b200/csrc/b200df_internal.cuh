@@ -105,6 +105,7 @@ struct b200df_field
   double* sqrt_table = nullptr;
   std::vector<double> sqrt_table_host;
   bool dirty = true;
+  bool uploaded = false;       // d2 holds caller-supplied values (b200df_field_upload_d2), not the engine's exact EDT
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::mutex mu;

@@ -461,6 +461,105 @@ __global__ void __launch_bounds__(64, 9) edt_march_kernel(const uint32_t* __rest
   }
 }
 
+// b200df_field_upload_d2: int32 d2 (and negative d2) -> the field's element type; occupancy = (d2 == 0).
+// Out-of-range values raise *bad (the upload is then refused).
+template <typename T>
+__global__ void narrow_kernel(const int32_t* __restrict__ d2, const int32_t* __restrict__ neg, T* __restrict__ out,
+                              T* __restrict__ out_neg, uint8_t* __restrict__ occ, long n, int max_d2,
+                              int* __restrict__ bad)
+{
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int v = d2[i];
+  bool ok = v >= 0 && v <= max_d2;
+  out[i] = (T)v;
+  occ[i] = v == 0 ? 1 : 0;
+  if (neg)
+  {
+    const int w = neg[i];
+    ok = ok && w >= 0 && w <= max_d2;
+    out_neg[i] = (T)w;
+  }
+  if (!ok)
+    atomicExch(bad, 1);
+}
+
+// PropagationDistanceField::getNearestCell (propagation_distance_field.h:411-431) without a stored closest point:
+// the first voxel (x-major scan of the offsets) of the other kind at exactly the cell's squared distance.
+template <typename T>
+__global__ void nearest_cell_kernel(GridDev g, const T* __restrict__ d2, const T* __restrict__ neg,
+                                    const uint8_t* __restrict__ occ, const double* __restrict__ sqrt_table, int max_d2,
+                                    const int32_t* __restrict__ ijk, long n, double* __restrict__ dist,
+                                    int32_t* __restrict__ pos, uint8_t* __restrict__ found)
+{
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int x = ijk[3 * i], y = ijk[3 * i + 1], z = ijk[3 * i + 2];
+  pos[3 * i] = x;
+  pos[3 * i + 1] = y;
+  pos[3 * i + 2] = z;
+  dist[i] = 0.0;
+  found[i] = 0;
+  if (x < 0 || x >= g.n[0] || y < 0 || y >= g.n[1] || z < 0 || z >= g.n[2])
+    return;
+  const long idx = x * g.stride1 + y * g.stride2 + z;
+  int target = d2[idx];
+  uint8_t want = 1;  // looking for an obstacle voxel
+  double sign = 1.0;
+  if (target == 0)
+  {
+    target = neg ? (int)neg[idx] : 0;
+    want = 0;  // inside an obstacle: looking for a free voxel
+    sign = -1.0;
+    if (target == 0)
+      return;
+  }
+  dist[i] = sign * sqrt_table[target];
+  if (target >= max_d2)
+    return;  // clamped: the nearest cell is unknown (the reference returns an uninitialised closest point here)
+  int r = 0;
+  while (r * r < target)
+    ++r;
+  for (int dx = -r; dx <= r; ++dx)
+  {
+    const int xx = x + dx;
+    if (xx < 0 || xx >= g.n[0])
+      continue;
+    for (int dy = -r; dy <= r; ++dy)
+    {
+      const int yy = y + dy;
+      const int rest = target - dx * dx - dy * dy;
+      if (yy < 0 || yy >= g.n[1] || rest < 0)
+        continue;
+      int dz = (int)sqrtf((float)rest);
+      while (dz * dz > rest)
+        --dz;
+      while ((dz + 1) * (dz + 1) <= rest)
+        ++dz;
+      if (dz * dz != rest)
+        continue;
+      for (int s = -1; s <= 1; s += 2)
+      {
+        const int zz = z + s * dz;
+        if (zz < 0 || zz >= g.n[2])
+          continue;
+        if ((occ[xx * g.stride1 + yy * g.stride2 + zz] != 0) == (want != 0))
+        {
+          pos[3 * i] = xx;
+          pos[3 * i + 1] = yy;
+          pos[3 * i + 2] = zz;
+          found[i] = 1;
+          return;
+        }
+        if (dz == 0)
+          break;
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void widen_kernel(const T* __restrict__ in, int32_t* __restrict__ out, long n)
 {
@@ -795,6 +894,7 @@ int rebuild_locked(b200df_field* f)
   B200DF_CUDA(cudaStreamSynchronize(f->stream));
   B200DF_CUDA(cudaEventElapsedTime(&f->last_rebuild_ms, f->ev0, f->ev1));
   f->dirty = false;
+  f->uploaded = false;  // the arrays hold the engine's own exact EDT again
   return B200DF_OK;
 }
 
@@ -1352,6 +1452,8 @@ int b200df_field_import_device(b200df_field* f, const void* occ_dev, const void*
                                void* stream)
 {
   B200DF_REQUIRE(f, "null field");
+  // a signed field's two arrays belong together: d2 without its negative half would leave a stale negative array
+  B200DF_REQUIRE(!(d2_dev && f->neg && !neg_d2_dev), "a signed field needs neg_d2_dev together with d2_dev");
   DeviceGuard dg(f->device);
   std::lock_guard<std::mutex> lk(f->mu);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1364,9 +1466,106 @@ int b200df_field_import_device(b200df_field* f, const void* occ_dev, const void*
     B200DF_CUDA(cudaMemcpyAsync(f->neg, neg_d2_dev, nb, cudaMemcpyDeviceToDevice, st));
   B200DF_CUDA(cudaStreamSynchronize(st));
   if (d2_dev)
-    f->dirty = false;
+    f->dirty = false;  // the imported distances are served as they are (they belong to the imported occupancy)
+  else if (occ_dev)
+    f->dirty = true;   // occupancy alone: the distances are stale and are rebuilt before the next query
   if (occ_dev)
     f->bits_valid = false;
+  return B200DF_OK;
+}
+
+int b200df_field_upload_d2(b200df_field* f, const int32_t* d2, const int32_t* neg_d2)
+{
+  B200DF_REQUIRE(f && d2, "null argument");
+  B200DF_REQUIRE(!f->desc.propagate_negative || neg_d2, "a signed field needs the negative distances too");
+  if (f->n_voxels == 0)
+    return B200DF_OK;
+  DeviceGuard dg(f->device);
+  std::lock_guard<std::mutex> lk(f->mu);
+  const size_t nb = (size_t)f->n_voxels * sizeof(int32_t);
+  DeviceBuffer a, b, bad;
+  B200DF_CUDA(cudaMalloc(&a.p, nb));
+  B200DF_CUDA(cudaMalloc(&bad.p, sizeof(int)));
+  B200DF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), f->stream));
+  B200DF_CUDA(cudaMemcpyAsync(a.p, d2, nb, cudaMemcpyHostToDevice, f->stream));
+  const bool with_neg = f->desc.propagate_negative && neg_d2;
+  if (with_neg)
+  {
+    B200DF_CUDA(cudaMalloc(&b.p, nb));
+    B200DF_CUDA(cudaMemcpyAsync(b.p, neg_d2, nb, cudaMemcpyHostToDevice, f->stream));
+  }
+  // staged into the EDT scratch first, so that a refused upload leaves the field untouched
+  const unsigned blocks = blocks_for(f->n_voxels, 256);
+  if (!f->scratch8)
+    B200DF_CUDA(cudaMalloc(&f->scratch8, (size_t)f->n_voxels));
+  if (f->elem_size == 1)
+    narrow_kernel<uint8_t><<<blocks, 256, 0, f->stream>>>(
+        static_cast<const int32_t*>(a.p), static_cast<const int32_t*>(b.p), reinterpret_cast<uint8_t*>(f->tmp_a),
+        reinterpret_cast<uint8_t*>(f->tmp_b), f->scratch8, f->n_voxels, f->max_d2, static_cast<int*>(bad.p));
+  else
+    narrow_kernel<uint16_t><<<blocks, 256, 0, f->stream>>>(static_cast<const int32_t*>(a.p),
+                                                           static_cast<const int32_t*>(b.p), f->tmp_a, f->tmp_b,
+                                                           f->scratch8, f->n_voxels, f->max_d2,
+                                                           static_cast<int*>(bad.p));
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  int host_bad = 0;
+  B200DF_CUDA(cudaMemcpyAsync(&host_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+  B200DF_CUDA(cudaStreamSynchronize(f->stream));
+  B200DF_REQUIRE(!host_bad, "uploaded squared distances must lie in [0, max_distance_sq_]");
+  const size_t ne = (size_t)f->n_voxels * f->elem_size;
+  B200DF_CUDA(cudaMemcpyAsync(f->d2, f->tmp_a, ne, cudaMemcpyDeviceToDevice, f->stream));
+  if (with_neg)
+    B200DF_CUDA(cudaMemcpyAsync(f->neg, f->tmp_b, ne, cudaMemcpyDeviceToDevice, f->stream));
+  B200DF_CUDA(cudaMemcpyAsync(f->occ, f->scratch8, (size_t)f->n_voxels, cudaMemcpyDeviceToDevice, f->stream));
+  B200DF_CUDA(cudaStreamSynchronize(f->stream));
+  f->dirty = false;
+  f->bits_valid = false;
+  f->uploaded = true;
+  return B200DF_OK;
+}
+
+int b200df_field_values_uploaded(const b200df_field* f, int32_t* uploaded)
+{
+  B200DF_REQUIRE(f && uploaded, "null argument");
+  *uploaded = f->uploaded && !f->dirty ? 1 : 0;
+  return B200DF_OK;
+}
+
+int b200df_field_nearest_cells(b200df_field* f, const int32_t* ijk, int64_t n, double* dist, int32_t* pos,
+                               uint8_t* found)
+{
+  B200DF_REQUIRE(f && n >= 0 && (n == 0 || (ijk && dist && pos && found)), "bad arguments");
+  if (n == 0)
+    return B200DF_OK;
+  DeviceGuard dg(f->device);
+  std::lock_guard<std::mutex> lk(f->mu);
+  int rc = rebuild_locked(f);
+  if (rc)
+    return rc;
+  DeviceBuffer dq, dd, dp, df;
+  B200DF_CUDA(cudaMalloc(&dq.p, (size_t)n * 3 * sizeof(int32_t)));
+  B200DF_CUDA(cudaMalloc(&dd.p, (size_t)n * sizeof(double)));
+  B200DF_CUDA(cudaMalloc(&dp.p, (size_t)n * 3 * sizeof(int32_t)));
+  B200DF_CUDA(cudaMalloc(&df.p, (size_t)n));
+  B200DF_CUDA(cudaMemcpyAsync(dq.p, ijk, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, f->stream));
+  const void* neg = f->desc.propagate_negative ? f->neg : nullptr;
+  if (f->elem_size == 1)
+    nearest_cell_kernel<uint8_t><<<blocks_for(n, 128), 128, 0, f->stream>>>(
+        f->grid, static_cast<const uint8_t*>(f->d2), static_cast<const uint8_t*>(neg), f->occ, f->sqrt_table, f->max_d2,
+        static_cast<const int32_t*>(dq.p), n, static_cast<double*>(dd.p), static_cast<int32_t*>(dp.p),
+        static_cast<uint8_t*>(df.p));
+  else
+    nearest_cell_kernel<uint16_t><<<blocks_for(n, 128), 128, 0, f->stream>>>(
+        f->grid, static_cast<const uint16_t*>(f->d2), static_cast<const uint16_t*>(neg), f->occ, f->sqrt_table,
+        f->max_d2, static_cast<const int32_t*>(dq.p), n, static_cast<double*>(dd.p), static_cast<int32_t*>(dp.p),
+        static_cast<uint8_t*>(df.p));
+  B200DF_LAUNCHED();
+  B200DF_CUDA(cudaGetLastError());
+  B200DF_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+  B200DF_CUDA(cudaMemcpyAsync(pos, dp.p, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, f->stream));
+  B200DF_CUDA(cudaMemcpyAsync(found, df.p, (size_t)n, cudaMemcpyDeviceToHost, f->stream));
+  B200DF_CUDA(cudaStreamSynchronize(f->stream));
   return B200DF_OK;
 }
 

@@ -121,7 +121,24 @@ int b200df_check_edges(const b200df_group* group, b200df_field* world, b200df_fi
   const size_t end_bytes = (size_t)chunk * nv * sizeof(double);
   std::vector<uint8_t> ang(std::max(nv, 1), 0);
   if (var_is_angular)
+  {
+    // 0 linear, 1 shortest arc, 2 followed by exactly three 3s = the x y z w variables of one floating joint
+    for (int v = 0; v < nv; ++v)
+    {
+      const int k = var_is_angular[v];
+      B200DF_REQUIRE(k >= 0 && k <= 3, "var_is_angular values must be 0..3");
+      if (k == 2)
+      {
+        B200DF_REQUIRE(v + 3 < nv && var_is_angular[v + 1] == 3 && var_is_angular[v + 2] == 3 &&
+                           var_is_angular[v + 3] == 3 && (v + 4 >= nv || var_is_angular[v + 4] != 3),
+                       "a quaternion is marked 2 3 3 3 (four variables inside the row)");
+        v += 3;
+      }
+      else
+        B200DF_REQUIRE(k != 3, "a 3 in var_is_angular must follow a 2 (quaternion x marks the start)");
+    }
     std::copy(var_is_angular, var_is_angular + nv, ang.begin());
+  }
   Pool::Ctx* ctx = group->stage->acquire();
   cudaError_t e = Pool::ensure_stream(ctx, 0);
   int rc = B200DF_OK;

@@ -488,6 +488,11 @@ int prepare_fields(const b200df_group* group, b200df_field* world, b200df_field*
     B200DF_REQUIRE(f->device == group->device, "field and group live on different devices");
     B200DF_REQUIRE(f->desc.resolution == group->desc.resolution, "field resolution differs from the group's");
     B200DF_REQUIRE(f->n_voxels < (1L << 31), "field too large for 32-bit voxel indices");
+    // the verdict kernels treat out-of-bounds spheres as free, which is what the reference's predicate
+    // (max_prop > dist with dist = the field's max_distance, collision_distance_field_types.cpp:216-222) says only
+    // when the field propagates at least as far as the group looks (CollisionEnvDistanceField uses one value for both)
+    B200DF_REQUIRE(f->desc.max_distance >= group->desc.max_propagation_distance,
+                   "field max_distance is smaller than the group's max_propagation_distance");
     int rc = field_prepare(f, v, nullptr);
     if (rc)
       return rc;

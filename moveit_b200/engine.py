@@ -382,6 +382,26 @@ class Field:
         B.check(B.load().b200df_field_download_d2(self.h, B.ptr(out, C.c_int32), int(negative)))
         return out
 
+    def upload_d2(self, d2, neg_d2=None):
+        """Reference-field mode: serve caller-supplied squared distances (e.g. the reference's own propagation
+        result) until the next occupancy edit."""
+        a = np.ascontiguousarray(d2, dtype=np.int32).reshape(self.dims)
+        b = None if neg_d2 is None else np.ascontiguousarray(neg_d2, dtype=np.int32).reshape(self.dims)
+        B.check(B.load().b200df_field_upload_d2(self.h, B.ptr(a, C.c_int32), B.ptr(b, C.c_int32) if b is not None else None))
+
+    def values_uploaded(self):
+        n = C.c_int32(0)
+        B.check(B.load().b200df_field_values_uploaded(self.h, C.byref(n)))
+        return bool(n.value)
+
+    def nearest_cells(self, ijk):
+        a = np.ascontiguousarray(np.reshape(ijk, (-1, 3)), dtype=np.int32)
+        n = len(a)
+        dist, pos, found = np.empty(n), np.empty((n, 3), dtype=np.int32), np.empty(n, dtype=np.uint8)
+        B.check(B.load().b200df_field_nearest_cells(self.h, B.ptr(a, C.c_int32), n, B.ptr(dist, C.c_double),
+                                                    B.ptr(pos, C.c_int32), B.ptr(found, C.c_uint8)))
+        return dist, pos, found.astype(bool)
+
     def occupancy(self):
         out = np.empty(self.dims, dtype=np.uint8)
         B.check(B.load().b200df_field_download_occupancy(self.h, B.ptr(out, C.c_uint8)))
