@@ -108,6 +108,9 @@ struct b200df_field
   bool uploaded = false;       // d2 holds caller-supplied values (b200df_field_upload_d2), not the engine's exact EDT
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int kEdtStreams = 4;  // z slabs of one rebuild run concurrently (edt.cu)
+  cudaStream_t edt_streams[kEdtStreams] = { nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_join[kEdtStreams] = { nullptr, nullptr, nullptr, nullptr };
   std::mutex mu;
   float last_rebuild_ms = 0.f;
 };
@@ -116,4 +119,7 @@ namespace b200df
 {
 // builds the EDT when dirty; fills the kernel view.  Caller holds no lock.
 int field_prepare(b200df_field* f, FieldDev* view, cudaStream_t wait_on);
+// edt.cu: the two-launch exact EDT from bit rows (even nz, clamp radius <= 31); field.cu keeps the windowed fallback
+bool edt_fast_applies(const b200df_field* f);
+int edt_fast(b200df_field* f, bool invert, void* out);
 }

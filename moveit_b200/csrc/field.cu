@@ -242,225 +242,6 @@ __global__ void edt_pass_axis_kernel(const uint16_t* __restrict__ in, OutT* __re
     out[i] = (OutT)(best > max_d2 ? kInf16 : best);  // anything beyond the clamp can never win later
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Fast path of the same exact EDT (nz even, R <= 31): bit-packed occupancy, z pass by bit scans, y and x passes as
-// "marching" min-plus passes on packed u16x2 voxel pairs with the DPX add-min instruction (VIADDMNMX.U16x2).
-//
-//   pack   : occ u8 -> 1 bit per voxel, rows of ceil(nz/32) words                 (reads V bytes, writes V/8)
-//   z pass : nearest set bit within +-31 of each voxel -> dz^2 (or INF)            (reads the bits, writes 2V)
-//   march  : a thread owns two z-adjacent voxels and walks the y (then x) axis once.  Input row t is added to the
-//            2R+1 open outputs t-R..t+R (one register each, ring indexed statically by unrolling 2R+1 steps);
-//            output t-R is complete after input t and is written out.  One VIADDMNMX per (input, output) pair and
-//            voxel pair, no re-reads: each pass reads 2V and writes 2V bytes (the last one writes sizeof(d2)*V).
-// Values above max_d2 are kept (they only grow) and clamped by the last pass; INF = 0x4000 leaves head-room for two
-// additions of R*R <= 961 in 16 bits.  The result equals the windowed passes above bit for bit.
-// ------------------------------------------------------------------------------------------------------------
-constexpr unsigned kInfPair = 0x40004000u;
-
-__global__ void pack_bits_kernel(const uint8_t* __restrict__ occ, uint32_t* __restrict__ bits, int nz, int wpr,
-                                 long n_words, bool invert)
-{
-  const long gw = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;  // one warp per output word
-  if (gw >= n_words)
-    return;
-  const int lane = threadIdx.x & 31;
-  const long row = gw / wpr;
-  const int z = 32 * (int)(gw % wpr) + lane;
-  const bool o = z < nz && ((occ[row * nz + z] != 0) != invert);
-  const unsigned m = __ballot_sync(0xffffffffu, o);
-  if (lane == 0)
-    bits[gw] = m;
-}
-
-// nz % 16 == 0: a thread turns 16 occupancy bytes (one 16-byte load; occupancy bytes are 0 or 1) into one half-word
-// of the bit row.  Block = (32, 8): threadIdx.y picks the row, threadIdx.x strides over the row's 16-voxel groups.
-__global__ void pack_bits16_kernel(const uint4* __restrict__ occ, uint16_t* __restrict__ bits16, int groups, int wpr,
-                                   long n_rows, bool invert)
-{
-  const long row = blockIdx.x * (long)blockDim.y + threadIdx.y;
-  if (row >= n_rows)
-    return;
-  const unsigned flip = invert ? 0x01010101u : 0u;
-  for (int h = threadIdx.x; h < groups; h += 32)
-  {
-    const uint4 v = occ[row * groups + h];
-    const unsigned n0 = ((((v.x & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
-    const unsigned n1 = ((((v.y & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
-    const unsigned n2 = ((((v.z & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
-    const unsigned n3 = ((((v.w & 0x01010101u) ^ flip) * 0x01020408u) >> 24) & 0xfu;
-    bits16[row * (2 * wpr) + h] = (uint16_t)(n0 | (n1 << 4) | (n2 << 8) | (n3 << 12));
-  }
-}
-
-__device__ __forceinline__ unsigned z_dist2(unsigned lo, unsigned hi, int R)
-{
-  // lo = bits [z-32, z) (bit 31 is z-1), hi = bits [z, z+32) (bit 0 is z)
-  const int up = hi ? __ffs(hi) - 1 : 64;
-  const int dn = lo ? __clz(lo) + 1 : 64;
-  const int d = min(up, dn);
-  return d <= R ? (unsigned)(d * d) : 0x4000u;
-}
-
-// Block = (64, 4): threadIdx.y picks the row, threadIdx.x strides over the row's voxel pairs.
-__global__ void edt_z_from_bits_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ out, int half, int wpr,
-                                       long n_rows, int R)
-{
-  const long row = blockIdx.x * (long)blockDim.y + threadIdx.y;
-  if (row >= n_rows)
-    return;
-  const uint32_t* br = bits + row * wpr;
-  uint32_t* orow = out + row * half;
-  for (int p = threadIdx.x; p < half; p += 64)
-  {
-    const int z0 = 2 * p;
-    const int wi = (z0 - 32) >> 5;  // -1 for the first 32 voxels of a row
-    const int o = z0 & 31;
-    const unsigned w0 = wi >= 0 ? br[wi] : 0u;
-    const unsigned w1 = br[wi + 1];
-    const unsigned w2 = wi + 2 < wpr ? br[wi + 2] : 0u;
-    const unsigned v0 = z_dist2(__funnelshift_r(w0, w1, o), __funnelshift_r(w1, w2, o), R);
-    const unsigned v1 = z_dist2(__funnelshift_r(w0, w1, o + 1), __funnelshift_r(w1, w2, o + 1), R);
-    orow[p] = v0 | (v1 << 16);
-  }
-}
-
-// nz % 8 == 0: a thread produces 8 consecutive voxels (one 16-byte store).  Only two bit scans per thread: the
-// distance to the next obstacle above is found once for the last voxel and carried down the run
-// (up[k] = occupied(k) ? 0 : up[k+1] + 1), the distance to the obstacle below once for the first voxel and carried up.
-// Block = (32, 8): threadIdx.y picks the row, threadIdx.x strides over the row's 8-voxel groups.
-__global__ void edt_z8_from_bits_kernel(const uint32_t* __restrict__ bits, uint4* __restrict__ out, int groups, int wpr,
-                                        long n_rows, int R)
-{
-  const long row = blockIdx.x * (long)blockDim.y + threadIdx.y;
-  if (row >= n_rows)
-    return;
-  const uint32_t* br = bits + row * wpr;
-  uint4* orow = out + row * groups;
-  for (int j = threadIdx.x; j < groups; j += 32)
-  {
-    const int z0 = 8 * j;
-    const int w = z0 >> 5, o = z0 & 31;  // o in {0, 8, 16, 24}
-    const unsigned w0 = w > 0 ? br[w - 1] : 0u;
-    const unsigned w1 = br[w];
-    const unsigned w2 = w + 1 < wpr ? br[w + 1] : 0u;
-    const unsigned below = __funnelshift_r(w0, w1, o);  // bits [z0-32, z0), bit 31 is z0-1
-    const unsigned here = __funnelshift_r(w1, w2, o);   // bits [z0, z0+32)
-    const unsigned next7 = (w2 >> o) & 0x7fu;           // bits [z0+32, z0+39)
-    const unsigned above7 = (here >> 7) | (next7 << 25);  // bits [z0+7, z0+39)
-    int up[8], dn[8];
-    up[7] = above7 ? __ffs(above7) - 1 : 64;
-#pragma unroll
-    for (int k = 6; k >= 0; --k)
-      up[k] = ((here >> k) & 1u) ? 0 : up[k + 1] + 1;
-    dn[0] = below ? __clz(below) + 1 : 64;
-#pragma unroll
-    for (int k = 1; k < 8; ++k)
-      dn[k] = ((here >> (k - 1)) & 1u) ? 1 : dn[k - 1] + 1;
-    unsigned v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-    {
-      const int d = min(up[k], dn[k]);
-      v[k] = d <= R ? (unsigned)(d * d) : 0x4000u;
-    }
-    orow[j] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-  }
-}
-
-// Lines: line L -> first pair (L / inner) * outer_stride + (L % inner), then `stride` pairs per step along the axis.
-// One ring revolution (2R+1 steps) is cut into two chunks whose inputs live in two register buffers: while one is
-// consumed the other is being loaded, so a thread always has ~R loads in flight.  Per step the fixed cost is one
-// load, one vote, one store and a few pointer adds; the 2R+1 taps are skipped for a whole warp when no lane's input
-// is finite (most rows of the y pass).
-template <int R, int U0, int CNT>
-__device__ __forceinline__ void march_chunk(const unsigned (&buf)[R + 1], unsigned (&acc)[2 * R + 1], int t_first,
-                                            int n_axis, bool live, uint32_t*& out32, uint16_t*& out16, long stride,
-                                            unsigned clamp, bool final_pass, bool out_u8)
-{
-  constexpr int W = 2 * R + 1;
-#pragma unroll
-  for (int j = 0; j < CNT; ++j)
-  {
-    const int u = U0 + j;
-    const unsigned f = buf[j];
-    if (__any_sync(0xffffffffu, f != kInfPair))
-    {
-#pragma unroll
-      for (int d = -R; d <= R; ++d)
-        acc[(u + d + W) % W] = __viaddmin_u16x2(f, (unsigned)(d * d) * 0x00010001u, acc[(u + d + W) % W]);
-    }
-    // output t-R has now seen every input within +-R of it
-    const int yo = t_first + j - R;
-    const int slot = (u + R + 1) % W;  // == (u - R) mod W
-    if (live && (unsigned)yo < (unsigned)n_axis)
-    {
-      unsigned v = acc[slot];
-      if (final_pass)
-        v = __vminu2(v, clamp);
-      if (out_u8)
-        *out16 = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));
-      else
-        *out32 = v;
-    }
-    out32 += stride;
-    out16 += stride;
-    acc[slot] = kInfPair;
-  }
-}
-
-template <int R, int CNT>
-__device__ __forceinline__ void march_load(unsigned (&buf)[R + 1], const uint32_t* p, long stride, int t_first,
-                                           int n_axis)
-{
-#pragma unroll
-  for (int j = 0; j < CNT; ++j)
-  {
-    buf[j] = (t_first + j < n_axis) ? *p : kInfPair;
-    p += stride;
-  }
-}
-
-template <int R, typename OutT, bool FINAL>
-__global__ void __launch_bounds__(64, 9) edt_march_kernel(const uint32_t* __restrict__ in, void* __restrict__ out_v,
-                                                       long n_lines, long inner, long outer_stride, long stride,
-                                                       int n_axis, int max_d2)
-{
-  constexpr int W = 2 * R + 1;
-  // a revolution is cut into four chunks (13+12+12+12 steps for R = 24) that alternate between two input buffers:
-  // half the registers of a two-chunk split, which is what lets every line of a 400^3 field be resident at once
-  // (2500 warps on 148 SMs need 17 warps/SM, i.e. <= 120 registers)
-  constexpr int C0 = (W + 3) / 4, C1 = (W + 2) / 4, C2 = (W + 1) / 4, C3 = W / 4;
-  static_assert(C0 + C1 + C2 + C3 == W && C0 <= R + 1, "chunking");
-  const long line0 = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const bool live = line0 < n_lines;
-  const long line = live ? line0 : n_lines - 1;  // surplus lanes shadow the last line (keeps the votes full)
-  const long base = (line / inner) * outer_stride + (line % inner);
-  const uint32_t* src = in + base;
-  unsigned acc[W];
-#pragma unroll
-  for (int j = 0; j < W; ++j)
-    acc[j] = kInfPair;
-  const unsigned clamp = (unsigned)max_d2 * 0x00010001u;
-  // output pointers trail the input by R steps; they start before the array and are only dereferenced in range
-  uint32_t* out32 = static_cast<uint32_t*>(out_v) + base - (long)R * stride;
-  uint16_t* out16 = static_cast<uint16_t*>(out_v) + base - (long)R * stride;
-  unsigned bufA[R + 1], bufB[R + 1];  // only the first C0 entries are used
-  march_load<R, C0>(bufA, src, stride, 0, n_axis);
-  for (int t0 = 0; t0 < n_axis + R; t0 += W)
-  {
-    constexpr bool kU8 = sizeof(OutT) == 1;
-    march_load<R, C1>(bufB, src + (long)(t0 + C0) * stride, stride, t0 + C0, n_axis);
-    march_chunk<R, 0, C0>(bufA, acc, t0, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
-    march_load<R, C2>(bufA, src + (long)(t0 + C0 + C1) * stride, stride, t0 + C0 + C1, n_axis);
-    march_chunk<R, C0, C1>(bufB, acc, t0 + C0, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
-    march_load<R, C3>(bufB, src + (long)(t0 + C0 + C1 + C2) * stride, stride, t0 + C0 + C1 + C2, n_axis);
-    march_chunk<R, C0 + C1, C2>(bufA, acc, t0 + C0 + C1, n_axis, live, out32, out16, stride, clamp, FINAL, kU8);
-    march_load<R, C0>(bufA, src + (long)(t0 + W) * stride, stride, t0 + W, n_axis);
-    march_chunk<R, C0 + C1 + C2, C3>(bufB, acc, t0 + C0 + C1 + C2, n_axis, live, out32, out16, stride, clamp, FINAL,
-                                     kU8);
-  }
-}
-
 // b200df_field_upload_d2: int32 d2 (and negative d2) -> the field's element type; occupancy = (d2 == 0).
 // Out-of-range values raise *bad (the upload is then refused).
 template <typename T>
@@ -784,24 +565,6 @@ int rasterize_into(b200df_field* f, int shape_type, const double* dims3, const d
   return B200DF_OK;
 }
 
-template <int R, typename T>
-int run_edt_march(b200df_field* f, T* out)
-{
-  const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
-  const long half = nz / 2;
-  const int threads = 64;
-  // y pass: lines = (x, z pair); x pass: lines = (y, z pair)
-  const long lines_y = (long)nx * half, lines_x = (long)ny * half;
-  edt_march_kernel<R, uint16_t, false><<<blocks_for(lines_y, threads), threads, 0, f->stream>>>(
-      reinterpret_cast<const uint32_t*>(f->tmp_a), f->tmp_b, lines_y, half, (long)ny * half, half, ny, f->max_d2);
-  B200DF_LAUNCHED();
-  edt_march_kernel<R, T, true><<<blocks_for(lines_x, threads), threads, 0, f->stream>>>(
-      reinterpret_cast<const uint32_t*>(f->tmp_b), out, lines_x, lines_x, 0, (long)ny * half, nx, f->max_d2);
-  B200DF_LAUNCHED();
-  B200DF_CUDA(cudaGetLastError());
-  return B200DF_OK;
-}
-
 template <typename T>
 int run_edt(b200df_field* f, bool invert, T* out)
 {
@@ -809,46 +572,8 @@ int run_edt(b200df_field* f, bool invert, T* out)
   const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
   const int threads = 256;
   const unsigned blocks = blocks_for(n, threads);
-  if (f->bits && nz % 2 == 0 && f->radius <= 31)
-  {
-    const int wpr = (nz + 31) / 32;
-    const long n_rows = (long)nx * ny;
-    if (!invert && f->bits_valid)
-    {
-      // the bit rows were kept current by reset / add_points: nothing to pack
-    }
-    else if (nz % 16 == 0)
-    {
-      pack_bits16_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
-          reinterpret_cast<const uint4*>(f->occ), reinterpret_cast<uint16_t*>(f->bits), nz / 16, wpr, n_rows, invert);
-      B200DF_LAUNCHED();
-    }
-    else
-    {
-      const long n_words = n_rows * wpr;
-      pack_bits_kernel<<<blocks_for(n_words * 32, threads), threads, 0, f->stream>>>(f->occ, f->bits, nz, wpr, n_words,
-                                                                                    invert);
-      B200DF_LAUNCHED();
-    }
-    f->bits_valid = !invert;  // the bit rows now mirror occ (or its complement, for the negative field)
-    // z distances of radius cells or more square to >= max_d2 and are written as INF right away (see `reach` below)
-    if (nz % 8 == 0)
-      edt_z8_from_bits_kernel<<<blocks_for(n_rows, 8), dim3(32, 8), 0, f->stream>>>(
-          f->bits, reinterpret_cast<uint4*>(f->tmp_a), nz / 8, wpr, n_rows, f->radius - 1);
-    else
-      edt_z_from_bits_kernel<<<blocks_for(n_rows, 4), dim3(64, 4), 0, f->stream>>>(
-          f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), nz / 2, wpr, n_rows, f->radius - 1);
-    B200DF_LAUNCHED();
-    // a tap at offset d adds d*d >= radius^2 >= max_d2 once |d| reaches the radius: such a candidate is clamped away
-    // by the final pass (and can never be the minimiser of a later pass below max_d2), so the marching window only
-    // needs +-(radius - 1)
-    const int reach = f->radius - 1;
-    if (reach <= 12)
-      return run_edt_march<12, T>(f, out);
-    if (reach <= 24)
-      return run_edt_march<24, T>(f, out);
-    return run_edt_march<30, T>(f, out);
-  }
+  if (edt_fast_applies(f))
+    return edt_fast(f, invert, out);  // edt.cu: bit rows -> plane kernel (z + y) -> axis kernel (x)
   if (invert)
     edt_pass_z_kernel<true><<<blocks, threads, 0, f->stream>>>(f->occ, f->tmp_a, nz, n, f->radius);
   else
@@ -987,6 +712,12 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out)
   B200DF_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
   B200DF_CUDA(cudaEventCreate(&f->ev0));
   B200DF_CUDA(cudaEventCreate(&f->ev1));
+  B200DF_CUDA(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < b200df_field::kEdtStreams; ++i)
+  {
+    B200DF_CUDA(cudaStreamCreateWithFlags(&f->edt_streams[i], cudaStreamNonBlocking));
+    B200DF_CUDA(cudaEventCreateWithFlags(&f->ev_join[i], cudaEventDisableTiming));
+  }
   const size_t nv = (size_t)std::max<long>(total, 1);
   B200DF_CUDA(cudaMalloc(&f->occ, nv));
   B200DF_CUDA(cudaMalloc(&f->d2, nv * f->elem_size));
@@ -1028,6 +759,15 @@ int b200df_field_destroy(b200df_field* f)
     cudaEventDestroy(f->ev0);
   if (f->ev1)
     cudaEventDestroy(f->ev1);
+  if (f->ev_fork)
+    cudaEventDestroy(f->ev_fork);
+  for (int i = 0; i < b200df_field::kEdtStreams; ++i)
+  {
+    if (f->ev_join[i])
+      cudaEventDestroy(f->ev_join[i]);
+    if (f->edt_streams[i])
+      cudaStreamDestroy(f->edt_streams[i]);
+  }
   if (f->stream)
     cudaStreamDestroy(f->stream);
   delete f;
