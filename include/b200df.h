@@ -95,6 +95,23 @@ enum
   B200DF_TYPE_ENVIRONMENT = 3,
 };
 
+/* which kernels a verdict call runs (b200df_check_route) */
+enum
+{
+  B200DF_ROUTE_EXACT = 0, /* one thread per state, fp64 */
+  B200DF_ROUTE_FAST = 1,  /* fp32 screening pass + exact re-run of the undecided states */
+  B200DF_ROUTE_SMALL = 2, /* one CTA per state (small batches; robots beyond the batched kernels' shared memory) */
+};
+/* why a B200DF_PRECISION_FAST call does not take the FAST route (bit mask) */
+enum
+{
+  B200DF_NOFAST_TABLES = 1, /* robot beyond the constant-bank tables: > 40 links, > 128 spheres or > 512 link pairs */
+  B200DF_NOFAST_SIGNED = 2, /* signed field and a sphere radius <= collision tolerance: fp64 signed predicate needed */
+  B200DF_NOFAST_BATCH = 4,  /* batch too small for the screening pass to pay (same verdicts either way) */
+  B200DF_NOFAST_SMEM = 8,   /* robot too large for the one-thread-per-state kernels: one CTA per state */
+};
+#define B200DF_MAX_LINK_FIELDS 32 /* links with geometry b200df_group_set_link_fields accepts (kernel bit masks) */
+
 typedef struct b200df_model b200df_model; /* immutable robot description on the device */
 typedef struct b200df_group b200df_group; /* immutable (model, link subset, ACM tables, thresholds) */
 typedef struct b200df_field b200df_field; /* PropagationDistanceField replacement (occupancy + exact EDT) */
@@ -220,8 +237,12 @@ int b200df_field_add_posed_body(b200df_field* field, int32_t shape_type, const d
  * decomposition; voxels shared with another object are cleared as well, like the reference (no ref-count) */
 int b200df_field_remove_posed_body(b200df_field* field, int32_t shape_type, const double* dims3,
                                    const double* pose12, double padding);
-/* occupied octree leaves (centre xyz + edge) -> points per getOcTreePoints (distance_field.cpp:236-280) */
+/* occupied octree leaves (centre xyz + edge) -> points per getOcTreePoints (distance_field.cpp:236-280): a leaf no
+ * bigger than a voxel is its centre, a bigger one a lattice accumulated with += resolution (Q19).  Expanded and
+ * voxelised on the device (one thread per lattice point; the loops are re-run literally for the rounding).  The
+ * remove form clears the same voxels (removePointsFromField of the same decomposition). */
 int b200df_field_add_octree_leaves(b200df_field* field, const double* leaves4, int64_t n);
+int b200df_field_remove_octree_leaves(b200df_field* field, const double* leaves4, int64_t n);
 /* Rebuilds the EDT if the occupancy changed (queries do this implicitly).  Returns the device time of the
  * rebuild in milliseconds through *ms when non-NULL. */
 int b200df_field_rebuild(b200df_field* field, float* ms);
@@ -278,6 +299,13 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
                        int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict);
 int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q_dev,
                               int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, void* stream);
+
+/* The kernels b200df_check_batch(_device) would run for these arguments; nothing is launched and the fields are not
+ * rebuilt.  *route = B200DF_ROUTE_*; *why_not_fast = B200DF_NOFAST_* bits when precision is FAST but the route is not.
+ * The fall-backs never change a verdict - they cost time (EXACT is ~3x slower than FAST) - and this call is how a
+ * caller (or a test) sees them instead of having them happen silently. */
+int b200df_check_route(const b200df_group* group, const b200df_field* world, const b200df_field* self, int q_dtype,
+                       int64_t n, int flags, int precision, int32_t* route, int32_t* why_not_fast);
 
 /* Batched motion validation: M straight joint-space motions qa[i] -> qb[i] (host, fp64 [m][n_vars]), each cut into
  * `segments` pieces; the states at t = j/segments, j = 1..segments, are interpolated on the device with the

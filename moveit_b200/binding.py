@@ -15,6 +15,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 CHECK_ROBOT, CHECK_SELF, CHECK_INTRA, CHECK_LINK_FIELDS = 1, 2, 4, 8
 Q_F32, Q_F64 = 0, 1
 PRECISION_EXACT, PRECISION_FAST, PRECISION_DEBUG_SWEEP, PRECISION_DEBUG_SCREEN = 0, 1, 2, 3
+ROUTE_EXACT, ROUTE_FAST, ROUTE_SMALL = 0, 1, 2
+NOFAST_TABLES, NOFAST_SIGNED, NOFAST_BATCH, NOFAST_SMEM = 1, 2, 4, 8
 TYPE_NONE, TYPE_SELF, TYPE_INTRA, TYPE_ENVIRONMENT = 0, 1, 2, 3
 
 c_dp = C.POINTER(C.c_double)
@@ -82,6 +84,7 @@ SYMBOLS = {
     "b200df_field_add_posed_body": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double]),
     "b200df_field_remove_posed_body": (C.c_int, [_VP, C.c_int32, c_dp, c_dp, C.c_double]),
     "b200df_field_add_octree_leaves": (C.c_int, [_VP, c_dp, C.c_int64]),
+    "b200df_field_remove_octree_leaves": (C.c_int, [_VP, c_dp, C.c_int64]),
     "b200df_field_rebuild": (C.c_int, [_VP, c_fp]),
     "b200df_field_download_d2": (C.c_int, [_VP, c_i32p, C.c_int]),
     "b200df_field_download_occupancy": (C.c_int, [_VP, c_u8p]),
@@ -98,6 +101,7 @@ SYMBOLS = {
     "b200df_field_nearest_cells": (C.c_int, [_VP, c_i32p, C.c_int64, c_dp, c_i32p, c_u8p]),
     "b200df_check_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
     "b200df_check_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP]),
+    "b200df_check_route": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_i32p, c_i32p]),
     "b200df_check_edges": (C.c_int, [_VP, _VP, _VP, c_dp, c_dp, C.c_int64, C.c_int32, c_u8p, C.c_int, C.c_int, c_i32p]),
     "b200df_gradients_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_dp, c_dp, c_u8p, c_dp]),
     "b200df_gradients_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, _VP]),

@@ -113,6 +113,12 @@ struct b200df_field
   cudaEvent_t ev_fork = nullptr, ev_join[kEdtStreams] = { nullptr, nullptr, nullptr, nullptr };
   std::mutex mu;
   float last_rebuild_ms = 0.f;
+  // staging of host point lists (add / remove / update points): device buffer + page-locked buffer, grown on demand
+  // and kept, so that a 1 M-point cloud costs neither a cudaMalloc / cudaFree pair nor the driver's pageable path
+  double* pts_dev = nullptr;
+  size_t pts_dev_bytes = 0;
+  char* pts_pin = nullptr;
+  size_t pts_pin_bytes = 0;
 };
 
 namespace b200df

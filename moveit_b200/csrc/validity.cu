@@ -902,6 +902,47 @@ int b200df_group_sphere_count(const b200df_group* g, int32_t* n)
   return B200DF_OK;
 }
 
+int b200df_check_route(const b200df_group* group, const b200df_field* world, const b200df_field* self, int q_dtype,
+                       int64_t n, int flags, int precision, int32_t* route, int32_t* why_not_fast)
+{
+  B200DF_REQUIRE(group && route && why_not_fast && n >= 0, "bad arguments");
+  B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown joint-value type");
+  B200DF_REQUIRE(precision == B200DF_PRECISION_EXACT || precision == B200DF_PRECISION_FAST, "unknown precision");
+  *why_not_fast = 0;
+  // the same decisions as run_verdict, in the same order
+  const bool pairs = (flags & B200DF_CHECK_INTRA) && group->dev.n_partners > 0;
+  if (n <= small_max_states() && small_supported(group))
+  {
+    *route = B200DF_ROUTE_SMALL;
+    if (precision == B200DF_PRECISION_FAST)
+      *why_not_fast = B200DF_NOFAST_BATCH;
+    return B200DF_OK;
+  }
+  if (small_supported(group) && verdict_smem_bytes(group->dev, 32, pairs, q_elem_size(q_dtype)) > 220 * 1024)
+  {
+    *route = B200DF_ROUTE_SMALL;
+    if (precision == B200DF_PRECISION_FAST)
+      *why_not_fast = B200DF_NOFAST_SMEM;
+    return B200DF_OK;
+  }
+  *route = B200DF_ROUTE_EXACT;
+  if (precision != B200DF_PRECISION_FAST)
+    return B200DF_OK;
+  int why = 0;
+  if (!fast_tables_ok(group))
+    why |= B200DF_NOFAST_TABLES;
+  const bool signed_world = (flags & B200DF_CHECK_ROBOT) && world && world->desc.propagate_negative;
+  const bool signed_self = (flags & B200DF_CHECK_SELF) && self && self->desc.propagate_negative;
+  if ((signed_world || signed_self) && !group->neg_irrelevant)
+    why |= B200DF_NOFAST_SIGNED;
+  if (n < kFastMinStates)
+    why |= B200DF_NOFAST_BATCH;
+  if (!why)
+    *route = B200DF_ROUTE_FAST;
+  *why_not_fast = why;
+  return B200DF_OK;
+}
+
 int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q_dev,
                               int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, void* stream)
 {

@@ -752,6 +752,7 @@ struct b200df_group::StagePool
 namespace b200df
 {
 // FAST path (validity_fast.cu)
+bool fast_tables_ok(const b200df_group* group);  // the robot fits FAST's constant-bank tables
 int fast_create(b200df_group* group);   // builds the fp32 tables; leaves group->fast null when unsupported
 void fast_destroy(b200df_group* group);
 // true when the FAST kernel can serve this call (unsigned fields, model fits the tables)

@@ -778,6 +778,11 @@ void fast_destroy(b200df_group* g)
   g->fast = nullptr;
 }
 
+bool fast_tables_ok(const b200df_group* g)
+{
+  return g->fast && g->fast->ok;
+}
+
 bool fast_supported(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int q_dtype, int flags)
 {
   if (!g->fast || !g->fast->ok || (q_dtype != B200DF_Q_F32 && q_dtype != B200DF_Q_F64))

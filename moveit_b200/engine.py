@@ -372,6 +372,10 @@ class Field:
         a = B.as_f64(np.reshape(leaves, (-1, 4)))
         B.check(B.load().b200df_field_add_octree_leaves(self.h, B.ptr(a, C.c_double), len(a)))
 
+    def remove_octree_leaves(self, leaves):
+        a = B.as_f64(np.reshape(leaves, (-1, 4)))
+        B.check(B.load().b200df_field_remove_octree_leaves(self.h, B.ptr(a, C.c_double), len(a)))
+
     def rebuild(self):
         ms = C.c_float(0)
         B.check(B.load().b200df_field_rebuild(self.h, C.byref(ms)))

@@ -73,11 +73,24 @@ enum ShapeType  // geometric_shapes/shapes.h values
   SPHERE = B200DF_SHAPE_SPHERE,
   CYLINDER = B200DF_SHAPE_CYLINDER,
   BOX = B200DF_SHAPE_BOX,
+  OCTREE = 8,        // shapes::OcTree: the <octomap> world object PlanningScene adds (planning_scene.cpp:1390-1412)
+  POINT_CLOUD = 100, // not a geometric_shapes type: a body-frame point list (how the plugin hands over shapes it
+                     // decomposed on the host with MoveIt's own BodyDecomposition, e.g. meshes)
+};
+// What the path reads of an octomap::OcTree: every node of the tree in begin_tree() order (all depths, inner nodes
+// included), each with its centre, edge length, occupancy (isNodeOccupied) and whether it is a leaf.
+struct OcTreeNodes
+{
+  std::vector<double> xyzs;             // [n][4] centre + size
+  std::vector<std::uint8_t> occupied;   // [n]
+  std::vector<std::uint8_t> leaf;       // [n]
 };
 struct Shape
 {
   ShapeType type = BOX;
   double dims[3] = { 0, 0, 0 };  // sphere: radius; cylinder: radius, length; box: x, y, z
+  std::shared_ptr<const OcTreeNodes> octree;           // OCTREE
+  std::shared_ptr<const std::vector<double>> points;   // POINT_CLOUD: [n][3], body frame
 };
 using ShapeConstPtr = std::shared_ptr<const Shape>;
 }  // namespace shapes
@@ -387,6 +400,13 @@ public:
     auto it = objects_.find(id);
     return it == objects_.end() ? ObjectConstPtr() : ObjectConstPtr(it->second);
   }
+  std::vector<std::string> getObjectIds() const  // world.h: sorted, like the std::map the reference keeps
+  {
+    std::vector<std::string> ids;
+    for (const auto& kv : objects_)
+      ids.push_back(kv.first);
+    return ids;
+  }
   ObserverHandle addObserver(const ObserverCallbackFn& cb)
   {
     observers_[++next_handle_] = cb;
@@ -490,6 +510,11 @@ struct GroupStateRepresentation  // collision_common_distance_field.h:120-167 (w
 {
   std::vector<std::string> link_names_;
   std::vector<GradientInfo> gradients_;
+  // dfce_ (collision_common_distance_field.h:139): the cache entry this representation was generated from.  A call
+  // that is handed a non-null gsr keeps using it (updateGroupStateRepresentationState, .cpp:1118-1170) - which is how
+  // ChompOptimizer keeps the ACM of its first call while passing acm = nullptr for every waypoint
+  // (chomp_optimizer.cpp:102 vs :924).  Opaque here: only CollisionEnvB200 looks inside.
+  std::shared_ptr<const void> dfce_;
 };
 using GroupStateRepresentationPtr = std::shared_ptr<GroupStateRepresentation>;
 
@@ -600,13 +625,8 @@ public:
     size_[1] = size_y;
     size_[2] = size_z;
     origin_ = origin;
-    initialize(link_body_decompositions, use_signed_distance_field, resolution, collision_tolerance,
-               max_propogation_distance);
-    world_field_ = newField();  // generateDistanceFieldCacheEntryWorld :1800-1816
-    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
-      notifyObjectChange(o, a);
-    });
-    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+    construct(link_body_decompositions, use_signed_distance_field, resolution, collision_tolerance,
+              max_propogation_distance);
   }
 
   // copy onto another world, .h:86 / .cpp:95-116 (the allocator's allocateEnv(orig, world))
@@ -615,13 +635,8 @@ public:
   {
     std::copy(other.size_, other.size_ + 3, size_);
     origin_ = other.origin_;
-    initialize(other.link_spheres_, other.use_signed_distance_field_, other.resolution_, other.collision_tolerance_,
-               other.max_propogation_distance_);
-    world_field_ = newField();
-    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
-      notifyObjectChange(o, a);
-    });
-    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+    construct(other.link_spheres_, other.use_signed_distance_field_, other.resolution_, other.collision_tolerance_,
+              other.max_propogation_distance_);
   }
 
   CollisionEnvB200(const CollisionEnvB200&) = delete;
@@ -637,38 +652,52 @@ public:
   }
 
   // ---- single-state API of CollisionEnv (each call is a batch of one) -----------------------------------
+  // Error contract (collision_env.h has no error channel: void methods, results through CollisionResult): no
+  // exception ever leaves a public method.  A failing call (CUDA error, lost device, inconsistent model) is recorded
+  // (lastError(), errorCount(), one line on stderr) and answers FAIL-CLOSED: res.collision = true, a batch verdict of
+  // all ones, first_invalid = 1 - a planner then treats the state as invalid instead of driving through an obstacle
+  // it could not test.
   void checkSelfCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
   {
-    checkSelfCollisionHelper(req, res, state, nullptr);  // .cpp:238-244
+    if (!guard("checkSelfCollision", [&] { checkSelfCollisionHelper(req, res, state, nullptr); }))  // .cpp:238-244
+      failClosed(res);
   }
   void checkSelfCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
                           const AllowedCollisionMatrix& acm) const
   {
-    checkSelfCollisionHelper(req, res, state, &acm);  // .cpp:254-261
+    if (!guard("checkSelfCollision", [&] { checkSelfCollisionHelper(req, res, state, &acm); }))  // .cpp:254-261
+      failClosed(res);
   }
   void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
   {
-    run(req, res, state, nullptr, B200DF_CHECK_ROBOT, false);  // .cpp:1466-1487 (no self field generated, Q13)
+    // .cpp:1466-1487 (no self field generated, Q13)
+    if (!guard("checkRobotCollision", [&] { run(req, res, state, nullptr, B200DF_CHECK_ROBOT, false); }))
+      failClosed(res);
   }
   void checkRobotCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
                            const AllowedCollisionMatrix& acm) const
   {
-    run(req, res, state, &acm, B200DF_CHECK_ROBOT, true);  // .cpp:1500-1519
+    if (!guard("checkRobotCollision", [&] { run(req, res, state, &acm, B200DF_CHECK_ROBOT, true); }))  // .cpp:1500-1519
+      failClosed(res);
   }
-  // continuous check: unimplemented in the reference too (.cpp:1521-1534)
+  // continuous check: unimplemented in the reference too (.cpp:1521-1534: logs an error, leaves the result alone)
   void checkRobotCollision(const CollisionRequest&, CollisionResult&, const core::RobotState&, const core::RobotState&,
                            const AllowedCollisionMatrix&) const
   {
-    last_error_ = "Continuous collision checking not implemented";
+    recordError("checkRobotCollision(state1, state2)", "Continuous collision checking not implemented");
   }
   void checkCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state) const
   {
-    run(req, res, state, nullptr, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT, true);  // .cpp:1401-1416
+    const int all = B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT;
+    if (!guard("checkCollision", [&] { run(req, res, state, nullptr, all, true); }))  // .cpp:1401-1416
+      failClosed(res);
   }
   void checkCollision(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
                       const AllowedCollisionMatrix& acm) const
   {
-    run(req, res, state, &acm, B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT, true);  // .cpp:1441-1464
+    const int all = B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT;
+    if (!guard("checkCollision", [&] { run(req, res, state, &acm, all, true); }))  // .cpp:1441-1464
+      failClosed(res);
   }
   std::size_t cacheGenerations() const
   {
@@ -677,12 +706,16 @@ public:
   }
   // distanceRobot / distanceSelf are stubs in the reference (.h:108-123,178-198); defined here as the minimum over
   // the group's spheres of (world-field distance - radius)
+  // (a failing call answers 0.0 = "touching", the conservative value, and records the error)
   double distanceRobot(const core::RobotState& state, const std::string& group_name = "") const
   {
-    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(group_name, state, nullptr, false);
     double d = 0.0;
-    checkStatus(b200df_distance_batch(e->group, world_field_, state.getVariablePositions(), B200DF_Q_F64, 1, &d),
-                "b200df_distance_batch");
+    if (!guard("distanceRobot", [&] {
+          std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(group_name, state, nullptr, false);
+          checkStatus(b200df_distance_batch(e->group, world_field_, state.getVariablePositions(), B200DF_Q_F64, 1, &d),
+                      "b200df_distance_batch");
+        }))
+      d = 0.0;
     return d;
   }
 
@@ -691,14 +724,24 @@ public:
                              const AllowedCollisionMatrix* acm, GroupStateRepresentationPtr& gsr) const
   {
     std::vector<GroupStateRepresentationPtr> one;
-    getCollisionGradientsBatch(req, state.getVariablePositions(), 1, acm, one, &state);
-    gsr = one[0];
+    if (getCollisionGradientsBatch(req, state.getVariablePositions(), 1, acm, one, &state, gsr) && !one.empty())
+      gsr = one[0];
+    else
+      gsr.reset();  // the reference has no failure path here; a null gsr is what a caller can test for
   }
 
   // getAllCollisions .cpp:1559-1578: self field, intra group and environment are all visited (each stops on its own
   // at max_contacts); with req.contacts == false this is the logical OR the verdict kernel computes
   void getAllCollisions(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
                         const AllowedCollisionMatrix* acm) const
+  {
+    if (!guard("getAllCollisions", [&] { getAllCollisionsImpl(req, res, state, acm); }))
+      failClosed(res);
+  }
+
+private:
+  void getAllCollisionsImpl(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                            const AllowedCollisionMatrix* acm) const
   {
     std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, state, acm, true);
     const int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
@@ -715,25 +758,55 @@ public:
     contactsFromSpheres(req, res, state, *e, flags, /*stop_when_done=*/false);
   }
 
+public:
   // ---- batched entry points (new): N states, row-major [n][variable count] -------------------------------
   // verdict[i] = res.collision of the corresponding single-state call with req.contacts == false.
   // which: B200DF_CHECK_ROBOT = checkRobotCollision, SELF|INTRA = checkSelfCollision, all three = checkCollision.
   // The non-group links are posed by reference_state (the scene's current state) for the self field, exactly
   // like the cache entry of the reference, which is built from the first state it sees and then reused while the
   // non-group joints stay within EPSILON.
-  void checkCollisionBatch(const CollisionRequest& req, const double* states, std::int64_t n,
+  // Returns false (and fills verdict with ones: fail-closed) when the call could not be carried out.
+  bool checkCollisionBatch(const CollisionRequest& req, const double* states, std::int64_t n,
                            const AllowedCollisionMatrix* acm, int which, const core::RobotState& reference_state,
                            std::uint8_t* verdict) const
   {
-    const bool need_self = (which & B200DF_CHECK_SELF) != 0;
-    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, need_self);
-    int flags = which;
-    if (!e->self_field)
-      flags &= ~B200DF_CHECK_SELF;
-    // FAST: fp32 screening + exact re-run of the undecided states = the EXACT verdicts at about half the time
-    checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
-                                   B200DF_PRECISION_FAST, verdict),
-                "b200df_check_batch");
+    const bool ok = guard("checkCollisionBatch", [&] {
+      const bool need_self = (which & B200DF_CHECK_SELF) != 0;
+      std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, need_self);
+      int flags = which;
+      if (!e->self_field)
+        flags &= ~B200DF_CHECK_SELF;
+      // FAST: fp32 screening + exact re-run of the undecided states = the EXACT verdicts at about half the time
+      checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
+                                     B200DF_PRECISION_FAST, verdict),
+                  "b200df_check_batch");
+    });
+    if (!ok && verdict && n > 0)
+      std::fill(verdict, verdict + n, std::uint8_t(1));
+    return ok;
+  }
+
+  // Which kernels checkCollisionBatch would run for a batch of n states (nothing is launched): B200DF_ROUTE_* and, when
+  // the FAST screening pass is not used, the B200DF_NOFAST_* reasons - a robot beyond the FAST tables silently runs
+  // the exact kernels (same verdicts, 2-4x slower), and this is where a caller sees it.
+  bool checkCollisionBatchRoute(const CollisionRequest& req, std::int64_t n, const AllowedCollisionMatrix* acm, int which,
+                                const core::RobotState& reference_state, int& route, int& why_not_fast) const
+  {
+    route = B200DF_ROUTE_EXACT;
+    why_not_fast = 0;
+    return guard("checkCollisionBatchRoute", [&] {
+      std::shared_ptr<const CacheEntry> e =
+          getDistanceFieldCacheEntry(req.group_name, reference_state, acm, (which & B200DF_CHECK_SELF) != 0);
+      int flags = which;
+      if (!e->self_field)
+        flags &= ~B200DF_CHECK_SELF;
+      std::int32_t r = 0, w = 0;
+      checkStatus(b200df_check_route(e->group, world_field_, e->self_field, B200DF_Q_F64, n, flags, B200DF_PRECISION_FAST,
+                                     &r, &w),
+                  "b200df_check_route");
+      route = r;
+      why_not_fast = w;
+    });
   }
 
   // PlanningScene::isPathValid's waypoint loop (planning_scene.cpp:2257-2312), collision part: every waypoint in one
@@ -763,9 +836,22 @@ public:
   // of ompl::base::DiscreteMotionValidator::checkMotion over StateValidityChecker::isValid
   // (ompl_interface/src/detail/state_validity_checker.cpp:76-121).  first_invalid[i]: 0 = valid, else the first
   // colliding sample j (state at t = j/segments); OMPL's lastValid fraction is (j-1)/segments.
-  void checkMotionBatch(const CollisionRequest& req, const double* from, const double* to, std::int64_t m,
+  bool checkMotionBatch(const CollisionRequest& req, const double* from, const double* to, std::int64_t m,
                         int segments, const AllowedCollisionMatrix* acm, const core::RobotState& reference_state,
                         std::int32_t* first_invalid, int precision = B200DF_PRECISION_FAST) const
+  {
+    const bool ok = guard("checkMotionBatch", [&] {
+      checkMotionBatchImpl(req, from, to, m, segments, acm, reference_state, first_invalid, precision);
+    });
+    if (!ok && first_invalid && m > 0)
+      std::fill(first_invalid, first_invalid + m, std::int32_t(1));  // fail-closed: invalid from the first sample on
+    return ok;
+  }
+
+private:
+  void checkMotionBatchImpl(const CollisionRequest& req, const double* from, const double* to, std::int64_t m,
+                            int segments, const AllowedCollisionMatrix* acm, const core::RobotState& reference_state,
+                            std::int32_t* first_invalid, int precision) const
   {
     std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, reference_state, acm, true);
     int flags = B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT | (e->self_field ? B200DF_CHECK_SELF : 0);
@@ -790,16 +876,62 @@ public:
                 "b200df_check_edges");
   }
 
-  void getCollisionGradientsBatch(const CollisionRequest& req, const double* states, std::int64_t n,
+public:
+  // Returns false (out cleared) when the call could not be carried out.  gradientTerms() tells which terms of
+  // getCollisionGradients the last successfully generated group entry computes.
+  // reuse: a representation from an earlier call; when given (and generated by this env) its cache entry - group,
+  // ACM tables, self field, link fields - serves the call and req.group_name / acm are not looked at, like the
+  // reference's `if (!gsr) generate... else updateGroupStateRepresentationState` (.cpp:1541-1549).
+  bool getCollisionGradientsBatch(const CollisionRequest& req, const double* states, std::int64_t n,
                                   const AllowedCollisionMatrix* acm, std::vector<GroupStateRepresentationPtr>& out,
-                                  const core::RobotState* reference_state = nullptr) const
+                                  const core::RobotState* reference_state = nullptr,
+                                  const GroupStateRepresentationPtr& reuse = GroupStateRepresentationPtr()) const
   {
-    core::RobotState ref(robot_model_);
-    if (reference_state)
-      ref = *reference_state;
-    else if (n > 0)
-      ref.setVariablePositions(states);
-    std::shared_ptr<const CacheEntry> e = getDistanceFieldCacheEntry(req.group_name, ref, acm, true);
+    out.clear();
+    const bool ok = guard("getCollisionGradientsBatch",
+                          [&] { gradientsBatchImpl(req, states, n, acm, out, reference_state, reuse); });
+    if (!ok)
+      out.clear();
+    return ok;
+  }
+
+  // The per-link PosedDistanceField term of getSelfProximityGradients (.cpp:395-418) needs one bit per link with
+  // geometry in the kernel's masks: groups with more than B200DF_MAX_LINK_FIELDS such links get gradients WITHOUT
+  // that term (self field, intra group and environment terms are unaffected).  Not silent: this returns
+  // LINK_FIELDS_UNSUPPORTED for such a group and a warning is recorded once per generated entry.
+  enum LinkFieldTerm
+  {
+    LINK_FIELDS_APPLIED = 0,
+    LINK_FIELDS_NOT_REQUESTED = 1,  // null / empty ACM: the reference skips the term as well (.cpp:388-392)
+    LINK_FIELDS_UNSUPPORTED = 2,
+  };
+  LinkFieldTerm linkFieldTerm() const
+  {
+    std::lock_guard<std::mutex> lk(update_cache_lock_);
+    return dfce_ ? dfce_->link_field_term : LINK_FIELDS_NOT_REQUESTED;
+  }
+
+private:
+  void gradientsBatchImpl(const CollisionRequest& req, const double* states, std::int64_t n,
+                          const AllowedCollisionMatrix* acm, std::vector<GroupStateRepresentationPtr>& out,
+                          const core::RobotState* reference_state, const GroupStateRepresentationPtr& reuse) const
+  {
+    std::shared_ptr<const CacheEntry> e;
+    if (reuse && reuse->dfce_)
+    {
+      std::lock_guard<std::mutex> lk(update_cache_lock_);
+      if (live_entries_.count(reuse->dfce_.get()))  // generated by THIS env (an entry of another env is ignored)
+        e = std::static_pointer_cast<const CacheEntry>(reuse->dfce_);
+    }
+    if (!e)
+    {
+      core::RobotState ref(robot_model_);
+      if (reference_state)
+        ref = *reference_state;
+      else if (n > 0)
+        ref.setVariablePositions(states);
+      e = getDistanceFieldCacheEntry(req.group_name, ref, acm, true);
+    }
     const std::size_t S = e->sphere_radii.size();
     PinnedBuffer<double> dist(n * S), grad(n * S * 3), cen(n * S * 3);
     PinnedBuffer<std::uint8_t> type(n * S);
@@ -812,6 +944,7 @@ public:
     for (std::int64_t i = 0; i < n; ++i)
     {
       auto gsr = std::make_shared<GroupStateRepresentation>();
+      gsr->dfce_ = e;
       gsr->link_names_ = e->link_names;
       gsr->gradients_.resize(e->link_names.size());
       for (std::size_t l = 0; l < e->link_names.size(); ++l)
@@ -833,18 +966,31 @@ public:
     }
   }
 
+public:
   void setWorld(const WorldPtr& world)  // .cpp:1702-1721
   {
     if (world == world_)
       return;
     world_->removeObserver(observer_handle_);
     world_ = world;
-    checkStatus(b200df_field_reset(world_field_), "b200df_field_reset");
-    posed_objects_.clear();
+    {
+      std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+      world_in_sync_ = false;  // resyncWorldLocked() below (through the observer) rebuilds the field from scratch
+    }
     observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
       notifyObjectChange(o, a);
     });
-    world_->notifyObserverAllObjects(observer_handle_, World::CREATE);
+    std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+    if (!valid_)
+      return;
+    try
+    {
+      resyncWorldLocked();
+    }
+    catch (const std::exception& ex)
+    {
+      recordError("setWorld", ex.what());  // world_in_sync_ stays false: checks retry, then answer fail-closed
+    }
   }
   const WorldPtr& getWorld() const
   {
@@ -854,15 +1000,33 @@ public:
   {
     return world_field_;
   }
-  float rebuildWorldField() const  // forces the pending EDT rebuild; returns its device time in ms
+  float rebuildWorldField() const  // forces the pending EDT rebuild; returns its device time in ms (-1 on failure)
   {
     float ms = 0.f;
-    checkStatus(b200df_field_rebuild(world_field_, &ms), "b200df_field_rebuild");
+    if (!guard("rebuildWorldField", [&] { checkStatus(b200df_field_rebuild(world_field_, &ms), "b200df_field_rebuild"); }))
+      return -1.f;
     return ms;
   }
-  const std::string& lastError() const
+  // see changeShapeInWorldField: false (default) = the reference env's all-nodes octree ingestion (Q9), true =
+  // occupied leaves only.  Takes effect for objects added afterwards.
+  void setOctreeOccupiedLeavesOnly(bool on)
   {
+    std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+    octree_occupied_leaves_only_ = on;
+  }
+  bool valid() const  // false: construction failed (no CUDA device, ...); every check then answers fail-closed
+  {
+    return valid_;
+  }
+  std::string lastError() const  // a copy: the string is written by concurrent const callers
+  {
+    std::lock_guard<std::mutex> lk(error_lock_);
     return last_error_;
+  }
+  std::size_t errorCount() const
+  {
+    std::lock_guard<std::mutex> lk(error_lock_);
+    return error_count_;
   }
 
 private:
@@ -905,6 +1069,7 @@ private:
     b200df_group* group = nullptr;
     b200df_field* self_field = nullptr;
     std::vector<b200df_field*> link_fields;  // GroupStateRepresentation::link_distance_fields_, per geometry link
+    LinkFieldTerm link_field_term = LINK_FIELDS_NOT_REQUESTED;
     ~CacheEntry()
     {
       b200df_group_destroy(group);
@@ -913,6 +1078,100 @@ private:
         b200df_field_destroy(f);
     }
   };
+
+  // ---- error handling ---------------------------------------------------------------------------------
+  void recordError(const char* where, const std::string& what, bool count_as_error = true) const
+  {
+    {
+      std::lock_guard<std::mutex> lk(error_lock_);
+      last_error_ = std::string(where) + ": " + what;
+      if (count_as_error)
+        ++error_count_;
+    }
+    std::fprintf(stderr, "[b200df] %s %s: %s\n", count_as_error ? "ERROR" : "WARN", where, what.c_str());  // ROS_ERROR_NAMED
+  }
+  static void failClosed(CollisionResult& res)
+  {
+    res.collision = true;
+  }
+  template <typename F>
+  bool guard(const char* where, F&& f) const noexcept
+  {
+    try
+    {
+      if (!valid_)
+        throw B200Error("the environment failed to initialise (" + init_error_ + ")");
+      {
+        // a world change that could not be applied leaves the field out of date: rebuild it from the World before
+        // answering, or answer fail-closed
+        std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+        if (!world_in_sync_)
+          const_cast<CollisionEnvB200*>(this)->resyncWorldLocked();
+      }
+      f();
+      return true;
+    }
+    catch (const std::exception& ex)
+    {
+      recordError(where, ex.what());
+    }
+    catch (...)
+    {
+      recordError(where, "unknown exception");
+    }
+    return false;
+  }
+
+  void construct(const LinkSpheres& link_body_decompositions, bool use_signed_distance_field, double resolution,
+                 double collision_tolerance, double max_propogation_distance) noexcept
+  {
+    try
+    {
+      initialize(link_body_decompositions, use_signed_distance_field, resolution, collision_tolerance,
+                 max_propogation_distance);
+      world_field_ = newField();  // generateDistanceFieldCacheEntryWorld :1800-1816
+      valid_ = true;
+    }
+    catch (const std::exception& ex)
+    {
+      init_error_ = ex.what();
+      recordError("CollisionEnvB200", init_error_);
+    }
+    observer_handle_ = world_->addObserver([this](const World::ObjectConstPtr& o, World::Action a) {
+      notifyObjectChange(o, a);
+    });
+    if (valid_)
+    {
+      std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+      try
+      {
+        resyncWorldLocked();
+      }
+      catch (const std::exception& ex)
+      {
+        recordError("CollisionEnvB200", ex.what());  // world_in_sync_ stays false: the first check retries
+      }
+    }
+  }
+
+  // reset the world field and add every object of the World again (notifyObserverAllObjects(CREATE), .cpp:89-92).
+  // Caller holds update_cache_lock_world_.  Throws on failure, leaving world_in_sync_ false.
+  void resyncWorldLocked()
+  {
+    world_in_sync_ = false;
+    checkStatus(b200df_field_reset(world_field_), "b200df_field_reset");
+    posed_objects_.clear();
+    for (const std::string& id : world_->getObjectIds())
+    {
+      World::ObjectConstPtr now = world_->getObject(id);
+      if (!now)
+        continue;
+      for (std::size_t i = 0; i < now->shapes_.size(); ++i)
+        addShapeToWorldField(*now->shapes_[i], now->shape_poses_[i]);
+      posed_objects_[id] = now;
+    }
+    world_in_sync_ = true;
+  }
 
   // initialize .cpp:123-161 + addLinkBodyDecompositions .cpp:1065-1093
   void initialize(const LinkSpheres& link_body_decompositions, bool use_signed_distance_field, double resolution,
@@ -1078,15 +1337,93 @@ private:
 
   // notifyObjectChange .cpp:1723-1747 + updateDistanceObject :1749-1798.  Every shape goes through the
   // BodyDecomposition route with the default padding 0.01 (collision_distance_field_types.h:227, Q10).
-  void notifyObjectChange(const World::ObjectConstPtr& obj, World::Action action)
+  void notifyObjectChange(const World::ObjectConstPtr& obj, World::Action action) noexcept
   {
     std::lock_guard<std::mutex> lk(update_cache_lock_world_);
+    if (!valid_)
+      return;
+    try
+    {
+      if (!world_in_sync_)
+        resyncWorldLocked();  // includes this change: the World already holds it
+      else
+        applyObjectChangeLocked(obj, action);
+    }
+    catch (const std::exception& ex)
+    {
+      world_in_sync_ = false;  // checks answer fail-closed until a resync succeeds
+      recordError("notifyObjectChange", ex.what());
+    }
+  }
+
+  // The points a world shape contributes (updateDistanceObject .cpp:1749-1798), added (value = true) or taken out
+  // again (removePointsFromField of the stored decomposition, :1731-1743).
+  //  - OCTREE: PosedBodyPointDecomposition(octree) (types.cpp:355-366) lists the centre of EVERY node begin_tree()
+  //    visits - inner nodes and free leaves included, no pose applied (Q9).  That is the default here too (parity).
+  //    setOctreeOccupiedLeavesOnly(true) switches to what DistanceField::addOcTreeToField (distance_field.cpp:254-287)
+  //    does for the same tree: occupied leaves only, leaves bigger than a voxel expanded to a lattice (on the GPU).
+  //  - primitives: BodyDecomposition in the body frame with the default padding 0.01, then posed (Q10), on the GPU.
+  //  - POINT_CLOUD: body-frame points posed by the shape transform (PosedBodyPointDecomposition::updatePose).
+  void changeShapeInWorldField(const shapes::Shape& shape, const Isometry3d& pose, bool add)
+  {
+    if (shape.type == shapes::OCTREE)
+    {
+      if (!shape.octree)
+        return;
+      const shapes::OcTreeNodes& t = *shape.octree;
+      const std::size_t n = t.occupied.size();
+      if (octree_occupied_leaves_only_)
+      {
+        std::vector<double> leaves;
+        for (std::size_t i = 0; i < n; ++i)
+          if (t.leaf[i] && t.occupied[i])
+            leaves.insert(leaves.end(), &t.xyzs[4 * i], &t.xyzs[4 * i] + 4);
+        checkStatus(add ? b200df_field_add_octree_leaves(world_field_, leaves.data(), (int64_t)(leaves.size() / 4)) :
+                          b200df_field_remove_octree_leaves(world_field_, leaves.data(), (int64_t)(leaves.size() / 4)),
+                    "b200df_field_*_octree_leaves");
+        return;
+      }
+      std::vector<double> pts(3 * n);
+      for (std::size_t i = 0; i < n; ++i)
+        std::copy(&t.xyzs[4 * i], &t.xyzs[4 * i] + 3, &pts[3 * i]);
+      checkStatus(add ? b200df_field_add_points(world_field_, pts.data(), (int64_t)n) :
+                        b200df_field_remove_points(world_field_, pts.data(), (int64_t)n),
+                  "b200df_field_*_points");
+      return;
+    }
+    if (shape.type == shapes::POINT_CLOUD)
+    {
+      if (!shape.points)
+        return;
+      const std::vector<double>& b = *shape.points;
+      std::vector<double> pts(b.size());
+      for (std::size_t i = 0; i + 2 < b.size(); i += 3)
+      {
+        const Vector3d w = pose * Vector3d{ b[i], b[i + 1], b[i + 2] };
+        pts[i] = w.x;
+        pts[i + 1] = w.y;
+        pts[i + 2] = w.z;
+      }
+      checkStatus(add ? b200df_field_add_points(world_field_, pts.data(), (int64_t)(pts.size() / 3)) :
+                        b200df_field_remove_points(world_field_, pts.data(), (int64_t)(pts.size() / 3)),
+                  "b200df_field_*_points");
+      return;
+    }
+    checkStatus(add ? b200df_field_add_posed_body(world_field_, shape.type, shape.dims, pose.m, 0.01) :
+                      b200df_field_remove_posed_body(world_field_, shape.type, shape.dims, pose.m, 0.01),
+                "b200df_field_*_posed_body");
+  }
+  void addShapeToWorldField(const shapes::Shape& shape, const Isometry3d& pose)
+  {
+    changeShapeInWorldField(shape, pose, true);
+  }
+
+  void applyObjectChangeLocked(const World::ObjectConstPtr& obj, World::Action action)
+  {
     auto cur = posed_objects_.find(obj->id_);
     if (cur != posed_objects_.end() && (action == World::DESTROY || (action & (World::MOVE_SHAPE | World::REMOVE_SHAPE))))
       for (std::size_t i = 0; i < cur->second->shapes_.size(); ++i)
-        checkStatus(b200df_field_remove_posed_body(world_field_, cur->second->shapes_[i]->type,
-                                                   cur->second->shapes_[i]->dims, cur->second->shape_poses_[i].m, 0.01),
-                    "b200df_field_remove_posed_body");
+        changeShapeInWorldField(*cur->second->shapes_[i], cur->second->shape_poses_[i], false);
     World::ObjectConstPtr now = world_->getObject(obj->id_);
     if (now)
     {
@@ -1094,9 +1431,7 @@ private:
       {
         // CREATE / ADD_SHAPE re-add every shape of the object like the reference (add_points holds all of them)
         for (std::size_t i = 0; i < now->shapes_.size(); ++i)
-          checkStatus(b200df_field_add_posed_body(world_field_, now->shapes_[i]->type, now->shapes_[i]->dims,
-                                                  now->shape_poses_[i].m, 0.01),
-                      "b200df_field_add_posed_body");
+          addShapeToWorldField(*now->shapes_[i], now->shape_poses_[i]);
       }
       posed_objects_[obj->id_] = now;
     }
@@ -1120,6 +1455,9 @@ private:
       return cur;
     ++cache_generations_;
     dfce_ = generateDistanceFieldCacheEntry(group_name, state, acm, generate_distance_field);
+    for (auto it = live_entries_.begin(); it != live_entries_.end();)  // forget entries nobody holds any more
+      it = it->second.expired() ? live_entries_.erase(it) : std::next(it);
+    live_entries_[dfce_.get()] = dfce_;
     return dfce_;
   }
 
@@ -1141,7 +1479,7 @@ private:
     const std::vector<core::LinkModel>& links = e.model->links;
     std::set<int> in(e.link_indices.begin(), e.link_indices.end());
     for (int i = 0; i < (int)links.size(); ++i)
-      if (!links[i].shapes.empty() && !in.count(i))
+      if (!links[i].shapes.empty() && !in.count(i) && !(e.model->attached_body[i] >= 0 && in.count(links[i].parent)))
         return true;
     return false;
   }
@@ -1163,12 +1501,20 @@ private:
         e->link_indices.push_back(i);
     else
       e->link_indices = robot_model_->getUpdatedLinkModelIndices(group_name);
+    // attached bodies of the group's links follow the links (dfce->attached_body_names_, :806-812).  The reference
+    // only fills that list inside `if (acm)`: without an ACM a body attached to a group link takes part in no test at
+    // all (neither self field, nor intra group, nor environment) - a grasped object would otherwise always collide
+    // with the gripper link it overlaps.
+    std::set<int> group_attached;
     {
-      // attached bodies of the group's links follow the links (dfce->attached_body_names_, :806-812)
       std::set<int> in_group(e->link_indices.begin(), e->link_indices.end());
       for (int i = n_robot_links; i < (int)links.size(); ++i)
         if (in_group.count(links[i].parent))
-          e->link_indices.push_back(i);
+        {
+          group_attached.insert(i);
+          if (acm)
+            e->link_indices.push_back(i);
+        }
     }
     if (acm)
     {
@@ -1274,7 +1620,9 @@ private:
       bool any = false;
       for (int li = 0; li < (int)links.size(); ++li)
       {
-        if (links[li].shapes.empty() || in.count(li))
+        // :925-945: links outside the group and the bodies attached to THOSE links; a body attached to a group link
+        // is never part of the self field
+        if (links[li].shapes.empty() || in.count(li) || group_attached.count(li))
           continue;
         any = true;
         Isometry3d pose;
@@ -1301,8 +1649,19 @@ private:
   void generateLinkDistanceFields(CacheEntry& e) const
   {
     const std::size_t G = e.geom_model_index.size();
-    if (G == 0 || G > 32)
+    if (G == 0)
       return;
+    if (G > B200DF_MAX_LINK_FIELDS)
+    {
+      e.link_field_term = LINK_FIELDS_UNSUPPORTED;
+      recordError("generateLinkDistanceFields",
+                  "group '" + e.group_name + "' has " + std::to_string(G) + " links with geometry (more than " +
+                      std::to_string(B200DF_MAX_LINK_FIELDS) +
+                      "): gradients are computed WITHOUT the per-link distance-field term of getSelfProximityGradients",
+                  /*count_as_error=*/false);
+      return;
+    }
+    e.link_field_term = LINK_FIELDS_APPLIED;
     const ModelEntry& me = *e.model;
     std::vector<std::uint8_t> enabled(G * G, 0);
     for (std::size_t a = 0; a < G; ++a)
@@ -1503,10 +1862,212 @@ private:
   World::ObserverHandle observer_handle_ = 0;
   mutable std::mutex update_cache_lock_, update_cache_lock_world_;  // .h:295,302
   mutable std::shared_ptr<const CacheEntry> dfce_;
+  mutable std::map<const void*, std::weak_ptr<const CacheEntry>> live_entries_;  // entries handed out through a gsr
   mutable std::size_t cache_generations_ = 0;  // how often the entry had to be regenerated (guarded by update_cache_lock_)
+  bool valid_ = false;             // construction succeeded
+  std::string init_error_;
+  bool world_in_sync_ = false;     // guarded by update_cache_lock_world_
+  bool octree_occupied_leaves_only_ = false;
+  mutable std::mutex error_lock_;  // last_error_ / error_count_ are written by concurrent const callers
   mutable std::string last_error_;
+  mutable std::size_t error_count_ = 0;
 };
 using CollisionEnvB200Ptr = std::shared_ptr<CollisionEnvB200>;
+
+// ------------------------------------------------------------------------------------------------------------
+// CollisionEnvHybridB200 - collision_env_hybrid.h:50-151 / .cpp:47-179: the class CHOMP dynamic_casts the active
+// collision env to (chomp_optimizer.cpp:81-88).  The reference derives it from CollisionEnvFCL (the mesh-exact sibling
+// backend answers the CollisionEnv virtuals) and forwards every *DistanceField method and getCollisionGradients to a
+// CollisionEnvDistanceField member built on the same World.  Here the base is a template parameter: the plugin
+// instantiates it with collision_detection::CollisionEnvFCL (moveit_b200/plugin/), this image with the stand-in
+// below, which has the constructors / getWorld / setWorld the hybrid uses and nothing else.
+// ------------------------------------------------------------------------------------------------------------
+class CollisionEnvNoMeshBackend
+{
+public:
+  explicit CollisionEnvNoMeshBackend(const core::RobotModelConstPtr& model, double = 0.0, double = 1.0)
+    : robot_model_(model), world_(std::make_shared<World>())
+  {
+  }
+  CollisionEnvNoMeshBackend(const core::RobotModelConstPtr& model, const WorldPtr& world, double = 0.0, double = 1.0)
+    : robot_model_(model), world_(world)
+  {
+  }
+  CollisionEnvNoMeshBackend(const CollisionEnvNoMeshBackend& other, const WorldPtr& world)
+    : robot_model_(other.robot_model_), world_(world)
+  {
+  }
+  virtual ~CollisionEnvNoMeshBackend() = default;
+  const WorldPtr& getWorld() const
+  {
+    return world_;
+  }
+  virtual void setWorld(const WorldPtr& world)
+  {
+    world_ = world;
+  }
+
+protected:
+  core::RobotModelConstPtr robot_model_;
+  WorldPtr world_;
+};
+
+template <class MeshBackend = CollisionEnvNoMeshBackend>
+class CollisionEnvHybridB200T : public MeshBackend
+{
+public:
+  using LinkSpheres = CollisionEnvB200::LinkSpheres;
+
+  explicit CollisionEnvHybridB200T(const core::RobotModelConstPtr& robot_model,
+                                   const LinkSpheres& link_body_decompositions = {}, double size_x = DEFAULT_SIZE_X,
+                                   double size_y = DEFAULT_SIZE_Y, double size_z = DEFAULT_SIZE_Z,
+                                   const Vector3d& origin = Vector3d(),
+                                   bool use_signed_distance_field = DEFAULT_USE_SIGNED_DISTANCE_FIELD,
+                                   double resolution = DEFAULT_RESOLUTION,
+                                   double collision_tolerance = DEFAULT_COLLISION_TOLERANCE,
+                                   double max_propogation_distance = DEFAULT_MAX_PROPOGATION_DISTANCE,
+                                   double padding = 0.0, double scale = 1.0)
+    : MeshBackend(robot_model)
+    , cenv_distance_(new CollisionEnvB200(robot_model, this->getWorld(), link_body_decompositions, size_x, size_y,
+                                          size_z, origin, use_signed_distance_field, resolution, collision_tolerance,
+                                          max_propogation_distance, padding, scale))
+  {
+  }
+  CollisionEnvHybridB200T(const core::RobotModelConstPtr& robot_model, const WorldPtr& world,
+                          const LinkSpheres& link_body_decompositions = {}, double size_x = DEFAULT_SIZE_X,
+                          double size_y = DEFAULT_SIZE_Y, double size_z = DEFAULT_SIZE_Z,
+                          const Vector3d& origin = Vector3d(),
+                          bool use_signed_distance_field = DEFAULT_USE_SIGNED_DISTANCE_FIELD,
+                          double resolution = DEFAULT_RESOLUTION,
+                          double collision_tolerance = DEFAULT_COLLISION_TOLERANCE,
+                          double max_propogation_distance = DEFAULT_MAX_PROPOGATION_DISTANCE, double padding = 0.0,
+                          double scale = 1.0)
+    : MeshBackend(robot_model, world, padding, scale)
+    , cenv_distance_(new CollisionEnvB200(robot_model, this->getWorld(), link_body_decompositions, size_x, size_y,
+                                          size_z, origin, use_signed_distance_field, resolution, collision_tolerance,
+                                          max_propogation_distance, padding, scale))
+  {
+  }
+  CollisionEnvHybridB200T(const CollisionEnvHybridB200T& other, const WorldPtr& world)
+    : MeshBackend(other, world), cenv_distance_(new CollisionEnvB200(*other.getCollisionWorldDistanceField(), world))
+  {
+  }
+
+  // .cpp:77-172 - every overload forwards; the gsr overloads hand back the representation of the call
+  void checkSelfCollisionDistanceField(const CollisionRequest& req, CollisionResult& res,
+                                       const core::RobotState& state) const
+  {
+    cenv_distance_->checkSelfCollision(req, res, state);
+  }
+  void checkSelfCollisionDistanceField(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                                       const AllowedCollisionMatrix& acm) const
+  {
+    cenv_distance_->checkSelfCollision(req, res, state, acm);
+  }
+  void checkCollisionDistanceField(const CollisionRequest& req, CollisionResult& res,
+                                   const core::RobotState& state) const
+  {
+    cenv_distance_->checkCollision(req, res, state);
+  }
+  void checkCollisionDistanceField(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                                   const AllowedCollisionMatrix& acm) const
+  {
+    cenv_distance_->checkCollision(req, res, state, acm);
+  }
+  void checkRobotCollisionDistanceField(const CollisionRequest& req, CollisionResult& res,
+                                        const core::RobotState& state) const
+  {
+    cenv_distance_->checkRobotCollision(req, res, state);
+  }
+  void checkRobotCollisionDistanceField(const CollisionRequest& req, CollisionResult& res,
+                                        const core::RobotState& state, const AllowedCollisionMatrix& acm) const
+  {
+    cenv_distance_->checkRobotCollision(req, res, state, acm);
+  }
+  // the gsr variants (.cpp:84-90, 100-107, 115-121, 131-138, 146-152, 161-168): same verdict; gsr receives the
+  // representation (posed spheres, distances, gradients) of this state, generated from / reusing its cache entry
+  void checkCollisionDistanceField(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                                   const AllowedCollisionMatrix& acm, GroupStateRepresentationPtr& gsr) const
+  {
+    cenv_distance_->checkCollision(req, res, state, acm);
+    cenv_distance_->getCollisionGradients(req, res, state, &acm, gsr);
+  }
+  void checkCollisionDistanceField(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                                   GroupStateRepresentationPtr& gsr) const
+  {
+    cenv_distance_->checkCollision(req, res, state);
+    cenv_distance_->getCollisionGradients(req, res, state, nullptr, gsr);
+  }
+
+  void setWorld(const WorldPtr& world) override  // .cpp:174-181
+  {
+    if (world == this->getWorld())
+      return;
+    cenv_distance_->setWorld(world);
+    MeshBackend::setWorld(world);
+  }
+
+  // .cpp:183-188 - the CHOMP entry point
+  void getCollisionGradients(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                             const AllowedCollisionMatrix* acm, GroupStateRepresentationPtr& gsr) const
+  {
+    cenv_distance_->getCollisionGradients(req, res, state, acm, gsr);
+  }
+  // all waypoints of all candidate trajectories in one launch (the batched form of ChompOptimizer's loop)
+  bool getCollisionGradientsBatch(const CollisionRequest& req, const double* states, std::int64_t n,
+                                  const AllowedCollisionMatrix* acm, std::vector<GroupStateRepresentationPtr>& out,
+                                  const core::RobotState* reference_state = nullptr,
+                                  const GroupStateRepresentationPtr& reuse = GroupStateRepresentationPtr()) const
+  {
+    return cenv_distance_->getCollisionGradientsBatch(req, states, n, acm, out, reference_state, reuse);
+  }
+  void getAllCollisions(const CollisionRequest& req, CollisionResult& res, const core::RobotState& state,
+                        const AllowedCollisionMatrix* acm) const
+  {
+    cenv_distance_->getAllCollisions(req, res, state, acm);
+  }
+  const std::shared_ptr<const CollisionEnvB200> getCollisionWorldDistanceField() const  // collision_env_hybrid.h:141-144
+  {
+    return cenv_distance_;
+  }
+
+protected:
+  std::shared_ptr<CollisionEnvB200> cenv_distance_;
+};
+using CollisionEnvHybridB200 = CollisionEnvHybridB200T<>;
+
+// CollisionDetectorAllocatorHybrid (collision_detector_allocator_hybrid.h): NAME "HYBRID" in the reference
+class CollisionDetectorAllocatorHybridB200
+{
+public:
+  static const std::string& NAME()
+  {
+    static const std::string name = "HYBRID_B200";
+    return name;
+  }
+  const std::string& getName() const
+  {
+    return NAME();
+  }
+  std::shared_ptr<CollisionEnvHybridB200> allocateEnv(const WorldPtr& world,
+                                                       const core::RobotModelConstPtr& robot_model) const
+  {
+    return std::make_shared<CollisionEnvHybridB200>(robot_model, world);
+  }
+  std::shared_ptr<CollisionEnvHybridB200> allocateEnv(const std::shared_ptr<const CollisionEnvHybridB200>& orig,
+                                                       const WorldPtr& world) const
+  {
+    return std::make_shared<CollisionEnvHybridB200>(*orig, world);
+  }
+  std::shared_ptr<CollisionEnvHybridB200> allocateEnv(const core::RobotModelConstPtr& robot_model) const
+  {
+    return std::make_shared<CollisionEnvHybridB200>(robot_model);
+  }
+  static std::shared_ptr<CollisionDetectorAllocatorHybridB200> create()
+  {
+    return std::make_shared<CollisionDetectorAllocatorHybridB200>();
+  }
+};
 
 // CollisionDetectorAllocatorTemplate<CollisionEnvB200, CollisionDetectorAllocatorB200>, collision_detector_allocator.h:73-98
 class CollisionDetectorAllocatorB200

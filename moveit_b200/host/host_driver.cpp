@@ -104,36 +104,48 @@ static int fieldStreamTest(const std::string& prefix, const char* foreign)
   return 0;
 }
 
-int main(int argc, char** argv)
+struct Scenario
 {
-  if (argc >= 3 && std::string(argv[1]) == "--field-stream")
+  std::string robot_name;
+  std::shared_ptr<core::RobotModel> model;
+  CollisionEnvB200::LinkSpheres overrides;
+  int use_acm = 0;
+  std::shared_ptr<AllowedCollisionMatrix> acm;
+  double size[3], center[3], res = 0.02, max_dist = 0.25, tol = 0.0;
+  int use_signed = 0;
+  WorldPtr world;
+  std::vector<std::string> object_ids;
+  std::vector<core::AttachedBody> attached;
+  std::string group_name;
+  int n_single = 0, n_contacts = 0, n_grad = 0, mutate = 0;
+  std::size_t max_contacts = 1, max_per_pair = 1;
+};
+
+static Scenario parseScenario(const char* path)
+{
+  Scenario sc;
+  std::string& robot_name = sc.robot_name;
+  CollisionEnvB200::LinkSpheres& overrides = sc.overrides;
+  int& use_acm = sc.use_acm;
+  double(&size)[3] = sc.size;
+  double(&center)[3] = sc.center;
+  double &res = sc.res, &max_dist = sc.max_dist, &tol = sc.tol;
+  int& use_signed = sc.use_signed;
+  std::vector<std::string>& object_ids = sc.object_ids;
+  std::vector<core::AttachedBody>& attached = sc.attached;
+  std::string& group_name = sc.group_name;
+  int &n_single = sc.n_single, &n_contacts = sc.n_contacts, &n_grad = sc.n_grad, &mutate = sc.mutate;
+  std::size_t &max_contacts = sc.max_contacts, &max_per_pair = sc.max_per_pair;
   {
-    try
-    {
-      return fieldStreamTest(argv[2], argc > 3 ? argv[3] : nullptr);
-    }
-    catch (const std::exception& ex)
-    {
-      std::fprintf(stderr, "host_driver failed: %s\n", ex.what());
-      return 1;
-    }
-  }
-  if (argc < 4)
-  {
-    std::fprintf(stderr, "usage: host_driver <scenario.txt> <states.f64> <out_prefix>\n");
-    return 2;
-  }
-  try
-  {
-    std::ifstream in(argv[1]);
+    std::ifstream in(path);
     if (!in)
       throw std::runtime_error("cannot open scenario");
     in.precision(17);
-    std::string tok, robot_name;
+    std::string tok;
     int n_links = 0;
     in >> tok >> robot_name >> n_links;
     auto model = std::make_shared<core::RobotModel>(robot_name);
-    CollisionEnvB200::LinkSpheres overrides;
+    sc.model = model;
     for (int i = 0; i < n_links; ++i)
     {
       core::LinkModel l;
@@ -180,23 +192,22 @@ int main(int argc, char** argv)
       model->addJointModelGroup(name, joints);
     }
     // default ACM of a PlanningScene: every pair NEVER, SRDF disable_collisions pairs ALWAYS
-    int use_acm = 0, n_disabled = 0;
+    int n_disabled = 0;
     in >> tok >> use_acm >> n_disabled;
-    AllowedCollisionMatrix acm(model->getLinkModelNames(), false);
+    sc.acm = std::make_shared<AllowedCollisionMatrix>(model->getLinkModelNames(), false);
+    AllowedCollisionMatrix& acm = *sc.acm;
     for (int k = 0; k < n_disabled; ++k)
     {
       std::string a, b;
       in >> a >> b;
       acm.setEntry(a, b, true);
     }
-    double size[3], center[3], res, max_dist, tol;
-    int use_signed;
     in >> tok >> size[0] >> size[1] >> size[2] >> center[0] >> center[1] >> center[2] >> res >> max_dist >>
         use_signed >> tol;
     int n_objects = 0;
     in >> tok >> n_objects;
     auto world = std::make_shared<World>();
-    std::vector<std::string> object_ids;
+    sc.world = world;
     for (int k = 0; k < n_objects; ++k)
     {
       std::string id;
@@ -210,7 +221,6 @@ int main(int argc, char** argv)
     }
     int n_attached = 0;
     in >> tok >> n_attached;
-    std::vector<core::AttachedBody> attached;
     for (int k = 0; k < n_attached; ++k)
     {
       core::AttachedBody b;
@@ -234,14 +244,337 @@ int main(int argc, char** argv)
       }
       attached.push_back(b);
     }
-    std::string group_name;
-    int n_single = 0, n_contacts = 0, n_grad = 0, mutate = 0;
-    std::size_t max_contacts = 1, max_per_pair = 1;
     in >> tok >> group_name >> n_single >> n_contacts >> max_contacts >> max_per_pair >> n_grad >> mutate;
     if (group_name == "-")
       group_name.clear();
     if (!in)
       throw std::runtime_error("scenario parse error");
+
+  }
+  return sc;
+}
+
+// Reads every row of a raw float64 file as one state of the model.
+static std::vector<double> readStates(const char* path, int nvar, std::int64_t* n)
+{
+  std::ifstream sf(path, std::ios::binary | std::ios::ate);
+  if (!sf)
+    throw std::runtime_error("cannot open the state file");
+  const std::streamsize bytes = sf.tellg();
+  sf.seekg(0);
+  *n = bytes / (std::streamsize)(sizeof(double) * nvar);
+  std::vector<double> q((std::size_t)*n * nvar);
+  sf.read(reinterpret_cast<char*>(q.data()), bytes);
+  return q;
+}
+
+static void appendGsr(const GroupStateRepresentation& gsr, std::vector<double>& out)
+{
+  for (const GradientInfo& gi : gsr.gradients_)
+    for (std::size_t s = 0; s < gi.distances.size(); ++s)
+      out.insert(out.end(), { gi.distances[s], gi.gradients[s].x, gi.gradients[s].y, gi.gradients[s].z,
+                              (double)gi.types[s], gi.sphere_locations[s].x, gi.sphere_locations[s].y,
+                              gi.sphere_locations[s].z });
+}
+
+// host_driver --chomp <scenario> <states> <prefix> <waypoints per trajectory>
+// The consumer side of ChompOptimizer (moveit_planners/chomp/chomp_motion_planner/src/chomp_optimizer.cpp) on the
+// hybrid env CHOMP casts the active collision env to (:81-88):
+//   initialize() :93-106    getCollisionGradients(req, res, state, &acm, gsr)   - the ACM enters the gsr's cache entry
+//   performForwardKinematics() :895-965, per waypoint: getCollisionGradients(req, res, state, nullptr, gsr), then the
+//       loop over gsr->gradients_ that reads sphere_locations, distances, sphere_radii, gradients and flags the point
+//       as colliding when distance - radius < radius
+// written out per waypoint; then the same trajectories through ONE getCollisionGradientsBatch call reusing the gsr,
+// which has to give the same numbers.
+static int chompTest(const char* scen_path, const char* states_path, const std::string& prefix, int waypoints)
+{
+  Scenario sc = parseScenario(scen_path);
+  std::int64_t n = 0;
+  const int nvar = sc.model->getVariableCount();
+  std::vector<double> q = readStates(states_path, nvar, &n);
+  const Vector3d origin{ sc.center[0], sc.center[1], sc.center[2] };
+  auto hy = std::make_shared<CollisionEnvHybridB200>(sc.model, sc.world, sc.overrides, sc.size[0], sc.size[1], sc.size[2],
+                                                     origin, sc.use_signed != 0, sc.res, sc.tol, sc.max_dist);
+  // what ChompOptimizer does with the planning scene's env: a dynamic_cast to the hybrid class
+  const CollisionEnvNoMeshBackend* base = hy.get();
+  const CollisionEnvHybridB200* hy_env = dynamic_cast<const CollisionEnvHybridB200*>(base);
+  if (!hy_env)
+    throw std::runtime_error("dynamic_cast to the hybrid env failed");
+  CollisionRequest req;
+  req.group_name = sc.group_name;
+  core::RobotState state(sc.model);
+  GroupStateRepresentationPtr gsr;
+  CollisionResult res;
+  hy_env->getCollisionGradients(req, res, state, &*sc.acm, gsr);  // ChompOptimizer::initialize
+  if (!gsr)
+    throw std::runtime_error(hy_env->getCollisionWorldDistanceField()->lastError());
+  std::size_t num_collision_points = 0;
+  for (const GradientInfo& gi : gsr->gradients_)
+    num_collision_points += gi.gradients.size();
+  std::vector<double> loop_out, batch_out;
+  std::vector<std::uint8_t> in_collision;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (std::int64_t i = 0; i < n; ++i)  // performForwardKinematics over every waypoint of every trajectory
+  {
+    state.setVariablePositions(&q[(std::size_t)i * nvar]);
+    CollisionResult r;
+    hy_env->getCollisionGradients(req, r, state, nullptr, gsr);
+    if (!gsr)
+      throw std::runtime_error(hy_env->getCollisionWorldDistanceField()->lastError());
+    bool colliding = false;
+    for (const GradientInfo& info : gsr->gradients_)
+      for (std::size_t k = 0; k < info.sphere_locations.size(); ++k)
+        if (info.distances[k] - info.sphere_radii[k] < info.sphere_radii[k])
+          colliding = true;
+    in_collision.push_back(colliding ? 1 : 0);
+    appendGsr(*gsr, loop_out);
+  }
+  const double us_loop = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  const auto t1 = std::chrono::steady_clock::now();
+  std::vector<GroupStateRepresentationPtr> all;
+  if (!hy_env->getCollisionGradientsBatch(req, q.data(), n, nullptr, all, nullptr, gsr))
+    throw std::runtime_error(hy_env->getCollisionWorldDistanceField()->lastError());
+  const double us_batch = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
+  for (const GroupStateRepresentationPtr& g : all)
+    appendGsr(*g, batch_out);
+  if (batch_out != loop_out)
+    throw std::runtime_error("batched gradients differ from the per-waypoint loop");
+  if (loop_out.size() != (std::size_t)n * num_collision_points * 8)
+    throw std::runtime_error("collision point count changed between waypoints");
+  writeFile(prefix + ".chomp.f64", loop_out);
+  writeFile(prefix + ".chomp_collision.u8", in_collision);
+  std::printf("chomp test ok: %lld trajectories x %d waypoints, %zu collision points, per-waypoint loop %.1f us/waypoint, "
+              "one batched call %.2f us/waypoint, link-field term %d\n",
+              (long long)(n / std::max(1, waypoints)), waypoints, num_collision_points, us_loop / std::max<std::int64_t>(n, 1),
+              us_batch / std::max<std::int64_t>(n, 1), (int)hy_env->getCollisionWorldDistanceField()->linkFieldTerm());
+  return 0;
+}
+
+// host_driver --contract
+// The error contract of the CollisionEnv boundary (collision_env.h: void methods, no exceptions, results only through
+// CollisionResult): an env that cannot work - no CUDA device (this is what the CPU-only test box sees) or a field the
+// engine refuses (resolution 0) - must construct without throwing and answer every call FAIL-CLOSED.
+static int contractTest()
+{
+  auto model = std::make_shared<core::RobotModel>("contract_bot");
+  core::LinkModel base;
+  base.name = "base";
+  base.joint_name = "fixed_base";
+  base.joint_type = core::FIXED;
+  shapes::Shape sp;
+  sp.type = shapes::SPHERE;
+  sp.dims[0] = 0.04;
+  base.shapes.push_back(sp);
+  base.shape_origins.push_back(Isometry3d::Identity());
+  model->addLink(base);
+  core::LinkModel arm;
+  arm.name = "arm";
+  arm.parent = 0;
+  arm.joint_name = "j1";
+  arm.joint_type = core::REVOLUTE;
+  arm.shapes.push_back(sp);
+  arm.shape_origins.push_back(Isometry3d::Identity());
+  model->addLink(arm);
+  auto world = std::make_shared<World>();
+  auto box = std::make_shared<shapes::Shape>();
+  box->type = shapes::BOX;
+  box->dims[0] = box->dims[1] = box->dims[2] = 0.02;
+  world->addToObject("box", box, Isometry3d::Identity());
+  int n_dev = 0;
+  b200df_device_count(&n_dev);
+  // with a device the env is made to fail through a resolution the engine refuses; without one it fails by itself
+  const double resolution = n_dev > 0 ? 0.0 : 0.02;
+  auto check = [](bool ok, const char* what) {
+    if (!ok)
+      throw std::runtime_error(std::string("contract test: ") + what);
+  };
+  CollisionEnvB200Ptr env;
+  try
+  {
+    env = std::make_shared<CollisionEnvB200>(model, world, CollisionEnvB200::LinkSpheres(), 0.1, 0.1, 0.2, Vector3d(),
+                                             false, resolution);
+  }
+  catch (...)
+  {
+    check(false, "the constructor threw");
+  }
+  check(!env->valid() && !env->lastError().empty(), "a failed env must say so");
+  AllowedCollisionMatrix acm(model->getLinkModelNames(), false);
+  core::RobotState st(model);
+  CollisionRequest req;
+  try
+  {
+    const std::size_t before = env->errorCount();
+    CollisionResult a, b, c, d, e, f, g;
+    env->checkCollision(req, a, st);
+    env->checkCollision(req, b, st, acm);
+    env->checkSelfCollision(req, c, st);
+    env->checkSelfCollision(req, d, st, acm);
+    env->checkRobotCollision(req, e, st);
+    env->checkRobotCollision(req, f, st, acm);
+    env->getAllCollisions(req, g, st, &acm);
+    check(a.collision && b.collision && c.collision && d.collision && e.collision && f.collision && g.collision,
+          "a check that could not run must report a collision (fail-closed)");
+    check(env->errorCount() >= before + 7, "every failed call is counted");
+    std::vector<double> q(3 * (std::size_t)model->getVariableCount(), 0.0);
+    std::vector<std::uint8_t> v(3, 0);
+    check(!env->checkCollisionBatch(req, q.data(), 3, &acm, B200DF_CHECK_ROBOT, st, v.data()), "batch must report failure");
+    check(v[0] == 1 && v[1] == 1 && v[2] == 1, "batch verdicts must be fail-closed");
+    std::vector<std::int32_t> first(1, 0);
+    check(!env->checkMotionBatch(req, q.data(), q.data(), 1, 4, &acm, st, first.data()) && first[0] == 1,
+          "motion batch must be fail-closed");
+    std::vector<std::size_t> invalid;
+    check(!env->isPathValid(req, q.data(), 3, &acm, st, &invalid) && invalid.size() == 3, "isPathValid must be false");
+    GroupStateRepresentationPtr gsr;
+    CollisionResult r;
+    env->getCollisionGradients(req, r, st, &acm, gsr);
+    check(!gsr, "failed gradients leave a null gsr");
+    check(env->distanceRobot(st) == 0.0, "failed distance query answers 0 (touching)");
+    check(env->rebuildWorldField() < 0.f, "failed rebuild is signalled");
+    // world changes and setWorld on a failed env are absorbed as well
+    world->addToObject("box2", box, Isometry3d::Identity());
+    world->removeObject("box");
+    env->setWorld(std::make_shared<World>());
+    CollisionEnvHybridB200 hy(model, world, CollisionEnvB200::LinkSpheres(), 0.1, 0.1, 0.2, Vector3d(), false, resolution);
+    CollisionResult h;
+    hy.checkCollisionDistanceField(req, h, st, acm);
+    check(h.collision, "hybrid forwards the fail-closed verdict");
+    auto alloc = CollisionDetectorAllocatorB200::create();
+    CollisionEnvB200Ptr copy = alloc->allocateEnv(env, world);
+    check(copy && (n_dev > 0 || !copy->valid()), "allocateEnv(orig, world) must not throw");
+  }
+  catch (const std::runtime_error&)
+  {
+    throw;
+  }
+  catch (...)
+  {
+    check(false, "a public method threw");
+  }
+  std::printf("contract test ok: %zu errors recorded, last: %s\n", env->errorCount(), env->lastError().c_str());
+  return 0;
+}
+
+// host_driver --octree <nodes.txt> <prefix>
+// An <octomap> world object (shapes::OcTree, planning_scene.cpp:1390-1412) through the env's World observer:
+// nodes.txt lists every node of the tree in begin_tree() order as "x y z size occupied leaf".  Written out: the world
+// field's d^2 with the reference env's all-nodes ingestion (Q9), with occupied leaves only, and after the object was
+// removed again.
+static int octreeTest(const char* nodes_path, const std::string& prefix)
+{
+  auto nodes = std::make_shared<shapes::OcTreeNodes>();
+  {
+    std::ifstream in(nodes_path);
+    double x, y, z, size;
+    int occ, leaf;
+    while (in >> x >> y >> z >> size >> occ >> leaf)
+    {
+      nodes->xyzs.insert(nodes->xyzs.end(), { x, y, z, size });
+      nodes->occupied.push_back((std::uint8_t)occ);
+      nodes->leaf.push_back((std::uint8_t)leaf);
+    }
+  }
+  auto model = std::make_shared<core::RobotModel>("octree_bot");
+  core::LinkModel base;
+  base.name = "base";
+  base.joint_name = "fixed_base";
+  base.joint_type = core::FIXED;
+  model->addLink(base);
+  auto dump = [&](const CollisionEnvB200& env, const std::string& name) {
+    distance_field_b200::PropagationDistanceFieldB200 view(env.getDistanceField());
+    std::vector<std::int32_t> d2 = view.distanceSquares();
+    std::ofstream f(prefix + name, std::ios::binary);
+    f.write(reinterpret_cast<const char*>(d2.data()), (std::streamsize)(d2.size() * sizeof(std::int32_t)));
+  };
+  auto tree = std::make_shared<shapes::Shape>();
+  tree->type = shapes::OCTREE;
+  tree->octree = nodes;
+  for (int mode = 0; mode < 2; ++mode)
+  {
+    auto world = std::make_shared<World>();
+    CollisionEnvB200 env(model, world, CollisionEnvB200::LinkSpheres(), 1.0, 1.0, 1.0, Vector3d{ 0.5, 0.5, 0.5 }, false,
+                         0.02);
+    if (!env.valid())
+      throw std::runtime_error(env.lastError());
+    env.setOctreeOccupiedLeavesOnly(mode == 1);
+    world->addToObject("<octomap>", tree, Isometry3d::Identity());
+    dump(env, mode == 0 ? ".q9.d2.i32" : ".leaves.d2.i32");
+    // a second env allocated on the already populated world sees the same tree (notifyObserverAllObjects(CREATE))
+    if (mode == 0)
+    {
+      CollisionEnvB200 late(model, world, CollisionEnvB200::LinkSpheres(), 1.0, 1.0, 1.0, Vector3d{ 0.5, 0.5, 0.5 },
+                            false, 0.02);
+      dump(late, ".late.d2.i32");
+    }
+    world->removeObject("<octomap>");
+    dump(env, mode == 0 ? ".q9_removed.d2.i32" : ".leaves_removed.d2.i32");
+    if (env.errorCount() != 0)
+      throw std::runtime_error(env.lastError());
+  }
+  std::printf("octree test ok: %zu nodes\n", nodes->occupied.size());
+  return 0;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc >= 3 && std::string(argv[1]) == "--field-stream")
+  {
+    try
+    {
+      return fieldStreamTest(argv[2], argc > 3 ? argv[3] : nullptr);
+    }
+    catch (const std::exception& ex)
+    {
+      std::fprintf(stderr, "host_driver failed: %s\n", ex.what());
+      return 1;
+    }
+  }
+  if (argc >= 2 && (std::string(argv[1]) == "--contract" || std::string(argv[1]) == "--chomp" ||
+                    std::string(argv[1]) == "--octree"))
+  {
+    try
+    {
+      if (std::string(argv[1]) == "--contract")
+        return contractTest();
+      if (std::string(argv[1]) == "--octree")
+      {
+        if (argc < 4)
+          throw std::runtime_error("usage: host_driver --octree <nodes.txt> <prefix>");
+        return octreeTest(argv[2], argv[3]);
+      }
+      if (argc < 6)
+        throw std::runtime_error("usage: host_driver --chomp <scenario> <states.f64> <prefix> <waypoints>");
+      return chompTest(argv[2], argv[3], argv[4], std::atoi(argv[5]));
+    }
+    catch (const std::exception& ex)
+    {
+      std::fprintf(stderr, "host_driver failed: %s\n", ex.what());
+      return 1;
+    }
+  }
+  if (argc < 4)
+  {
+    std::fprintf(stderr, "usage: host_driver <scenario.txt> <states.f64> <out_prefix>\n");
+    return 2;
+  }
+  try
+  {
+    Scenario sc = parseScenario(argv[1]);
+    const std::string& robot_name = sc.robot_name;
+    std::shared_ptr<core::RobotModel> model = sc.model;
+    CollisionEnvB200::LinkSpheres& overrides = sc.overrides;
+    const int use_acm = sc.use_acm;
+    AllowedCollisionMatrix& acm = *sc.acm;
+    double(&size)[3] = sc.size;
+    double(&center)[3] = sc.center;
+    const double res = sc.res, max_dist = sc.max_dist, tol = sc.tol;
+    const int use_signed = sc.use_signed;
+    WorldPtr world = sc.world;
+    std::vector<std::string>& object_ids = sc.object_ids;
+    std::vector<core::AttachedBody>& attached = sc.attached;
+    std::string group_name = sc.group_name;
+    const int n_single = sc.n_single, n_contacts = sc.n_contacts, n_grad = sc.n_grad, mutate = sc.mutate;
+    const std::size_t max_contacts = sc.max_contacts, max_per_pair = sc.max_per_pair;
 
     // states
     std::ifstream sf(argv[2], std::ios::binary | std::ios::ate);

@@ -1139,3 +1139,34 @@ def test_edge_check_slerps_floating_joints(gpu, oracle):
     assert 0 < (got == 0).sum() < M
     lin = e.group.check_edges(qa, qb, K, e.world, flags=flags, precision=0)  # plain lerp of the quaternion: not the same
     assert not np.array_equal(lin, got)
+
+
+def test_check_route_reports_the_kernel_and_why_fast_is_not_used(gpu, oracle):
+    """b200df_check_route: the EXACT fall-back of a FAST call is visible to the caller, never silent."""
+    import ctypes as C
+    from moveit_b200 import binding as B
+    from common import FUZZ_CASES, random_robot
+
+    def route(e, n, precision=B.PRECISION_FAST, flags=CHECK_ROBOT | CHECK_INTRA, dtype=B.Q_F32, world=None):
+        r, w = C.c_int32(-1), C.c_int32(-1)
+        B.check(B.load().b200df_check_route(e.group.h, (world or e.world).h, None, dtype, n, flags, precision,
+                                            C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    e = EngineSetup(rd.panda(), scenarios.FIELD_A, scenarios.random_scene())
+    assert route(e, 10_000_000) == (B.ROUTE_FAST, 0)
+    assert route(e, 10_000_000, precision=B.PRECISION_EXACT) == (B.ROUTE_EXACT, 0)
+    assert route(e, 100) == (B.ROUTE_SMALL, B.NOFAST_BATCH)
+    assert route(e, 40_000) == (B.ROUTE_EXACT, B.NOFAST_BATCH)
+    # a robot beyond FAST's constant-bank tables (> 128 spheres): exact kernels, and the reason says so
+    seed, n_links, floating, kw = FUZZ_CASES[3]
+    big = random_robot(seed, n_links, floating, **kw)
+    eb = EngineSetup(big, scenarios.FIELD_DEFAULT, scenarios.random_scene(seed=9, n_boxes=2, n_cylinders=1))
+    r, w = route(eb, 1_000_000)
+    assert r != B.ROUTE_FAST and (w & (B.NOFAST_TABLES | B.NOFAST_SMEM))
+    # a signed world field with a collision tolerance above some radius needs the fp64 signed predicate
+    es = EngineSetup(rd.panda(), scenarios.FIELD_A, scenarios.random_scene(), signed=True, tol=0.2)
+    r, w = route(es, 1_000_000)
+    assert r == B.ROUTE_EXACT and (w & B.NOFAST_SIGNED)
+    es2 = EngineSetup(rd.panda(), scenarios.FIELD_A, scenarios.random_scene(), signed=True)
+    assert route(es2, 1_000_000) == (B.ROUTE_FAST, 0)  # radius > tolerance everywhere: the negative field is irrelevant

@@ -260,3 +260,146 @@ def test_random_robots_through_the_cpp_env(gpu, oracle, tmp_path, case):
     assert 0 < both.sum() < len(q)
     single = np.fromfile(prefix + ".single.u8", dtype=np.uint8)
     assert np.array_equal(single & 1, robot[:16]) and np.array_equal((single >> 2) & 1, both[:16])
+
+
+def test_boundary_contract_without_a_device():
+    """collision_env.h gives a CollisionEnv no error channel (void methods, no exceptions).  On this CPU-only box the
+    env cannot initialise: it must construct anyway, never throw, record every failure and answer FAIL-CLOSED
+    (res.collision = true, batch verdicts of ones) - through the plain env, the hybrid env and the allocator."""
+    exe = _build_driver()
+    r = subprocess.run([exe, "--contract"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout
+    assert "contract test ok" in r.stdout and "errors recorded" in r.stdout
+    assert "[b200df] ERROR" in r.stderr  # the ROS_ERROR stand-in: failures are logged, not swallowed
+
+
+@pytest.mark.gpu
+def test_boundary_contract_with_a_device(gpu):
+    """The same contract on the GPU box, where the failure is provoked by a field the engine refuses (resolution 0)."""
+    exe = _build_driver()
+    r = subprocess.run([exe, "--contract"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout
+    assert "contract test ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_chomp_consumer_loop_through_the_hybrid_env(gpu, oracle, tmp_path):
+    """ChompOptimizer's use of the path (chomp_optimizer.cpp:81-106, 895-965) on CollisionEnvHybridB200: one
+    getCollisionGradients with the scene ACM creates the GroupStateRepresentation, then 100 waypoints x 6 trajectories
+    reuse it with acm = nullptr (the gsr's cache entry keeps the ACM and the per-link distance fields); the same
+    waypoints through ONE batched call must give identical numbers (the driver checks that), and everything is compared
+    with the oracle's getCollisionGradients."""
+    exe = _build_driver()
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=41)
+    fa = scenarios.FIELD_A
+    n_traj, n_wp = 6, 100
+    q = scenarios.chomp_trajectories(desc, n_traj, n_wp).reshape(-1, desc.nvar)
+    scen, states, prefix = str(tmp_path / "scen.txt"), str(tmp_path / "q.f64"), str(tmp_path / "out")
+    scenario_io.write_scenario(scen, desc, fa, objs, group="panda_arm")
+    np.ascontiguousarray(q, dtype=np.float64).tofile(states)
+    r = subprocess.run([exe, "--chomp", scen, states, prefix, str(n_wp)], capture_output=True, text=True)
+    assert r.returncode == 0 and "chomp test ok" in r.stdout, r.stderr[-2000:] + r.stdout
+    assert "link-field term 0" in r.stdout  # LINK_FIELDS_APPLIED
+    print(r.stdout.strip())
+    o = OracleSetup(oracle, desc, fa, objs, group="panda_arm", self_state=np.zeros(desc.nvar))
+    o.env.build_link_fields()
+    ref = o.env.gradients_batch(q, flags=7)
+    g = np.fromfile(prefix + ".chomp.f64").reshape(len(q), -1, 8)
+    assert g.shape[1] == ref["dist"].shape[1]
+    assert np.array_equal(g[:, :, 4].astype(np.int32), ref["type"])
+    assert np.max(np.abs(g[:, :, 5:8] - ref["centers"])) < 1e-12
+    fin = ref["dist"] < 1e300
+    assert np.array_equal(fin, g[:, :, 0] < 1e300)
+    assert np.max(np.abs(g[:, :, 0][fin] - ref["dist"][fin])) <= 1e-5
+    assert np.max(np.abs(g[:, :, 1:4] - ref["grad"])) <= 1e-5
+    # CHOMP's per-point collision flag (distance - radius < radius) from the oracle's numbers
+    radii = np.concatenate([np.reshape(o.model_desc["spheres"][li], (-1, 4))[:, 3] for li in o.group_links
+                            if o.model_desc["has_geometry"][li]])
+    assert radii.shape == (g.shape[1],)
+    flag = np.fromfile(prefix + ".chomp_collision.u8", dtype=np.uint8)
+    want = (ref["dist"] - radii[None, :] < radii[None, :]).any(axis=1)  # DBL_MAX distances never satisfy it
+    assert flag.shape == (len(q),) and 0 < flag.sum() <= len(q)
+    assert np.array_equal(flag.astype(bool), want)
+
+
+@pytest.mark.gpu
+def test_attached_body_without_an_acm_takes_part_in_no_test(gpu, oracle, tmp_path):
+    """generateDistanceFieldCacheEntry only lists attached bodies inside `if (acm)` (.cpp:806-834): without an ACM a
+    grasped object is tested against nothing - not the self field, not the other links, not the environment.  The
+    verdicts must be those of the bare robot (round-1 advisor finding: the mirror used to report the box colliding
+    with the hand it is attached to)."""
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=41)
+    fa = scenarios.FIELD_A
+    q = desc.sample_states(2000, 778)
+    pose = rd.rpy_xyz_to_pose((0.0, 0.0, 0.22), (0.1, 0.2, 0.3))
+    attached = [("grasped_box", "panda_hand", [(rd.SHAPE_BOX, (0.06, 0.10, 0.08), pose)], ["panda_hand"])]
+    prefix = _run(tmp_path, desc, fa, objs, q, group="", use_acm=False, n_single=16, attached=attached)
+    plain = OracleSetup(oracle, desc, fa, objs, use_acm=False, self_state=np.zeros(desc.nvar))
+    robot = np.fromfile(prefix + ".robot.u8", dtype=np.uint8)
+    both = np.fromfile(prefix + ".all.u8", dtype=np.uint8)
+    assert np.array_equal(robot, plain.env.check_batch(q, mode=1, n_threads=4))
+    assert np.array_equal(np.fromfile(prefix + ".self.u8", dtype=np.uint8), plain.env.check_batch(q, mode=2, n_threads=4))
+    assert np.array_equal(both, plain.env.check_batch(q, mode=4, n_threads=4))
+    assert 0 < robot.sum() < len(q)  # (without an ACM adjacent links always touch: `both` is all ones either way)
+    single = np.fromfile(prefix + ".single.u8", dtype=np.uint8)
+    assert np.array_equal(single & 1, robot[:16]) and np.array_equal((single >> 2) & 1, both[:16])
+
+
+def _synthetic_octree(seed=3, res=0.02):
+    """A small octomap-like tree over [0, 1.28)^3 in begin_tree() order (depth first, parents before children): inner
+    nodes, occupied and free leaves at the voxel size, at 2x and at 4x the voxel size (pruned nodes)."""
+    rng = np.random.default_rng(seed)
+    nodes = []
+
+    def visit(cx, cy, cz, size, depth):
+        leaf_here = size <= res or (size <= 4 * res and rng.random() < 0.25) or rng.random() < 0.15 * depth - 0.25
+        occupied = rng.random() < 0.3
+        nodes.append((cx, cy, cz, size, int(occupied), int(leaf_here)))
+        if leaf_here:
+            return
+        h = size / 4
+        for dx in (-h, h):
+            for dy in (-h, h):
+                for dz in (-h, h):
+                    if rng.random() < 0.55:  # octomap only allocates children it has seen
+                        visit(cx + dx, cy + dy, cz + dz, size / 2, depth + 1)
+
+    visit(0.64, 0.64, 0.64, 1.28, 0)
+    return np.array(nodes)
+
+
+@pytest.mark.gpu
+def test_octomap_world_object_through_the_env(gpu, oracle, tmp_path):
+    """The OCTREE branch of updateDistanceObject (.cpp:1773-1790): with the reference env's semantics every node
+    begin_tree() visits contributes its centre (Q9, types.cpp:355-366); with setOctreeOccupiedLeavesOnly the occupied
+    leaves go through the GPU form of getOcTreePoints (distance_field.cpp:254-279, big leaves become a lattice).
+    Both against the oracle's field fed with the points the reference would add; removal empties the field again."""
+    exe = _build_driver()
+    nodes = _synthetic_octree()
+    assert len(nodes) > 300 and (nodes[:, 5] == 0).sum() > 20 and ((nodes[:, 3] > 0.03) & (nodes[:, 5] == 1)).sum() > 5
+    path, prefix = str(tmp_path / "nodes.txt"), str(tmp_path / "oct")
+    with open(path, "w") as f:
+        for x, y, z, size, occ, leaf in nodes:
+            f.write("%r %r %r %r %d %d\n" % (float(x), float(y), float(z), float(size), int(occ), int(leaf)))
+    r = subprocess.run([exe, "--octree", path, prefix], capture_output=True, text=True)
+    assert r.returncode == 0 and "octree test ok" in r.stdout, r.stderr[-2000:] + r.stdout
+    dims = (50, 50, 50)
+
+    def field_with(points):
+        o = oracle.Field((1.0, 1.0, 1.0), 0.02, (0.0, 0.0, 0.0), 0.25)
+        assert o.dims == dims
+        o.add_points(points)
+        o.make_exact()
+        return o.d2()
+
+    load = lambda name: np.fromfile(prefix + name, dtype=np.int32).reshape(dims)
+    q9 = field_with(nodes[:, :3])
+    assert np.array_equal(load(".q9.d2.i32"), q9) and np.array_equal(load(".late.d2.i32"), q9)
+    occ_leaves = nodes[(nodes[:, 4] == 1) & (nodes[:, 5] == 1)][:, :4]
+    leaves = field_with(oracle.octree_points(0.02, [tuple(l) for l in occ_leaves]))
+    assert np.array_equal(load(".leaves.d2.i32"), leaves)
+    assert not np.array_equal(q9, leaves)
+    empty = field_with(np.zeros((0, 3)))
+    assert np.array_equal(load(".q9_removed.d2.i32"), empty) and np.array_equal(load(".leaves_removed.d2.i32"), empty)
