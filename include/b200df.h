@@ -343,6 +343,30 @@ int b200df_distance_batch(const b200df_group* group, b200df_field* world, const 
 /* posed sphere centres (PosedBodySphereDecomposition::updatePose, types.cpp:390-397): out[n][S][3] */
 int b200df_sphere_centers(const b200df_group* group, const void* q, int q_dtype, int64_t n, double* centers);
 
+/* ---- single-process multi-GPU ---------------------------------------------------------------------------------
+ * MoveIt is ONE process whose planner threads share a const PlanningScene
+ * (moveit_ros/planning/planning_components_tools/src/evaluate_collision_checking_speed.cpp:44-57,121-124): a
+ * b200df_multi replicates one (model, group) on several devices of the calling process.  Fields are replicated by
+ * b200df_multi_set_field (rebuild once on the source's device, then one peer copy of occupancy + distances per replica
+ * over NVLink; call it again after every change of the source - the only exchange of the path, no collective).
+ * b200df_multi_check_batch cuts the batch into contiguous N/G shards, drives each device from its own host thread
+ * through b200df_check_batch (H2D, kernels, D2H of its shard) and the verdicts land in the caller's single buffer:
+ * the same bytes b200df_check_batch would have written. */
+typedef struct b200df_multi b200df_multi;
+int b200df_multi_create(const b200df_model_desc* model, const b200df_group_desc* group, const int32_t* devices,
+                        int32_t n_devices, b200df_multi** out);
+int b200df_multi_destroy(b200df_multi* multi);
+int b200df_multi_device_count(const b200df_multi* multi, int32_t* n);
+/* which: 0 = world field, 1 = self field; src may live on any device; NULL drops the replicas */
+int b200df_multi_set_field(b200df_multi* multi, int which, b200df_field* src);
+int b200df_multi_field(const b200df_multi* multi, int which, int32_t device_slot, b200df_field** out); /* a replica */
+int b200df_multi_check_batch(const b200df_multi* multi, const void* q, int q_dtype, int64_t n, int flags, int precision,
+                             uint8_t* verdict);
+/* device-resident shards: q_dev[i] / verdict_dev[i] live on device slot i, n[i] states each, streams[i] (may be NULL)
+ * is a stream of that device; queues the work on every device and returns without synchronising */
+int b200df_multi_check_batch_device(const b200df_multi* multi, const void* const* q_dev, int q_dtype, const int64_t* n,
+                                    int flags, int precision, uint8_t* const* verdict_dev, void* const* streams);
+
 /* page-locked host memory for batch inputs / results: the host-buffer entry points copy at PCIe speed from / to such
  * buffers (pageable memory costs an extra staging copy in the driver; 342 MB of CHOMP gradients: 8 ms vs 78 ms) */
 int b200df_host_alloc(size_t bytes, void** out);

@@ -107,6 +107,13 @@ SYMBOLS = {
     "b200df_gradients_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "b200df_distance_batch": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int64, c_dp]),
     "b200df_sphere_centers": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, c_dp]),
+    "b200df_multi_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(GroupDesc), c_i32p, C.c_int32, _VPP]),
+    "b200df_multi_destroy": (C.c_int, [_VP]),
+    "b200df_multi_device_count": (C.c_int, [_VP, c_i32p]),
+    "b200df_multi_set_field": (C.c_int, [_VP, C.c_int, _VP]),
+    "b200df_multi_field": (C.c_int, [_VP, C.c_int, C.c_int32, _VPP]),
+    "b200df_multi_check_batch": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, c_u8p]),
+    "b200df_multi_check_batch_device": (C.c_int, [_VP, _VPP, C.c_int, c_i64p, C.c_int, C.c_int, _VPP, _VPP]),
     "b200df_host_alloc": (C.c_int, [C.c_size_t, _VPP]),
     "b200df_host_free": (C.c_int, [_VP]),
     "b200df_launch_count": (C.c_int64, []),

@@ -26,6 +26,22 @@ int current_device()
     dev = 0;
   return dev;
 }
+ThreadDeviceScope::ThreadDeviceScope(int dev)
+{
+  prev_choice = t_device;
+  if (cudaGetDevice(&prev_cuda) != cudaSuccess)
+    prev_cuda = -1;
+  status = cudaSetDevice(dev);
+  if (status == cudaSuccess)
+    t_device = dev;
+}
+
+ThreadDeviceScope::~ThreadDeviceScope()
+{
+  t_device = prev_choice;
+  if (prev_cuda >= 0)
+    cudaSetDevice(prev_cuda);
+}
 }  // namespace b200df
 
 extern "C" {

@@ -61,6 +61,15 @@ struct DeviceGuard
 
 int current_device();  // device chosen by b200df_set_device on this thread (default: CUDA current device)
 
+// handles created inside the scope live on `dev`; the thread's own choice (b200df_set_device or none) comes back after
+struct ThreadDeviceScope
+{
+  int prev_choice = -1, prev_cuda = -1;
+  cudaError_t status = cudaSuccess;
+  explicit ThreadDeviceScope(int dev);
+  ~ThreadDeviceScope();
+};
+
 // Geometry of a voxel grid as the kernels see it (voxel_grid.h:367-399).
 struct GridDev
 {

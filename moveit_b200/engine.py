@@ -118,6 +118,111 @@ def link_distance_fields(model_desc, group_links, acm_entry, resolution=DEFAULT_
     return fields, enabled
 
 
+def _model_desc_struct(model_desc, keep):
+    """model dict -> B.ModelDesc (ctypes); `keep` receives the arrays the struct points into."""
+    L = len(model_desc["parent"])
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    sph_off = np.zeros(L + 1, dtype=np.int32)
+    pt_off = np.zeros(L + 1, dtype=np.int64)
+    for i in range(L):
+        sph_off[i + 1] = sph_off[i] + len(model_desc["spheres"][i])
+        pt_off[i + 1] = pt_off[i] + len(model_desc["points"][i])
+    sph = arr(np.concatenate([np.reshape(s, (-1, 4)) for s in model_desc["spheres"]]) if L else np.zeros((0, 4)),
+              np.float64)
+    pts = arr(np.concatenate([np.reshape(p, (-1, 3)) for p in model_desc["points"]]) if L else np.zeros((0, 3)),
+              np.float64)
+    d = B.ModelDesc()
+    d.n_links = L
+    d.n_vars = int(model_desc["nvar"])
+    d.parent = B.ptr(arr(model_desc["parent"], np.int32), C.c_int32)
+    d.joint_type = B.ptr(arr(model_desc["joint_type"], np.int32), C.c_int32)
+    d.axis = B.ptr(arr(model_desc["axis"], np.float64), C.c_double)
+    d.origin = B.ptr(arr(model_desc["origin"], np.float64), C.c_double)
+    d.origin_is_identity = B.ptr(arr(model_desc["origin_is_identity"], np.int32), C.c_int32)
+    d.var_index = B.ptr(arr(model_desc["var_index"], np.int32), C.c_int32)
+    d.mimic_var = B.ptr(arr(model_desc["mimic_var"], np.int32), C.c_int32)
+    d.mimic_mult = B.ptr(arr(model_desc["mimic_mult"], np.float64), C.c_double)
+    d.mimic_offset = B.ptr(arr(model_desc["mimic_offset"], np.float64), C.c_double)
+    d.has_geometry = B.ptr(arr(model_desc["has_geometry"], np.int32), C.c_int32)
+    d.sphere_offset = B.ptr(arr(sph_off, np.int32), C.c_int32)
+    d.spheres = B.ptr(sph, C.c_double)
+    d.bsphere = B.ptr(arr(np.stack(model_desc["bsphere"]), np.float64), C.c_double)
+    d.point_offset = B.ptr(arr(pt_off, np.int64), C.c_int64)
+    d.points = B.ptr(pts, C.c_double)
+    return d
+
+
+def _group_desc_struct(group_links, self_enabled, intra_enabled, resolution, tolerance, max_propagation, keep):
+    gl = np.ascontiguousarray(group_links, dtype=np.int32)
+    se = np.ascontiguousarray(self_enabled, dtype=np.uint8)
+    ie = np.ascontiguousarray(intra_enabled, dtype=np.uint8)
+    keep.extend([gl, se, ie])
+    d = B.GroupDesc()
+    d.n_group_links = len(gl)
+    d.group_links = B.ptr(gl, C.c_int32)
+    d.self_enabled = B.ptr(se, C.c_uint8)
+    d.intra_enabled = B.ptr(ie, C.c_uint8)
+    d.resolution = resolution
+    d.collision_tolerance = tolerance
+    d.max_propagation_distance = max_propagation
+    return d
+
+
+class MultiGroup:
+    """b200df_multi: one (model, group) replicated on several devices of THIS process; batches are sharded over them
+    by host threads inside the library (the single-process form of sharding.py's torchrun ranks)."""
+
+    def __init__(self, model_desc, group_links, self_enabled, intra_enabled, devices, resolution=DEFAULT_RESOLUTION,
+                 tolerance=DEFAULT_COLLISION_TOLERANCE, max_propagation=DEFAULT_MAX_PROPAGATION):
+        keep = []
+        md = _model_desc_struct(model_desc, keep)
+        gd = _group_desc_struct(group_links, self_enabled, intra_enabled, resolution, tolerance, max_propagation, keep)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        B.check(B.load().b200df_multi_create(C.byref(md), C.byref(gd), B.ptr(dev, C.c_int32), len(dev), C.byref(h)))
+        self.h = h
+        self.devices = [int(d) for d in dev]
+        self.n_vars = int(model_desc["nvar"])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            B.load().b200df_multi_destroy(self.h)
+            self.h = None
+
+    def set_field(self, which, field):
+        """which: 0 world, 1 self.  Rebuilds `field` if needed and copies it to every replica (peer copies)."""
+        B.check(B.load().b200df_multi_set_field(self.h, which, field.h if field is not None else None))
+
+    def replica_d2(self, which, slot, dims):
+        f = C.c_void_p()
+        B.check(B.load().b200df_multi_field(self.h, which, slot, C.byref(f)))
+        out = np.empty(dims, dtype=np.int32)
+        B.check(B.load().b200df_field_download_d2(f, B.ptr(out, C.c_int32), 0))
+        return out
+
+    def check(self, q, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT):
+        q, dt = _q_array(q, self.n_vars)
+        out = np.empty(len(q), dtype=np.uint8)
+        B.check(B.load().b200df_multi_check_batch(self.h, q.ctypes.data_as(C.c_void_p), dt, len(q), flags, precision,
+                                                  B.ptr(out, C.c_uint8)))
+        return out
+
+    def check_device(self, q_ptrs, q_dtype, counts, verdict_ptrs, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT,
+                     streams=None):
+        n = len(self.devices)
+        qa = (C.c_void_p * n)(*[C.c_void_p(p) for p in q_ptrs])
+        va = (C.c_void_p * n)(*[C.c_void_p(p) for p in verdict_ptrs])
+        sa = (C.c_void_p * n)(*[C.c_void_p(s) if s else None for s in (streams or [None] * n)])
+        cnt = np.ascontiguousarray(counts, dtype=np.int64)
+        B.check(B.load().b200df_multi_check_batch_device(self.h, qa, q_dtype, B.ptr(cnt, C.c_int64), flags, precision,
+                                                         va, sa))
+
+
 class Model:
     def __init__(self, model_desc):
         self.desc = model_desc

@@ -219,9 +219,8 @@ inline ParamValue parseBlock(const std::vector<Line>& lines, std::size_t& i, int
     while (i < lines.size() && lines[i].indent == indent && lines[i].text[0] == '-')
     {
       const std::string rest = trim(lines[i].text.substr(1));
-      const int inner = indent + 1 + (int)(lines[i].text.size() - 1 - trim(lines[i].text.substr(1)).size() >= 1 ?
-                                               lines[i].text.find_first_not_of(' ', 1) - 1 :
-                                               1);
+      const std::size_t off = lines[i].text.find_first_not_of(' ', 1);  // column of the item's content after "- "
+      const int inner = indent + (int)(off == std::string::npos ? 2 : off);
       if (rest.empty())
       {
         ++i;

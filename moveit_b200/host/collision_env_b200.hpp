@@ -635,6 +635,9 @@ public:
   {
     std::copy(other.size_, other.size_ + 3, size_);
     origin_ = other.origin_;
+    octree_occupied_leaves_only_ = other.octree_occupied_leaves_only_;
+    devices_ = other.devices_;
+    multi_min_states_ = other.multi_min_states_;
     construct(other.link_spheres_, other.use_signed_distance_field_, other.resolution_, other.collision_tolerance_,
               other.max_propogation_distance_);
   }
@@ -777,6 +780,14 @@ public:
       if (!e->self_field)
         flags &= ~B200DF_CHECK_SELF;
       // FAST: fp32 screening + exact re-run of the undecided states = the EXACT verdicts at about half the time
+      if (devices_.size() > 1 && n >= multi_min_states_)
+      {
+        // one process, several GPUs: contiguous N/G shards, one host thread per device inside the library
+        b200df_multi* multi = multiFor(*e);
+        checkStatus(b200df_multi_check_batch(multi, states, B200DF_Q_F64, n, flags, B200DF_PRECISION_FAST, verdict),
+                    "b200df_multi_check_batch");
+        return;
+      }
       checkStatus(b200df_check_batch(e->group, world_field_, e->self_field, states, B200DF_Q_F64, n, flags,
                                      B200DF_PRECISION_FAST, verdict),
                   "b200df_check_batch");
@@ -1014,6 +1025,21 @@ public:
     std::lock_guard<std::mutex> lk(update_cache_lock_world_);
     octree_occupied_leaves_only_ = on;
   }
+  // The CUDA devices checkCollisionBatch shards large batches over (empty / one entry: the device the env was created
+  // on).  MoveIt is one process (evaluate_collision_checking_speed.cpp:44-57): the replicas live in this process, the
+  // world field is re-replicated over NVLink after every change, nothing else is exchanged.
+  static constexpr std::int64_t kMultiMinStates = 1 << 18;
+  void setDevices(const std::vector<int>& devices, std::int64_t min_states = kMultiMinStates)
+  {
+    std::lock_guard<std::mutex> lk(update_cache_lock_);
+    devices_ = devices;
+    multi_min_states_ = min_states;
+    dfce_.reset();  // the next call regenerates the entry (and its replicas) for the new device list
+  }
+  const std::vector<int>& getDevices() const
+  {
+    return devices_;
+  }
   bool valid() const  // false: construction failed (no CUDA device, ...); every check then answers fail-closed
   {
     return valid_;
@@ -1042,6 +1068,31 @@ private:
     std::vector<double> points, spheres_flat, bsphere;
     std::vector<int64_t> point_offset;
     std::vector<int32_t> sphere_offset;
+    // the remaining arrays of the b200df_model_desc the model was created from (kept for the per-device replicas)
+    std::vector<int32_t> d_parent, d_jtype, d_ident, d_var, d_mimic_var, d_has_geom;
+    std::vector<double> d_axis, d_origin, d_mmult, d_moff;
+    int n_vars = 0;
+    void fillDesc(b200df_model_desc& d) const
+    {
+      d = b200df_model_desc{};
+      d.n_links = (int32_t)d_parent.size();
+      d.n_vars = n_vars;
+      d.parent = d_parent.data();
+      d.joint_type = d_jtype.data();
+      d.axis = d_axis.data();
+      d.origin = d_origin.data();
+      d.origin_is_identity = d_ident.data();
+      d.var_index = d_var.data();
+      d.mimic_var = d_mimic_var.data();
+      d.mimic_mult = d_mmult.data();
+      d.mimic_offset = d_moff.data();
+      d.has_geometry = d_has_geom.data();
+      d.sphere_offset = sphere_offset.data();
+      d.spheres = spheres_flat.data();
+      d.bsphere = bsphere.data();
+      d.point_offset = point_offset.data();
+      d.points = points.data();
+    }
     b200df_model* model = nullptr;
     ~ModelEntry()
     {
@@ -1070,14 +1121,55 @@ private:
     b200df_field* self_field = nullptr;
     std::vector<b200df_field*> link_fields;  // GroupStateRepresentation::link_distance_fields_, per geometry link
     LinkFieldTerm link_field_term = LINK_FIELDS_NOT_REQUESTED;
+    // single-process multi-GPU replicas of (model, group, self field, world field), created on first use
+    std::vector<int32_t> d_group_links;
+    std::vector<std::uint8_t> d_self_enabled, d_intra;
+    mutable std::mutex multi_lock;
+    mutable b200df_multi* multi = nullptr;
+    mutable std::size_t multi_world_generation = 0;
     ~CacheEntry()
     {
+      b200df_multi_destroy(multi);
       b200df_group_destroy(group);
       b200df_field_destroy(self_field);
       for (b200df_field* f : link_fields)
         b200df_field_destroy(f);
     }
   };
+
+  b200df_multi* multiFor(const CacheEntry& e) const
+  {
+    std::lock_guard<std::mutex> lk(e.multi_lock);
+    if (!e.multi)
+    {
+      b200df_model_desc md;
+      e.model->fillDesc(md);
+      b200df_group_desc gd{};
+      gd.n_group_links = (int32_t)e.d_group_links.size();
+      gd.group_links = e.d_group_links.data();
+      gd.self_enabled = e.d_self_enabled.data();
+      gd.intra_enabled = e.d_intra.data();
+      gd.resolution = resolution_;
+      gd.collision_tolerance = collision_tolerance_;
+      gd.max_propagation_distance = max_propogation_distance_;
+      std::vector<int32_t> dev(devices_.begin(), devices_.end());
+      checkStatus(b200df_multi_create(&md, &gd, dev.data(), (int32_t)dev.size(), &e.multi), "b200df_multi_create");
+      if (e.self_field)
+        checkStatus(b200df_multi_set_field(e.multi, 1, e.self_field), "b200df_multi_set_field(self)");
+      e.multi_world_generation = 0;
+    }
+    std::size_t gen;
+    {
+      std::lock_guard<std::mutex> wl(update_cache_lock_world_);
+      gen = world_generation_;
+    }
+    if (e.multi_world_generation != gen)
+    {
+      checkStatus(b200df_multi_set_field(e.multi, 0, world_field_), "b200df_multi_set_field(world)");
+      e.multi_world_generation = gen;
+    }
+    return e.multi;
+  }
 
   // ---- error handling ---------------------------------------------------------------------------------
   void recordError(const char* where, const std::string& what, bool count_as_error = true) const
@@ -1171,6 +1263,7 @@ private:
       posed_objects_[id] = now;
     }
     world_in_sync_ = true;
+    ++world_generation_;
   }
 
   // initialize .cpp:123-161 + addLinkBodyDecompositions .cpp:1065-1093
@@ -1296,24 +1389,19 @@ private:
     me->sphere_offset = sph_off;
     me->spheres_flat = spheres;
     me->bsphere = bsphere;
-    b200df_model_desc d{};
-    d.n_links = L;
-    d.n_vars = robot_model_->getVariableCount();
-    d.parent = parent.data();
-    d.joint_type = jtype.data();
-    d.axis = axis.data();
-    d.origin = origin.data();
-    d.origin_is_identity = ident.data();
-    d.var_index = var.data();
-    d.mimic_var = mimic_var.data();
-    d.mimic_mult = mmult.data();
-    d.mimic_offset = moff.data();
-    d.has_geometry = has_geom.data();
-    d.sphere_offset = sph_off.data();
-    d.spheres = spheres.data();
-    d.bsphere = bsphere.data();
-    d.point_offset = pt_off.data();
-    d.points = points.data();
+    me->d_parent = parent;
+    me->d_jtype = jtype;
+    me->d_ident = ident;
+    me->d_var = var;
+    me->d_mimic_var = mimic_var;
+    me->d_has_geom = has_geom;
+    me->d_axis = axis;
+    me->d_origin = origin;
+    me->d_mmult = mmult;
+    me->d_moff = moff;
+    me->n_vars = robot_model_->getVariableCount();
+    b200df_model_desc d;
+    me->fillDesc(d);
     checkStatus(b200df_model_create(&d, &me->model), "b200df_model_create");
     return me;
   }
@@ -1420,6 +1508,7 @@ private:
 
   void applyObjectChangeLocked(const World::ObjectConstPtr& obj, World::Action action)
   {
+    ++world_generation_;
     auto cur = posed_objects_.find(obj->id_);
     if (cur != posed_objects_.end() && (action == World::DESTROY || (action & (World::MOVE_SHAPE | World::REMOVE_SHAPE))))
       for (std::size_t i = 0; i < cur->second->shapes_.size(); ++i)
@@ -1609,6 +1698,9 @@ private:
     gd.collision_tolerance = collision_tolerance_;
     gd.max_propagation_distance = max_propogation_distance_;
     checkStatus(b200df_group_create(me.model, &gd, &e->group), "b200df_group_create");
+    e->d_group_links = gl;
+    e->d_self_enabled = self_enabled;
+    e->d_intra = intra;
     if (acm && acm->getSize() > 0)
       generateLinkDistanceFields(*e);
     if (generate_distance_field)  // :910-973: the links outside the group, posed by this state, as one point set
@@ -1868,6 +1960,9 @@ private:
   std::string init_error_;
   bool world_in_sync_ = false;     // guarded by update_cache_lock_world_
   bool octree_occupied_leaves_only_ = false;
+  std::size_t world_generation_ = 1;  // bumped by every world change (guarded by update_cache_lock_world_)
+  std::vector<int> devices_;
+  std::int64_t multi_min_states_ = kMultiMinStates;
   mutable std::mutex error_lock_;  // last_error_ / error_count_ are written by concurrent const callers
   mutable std::string last_error_;
   mutable std::size_t error_count_ = 0;

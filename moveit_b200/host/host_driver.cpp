@@ -9,6 +9,7 @@
 #include <sstream>
 #include <thread>
 
+#include "b200_config.hpp"
 #include "collision_env_b200.hpp"
 #include "distance_field_b200.hpp"
 
@@ -515,6 +516,80 @@ static int octreeTest(const char* nodes_path, const std::string& prefix)
   return 0;
 }
 
+// host_driver --config <params.yaml> <prefix> [namespace]
+// Reads the plugin's parameter namespace (b200_config.hpp; link_spheres in the format of
+// collision_distance_field_ros_helpers.h:46-120), writes what it understood, and allocates an env from it on a small
+// robot so that the values can be seen to arrive (field dimensions, sphere counts).
+static int configTest(const char* yaml_path, const std::string& prefix, const char* ns)
+{
+  std::ifstream in(yaml_path);
+  if (!in)
+    throw std::runtime_error("cannot open the parameter file");
+  const B200DistanceFieldConfig c = configFromYaml(in, ns ? ns : "");
+  std::ofstream out(prefix + ".config.txt");
+  out.precision(17);
+  out << "size " << c.size_x << " " << c.size_y << " " << c.size_z << "\n";
+  out << "origin " << c.origin.x << " " << c.origin.y << " " << c.origin.z << "\n";
+  out << "resolution " << c.resolution << "\n";
+  out << "collision_tolerance " << c.collision_tolerance << "\n";
+  out << "max_propogation_distance " << c.max_propogation_distance << "\n";
+  out << "use_signed_distance_field " << (c.use_signed_distance_field ? 1 : 0) << "\n";
+  out << "padding " << c.padding << "\n";
+  out << "octree_occupied_leaves_only " << (c.octree_occupied_leaves_only ? 1 : 0) << "\n";
+  out << "devices";
+  for (int d : c.devices)
+    out << " " << d;
+  out << "\n";
+  for (const auto& kv : c.link_spheres)
+  {
+    out << "link " << kv.first << " " << kv.second.size();
+    for (const CollisionSphere& s : kv.second)
+      out << " " << s.relative_vec_.x << " " << s.relative_vec_.y << " " << s.relative_vec_.z << " " << s.radius_;
+    out << "\n";
+  }
+  for (const std::string& w : c.warnings)
+    out << "warning " << w << "\n";
+  int n_dev = 0;
+  b200df_device_count(&n_dev);
+  if (n_dev > 0)
+  {
+    auto model = std::make_shared<core::RobotModel>("config_bot");
+    for (int i = 0; i < 2; ++i)
+    {
+      core::LinkModel l;
+      l.name = i == 0 ? "base" : "arm";
+      l.joint_name = i == 0 ? "fixed_base" : "j1";
+      l.parent = i - 1;
+      l.joint_type = i == 0 ? core::FIXED : core::REVOLUTE;
+      shapes::Shape box;
+      box.type = shapes::BOX;
+      box.dims[0] = box.dims[1] = 0.05;
+      box.dims[2] = 0.3;
+      l.shapes.push_back(box);
+      l.shape_origins.push_back(Isometry3d::Identity());
+      model->addLink(l);
+    }
+    B200DistanceFieldConfig one = c;
+    one.devices.clear();  // the test box has one GPU
+    ConfiguredAllocatorB200 alloc(one);
+    CollisionEnvB200Ptr env = alloc.allocateEnv(std::make_shared<World>(), model);
+    if (!env->valid())
+      throw std::runtime_error(env->lastError());
+    distance_field_b200::PropagationDistanceFieldB200 view(env->getDistanceField());
+    out << "field_cells " << view.getXNumCells() << " " << view.getYNumCells() << " " << view.getZNumCells() << "\n";
+    out << "field_max_distance " << view.getUninitializedDistance() << "\n";
+    CollisionRequest req;
+    core::RobotState st(model);
+    std::vector<GroupStateRepresentationPtr> gsr;
+    if (!env->getCollisionGradientsBatch(req, st.getVariablePositions(), 1, nullptr, gsr) || gsr.empty())
+      throw std::runtime_error(env->lastError());
+    for (std::size_t l = 0; l < gsr[0]->link_names_.size(); ++l)
+      out << "env_spheres " << gsr[0]->link_names_[l] << " " << gsr[0]->gradients_[l].sphere_radii.size() << "\n";
+  }
+  std::printf("config test ok: %zu link_spheres entries, %zu warnings\n", c.link_spheres.size(), c.warnings.size());
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   if (argc >= 3 && std::string(argv[1]) == "--field-stream")
@@ -530,12 +605,18 @@ int main(int argc, char** argv)
     }
   }
   if (argc >= 2 && (std::string(argv[1]) == "--contract" || std::string(argv[1]) == "--chomp" ||
-                    std::string(argv[1]) == "--octree"))
+                    std::string(argv[1]) == "--octree" || std::string(argv[1]) == "--config"))
   {
     try
     {
       if (std::string(argv[1]) == "--contract")
         return contractTest();
+      if (std::string(argv[1]) == "--config")
+      {
+        if (argc < 4)
+          throw std::runtime_error("usage: host_driver --config <params.yaml> <prefix> [namespace]");
+        return configTest(argv[2], argv[3], argc > 4 ? argv[4] : nullptr);
+      }
       if (std::string(argv[1]) == "--octree")
       {
         if (argc < 4)
@@ -590,6 +671,15 @@ int main(int argc, char** argv)
     const Vector3d origin{ center[0], center[1], center[2] };
     CollisionEnvB200Ptr env = std::make_shared<CollisionEnvB200>(model, world, overrides, size[0], size[1], size[2],
                                                                  origin, use_signed != 0, res, tol, max_dist);
+    if (const char* devs = std::getenv("B200DF_DRIVER_DEVICES"))  // "0,1": shard every batch over these devices
+    {
+      std::vector<int> list;
+      std::stringstream ss(devs);
+      std::string item;
+      while (std::getline(ss, item, ','))
+        list.push_back(std::atoi(item.c_str()));
+      env->setDevices(list, /*min_states=*/1);
+    }
     const std::string prefix = argv[3];
     const AllowedCollisionMatrix* acm_ptr = use_acm ? &acm : nullptr;
     CollisionRequest req;

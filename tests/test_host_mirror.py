@@ -403,3 +403,74 @@ def test_octomap_world_object_through_the_env(gpu, oracle, tmp_path):
     assert not np.array_equal(q9, leaves)
     empty = field_with(np.zeros((0, 3)))
     assert np.array_equal(load(".q9_removed.d2.i32"), empty) and np.array_equal(load(".leaves_removed.d2.i32"), empty)
+
+
+_PARAMS = """\
+# parameter namespace of the B200 distance-field detector (what `rosparam load` would put under the plugin's namespace)
+b200_distance_field:
+  size_x: 2.0
+  size_y: 2.5   # metres
+  size_z: 1.0
+  origin: {x: 0.1, y: -0.2, z: 0.5}
+  resolution: 0.025
+  max_propogation_distance: 0.3
+  collision_tolerance: 0.005
+  use_signed_distance_field: true
+  octree_occupied_leaves_only: yes
+  devices: [0, 1, 2]
+  link_spheres:
+    - link: base
+      spheres:
+        - {x: 0.0, y: 0.0, z: 0.05, radius: 0.08}
+        - {x: 0.0, y: 0.0, z: 0.15, radius: 0.06}
+        - {x: 0.0, y: 0.0, radius: 0.01}
+    - link: arm
+      spheres: none
+    - spheres: none
+    - link: tool
+      spheres:
+        - x: 0.1
+          y: 0.2
+          z: 0.3
+          radius: 0.04
+"""
+
+
+def _run_config(tmp_path):
+    exe = _build_driver()
+    path, prefix = str(tmp_path / "params.yaml"), str(tmp_path / "cfg")
+    open(path, "w").write(_PARAMS)
+    r = subprocess.run([exe, "--config", path, prefix, "b200_distance_field"], capture_output=True, text=True)
+    assert r.returncode == 0 and "config test ok" in r.stdout, r.stderr[-2000:] + r.stdout
+    out = {}
+    for line in open(prefix + ".config.txt"):
+        k, _, v = line.strip().partition(" ")
+        out.setdefault(k, []).append(v)
+    return out
+
+
+def test_plugin_configuration_reader(tmp_path):
+    """The plugin's parameter namespace (b200_config.hpp): field geometry with the reference's constructor defaults
+    (collision_env_distance_field.h:48-54) and `link_spheres` in the format - and with the warnings - of
+    loadLinkBodySphereDecompositions (collision_distance_field_ros_helpers.h:46-120)."""
+    c = _run_config(tmp_path)
+    assert [float(x) for x in c["size"][0].split()] == [2.0, 2.5, 1.0]
+    assert [float(x) for x in c["origin"][0].split()] == [0.1, -0.2, 0.5]
+    assert float(c["resolution"][0]) == 0.025 and float(c["max_propogation_distance"][0]) == 0.3
+    assert float(c["collision_tolerance"][0]) == 0.005 and c["use_signed_distance_field"] == ["1"]
+    assert c["octree_occupied_leaves_only"] == ["1"] and c["devices"] == ["0 1 2"]
+    links = {l.split()[0]: l.split()[1:] for l in c["link"]}
+    assert set(links) == {"base", "arm", "tool"}
+    assert links["arm"] == ["0"]  # spheres: none -> a link without spheres
+    assert links["base"][0] == "2" and [float(x) for x in links["base"][1:]] == [0, 0, 0.05, 0.08, 0, 0, 0.15, 0.06]
+    assert [float(x) for x in links["tool"][1:]] == [0.1, 0.2, 0.3, 0.04]
+    assert "All spheres must specify a value for z" in c["warning"] and "All link spheres must have link" in c["warning"]
+
+
+@pytest.mark.gpu
+def test_configured_allocator_builds_the_env_from_the_parameters(gpu, tmp_path):
+    c = _run_config(tmp_path)
+    assert c["field_cells"] == ["80 100 40"]  # int(size * (1 / resolution)), voxel_grid.h:387
+    assert float(c["field_max_distance"][0]) == 0.3
+    spheres = dict(l.split() for l in c["env_spheres"])
+    assert spheres == {"base": "2", "arm": "0"}  # the overrides replaced the derived spheres (.cpp:1085-1088)
