@@ -31,25 +31,55 @@ sys.path.insert(0, ROOT)
 
 STATES_PER_GPU = 10_000_000
 ALGO_BYTES_PER_STATE = 4 * 9 + 1  # fp32 joint values in, one verdict byte out
-# dram__bytes_read.sum + dram__bytes_write.sum per state from the committed ncu --set full captures (2 000 000 states):
-# profiles/r01_validity_fast_full.txt (72.79 MB + 1.01 MB) and profiles/r01_validity_v3_full.txt (72.81 MB + 1.50 MB)
-NCU_DRAM_BYTES_PER_STATE = {"fast": (72.788992e6 + 1.494784e6) / 2.0e6, "exact": (72.813312e6 + 1.502976e6) / 2.0e6}
-# smsp__inst_executed.sum of the same captures / 2 000 000 states: warp instructions the kernel issues per state
-NCU_WARP_INSTR_PER_STATE = {"fast": 844093209 / 2.0e6}
 
 
-def issue_roofline(precision, states_per_s_per_gpu, clocks):
+def ncu_counters(path, precision):
+    """Counters of the dominant kernel from the committed ncu --set full capture of this command
+    (profiles/summarize.py traffic): DRAM bytes, L2 sectors and warp instructions per state.  None when the file is
+    missing - the bench then reports traffic = null rather than a stale constant."""
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        k = d.get(precision)
+        if not k or not k.get("states_per_launch"):
+            return None
+        n = float(k["states_per_launch"])
+        return {"dram_bytes_per_state": (k["dram_bytes_read"] + k["dram_bytes_write"]) / n,
+                "l2_sector_bytes_per_state": 32.0 * (k.get("lts_sectors_read", 0) + k.get("lts_sectors_write", 0)) / n,
+                "warp_instructions_per_state": k.get("warp_instructions", 0) / n, "kernel": k.get("kernel"),
+                "source": os.path.relpath(path, ROOT) + " <- " + str(d.get("report"))}
+    except Exception:
+        return None
+
+
+def issue_roofline(counters, states_per_s_per_gpu, clocks):
     """The resource that actually binds the validity kernel: warp-instruction issue slots.  achieved = (warp
     instructions per state, counted by ncu on the committed capture) x (states/s measured in this run on one GPU);
     peak = 148 SMs x 4 schedulers x the SM clock sampled during the timed region."""
-    per_state = NCU_WARP_INSTR_PER_STATE.get(precision)
+    per_state = (counters or {}).get("warp_instructions_per_state")
     mhz = (clocks or {}).get("sm_mhz")
     if not per_state or not mhz:
         return None
     peak = 148 * 4 * mhz * 1e6
     achieved = per_state * states_per_s_per_gpu
     return {"achieved": achieved, "peak": peak, "unit": "warp-instructions/s", "frac": achieved / peak,
-            "warp_instructions_per_state": per_state, "source": "profiles/r01_validity_fast_full.txt x live rate"}
+            "warp_instructions_per_state": per_state, "source": counters["source"] + " x live rate"}
+
+
+def l2_roofline(counters, states_per_s_per_gpu, clocks):
+    """north_star asks for the lookup kernels' achieved L2 GB/s against the chip's peak: L2 sectors x 32 B per state
+    (ncu lts__t_sectors of the committed capture) x the live rate, against the L2 throughput ceiling the microarchitecture
+    guide measured (~6300 B per clock for the whole chip) at the SM clock sampled in this run."""
+    per_state = (counters or {}).get("l2_sector_bytes_per_state")
+    mhz = (clocks or {}).get("sm_mhz")
+    if not per_state or not mhz:
+        return None
+    peak = 6300.0 * mhz * 1e6 / 1e9
+    achieved = per_state * states_per_s_per_gpu / 1e9
+    return {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "l2_bytes_per_state": per_state,
+            "peak_source": "B300_MICROARCH.md LTS cap 6300 B/clk x sampled SM clock (guide figure, not measured here)",
+            "source": counters["source"] + " x live rate"}
 
 
 def parse():
@@ -64,6 +94,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-edt", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (BASELINE configs 1, 4, 5)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive --gpus N devices from ONE process through b200df_multi (how a MoveIt process would) "
+                         "instead of one torchrun rank per GPU")
+    ap.add_argument("--traffic-json", default=os.path.join(ROOT, "profiles", "r02_validity_traffic.json"),
+                    help="per-launch DRAM / L2 counters of the dominant kernel from an ncu --set full capture of this "
+                         "command (written by `python profiles/summarize.py traffic <rep> <json>`)")
     return ap.parse_args()
 
 
@@ -269,7 +305,8 @@ def edt_timings(engine, scenarios, B):
     out["field_b_roofline"] = {"bound": "hbm", "achieved": algo / (best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                "frac": algo / (best * 1e-3) / 1e9 / peak, "peak_source": src,
                                "algorithmic_bytes": algo,
-                               "note": "4 launches: pack bits, z pass, DPX marching y pass, DPX marching x pass"}
+                               "note": "2 launches per z slab (bit rows -> plane kernel: z distances on the fly + DPX "
+                                       "march along y; axis kernel: DPX march along x), 4 slabs on 4 streams"}
     t0 = time.perf_counter()
     g.reset()
     g.add_points(pts)
@@ -293,6 +330,148 @@ def edt_timings(engine, scenarios, B):
     except ImportError:
         pass
     return out
+
+
+def run_single_process(args):
+    """--single-process: ONE process drives --gpus N devices through b200df_multi, the way a MoveIt process (one
+    PlanningScene shared by planner threads) would; no torchrun, no NCCL.  Same workload, same per-device batch
+    (weak scaling), same timing rules: CUDA events on every device's stream, the slowest device counts."""
+    import torch
+    from moveit_b200 import binding as B
+    from moveit_b200 import engine, scenarios
+    from moveit_b200 import robot_description as rd
+    from moveit_b200.rng import uniform01
+
+    G = args.gpus
+    if not torch.cuda.is_available() or B.device_count() < G:
+        raise SystemExit("bench.py --single-process --gpus %d needs %d CUDA devices (no CPU fallback)" % (G, G))
+    devices = list(range(G))
+    B.check(B.load().b200df_set_device(0))
+    desc = rd.panda()
+    md = engine.assemble_model(desc, engine.body_decomposition, scenarios.FIELD_A["resolution"])
+    links = desc.group_links("")
+    se, ie = engine.resolve_acm(md, links, desc.acm_entry_matrix())
+    fa = scenarios.FIELD_A
+    multi = engine.MultiGroup(md, links, se, ie, devices, fa["resolution"], 0.0, fa["max_distance"])
+    src = engine.Field.centered(fa["size"], fa["resolution"], fa["center"], fa["max_distance"])
+    for t, dims, pose in scenarios.random_scene():
+        src.add_posed_body(t, dims, pose)
+    t0 = time.perf_counter()
+    multi.set_field(0, src)  # rebuild on device 0 + one peer copy per replica
+    replicate_first_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    multi.set_field(0, src)
+    replicate_ms = 1e3 * (time.perf_counter() - t0)
+    ref_d2 = src.d2()
+    for slot in range(G):
+        if not np.array_equal(multi.replica_d2(0, slot, src.dims), ref_d2):
+            raise SystemExit("replica %d of the world field differs from the source" % slot)
+
+    n = args.states
+    lim_lo = np.array([l[0] for l in desc.limits])
+    lim_hi = np.array([l[1] for l in desc.limits])
+    q_host = torch.empty((n * G, desc.nvar), dtype=torch.float32).pin_memory()
+    chunk = 1_000_000
+    for s in range(0, n * G, chunk):
+        m = min(chunk, n * G - s)
+        u = uniform01(scenarios.SEED_STATES, m * desc.nvar, offset=s * desc.nvar).reshape(m, desc.nvar)
+        qq = lim_lo + (lim_hi - lim_lo) * u
+        qq[:, 8] = qq[:, 7]
+        q_host[s:s + m] = torch.from_numpy(qq.astype(np.float32))
+    v_host = torch.empty(n * G, dtype=torch.uint8).pin_memory()
+    q_dev, v_dev, streams = [], [], []
+    for d in devices:
+        with torch.cuda.device(d):
+            q_dev.append(q_host[d * n:(d + 1) * n].to("cuda:%d" % d))
+            v_dev.append(torch.empty(n, dtype=torch.uint8, device="cuda:%d" % d))
+            streams.append(torch.cuda.Stream(device=d))
+    flags = B.CHECK_ROBOT | B.CHECK_INTRA
+    precision = {"fast": B.PRECISION_FAST, "exact": B.PRECISION_EXACT, "v1": 2}[args.precision]
+    counts = [n] * G
+
+    def step_device():
+        multi.check_device([q.data_ptr() for q in q_dev], B.Q_F32, counts, [v.data_ptr() for v in v_dev], flags,
+                           precision, [s.cuda_stream for s in streams])
+
+    def sync_all():
+        for d in devices:
+            torch.cuda.synchronize(d)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = B.load().b200df_launch_count()
+    ev = []
+    for d in devices:
+        with torch.cuda.device(d):
+            ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+    for d in devices:
+        ev[d][0].record(streams[d])
+    for _ in range(args.steps):
+        step_device()
+    for d in devices:
+        ev[d][1].record(streams[d])
+    sync_all()
+    per_dev_ms = [ev[d][0].elapsed_time(ev[d][1]) for d in devices]
+    ms_total = max(per_dev_ms)
+    launches = B.load().b200df_launch_count() - launches0
+
+    # every device's shard against device 0 running the same shard (a corrupt replica would show here)
+    agree = True
+    with torch.cuda.device(0):
+        probe = torch.empty(min(n, 100_000), dtype=torch.uint8, device="cuda:0")
+    m = probe.numel()
+    g0 = engine.Group(engine.Model(md), links, se, ie, fa["resolution"], 0.0, fa["max_distance"])
+    for d in devices:
+        qd = q_host[d * n:d * n + m].to("cuda:0")
+        g0.check_device(qd.data_ptr(), B.Q_F32, m, probe.data_ptr(), src, None, flags, B.PRECISION_EXACT, 0)
+        torch.cuda.synchronize(0)
+        if not torch.equal(probe.cpu(), v_dev[d][:m].cpu()):
+            agree = False
+    if not agree:
+        raise SystemExit("cross-device check failed: a device's verdicts differ from device 0's exact kernel")
+
+    # end to end: ONE b200df_multi_check_batch call on the whole N x G batch in page-locked memory
+    def step_host():
+        B.check(B.load().b200df_multi_check_batch(multi.h, ctypes.c_void_p(q_host.data_ptr()), B.Q_F32, n * G, flags,
+                                                  precision,
+                                                  ctypes.cast(v_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8))))
+
+    step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    same = all(bool(torch.equal(v_host[d * n:(d + 1) * n], v_dev[d].cpu())) for d in devices)
+    clocks = sampler.summary()
+    ms_per_step = ms_total / args.steps
+    peak, peak_src = measured_peak_hbm()
+    line = {
+        "metric": "state_validity_checks_per_sec", "value": n * G / (ms_per_step * 1e-3), "unit": "states/s",
+        "n_gpus": G, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64" if args.precision == "fast" else "f64", "data": "synthetic",
+        "config": dict(workload_config(n), parallelism="ONE process, b200df_multi: states sharded across devices, "
+                                                        "field replicated by peer copies (no NCCL, no torchrun)"),
+        "launch": "single-process",
+        "e2e": {"value": n * G * args.steps / e2e_s, "unit": "states/s", "h2d_bytes_per_step": n * G * desc.nvar * 4,
+                "d2h_bytes_per_step": n * G, "steps": args.steps,
+                "input": "one page-locked fp32 buffer of all N x G states, one b200df_multi_check_batch call per step",
+                "verdicts_match_device_path": same},
+        "gpu_launches": int(launches), "clocks": clocks, "per_device_ms_per_step": [x / args.steps for x in per_dev_ms],
+        "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_PER_STATE * n / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": ALGO_BYTES_PER_STATE * n / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "traffic": None, "peak_source": peak_src, "note": "per device; see the N=1 line for the counters"},
+        "field_replication": {"bytes_per_replica": int(np.prod(src.dims)) * 2, "first_call_ms": replicate_first_ms,
+                              "steady_ms": replicate_ms, "replicas_equal_source": True},
+        "cross_device_check": {"devices": G, "states_compared_per_device": m, "agree": agree},
+        "precision": args.precision,
+    }
+    emit(line)
 
 
 _REAL_STDOUT = None
@@ -326,6 +505,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.single_process:
+        if world > 1:
+            raise SystemExit("--single-process is launched without torchrun")
+        run_single_process(args)
         return
 
     import torch
@@ -429,51 +613,124 @@ def main():
         if not torch.equal(v_exact, v_dev):
             raise SystemExit("FAST and EXACT verdicts differ on the bench batch")
 
-    # ---- end-to-end through the host-buffer C-ABI call
-    e2e_steps = max(2, min(args.steps, 5))
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    # ---- every rank holds the same field and computes the same verdicts (a rank with a corrupt replica would
+    # otherwise go unnoticed: the throughput lines above never compare ranks)
+    cross = {"ranks": world}
+    nvox = world_field.dims[0] * world_field.dims[1] * world_field.dims[2]
+    d2_t = torch.empty(world_field.device_arrays()[2], dtype=torch.uint8, device=dev)
+    world_field.export_device(None, d2_t.data_ptr(), None, stream.cuda_stream)
+    torch.cuda.synchronize()
+    wts = (torch.arange(d2_t.numel(), device=dev, dtype=torch.int64) % 65521) + 1
+    field_sum = torch.stack([d2_t.to(torch.int64).sum(), (d2_t.to(torch.int64) * wts).sum()])
+    m = min(n, 100_000)
+    u = uniform01(scenarios.SEED_STATES, m * desc.nvar, offset=0).reshape(m, desc.nvar)
+    q0 = lim_lo + (lim_hi - lim_lo) * u
+    q0[:, 8] = q0[:, 7]
+    q0_dev = torch.from_numpy(q0.astype(np.float32)).to(dev)
+    v0 = torch.empty(m, dtype=torch.uint8, device=dev)
+    group.check_device(q0_dev.data_ptr(), B.Q_F32, m, v0.data_ptr(), world_field, None, flags, precision,
+                       stream.cuda_stream)
+    torch.cuda.synchronize()
+    v_sum = torch.stack([v0.to(torch.int64).sum(), (v0.to(torch.int64) * wts[:m]).sum()])
+    sums = torch.cat([field_sum, v_sum])
+    lo_s, hi_s = sums.clone(), sums.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    clocks = sampler.summary()  # sampled over both timed regions (device-resident and end-to-end)
+        dist.all_reduce(lo_s, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_s, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo_s, hi_s):
+        raise SystemExit("cross-rank check failed: ranks disagree on the replicated field or on the verdicts of the "
+                         "first %d global states (min %s max %s)" % (m, lo_s.tolist(), hi_s.tolist()))
+    if rank == 0 and not torch.equal(v0, v_dev[:m]):
+        raise SystemExit("rank 0: verdicts of the first states differ between two calls")
+    cross.update(field_checksum=[int(x) for x in field_sum.tolist()], verdict_checksum=[int(x) for x in v_sum.tolist()],
+                 states_compared=m, agree=True)
+
+    # ---- end-to-end through the host-buffer C-ABI call (page-locked fp32 rows, the fastest way in): args.steps steps
+    def timed_host(fn, steps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        t_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    e2e_steps = args.steps
+    e2e_s = timed_host(step_host, e2e_steps)
     same = bool(torch.equal(v_host.to(dev), v_dev))
+
+    # the shape a CollisionEnv caller really has: RobotState doubles in ordinary (pageable) memory, pageable verdicts
+    q64 = q_host.numpy().astype(np.float64)
+    v_page = np.empty(n, dtype=np.uint8)
+
+    def step_plugin():
+        B.check(B.load().b200df_check_batch(group.h, world_field.h, None, q64.ctypes.data_as(ctypes.c_void_p), B.Q_F64,
+                                            n, flags, precision, v_page.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+
+    plugin_steps = max(2, min(args.steps, 10))
+    plugin_s = timed_host(step_plugin, plugin_steps)
+    same_plugin = bool(np.array_equal(v_page, v_host.numpy()))
+    if not same_plugin:
+        # fp32 rows rounded from these very doubles were checked above: the verdicts must agree state by state
+        raise SystemExit("pageable fp64 call and pinned fp32 call disagree")
+
+    # what the host's PCIe fabric gives N concurrent plain copies of the same bytes (no kernels): the ceiling of e2e
+    def step_copy():
+        q_dev.copy_(q_host, non_blocking=True)
+        v_host.copy_(v_dev, non_blocking=True)
+
+    copy_s = timed_host(step_copy, max(3, min(args.steps, 10)))
+    copy_steps = max(3, min(args.steps, 10))
+    clocks = sampler.summary()  # sampled over the timed regions (device-resident and end-to-end)
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
         value = n * world / (ms_per_step * 1e-3)
         peak, peak_src = measured_peak_hbm()
         achieved = ALGO_BYTES_PER_STATE * n / (ms_per_step * 1e-3) / 1e9
+        counters = ncu_counters(args.traffic_json, args.precision)
+        per_gpu_rate = n * args.steps / (ms_total * 1e-3)
         line = {
             "metric": "state_validity_checks_per_sec", "value": value, "unit": "states/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64" if args.precision == "fast" else "f64",
             "data": "synthetic", "config": workload_config(n),
             "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "states/s",
-                    "h2d_bytes_per_step": n * desc.nvar * 4, "d2h_bytes_per_step": n,
-                    "verdicts_match_device_path": same},
+                    "h2d_bytes_per_step": n * desc.nvar * 4, "d2h_bytes_per_step": n, "steps": e2e_steps,
+                    "input": "page-locked fp32 rows (b200df_host_alloc-style), page-locked verdicts",
+                    "verdicts_match_device_path": same,
+                    "copy_ceiling_states_per_s": n * world * copy_steps / copy_s,
+                    "copy_ceiling_note": "the same H2D + D2H bytes as plain cudaMemcpyAsync on every rank at once, "
+                                         "no kernels: what the box's PCIe fabric allows e2e to reach"},
+            "e2e_plugin": {"value": n * world * plugin_steps / plugin_s, "unit": "states/s", "steps": plugin_steps,
+                           "input": "pageable fp64 rows (RobotState doubles in heap memory), pageable verdicts, "
+                                    "through b200df_check_batch: rows are narrowed to fp32 while being staged into "
+                                    "page-locked chunks by a few host threads, the undecided states go again as fp64",
+                           "h2d_bytes_per_step": n * desc.nvar * 4, "host_bytes_read_per_step": n * desc.nvar * 8,
+                           "d2h_bytes_per_step": n, "verdicts_match_pinned_fp32_call": same_plugin},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_STATE.get(args.precision, NCU_DRAM_BYTES_PER_STATE["exact"]) * n,
+                         "traffic": counters["dram_bytes_per_state"] * n if counters else None,
+                         "traffic_source": counters["source"] if counters else "no ncu capture file (--traffic-json)",
                          "peak_source": peak_src,
-                         "issue": issue_roofline(args.precision, n * args.steps / (ms_total * 1e-3), clocks),
+                         "issue": issue_roofline(counters, per_gpu_rate, clocks),
+                         "l2": l2_roofline(counters, per_gpu_rate, clocks),
                          "kernel": ("validity_fast_kernel<float, unsigned char, 128, pair thresholds in smem, simple joints, no self field> "
                                     "(+ validity_small_kernel on the undecided "
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
-                         "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = "
-                                 "ncu dram bytes/state of profiles/r01_validity_{fast,v3}_full.txt x states per launch. "
-                                 "The fused FK+lookup+pair kernel executes ~13.5 k warp instructions per 32 states and "
-                                 "is issue/latency bound by construction (DESIGN.md section 4); the HBM-bound "
-                                 "kernel of this path is the EDT, see edt_ms.field_b_roofline"},
+                         "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = ncu "
+                                 "dram bytes/state of the committed capture x states per launch. The fused "
+                                 "FK+lookup+pair kernel executes ~13 k warp instructions per 32 states and is "
+                                 "issue/latency bound by construction (DESIGN.md section 4): `issue` and `l2` are the "
+                                 "resources it actually loads; the HBM-bound kernel of this path is the EDT, see "
+                                 "edt_ms.field_b_roofline"},
             "colliding_fraction": colliding / n,
             "field_replication_bytes": replicated_bytes,
+            "cross_rank_check": cross,
             "precision": args.precision,
             "fast_undecided_fraction": undecided,
             "fast_equals_exact_on_batch": True if args.precision == "fast" else None,

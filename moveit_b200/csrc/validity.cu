@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <map>
 #include <memory>
 
@@ -963,6 +964,182 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
                      static_cast<cudaStream_t>(stream));
 }
 
+// fp64 -> fp32, round to nearest even (cvtpd2ps): exactly the conversion the kernels' own fp64 -> fp32 load performs.
+// The loop is the host-side cost of the narrowing path below; with 256-bit converts a core streams ~8 GB/s of doubles.
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void narrow_rows_avx2(float* dst, const double* src, size_t count)
+{
+  size_t k = 0;
+  for (; k + 8 <= count; k += 8)
+  {
+    const __m128 a = _mm256_cvtpd_ps(_mm256_loadu_pd(src + k));
+    const __m128 b = _mm256_cvtpd_ps(_mm256_loadu_pd(src + k + 4));
+    _mm_storeu_ps(dst + k, a);
+    _mm_storeu_ps(dst + k + 4, b);
+  }
+  for (; k < count; ++k)
+    dst[k] = (float)src[k];
+}
+#endif
+
+static void narrow_rows(float* dst, const double* src, size_t count)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2)
+  {
+    narrow_rows_avx2(dst, src, count);
+    return;
+  }
+#endif
+  for (size_t k = 0; k < count; ++k)
+    dst[k] = (float)src[k];
+}
+
+// FAST on pageable fp64 rows (the shape a CollisionEnv caller has: RobotState variables are doubles in ordinary heap
+// memory).  The screening pass works on the joint values rounded to fp32 anyway (the rounding is part of its error
+// margins), so the rows are narrowed on the host WHILE they are staged into page-locked memory: half the staging
+// writes and half the PCIe bytes (36 instead of 72 per Panda state).  Each of a few host threads runs an independent
+// pipeline over its own chunks - narrow into its pinned buffer, H2D, screening kernel, D2H of the verdict bytes - so
+// the conversion of one chunk overlaps the copies and kernels of the others.  Screening leaves 0 / 1 / 2 (undecided,
+// ~0.03 % of the states); afterwards exactly those rows travel as fp64 and are decided by the exact kernel, like the
+// device-side FAST path does.  Same verdicts as EXACT by the same argument.
+static int check_batch_narrowed(const b200df_group* group, const FieldDev& wf, const FieldDev& sf, int elem,
+                                const double* q, int64_t n, int flags, uint8_t* verdict,
+                                b200df_group::StagePool::Ctx* ctx)
+{
+  typedef b200df_group::StagePool::Ctx Ctx;
+  const int nv = group->dev.n_vars;
+  const size_t row32 = (size_t)nv * sizeof(float);
+  const int64_t cs = 1 << 18;
+  const int64_t n_chunks = (n + cs - 1) / cs;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(Ctx::kLanes, std::max(2u, hw / 2)), n_chunks));
+  // lane buffers: [fp32 rows | verdict bytes], pinned and device
+  const size_t v_at = ((size_t)cs * row32 + 255) & ~size_t(255);
+  const size_t lane_bytes = v_at + (size_t)cs;
+  for (int w = 0; w < T; ++w)
+  {
+    Ctx::Lane& l = ctx->lane[w];
+    if (!l.st)
+      B200DF_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    if (l.states < (size_t)cs || l.row < row32)
+    {
+      if (l.hq)
+        cudaFreeHost(l.hq);
+      cudaFree(l.dq);
+      cudaFree(l.amb);
+      l.hq = l.dq = nullptr;
+      l.amb = nullptr;
+      l.states = 0;
+      B200DF_CUDA(cudaHostAlloc(&l.hq, lane_bytes, cudaHostAllocDefault));
+      B200DF_CUDA(cudaMalloc(&l.dq, lane_bytes));
+      B200DF_CUDA(cudaMalloc(&l.amb, ((size_t)cs + 1) * sizeof(int)));
+      l.states = (size_t)cs;
+      l.row = row32;
+    }
+  }
+  struct Result
+  {
+    int rc = B200DF_OK;
+    cudaError_t e = cudaSuccess;
+    std::string msg;
+  };
+  std::vector<Result> res((size_t)T);
+  auto work = [&](int w) {
+    Result& r = res[(size_t)w];
+    r.e = cudaSetDevice(group->device);
+    Ctx::Lane& l = ctx->lane[w];
+    float* hq = static_cast<float*>(l.hq);
+    uint8_t* hv = static_cast<uint8_t*>(l.hq) + v_at;
+    uint8_t* dv = static_cast<uint8_t*>(l.dq) + v_at;
+    for (int64_t i = w; i < n_chunks && !r.rc && r.e == cudaSuccess; i += T)
+    {
+      const int64_t s0 = i * cs, m = std::min<int64_t>(cs, n - s0);
+      const double* src = q + (size_t)s0 * nv;
+      const size_t count = (size_t)m * nv;
+      narrow_rows(hq, src, count);
+      r.e = cudaMemcpyAsync(l.dq, hq, count * sizeof(float), cudaMemcpyHostToDevice, l.st);
+      if (r.e != cudaSuccess)
+        break;
+      r.rc = run_verdict(group, wf, sf, elem, l.dq, B200DF_Q_F32, m, flags, kPrecisionFastRaw, dv, l.st, l.amb + 1, l.amb);
+      if (r.rc)
+      {
+        r.msg = b200df_last_error();
+        break;
+      }
+      r.e = cudaMemcpyAsync(hv, dv, (size_t)m, cudaMemcpyDeviceToHost, l.st);
+      if (r.e == cudaSuccess)
+        r.e = cudaStreamSynchronize(l.st);
+      if (r.e == cudaSuccess)
+        std::memcpy(verdict + s0, hv, (size_t)m);
+    }
+  };
+  {
+    std::vector<std::thread> workers;
+    for (int w = 1; w < T; ++w)
+      workers.emplace_back(work, w);
+    work(0);
+    for (std::thread& t : workers)
+      t.join();
+  }
+  for (const Result& r : res)
+  {
+    if (r.rc)
+    {
+      set_error("%s", r.msg.c_str());
+      return r.rc;
+    }
+    B200DF_CUDA(r.e);
+  }
+  // the undecided states: their unrounded fp64 rows through the exact kernel
+  std::vector<int64_t> idx;
+  {
+    const uint64_t* w8 = reinterpret_cast<const uint64_t*>(verdict);
+    const int64_t head = ((uintptr_t)verdict & 7) ? std::min<int64_t>(n, 8 - (int64_t)((uintptr_t)verdict & 7)) : 0;
+    for (int64_t i = 0; i < head; ++i)
+      if (verdict[i] == 2)
+        idx.push_back(i);
+    w8 = reinterpret_cast<const uint64_t*>(verdict + head);
+    const int64_t words = (n - head) / 8;
+    for (int64_t k = 0; k < words; ++k)
+      if (w8[k] & 0x0202020202020202ull)
+        for (int64_t i = head + 8 * k; i < head + 8 * k + 8; ++i)
+          if (verdict[i] == 2)
+            idx.push_back(i);
+    for (int64_t i = head + 8 * words; i < n; ++i)
+      if (verdict[i] == 2)
+        idx.push_back(i);
+  }
+  if (idx.empty())
+    return B200DF_OK;
+  const int64_t k = (int64_t)idx.size();
+  const size_t row64 = (size_t)nv * sizeof(double);
+  const size_t need = (size_t)k * row64 + (size_t)k;
+  cudaError_t e = b200df_group::StagePool::ensure_hstage(ctx, 0, need);
+  if (e == cudaSuccess)
+    e = b200df_group::StagePool::ensure_scratch(ctx, 0, need);
+  if (e == cudaSuccess)
+    e = b200df_group::StagePool::ensure_stream(ctx, 0);
+  B200DF_CUDA(e);
+  char* hs = static_cast<char*>(ctx->hstage[0]);
+  char* ds = static_cast<char*>(ctx->scratch[0]);
+  for (int64_t j = 0; j < k; ++j)
+    std::memcpy(hs + (size_t)j * row64, q + (size_t)idx[(size_t)j] * nv, row64);
+  B200DF_CUDA(cudaMemcpyAsync(ds, hs, (size_t)k * row64, cudaMemcpyHostToDevice, ctx->stream[0]));
+  uint8_t* dv = reinterpret_cast<uint8_t*>(ds + (size_t)k * row64);
+  int rc = run_verdict(group, wf, sf, elem, ds, B200DF_Q_F64, k, flags, B200DF_PRECISION_EXACT, dv, ctx->stream[0]);
+  if (rc)
+    return rc;
+  uint8_t* hv = reinterpret_cast<uint8_t*>(hs + (size_t)k * row64);
+  B200DF_CUDA(cudaMemcpyAsync(hv, dv, (size_t)k, cudaMemcpyDeviceToHost, ctx->stream[0]));
+  B200DF_CUDA(cudaStreamSynchronize(ctx->stream[0]));
+  for (int64_t j = 0; j < k; ++j)
+    verdict[idx[(size_t)j]] = hv[j];
+  return B200DF_OK;
+}
+
 int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q, int q_dtype,
                        int64_t n, int flags, int precision, uint8_t* verdict)
 {
@@ -1009,6 +1186,19 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
       rc = B200DF_ERR_CUDA;
     }
     return rc;
+  }
+  if (precision == B200DF_PRECISION_FAST && q_dtype == B200DF_Q_F64 && n >= kFastMinStates && is_pageable_host(q) &&
+      !getenv("B200DF_NO_NARROWING"))
+  {
+    FieldDev wn = wf, sn = sf;
+    if (group->neg_irrelevant)
+      wn.neg = sn.neg = nullptr;
+    if (fast_supported(group, wn, sn, B200DF_Q_F32, flags))
+    {
+      rc = check_batch_narrowed(group, wf, sf, elem, static_cast<const double*>(q), n, flags, verdict, ctx);
+      group->stage->give_back(ctx);
+      return rc;
+    }
   }
   // Pageable caller memory: a cudaMemcpyAsync on it goes through the driver's own staging at a few GB/s and holds this
   // thread (the D2H even until the chunk's kernel is done, which serialises the pipeline).  Such batches are staged

@@ -655,6 +655,18 @@ struct b200df_group::StagePool
     // page-locked staging of large transfers from / to pageable caller memory, one per pipeline slot (grow-only)
     void* hstage[kSlots] = {};
     size_t hstage_bytes[kSlots] = {};
+    // lanes of the narrowing path (pageable fp64 rows -> fp32 screening): one independent pipeline per host thread
+    static constexpr int kLanes = 8;
+    struct Lane
+    {
+      cudaStream_t st = nullptr;
+      void* hq = nullptr;    // pinned: fp32 rows of one chunk, then the chunk's verdict bytes
+      void* dq = nullptr;    // device: the same
+      int* amb = nullptr;    // device scratch of the screening pass
+      size_t states = 0;     // chunk capacity the buffers were sized for
+      size_t row = 0;
+    };
+    Lane lane[kLanes];
   };
   std::mutex mu;
   std::vector<Ctx*> free_list;
@@ -680,6 +692,15 @@ struct b200df_group::StagePool
     for (void* p : c->hstage)
       if (p)
         cudaFreeHost(p);
+    for (Ctx::Lane& l : c->lane)
+    {
+      if (l.hq)
+        cudaFreeHost(l.hq);
+      cudaFree(l.dq);
+      cudaFree(l.amb);
+      if (l.st)
+        cudaStreamDestroy(l.st);
+    }
     delete c;
   }
   Ctx* acquire()

@@ -3,7 +3,12 @@
 
   python profiles/summarize.py rep  gpurun_out/prof.ncu-rep   profiles/<name>.txt
   python profiles/summarize.py list gpurun_out/launches.csv   profiles/<name>.txt
+  python profiles/summarize.py traffic gpurun_out/prof.ncu-rep profiles/<name>.json [states_per_launch]
+      per-launch DRAM bytes / L2 sectors / warp instructions of the validity kernels in the report, as the JSON
+      bench.py --traffic-json reads (keys "fast" and "exact"); merges into an existing file
 """
+import json
+import os
 import csv
 import io
 import subprocess
@@ -71,5 +76,56 @@ def launch_list(path, out):
             f.write("%-92s %8d %14.1f %7.2f%%\n" % (name, cnt, us, 100 * us / total))
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return 0.0
+
+
+def traffic(path, out, states=None):
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    col = {k: hdr.index(k) for k in hdr}
+
+    def val(r, k, to_bytes=False):
+        if k not in col:
+            return 0.0
+        v = _num(r[col[k]])
+        if to_bytes:
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[col[k]], 1.0)
+        return v
+
+    data = {}
+    if os.path.exists(out):
+        with open(out) as f:
+            data = json.load(f)
+    data["report"] = os.path.basename(path)
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        key = "fast" if "validity_fast_kernel" in name else "exact" if name.startswith("validity_kernel") or \
+            "::validity_kernel" in name else None
+        if key is None:
+            continue
+        n = float(states) if states else val(r, "launch__grid_size") * val(r, "launch__block_size")
+        dur = val(r, "gpu__time_duration.sum")
+        dur_us = dur * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[col["gpu__time_duration.sum"]], 1.0)
+        data[key] = {"kernel": name[:160], "states_per_launch": n,
+                     "dram_bytes_read": val(r, "dram__bytes_read.sum", True),
+                     "dram_bytes_write": val(r, "dram__bytes_write.sum", True),
+                     "lts_sectors_read": val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
+                     "lts_sectors_write": val(r, "lts__t_sectors.sum") - val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
+                     "lts_sector_hit_pct": val(r, "lts__t_sector_hit_rate.pct"),
+                     "warp_instructions": val(r, "smsp__inst_executed.sum"),
+                     "duration_us_under_ncu": dur_us,
+                     "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active")}
+    with open(out, "w") as f:
+        json.dump(data, f, indent=1)
+        f.write("\n")
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    fn = {"rep": rep, "list": launch_list, "traffic": traffic}[sys.argv[1]]
+    fn(*sys.argv[2:])
