@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200df.so")
-SOURCES = ["api.cu", "field.cu", "edt.cu", "validity.cu", "gradients.cu", "validity_fast.cu", "validity_small.cu", "motion.cu", "multi.cu"]
+SOURCES = ["api.cu", "field.cu", "edt.cu", "edt_tma.cu", "validity.cu", "gradients.cu", "validity_fast.cu", "validity_small.cu", "motion.cu", "multi.cu"]
 FMA_OK = {"validity_fast.cu"}  # fp32 screening kernel: only has to stay inside its error margins
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

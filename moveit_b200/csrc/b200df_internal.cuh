@@ -132,9 +132,17 @@ struct b200df_field
 
 namespace b200df
 {
+// 32-bit words per bit row of the occupancy mirror: rows are padded to 16 bytes, the stride TMA needs (edt_tma.cu)
+inline int bits_wpr(int nz)
+{
+  return ((nz + 127) / 128) * 4;
+}
 // builds the EDT when dirty; fills the kernel view.  Caller holds no lock.
 int field_prepare(b200df_field* f, FieldDev* view, cudaStream_t wait_on);
 // edt.cu: the two-launch exact EDT from bit rows (even nz, clamp radius <= 31); field.cu keeps the windowed fallback
 bool edt_fast_applies(const b200df_field* f);
 int edt_fast(b200df_field* f, bool invert, void* out);
+// edt_tma.cu: the same two passes with TMA-moved tiles (nz a multiple of 16); -1 = tensor map not available
+bool edt_tma_applies(const b200df_field* f);
+int edt_tma(b200df_field* f, void* out);
 }

@@ -1,4 +1,6 @@
-// Kernel 5, fast path: exact clamped squared EDT from bit-packed occupancy in TWO launches.
+// Kernel 5: exact clamped squared EDT from bit-packed occupancy - the bit-row packing kernels, the dispatch, and the
+// register-prefetch form of the two marching passes for grids the TMA form (edt_tma.cu) cannot take (nz not a multiple
+// of 16: tensor-map strides must be multiples of 16 bytes).
 //
 // Replaces PropagationDistanceField::propagatePositive / propagateNegative (reference:
 // moveit_core/distance_field/src/propagation_distance_field.cpp:389-505) for grids with an even nz and a clamp radius
@@ -6,23 +8,19 @@
 // to max_d2.  Any voxel whose true distance is below max_d2 has every axis offset <= reach = radius-1, so windows of
 // +-reach per axis are exact after the final clamp (a tap at the radius itself adds >= max_d2).
 //
-//   plane kernel (edt_plane_kernel): a thread owns the voxel pair (x, z0, z0+1) and marches along y.  The input of a
-//       step is the pair's squared z distance to the nearest obstacle of row (x, y), computed on the fly from the
-//       row's bit words (two bit scans) - the former z pass and its 2 bytes/voxel round trip through HBM are gone.
-//       Output: the 2-D (y, z) squared distance as u16x2, values >= max_d2 normalised to INF.
-//   axis kernel (edt_axis_kernel): the same march along x over the plane kernel's output, final clamp, u8 / u16 out.
+//   plane kernel: a thread owns the voxel pair (x, z0, z0+1) and marches along y.  The input of a step is the pair's
+//       squared z distance to the nearest obstacle of row (x, y), computed on the fly from the row's bit words (two bit
+//       scans).  Output: the 2-D (y, z) squared distance as u16x2, values >= max_d2 normalised to INF.
+//   axis kernel: the same march along x over the plane kernel's output, final clamp, u8 / u16 out.
 //
-// The march: input row t is added to the 2R+1 open outputs t-R..t+R, one VIADDMNMX.U16x2 (DPX) per (input, output)
-// pair and voxel pair, no re-reads.  The open outputs live in registers as a window of W + U - 1 values that is
-// addressed statically inside a block of U = 8 steps and shifted by U registers between blocks (6 moves per step).
-// Round 1 unrolled a full revolution of the ring instead (2R+1 steps x 2R+1 taps = 50 KB of code; its top stall was
-// instruction fetch); a block is 8 x 49 taps = 7 KB and stays in the instruction cache.  A block whose inputs are all
-// INF while the window holds nothing but INF (most of a sparse scene) emits INF rows and touches neither the taps nor
-// the shift.  Long lines are cut into segments (grid.y) that re-read a halo of R rows on either side: more and
-// shorter work items, which is what balances the SM sub-partitions (one warp per 64 voxels of a line is all the
-// parallelism a 400^3 pass has: 2500 warps for 592 sub-partitions).
+// The march: input row t is added to the 2R+1 open outputs t-R..t+R.  The open outputs live in registers as a window of
+// 2R + U values that is addressed statically inside a block of U steps and shifted by U registers between blocks.  A
+// block whose inputs are all INF while the window holds nothing but INF (most of a sparse scene) emits INF rows and
+// touches neither the taps nor the shift.  Long lines are cut into segments (grid.y) that re-read a halo of R rows on
+// either side: more and shorter work items, which is what balances the SM sub-partitions.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "b200df_internal.cuh"
 
@@ -31,17 +29,7 @@ using namespace b200df;
 namespace
 {
 constexpr unsigned kInfPair = 0x40004000u;  // leaves head-room for two additions of reach^2 <= 900 in 16 bits
-constexpr int kBlockSteps = 8;              // U: steps per statically addressed block
 constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ unsigned z_dist2(unsigned lo, unsigned hi, int reach)
-{
-  // lo = bits [z-32, z) (bit 31 is z-1), hi = bits [z, z+32) (bit 0 is z)
-  const int up = hi ? __ffs(hi) - 1 : 64;
-  const int dn = lo ? __clz(lo) + 1 : 64;
-  const int d = min(up, dn);
-  return d <= reach ? (unsigned)(d * d) : 0x4000u;
-}
 
 // values >= c (per half) -> 0x4000.  Halves are < 0x8000, so adding 0x8000 - c raises bit 15 exactly for those.
 __device__ __forceinline__ unsigned normalise_pair(unsigned v, unsigned bias_pair)
@@ -51,30 +39,212 @@ __device__ __forceinline__ unsigned normalise_pair(unsigned v, unsigned bias_pai
   return (v & ~mask) | (kInfPair & mask);
 }
 
-// ---- sources: what a marching thread reads per step ------------------------------------------------------------
-// All indices are 32-bit element indices from warp-uniform base pointers: base + t * stride compiles to one IMAD and
-// one IMAD.WIDE on the FMA pipe, which the marching loop leaves idle (its taps and compares are ALU-pipe work).
-struct BitsSource  // plane kernel: the pair's squared z distance, from the bit row of (x, t)
+struct BitWords  // the three words of a bit row a voxel pair can reach
 {
-  const uint32_t* bits;
-  unsigned row0;  // word index of (x, y = 0, word wi + 1)
+  unsigned a, b, c;
+};
+
+// ---- the march, second form: taps in pairs on both integer pipes ---------------------------------------------------
+// VIADDMNMX runs on the ALU pipe only, whose issue rate is one warp instruction per two cycles and scheduler, and a
+// march that is nothing but taps is bound by exactly that (ncu: ALU pipe 57 %, issue slots 55 %, math-pipe throttle the
+// top stall after the fixed-latency wait).  Here the additions go to the otherwise idle FMA pipe and the minima take
+// two candidates at once:
+//     s_a(k) = f_a * one + k^2      IMAD  (one == 1 is a kernel argument so that ptxas cannot fold it into an IADD3)
+//     acc[o] = min3(acc[o], s_a(|o - t_a|), s_b(|o - t_b|))      VIMNMX3.U16x2
+// Two adjacent input rows (t, t + 1) are swept together from their centre outwards, so that every sum is used for the
+// offsets +k and -k right after it was formed (three sums of the second row live at any time): per input row 24 IMAD
+// + 25 VIMNMX3 instead of 49 VIADDMNMX - half the ALU-pipe cycles, the same number of issue slots.
+__device__ __forceinline__ unsigned add_k2(unsigned f, unsigned one, unsigned k2pair)
+{
+  unsigned r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(f), "r"(one), "r"(k2pair));
+  return r;
+}
+
+template <int R, int N, int J>
+__device__ __forceinline__ void tap_pair(unsigned (&acc)[N], unsigned fa, unsigned fb, unsigned one)
+{
+  constexpr int c = J + R;  // window entry of row a's own position; row b's is c + 1
+  unsigned b_prev = fb;
+  unsigned b_cur = add_k2(fb, one, 0x00010001u);
+  acc[c] = __vimin3_u16x2(acc[c], fa, b_cur);
+#pragma unroll
+  for (int k = 1; k <= R; ++k)
+  {
+    const unsigned a = add_k2(fa, one, (unsigned)(k * k) * 0x00010001u);
+    if (k < R)
+    {
+      const unsigned b_next = add_k2(fb, one, (unsigned)((k + 1) * (k + 1)) * 0x00010001u);
+      acc[c - k] = __vimin3_u16x2(acc[c - k], a, b_next);  // offset -(k + 1) from row b
+      acc[c + k] = __vimin3_u16x2(acc[c + k], a, b_prev);  // offset k - 1 from row b
+      b_prev = b_cur;
+      b_cur = b_next;
+    }
+    else
+    {
+      acc[c - k] = __vminu2(acc[c - k], a);
+      acc[c + k] = __vimin3_u16x2(acc[c + k], a, b_prev);
+    }
+  }
+  acc[c + R + 1] = __vminu2(acc[c + R + 1], b_cur);
+}
+
+template <int R, int U, int N, int P>
+struct TapPairs  // pairs P, P + 1, ... of a block, each behind its own warp-uniform test
+{
+  static __device__ __forceinline__ void run(unsigned (&acc)[N], const unsigned (&f)[U], unsigned busy, unsigned one)
+  {
+    if ((busy >> P) & 1u)
+      tap_pair<R, N, 2 * P>(acc, f[2 * P], f[2 * P + 1], one);
+    TapPairs<R, U, N, P + 1>::run(acc, f, busy, one);
+  }
+};
+template <int R, int U, int N>
+struct TapPairs<R, U, N, U / 2>
+{
+  static __device__ __forceinline__ void run(unsigned (&)[N], const unsigned (&)[U], unsigned, unsigned)
+  {
+  }
+};
+
+// Outputs [oa, ob) of one line from inputs [oa - R, ob + R) clipped to [0, n_axis).  A block is U input rows; its
+// inputs were fetched one (plane kernel) or two (axis kernel) blocks earlier.  Everything that decides the path through
+// a block is warp-uniform: which pairs of rows hold a finite value in some lane (one REDUX.OR of per-lane pair masks),
+// whether the window holds anything but INF, whether all U outputs / all U prefetched rows lie inside the array.
+template <int R, int U, int AHEAD, typename Src, typename Sink>
+__device__ __forceinline__ void march2(Src& src, Sink& sink, int oa, int ob, int n_axis, unsigned one)
+{
+  constexpr int W = 2 * R + 1, N = W + U - 1;
+  static_assert(U % 2 == 0 && (AHEAD == 1 || AHEAD == 2), "");
+  unsigned acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    acc[i] = kInfPair;
+  const int t_end = min(ob + R, n_axis);
+  int t0 = max(oa - R, 0);
+  typename Src::Raw raw[AHEAD][U];
+  src.seek(t0);
+#pragma unroll
+  for (int a = 0; a < AHEAD; ++a)
+  {
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      raw[a][j] = (t0 + a * U + j < t_end) ? src.load(j) : Src::none();
+    src.advance(U);
+  }
+  sink.seek(t0 - R);
+  int quiet = 2 * R;  // INF rows since the last finite one; the window holds only INF from 2R on
+  for (; t0 < ob + R; t0 += U)
+  {
+    unsigned f[U];
+    unsigned lane_busy = 0;
+#pragma unroll
+    for (int j = 0; j < U; j += 2)
+      if (src.maybe_finite(raw[0][j]) || src.maybe_finite(raw[0][j + 1]))
+        lane_busy |= 1u << (j / 2);
+    const unsigned busy = __reduce_or_sync(kFull, lane_busy);
+    if (busy)
+    {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        f[j] = src.convert(raw[0][j]);
+    }
+    // rows t0 + AHEAD * U ... go in flight
+    const int tn = t0 + AHEAD * U;
+#pragma unroll
+    for (int a = 0; a + 1 < AHEAD; ++a)
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        raw[a][j] = raw[a + 1][j];
+    if (tn + U <= t_end)
+    {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        raw[AHEAD - 1][j] = src.load(j);
+    }
+    else
+    {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        raw[AHEAD - 1][j] = (tn + j < t_end) ? src.load(j) : Src::none();
+    }
+    src.advance(U);
+    const int o0 = t0 - R;  // output row completed by step 0 of the block
+    const bool inside = o0 >= oa && o0 + U <= ob;
+    const bool some = o0 + U > oa && o0 < ob;
+    if (!busy && quiet >= 2 * R)
+    {
+      if (inside)
+      {
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          sink.emit_inf(j);
+      }
+      else if (some)
+      {
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (o0 + j >= oa && o0 + j < ob)
+            sink.emit_inf(j);
+      }
+      sink.advance(U);
+      continue;
+    }
+    if (busy)
+    {
+      TapPairs<R, U, N, 0>::run(acc, f, busy, one);
+      quiet = 0;
+    }
+    else
+      quiet += U;
+    if (inside)
+    {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        sink.emit(j, acc[j]);
+    }
+    else if (some)
+    {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (o0 + j >= oa && o0 + j < ob)
+          sink.emit(j, acc[j]);
+    }
+    sink.advance(U);
+#pragma unroll
+    for (int k = 0; k < W - 1; ++k)
+      acc[k] = acc[k + U];
+#pragma unroll
+    for (int k = W - 1; k < N; ++k)
+      acc[k] = kInfPair;
+  }
+}
+
+// sources / sinks of march2: a moving row pointer, rows addressed as pointer + j * stride inside a block
+struct BitsSource2
+{
+  const uint32_t* p;  // word wi + 1 of the row of the current block's first step
   unsigned wpr;
   int o, reach;
   bool has0, has2;
-  struct Raw
+  typedef BitWords Raw;
+  __device__ __forceinline__ void seek(int t)
   {
-    unsigned a, b, c;
-  };
-  __device__ __forceinline__ Raw load(int t) const
+    p += (size_t)t * wpr;
+  }
+  __device__ __forceinline__ void advance(int n)
   {
-    const uint32_t* br = bits + (row0 + (unsigned)t * wpr);
+    p += (size_t)n * wpr;
+  }
+  __device__ __forceinline__ Raw load(int j) const
+  {
+    const uint32_t* br = p + (unsigned)j * wpr;
     Raw r;
     r.a = has0 ? __ldg(br - 1) : 0u;
     r.b = __ldg(br);
     r.c = has2 ? __ldg(br + 1) : 0u;
     return r;
   }
-  static constexpr bool kExactTest = false;  // words in reach of the pair may still hold no obstacle within reach
   static __device__ __forceinline__ Raw none()
   {
     return Raw{ 0u, 0u, 0u };
@@ -85,11 +255,8 @@ struct BitsSource  // plane kernel: the pair's squared z distance, from the bit 
   }
   __device__ __forceinline__ unsigned convert(const Raw& r) const
   {
-    // voxel z0: bits below in lo0 (bit 31 is z0-1), bits from z0 up in hi0 (bit 0 is z0); voxel z0+1 likewise.
-    // Two scans instead of four: the distance up is found for z0+1 and carried down, the distance down for z0 and
-    // carried up.
     const unsigned lo0 = __funnelshift_r(r.a, r.b, o), hi0 = __funnelshift_r(r.b, r.c, o);
-    const unsigned above1 = hi0 >> 1;  // bits [z0+1, z0+32): enough for reach <= 30
+    const unsigned above1 = hi0 >> 1;
     const int up1 = above1 ? __ffs(above1) - 1 : 64;
     const int dn0 = lo0 ? __clz(lo0) + 1 : 64;
     const bool occ0 = hi0 & 1u;
@@ -102,15 +269,22 @@ struct BitsSource  // plane kernel: the pair's squared z distance, from the bit 
   }
 };
 
-struct PairSource  // axis kernel: u16x2 pairs written by the plane kernel
+struct PairSource2
 {
-  const uint32_t* in;
-  unsigned base, stride;
+  const uint32_t* p;
+  unsigned stride;
   typedef unsigned Raw;
-  static constexpr bool kExactTest = true;
-  __device__ __forceinline__ Raw load(int t) const
+  __device__ __forceinline__ void seek(int t)
   {
-    return __ldg(in + (base + (unsigned)t * stride));
+    p += (size_t)t * stride;
+  }
+  __device__ __forceinline__ void advance(int n)
+  {
+    p += (size_t)n * stride;
+  }
+  __device__ __forceinline__ Raw load(int j) const
+  {
+    return __ldg(p + (unsigned)j * stride);
   }
   static __device__ __forceinline__ Raw none()
   {
@@ -126,217 +300,66 @@ struct PairSource  // axis kernel: u16x2 pairs written by the plane kernel
   }
 };
 
-// ---- sinks: where a finished output row goes -------------------------------------------------------------------
-struct PairSink  // intermediate: u16x2, >= max_d2 -> INF (can never win below the clamp later)
+struct PairSink2
 {
-  uint32_t* out;
-  unsigned base, stride;
+  uint32_t* p;  // may point before the array while the first outputs are still outside [oa, ob): never dereferenced then
+  unsigned stride;
   unsigned bias_pair;
   bool live;
-  __device__ __forceinline__ void emit(int o, unsigned v) const
+  __device__ __forceinline__ void seek(int o)
   {
-    if (live)
-      out[base + (unsigned)o * stride] = normalise_pair(v, bias_pair);
+    p += (ptrdiff_t)o * (ptrdiff_t)stride;
   }
-  __device__ __forceinline__ void emit_inf(int o) const
+  __device__ __forceinline__ void advance(int n)
+  {
+    p += (size_t)n * stride;
+  }
+  __device__ __forceinline__ void emit(int j, unsigned v) const
   {
     if (live)
-      out[base + (unsigned)o * stride] = kInfPair;
+      p[(unsigned)j * stride] = normalise_pair(v, bias_pair);
+  }
+  __device__ __forceinline__ void emit_inf(int j) const
+  {
+    if (live)
+      p[(unsigned)j * stride] = kInfPair;
   }
 };
 
 template <typename OutT>
-struct FinalSink  // final: clamp to max_d2, narrow to the field's element type
+struct FinalSink2
 {
-  void* out;
-  unsigned base, stride;
+  typedef typename std::conditional<sizeof(OutT) == 1, uint16_t, uint32_t>::type Store;
+  Store* p;
+  unsigned stride;
   unsigned clamp_pair;
   bool live;
-  __device__ __forceinline__ void put(int o, unsigned v) const
+  __device__ __forceinline__ void seek(int o)
+  {
+    p += (ptrdiff_t)o * (ptrdiff_t)stride;
+  }
+  __device__ __forceinline__ void advance(int n)
+  {
+    p += (size_t)n * stride;
+  }
+  __device__ __forceinline__ void put(int j, unsigned v) const
   {
     if (!live)
       return;
-    const unsigned i = base + (unsigned)o * stride;
     if (sizeof(OutT) == 1)
-      static_cast<uint16_t*>(out)[i] = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));
+      p[(unsigned)j * stride] = (Store)((v & 0xffu) | ((v >> 8) & 0xff00u));
     else
-      static_cast<uint32_t*>(out)[i] = v;
+      p[(unsigned)j * stride] = (Store)v;
   }
-  __device__ __forceinline__ void emit(int o, unsigned v) const
+  __device__ __forceinline__ void emit(int j, unsigned v) const
   {
-    put(o, __vminu2(v, clamp_pair));
+    put(j, __vminu2(v, clamp_pair));
   }
-  __device__ __forceinline__ void emit_inf(int o) const
+  __device__ __forceinline__ void emit_inf(int j) const
   {
-    put(o, clamp_pair);
+    put(j, clamp_pair);
   }
 };
-
-// ---- the march ----------------------------------------------------------------------------------------------------
-// Outputs [oa, ob) of one line; reads inputs [oa - R, ob + R) clipped to [0, n_axis).  Every range test is on
-// warp-uniform values (t0, oa, ob).  Inputs are fetched two blocks (16 rows) ahead: a block that turns out to be all
-// INF costs a dozen instructions, so one block of look-ahead does not cover the memory latency.
-// Three ways through a block of U input rows:
-//   - no finite input and the window holds only INF: emit INF rows (nothing else to do)
-//   - no finite input, window not yet drained: emit the finished rows, shift the window
-//   - otherwise: all U x (2R+1) taps as one straight-line sequence; the shift by U registers is folded into the
-//     destination registers of the last tap of every window entry, so the busy path has no register moves at all
-// Step-granular variant for the plane kernel, whose finite rows are few (16 % of a sparse scene's rows) and scattered:
-// the taps of a row are skipped unless some lane's input is finite; one block of look-ahead.
-template <int R, typename Src, typename Sink>
-__device__ __forceinline__ void march_steps(const Src& src, const Sink& sink, int oa, int ob, int n_axis)
-{
-  constexpr int W = 2 * R + 1, U = kBlockSteps, N = W + U - 1;
-  unsigned acc[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    acc[i] = kInfPair;
-  const int t_end = min(ob + R, n_axis);
-  typename Src::Raw raw[U];
-  int t0 = max(oa - R, 0);
-#pragma unroll
-  for (int j = 0; j < U; ++j)
-    raw[j] = (t0 + j < t_end) ? src.load(t0 + j) : Src::none();
-  int clean = W;  // INF steps since the last finite input; the window holds only INF once it reaches 2R
-  for (; t0 < ob + R; t0 += U)
-  {
-    unsigned f[U];
-    unsigned m = 0;
-#pragma unroll
-    for (int j = 0; j < U; ++j)
-    {
-      f[j] = kInfPair;
-      if (__any_sync(kFull, src.maybe_finite(raw[j])))
-      {
-        f[j] = src.convert(raw[j]);
-        if (Src::kExactTest || __any_sync(kFull, f[j] != kInfPair))
-          m |= 1u << j;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j)  // next block's inputs are in flight while this one is processed
-      raw[j] = (t0 + U + j < t_end) ? src.load(t0 + U + j) : Src::none();
-    const int o0 = t0 - R;  // output row completed by step 0 of the block
-    const bool inside = o0 >= oa && o0 + U <= ob;
-    if (m == 0 && clean >= W)
-    {
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-        if (inside || (o0 + j >= oa && o0 + j < ob))
-          sink.emit_inf(o0 + j);
-      continue;
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j)
-    {
-      if ((m >> j) & 1u)
-      {
-#pragma unroll
-        for (int k = 0; k < W; ++k)
-          acc[j + k] = __viaddmin_u16x2(f[j], (unsigned)((k - R) * (k - R)) * 0x00010001u, acc[j + k]);
-        clean = 0;
-      }
-      else
-        ++clean;
-      if (inside || (o0 + j >= oa && o0 + j < ob))  // has now seen every input within +-R of it
-        sink.emit(o0 + j, acc[j]);
-    }
-#pragma unroll
-    for (int k = 0; k < W - 1; ++k)
-      acc[k] = acc[k + U];
-#pragma unroll
-    for (int k = W - 1; k < N; ++k)
-      acc[k] = kInfPair;
-  }
-}
-
-template <int R, typename Src, typename Sink>
-__device__ __forceinline__ void march(const Src& src, const Sink& sink, int oa, int ob, int n_axis)
-{
-  constexpr int W = 2 * R + 1, U = kBlockSteps, N = W + U - 1;
-  unsigned acc[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    acc[i] = kInfPair;
-  const int t_end = min(ob + R, n_axis);
-  typename Src::Raw raw_a[U], raw_b[U];
-  int t0 = max(oa - R, 0);  // rows before the array are INF: nothing to add, nothing to emit (their outputs are < oa)
-#pragma unroll
-  for (int j = 0; j < U; ++j)
-  {
-    raw_a[j] = (t0 + j < t_end) ? src.load(t0 + j) : Src::none();
-    raw_b[j] = (t0 + U + j < t_end) ? src.load(t0 + U + j) : Src::none();
-  }
-  int drained = 1;  // the window holds only INF
-  int quiet = 0;    // INF rows since the last finite one
-  for (; t0 < ob + R; t0 += U)
-  {
-    unsigned f[U];
-    bool lane_finite = false;
-#pragma unroll
-    for (int j = 0; j < U; ++j)
-      lane_finite = lane_finite || src.maybe_finite(raw_a[j]);
-    bool busy = __any_sync(kFull, lane_finite);
-    if (busy)
-    {
-      lane_finite = false;
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-      {
-        f[j] = src.convert(raw_a[j]);
-        lane_finite = lane_finite || f[j] != kInfPair;
-      }
-      busy = Src::kExactTest || __any_sync(kFull, lane_finite);
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j)  // rows t0 + 2U ... are now in flight behind the block after this one
-    {
-      raw_a[j] = raw_b[j];
-      raw_b[j] = (t0 + 2 * U + j < t_end) ? src.load(t0 + 2 * U + j) : Src::none();
-    }
-    const int o0 = t0 - R;  // output row completed by step 0 of the block
-    const bool inside = o0 >= oa && o0 + U <= ob;
-    if (!busy)
-    {
-      if (drained)
-      {
-#pragma unroll
-        for (int j = 0; j < U; ++j)
-          if (inside || (o0 + j >= oa && o0 + j < ob))
-            sink.emit_inf(o0 + j);
-        continue;
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-        if (inside || (o0 + j >= oa && o0 + j < ob))
-          sink.emit(o0 + j, acc[j]);
-      quiet += U;
-      drained = quiet >= 2 * R;
-    }
-    else
-    {
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-      {
-#pragma unroll
-        for (int k = 0; k < W; ++k)
-          acc[j + k] = __viaddmin_u16x2(f[j], (unsigned)((k - R) * (k - R)) * 0x00010001u, acc[j + k]);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-        if (inside || (o0 + j >= oa && o0 + j < ob))  // has now seen every input within +-R of it
-          sink.emit(o0 + j, acc[j]);
-      quiet = 0;
-      drained = 0;
-    }
-#pragma unroll
-    for (int k = 0; k < W - 1; ++k)
-      acc[k] = acc[k + U];
-#pragma unroll
-    for (int k = W - 1; k < N; ++k)
-      acc[k] = kInfPair;
-  }
-}
 
 // One warp per CTA: the block scheduler hands a new line group to whichever SM has a slot free, which is what evens
 // out heavy (all rows finite) and light (all INF) groups.
@@ -344,10 +367,11 @@ __device__ __forceinline__ void march(const Src& src, const Sink& sink, int oa, 
 // independent, so the slabs of one rebuild run as separate launches on separate streams.  Their tails (the last,
 // heaviest line groups of a launch leave most SM sub-partitions idle) then overlap with the next slab's work, and a
 // slab's intermediate plane-kernel output (32 MB for a quarter of Field B) is still in L2 when its axis kernel reads it.
-template <int R>
-__global__ void __launch_bounds__(32) edt_plane_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ out,
-                                                       unsigned n_lines, unsigned half, unsigned zp0, unsigned slab,
-                                                       int ny, unsigned wpr, int reach, int max_d2, int seg_len)
+template <int R, int U, int AHEAD>
+__global__ void __launch_bounds__(32) edt_plane2_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ out,
+                                                        unsigned n_lines, unsigned half, unsigned zp0, unsigned slab,
+                                                        int ny, unsigned wpr, int reach, int max_d2, int seg_len,
+                                                        unsigned one)
 {
   const unsigned line0 = blockIdx.x * 32u + threadIdx.x;
   const bool live = line0 < n_lines;
@@ -355,32 +379,27 @@ __global__ void __launch_bounds__(32) edt_plane_kernel(const uint32_t* __restric
   const unsigned x = line / slab, zp = zp0 + line % slab;
   const int z0 = 2 * (int)zp;
   const int wi = (z0 - 32) >> 5;  // -1 for the first 32 voxels of a row
-  BitsSource src;
-  src.bits = bits;
-  src.row0 = x * (unsigned)ny * wpr + (unsigned)(wi + 1);
+  BitsSource2 src;
+  src.p = bits + ((size_t)x * (unsigned)ny * wpr + (unsigned)(wi + 1));
   src.wpr = wpr;
   src.o = z0 & 31;
   src.reach = reach;
   src.has0 = wi >= 0;
   src.has2 = wi + 2 < (int)wpr;
-  PairSink sink;
-  sink.out = out;
-  sink.base = x * (unsigned)ny * half + zp;
+  PairSink2 sink;
+  sink.p = out + ((size_t)x * (unsigned)ny * half + zp);
   sink.stride = half;
   sink.bias_pair = (unsigned)(0x8000 - max_d2) * 0x00010001u;
   sink.live = live;
   const int oa = blockIdx.y * seg_len;
-  march_steps<R>(src, sink, oa, min(oa + seg_len, ny), ny);
+  march2<R, U, AHEAD>(src, sink, oa, min(oa + seg_len, ny), ny, one);
 }
 
-// TILED: a warp covers 4 y rows x 8 voxel pairs (16 z) instead of 32 consecutive pairs of one row - the same four
-// 32-byte sectors per access, but a compact footprint touches fewer "finite" rows (needs half % 8 == 0, ny % 4 == 0).
-template <int R, typename OutT, bool TILED>
-__global__ void __launch_bounds__(32) edt_axis_kernel(const uint32_t* __restrict__ in, void* __restrict__ out,
-                                                      unsigned n_lines, unsigned half, unsigned zp0, unsigned slab,
-                                                      unsigned plane, int nx, int max_d2, int seg_len)
+template <int R, int U, int AHEAD, typename OutT, bool TILED>
+__global__ void __launch_bounds__(32) edt_axis2_kernel(const uint32_t* __restrict__ in, void* __restrict__ out,
+                                                       unsigned n_lines, unsigned half, unsigned zp0, unsigned slab,
+                                                       unsigned plane, int nx, int max_d2, int seg_len, unsigned one)
 {
-  // n_lines = ny * slab lines of this slab; a line is the pair (y, zp0 + zp), zp < slab
   unsigned y, zp;
   bool live;
   if (TILED)
@@ -400,18 +419,16 @@ __global__ void __launch_bounds__(32) edt_axis_kernel(const uint32_t* __restrict
     zp = line % slab;
   }
   const unsigned q = y * half + zp0 + zp;
-  PairSource src;
-  src.in = in;
-  src.base = q;
+  PairSource2 src;
+  src.p = in + q;
   src.stride = plane;
-  FinalSink<OutT> sink;
-  sink.out = out;
-  sink.base = q;
+  FinalSink2<OutT> sink;
+  sink.p = static_cast<typename FinalSink2<OutT>::Store*>(out) + q;
   sink.stride = plane;
   sink.clamp_pair = (unsigned)max_d2 * 0x00010001u;
   sink.live = live;
   const int oa = blockIdx.y * seg_len;
-  march<R>(src, sink, oa, min(oa + seg_len, nx), nx);
+  march2<R, U, AHEAD>(src, sink, oa, min(oa + seg_len, nx), nx, one);
 }
 
 // ---- occupancy bytes -> bit rows ------------------------------------------------------------------------------------
@@ -477,23 +494,14 @@ template <int R, typename T>
 int run_march(b200df_field* f, T* out)
 {
   const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
-  const int half = nz / 2, wpr = (nz + 31) / 32, reach = f->radius - 1;
+  const int half = nz / 2, wpr = bits_wpr(nz), reach = f->radius - 1;
   // z slabs (multiples of 8 pairs, so that the tiled footprint and the 32-byte sectors stay whole)
   int n_slabs = env_int("B200DF_EDT_SLABS", 0);
   if (n_slabs <= 0)
     n_slabs = f->n_voxels >= (8L << 20) ? 4 : 1;
   n_slabs = std::max(1, std::min(n_slabs, std::min(half / 8, (int)b200df_field::kEdtStreams)));
   const bool tiled_ok = half % 8 == 0 && ny % 4 == 0 && !env_int("B200DF_EDT_LINEAR", 0);
-  static bool attr_done = false;
-  if (!attr_done)
-  {
-    cudaFuncSetAttribute(edt_plane_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(edt_axis_kernel<R, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(edt_axis_kernel<R, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
-  }
-  // dynamic shared memory is only an occupancy knob here (experiments)
-  const int smem_y = env_int("B200DF_EDT_SMEM_Y", 0), smem_x = env_int("B200DF_EDT_SMEM_X", 0);
+  const int smem_y = 0, smem_x = 0;
   if (n_slabs > 1)
     B200DF_CUDA(cudaEventRecord(f->ev_fork, f->stream));
   int zp0 = 0;
@@ -515,21 +523,30 @@ int run_march(b200df_field* f, T* out)
     const int seg_y = pick_segments(warps_y * n_slabs, ny, reach, "B200DF_EDT_SEG_Y");
     const int seg_x = pick_segments(warps_x * n_slabs, nx, reach, "B200DF_EDT_SEG_X");
     const int len_y = (ny + seg_y - 1) / seg_y, len_x = (nx + seg_x - 1) / seg_x;
-    edt_plane_kernel<R><<<dim3((unsigned)warps_y, (unsigned)((ny + len_y - 1) / len_y)), 32, smem_y, st>>>(
-        f->bits, reinterpret_cast<uint32_t*>(f->tmp_a), (unsigned)lines_y, (unsigned)half, (unsigned)zp0,
-        (unsigned)slab, ny, (unsigned)wpr, reach, f->max_d2, len_y);
-    B200DF_LAUNCHED();
+    const dim3 grid_y((unsigned)warps_y, (unsigned)((ny + len_y - 1) / len_y));
     const dim3 grid_x((unsigned)warps_x, (unsigned)((nx + len_x - 1) / len_x));
     const unsigned plane = (unsigned)ny * (unsigned)half;
-    if (tiled_ok && slab % 8 == 0)
-      edt_axis_kernel<R, T, true><<<grid_x, 32, smem_x, st>>>(reinterpret_cast<const uint32_t*>(f->tmp_a), out,
-                                                              (unsigned)lines_x, (unsigned)half, (unsigned)zp0,
-                                                              (unsigned)slab, plane, nx, f->max_d2, len_x);
-    else
-      edt_axis_kernel<R, T, false><<<grid_x, 32, smem_x, st>>>(reinterpret_cast<const uint32_t*>(f->tmp_a), out,
-                                                               (unsigned)lines_x, (unsigned)half, (unsigned)zp0,
-                                                               (unsigned)slab, plane, nx, f->max_d2, len_x);
-    B200DF_LAUNCHED();
+    uint32_t* mid = reinterpret_cast<uint32_t*>(f->tmp_a);
+    const bool tiled = tiled_ok && slab % 8 == 0;
+    {
+#define B200DF_PLANE2(U, A)                                                                                         \
+  edt_plane2_kernel<R, U, A><<<grid_y, 32, smem_y, st>>>(f->bits, mid, (unsigned)lines_y, (unsigned)half,           \
+                                                         (unsigned)zp0, (unsigned)slab, ny, (unsigned)wpr, reach,   \
+                                                         f->max_d2, len_y, 1u)
+#define B200DF_AXIS2(U, A, TL)                                                                                      \
+  edt_axis2_kernel<R, U, A, T, TL><<<grid_x, 32, smem_x, st>>>(mid, out, (unsigned)lines_x, (unsigned)half,         \
+                                                               (unsigned)zp0, (unsigned)slab, plane, nx, f->max_d2, \
+                                                               len_x, 1u)
+      B200DF_PLANE2(8, 1);
+      B200DF_LAUNCHED();
+      if (tiled)
+        B200DF_AXIS2(16, 1, true);
+      else
+        B200DF_AXIS2(16, 1, false);
+      B200DF_LAUNCHED();
+#undef B200DF_PLANE2
+#undef B200DF_AXIS2
+    }
     if (n_slabs > 1)
     {
       B200DF_CUDA(cudaEventRecord(f->ev_join[s], st));
@@ -553,7 +570,7 @@ bool edt_fast_applies(const b200df_field* f)
 int edt_fast(b200df_field* f, bool invert, void* out)
 {
   const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
-  const int wpr = (nz + 31) / 32;
+  const int wpr = bits_wpr(nz);
   const long n_rows = (long)nx * ny;
   if (!invert && f->bits_valid)
   {
@@ -572,6 +589,12 @@ int edt_fast(b200df_field* f, bool invert, void* out)
     B200DF_LAUNCHED();
   }
   f->bits_valid = !invert;  // the bit rows now mirror occ (or its complement, for the negative field)
+  if (edt_tma_applies(f))
+  {
+    const int rc = edt_tma(f, out);
+    if (rc != -1)
+      return rc;
+  }
   const int reach = f->radius - 1;
   if (f->elem_size == 1)
   {

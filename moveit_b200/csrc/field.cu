@@ -537,7 +537,7 @@ __global__ void unpack_occupancy_kernel(const uint8_t* __restrict__ in, uint8_t*
 
 inline size_t bits_bytes(const b200df_field* f)
 {
-  return (size_t)f->grid.n[0] * f->grid.n[1] * ((f->grid.n[2] + 31) / 32) * sizeof(uint32_t);
+  return (size_t)f->grid.n[0] * f->grid.n[1] * bits_wpr(f->grid.n[2]) * sizeof(uint32_t);
 }
 
 inline unsigned blocks_for(long n, int threads)
@@ -840,7 +840,7 @@ int b200df_field_create(const b200df_field_desc* desc, b200df_field** out)
   B200DF_CUDA(cudaMalloc(&f->tmp_b, nv * sizeof(uint16_t)));
   if (total > 0 && f->grid.n[2] % 2 == 0 && f->radius <= 31 && !getenv("B200DF_EDT_WINDOWED"))
   {
-    const size_t bit_bytes = (size_t)f->grid.n[0] * f->grid.n[1] * ((f->grid.n[2] + 31) / 32) * sizeof(uint32_t);
+    const size_t bit_bytes = (size_t)f->grid.n[0] * f->grid.n[1] * bits_wpr(f->grid.n[2]) * sizeof(uint32_t);
     B200DF_CUDA(cudaMalloc(&f->bits, bit_bytes));
     B200DF_CUDA(cudaMemset(f->bits, 0, bit_bytes));  // padding bits of a row stay 0 (= no obstacle) forever
   }
@@ -941,7 +941,7 @@ static int scatter_host_points(b200df_field* f, const double* xyz, int64_t n, ui
     f->pts_dev_bytes = bytes;
   }
   const bool mirror = vol == f->occ && value == 1 && !orv && f->bits && f->bits_valid;
-  const int wpr = (f->grid.n[2] + 31) / 32;
+  const int wpr = bits_wpr(f->grid.n[2]);
   const int64_t kSlicePoints = (int64_t)(4 << 20) / 24;  // ~4 MB of points per slice
   const unsigned hw = std::thread::hardware_concurrency();
   const int n_workers = (int)std::min<int64_t>(std::min<unsigned>((unsigned)b200df_field::kEdtStreams, std::max(1u, hw / 2)),
@@ -1024,7 +1024,7 @@ int b200df_field_add_points_device(b200df_field* f, const double* xyz_dev, int64
   {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     scatter_points_kernel<<<blocks_for(n, 256), 256, 0, st>>>(f->grid, xyz_dev, n, f->occ, 1, false,
-                                                              f->bits_valid ? f->bits : nullptr, (f->grid.n[2] + 31) / 32);
+                                                              f->bits_valid ? f->bits : nullptr, bits_wpr(f->grid.n[2]));
     B200DF_LAUNCHED();
     B200DF_CUDA(cudaGetLastError());
     // the rebuild runs on the field's own stream: order it after the caller's scatter
@@ -1156,7 +1156,7 @@ static int octree_leaves(b200df_field* f, const double* leaves4, int64_t n, uint
     octree_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, f->stream>>>(
         f->grid, static_cast<const double*>(dl.p), n, static_cast<const int*>(dc.p),
         static_cast<const unsigned long long*>(doff.p), total, res, f->occ, value, mirror ? f->bits : nullptr,
-        (f->grid.n[2] + 31) / 32);
+        bits_wpr(f->grid.n[2]));
     B200DF_LAUNCHED();
     B200DF_CUDA(cudaGetLastError());
     B200DF_CUDA(cudaStreamSynchronize(f->stream));
