@@ -31,6 +31,12 @@ using namespace b200df;
 
 namespace
 {
+#ifndef B200DF_EDT_S
+#define B200DF_EDT_S 2
+#endif
+#ifndef B200DF_EDT_MINB
+#define B200DF_EDT_MINB 16  // CTAs (= warps) per SM the plane kernel is compiled for: caps it at 128 registers
+#endif
 constexpr unsigned kBias = 0x2000u;
 constexpr unsigned kBiasPair = 0x20002000u;
 constexpr unsigned kFull = 0xffffffffu;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(32)
 // The plane kernel runs the same loop on bit tiles: a row is turned into distances only inside a pair that holds
 // obstacle bits (bits that all lie out of reach give values at or below BIAS, which change nothing).
 template <int R, int U, int S>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, R <= 24 ? B200DF_EDT_MINB : 8)
     edt_plane_tma_kernel(const __grid_constant__ CUtensorMap bits_map, const __grid_constant__ CUtensorMap out_map,
                          int tiles_z, int zp0, int ny, int reach, int max_d2, int seg_len, unsigned one)
 {
@@ -666,7 +672,7 @@ int env_int(const char* name, int fallback)
 template <int R, typename T, int U>
 int run_u(b200df_field* f, T* out)
 {
-  constexpr int S = U >= 16 ? 2 : 4, SB = U >= 24 ? 2 : U >= 16 ? 3 : 6;
+  constexpr int S = U >= 16 ? B200DF_EDT_S : 4, SB = U >= 24 ? 2 : U >= 16 ? 3 : 6;
   const int nz = f->grid.n[2], ny = f->grid.n[1], nx = f->grid.n[0];
   const int half = nz / 2, wpr = bits_wpr(nz), reach = f->radius - 1;
   CUtensorMap mid_store, mid_load, out_store, bits_map;
