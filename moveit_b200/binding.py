@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200df.so")
+# B200DF_LIB: a differently built copy of the same library (kernel tuning experiments, tools/build_variant.py)
+LIB_PATH = os.environ.get("B200DF_LIB") or os.path.join(_HERE, "libb200df.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 CHECK_ROBOT, CHECK_SELF, CHECK_INTRA, CHECK_LINK_FIELDS = 1, 2, 4, 8
