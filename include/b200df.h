@@ -335,6 +335,18 @@ int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world
                                   const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
                                   double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream);
 
+/* The two calls above with single-precision outputs: dist, grad and centers are the fp64 results rounded once while
+ * they are written (type stays exact; "no candidate", DBL_MAX in the fp64 form, is FLT_MAX).  north_star's tolerance
+ * for this path is 1e-5 m; rounding costs < 5e-7 for distances below 1 m and gradient components below 8.  29 bytes
+ * per sphere instead of 57 cross PCIe - the host-buffer call is bound by exactly that copy (CHOMP's consumer,
+ * chomp_optimizer.cpp:924-961, reads the values into its own arrays either way). */
+int b200df_gradients_batch_f32(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                               int q_dtype, int64_t n, int flags, float* dist, float* grad, uint8_t* type,
+                               float* centers);
+int b200df_gradients_batch_device_f32(const b200df_group* group, b200df_field* world, b200df_field* self,
+                                      const void* q_dev, int q_dtype, int64_t n, int flags, float* dist_dev,
+                                      float* grad_dev, uint8_t* type_dev, float* centers_dev, void* stream);
+
 /* distanceRobot / distanceSelf are stubs in the reference (collision_env_distance_field.h:108-123,178-198, F5).
  * Defined here as min over group spheres of (field distance - radius); out[n]. */
 int b200df_distance_batch(const b200df_group* group, b200df_field* world, const void* q, int q_dtype, int64_t n,

@@ -106,6 +106,9 @@ SYMBOLS = {
     "b200df_check_edges": (C.c_int, [_VP, _VP, _VP, c_dp, c_dp, C.c_int64, C.c_int32, c_u8p, C.c_int, C.c_int, c_i32p]),
     "b200df_gradients_batch": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_dp, c_dp, c_u8p, c_dp]),
     "b200df_gradients_batch_device": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, _VP]),
+    "b200df_gradients_batch_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, c_fp, c_fp, c_u8p, c_fp]),
+    "b200df_gradients_batch_device_f32": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int64, C.c_int, _VP, _VP, _VP, _VP,
+                                                    _VP]),
     "b200df_distance_batch": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int64, c_dp]),
     "b200df_sphere_centers": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, c_dp]),
     "b200df_multi_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(GroupDesc), c_i32p, C.c_int32, _VPP]),

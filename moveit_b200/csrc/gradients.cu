@@ -305,13 +305,27 @@ __device__ __forceinline__ void posed_rel(const double* pose, double x, double y
 
 // COOP (small batches): GS = 4 states per CTA and one warp walks one state (warp_fk), so a 100-waypoint trajectory
 // spreads over 25 SMs and phase 1 costs one FK chain; otherwise 32 states per CTA, one thread per state's FK.
-template <typename QT, typename FT, bool LF, int GS, int NT, bool COOP>
+// OT: element type of the distance / gradient / centre outputs.  float = the fp64 results rounded once on the way out
+// (north_star asks for 1e-5 m there; rounding a distance below 1 m or a gradient component below 8 costs < 5e-7), "no
+// candidate" (DBL_MAX) becomes FLT_MAX: half the bytes to write and to carry over PCIe.
+template <typename OT>
+__device__ __forceinline__ OT to_out(double v)
+{
+  return (OT)v;
+}
+template <>
+__device__ __forceinline__ float to_out<float>(double v)
+{
+  return v >= (double)FLT_MAX ? FLT_MAX : (float)v;
+}
+
+template <typename QT, typename FT, typename OT, bool LF, int GS, int NT, bool COOP>
 __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
                                                                         const QT* __restrict__ q, long n, int flags,
-                                                                        double* __restrict__ out_dist,
-                                                                        double* __restrict__ out_grad,
+                                                                        OT* __restrict__ out_dist,
+                                                                        OT* __restrict__ out_grad,
                                                                         uint8_t* __restrict__ out_type,
-                                                                        double* __restrict__ out_cen)
+                                                                        OT* __restrict__ out_cen)
 {
   extern __shared__ double smem[];
   const int tid = threadIdx.x;
@@ -572,16 +586,16 @@ __global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldD
     if (flags & B200DF_CHECK_ROBOT)
       field_taps_finish(wf, s_sqrt_w, wt, g.max_prop, B200DF_TYPE_ENVIRONMENT, best, gx, gy, gz, bt);
     const long o = state * S + k;
-    out_dist[o] = best;
-    out_grad[3 * o] = gx;
-    out_grad[3 * o + 1] = gy;
-    out_grad[3 * o + 2] = gz;
+    out_dist[o] = to_out<OT>(best);
+    out_grad[3 * o] = to_out<OT>(gx);
+    out_grad[3 * o + 1] = to_out<OT>(gy);
+    out_grad[3 * o + 2] = to_out<OT>(gz);
     out_type[o] = (uint8_t)bt;
     if (out_cen)
     {
-      out_cen[3 * o] = cx;
-      out_cen[3 * o + 1] = cy;
-      out_cen[3 * o + 2] = cz;
+      out_cen[3 * o] = to_out<OT>(cx);
+      out_cen[3 * o + 1] = to_out<OT>(cy);
+      out_cen[3 * o + 2] = to_out<OT>(cz);
     }
   }
 }
@@ -693,23 +707,22 @@ size_t gather_smem_bytes(const GroupDev& g, const FieldDev& wf, const FieldDev& 
   return b;
 }
 
-template <typename QT, typename FT, bool LF, int GS, int NT, bool COOP>
+template <typename QT, typename FT, typename OT, bool LF, int GS, int NT, bool COOP>
 int launch_gather_variant(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n,
-                          int flags, double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream,
-                          size_t bytes)
+                          int flags, OT* dist, OT* grad, uint8_t* type, OT* centers, cudaStream_t stream, size_t bytes)
 {
-  B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, LF, GS, NT, COOP>, bytes));
+  B200DF_CUDA(allow_dynamic_smem(gradients_gather_kernel<QT, FT, OT, LF, GS, NT, COOP>, bytes));
   const unsigned grid = (unsigned)((n + GS - 1) / GS);
-  gradients_gather_kernel<QT, FT, LF, GS, NT, COOP><<<grid, NT, bytes, stream>>>(
+  gradients_gather_kernel<QT, FT, OT, LF, GS, NT, COOP><<<grid, NT, bytes, stream>>>(
       g, wf, sf, static_cast<const QT*>(q), n, flags, dist, grad, type, centers);
   B200DF_LAUNCHED();
   B200DF_CUDA(cudaGetLastError());
   return B200DF_OK;
 }
 
-template <typename QT, typename FT>
+template <typename QT, typename FT, typename OT>
 int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, const void* q, int64_t n, int flags,
-                  double* dist, double* grad, uint8_t* type, double* centers, cudaStream_t stream)
+                  OT* dist, OT* grad, uint8_t* type, OT* centers, cudaStream_t stream)
 {
   const bool lf = (flags & B200DF_CHECK_LINK_FIELDS) != 0;
   const size_t coop_bytes = gather_smem_bytes(g, wf, sf, sizeof(QT), lf, kCoopStates, kCoopThreads, true);
@@ -718,10 +731,10 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
   if ((n <= kCoopMaxStates || big_bytes > 220 * 1024) && coop_bytes <= 200 * 1024)
   {
     if (lf)
-      return launch_gather_variant<QT, FT, true, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
-                                                                                  type, centers, stream, coop_bytes);
-    return launch_gather_variant<QT, FT, false, kCoopStates, kCoopThreads, true>(g, wf, sf, q, n, flags, dist, grad,
-                                                                                 type, centers, stream, coop_bytes);
+      return launch_gather_variant<QT, FT, OT, true, kCoopStates, kCoopThreads, true>(
+          g, wf, sf, q, n, flags, dist, grad, type, centers, stream, coop_bytes);
+    return launch_gather_variant<QT, FT, OT, false, kCoopStates, kCoopThreads, true>(
+        g, wf, sf, q, n, flags, dist, grad, type, centers, stream, coop_bytes);
   }
   const size_t bytes = big_bytes;
   if (bytes > 220 * 1024)
@@ -730,23 +743,24 @@ int launch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, con
     return B200DF_ERR_UNSUPPORTED;
   }
   if (lf)
-    return launch_gather_variant<QT, FT, true, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
-                                                                                 type, centers, stream, bytes);
-  return launch_gather_variant<QT, FT, false, kGradStates, kGradThreads, false>(g, wf, sf, q, n, flags, dist, grad,
-                                                                                type, centers, stream, bytes);
+    return launch_gather_variant<QT, FT, OT, true, kGradStates, kGradThreads, false>(
+        g, wf, sf, q, n, flags, dist, grad, type, centers, stream, bytes);
+  return launch_gather_variant<QT, FT, OT, false, kGradStates, kGradThreads, false>(
+      g, wf, sf, q, n, flags, dist, grad, type, centers, stream, bytes);
 }
 
+template <typename OT>
 int dispatch_gather(const GroupDev& g, const FieldDev& wf, const FieldDev& sf, int elem, const void* q,
-                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
-                           double* centers, cudaStream_t stream)
+                    int q_dtype, int64_t n, int flags, OT* dist, OT* grad, uint8_t* type, OT* centers,
+                    cudaStream_t stream)
 {
   if (q_dtype == B200DF_Q_F32 && elem == 1)
-    return launch_gather<float, uint8_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+    return launch_gather<float, uint8_t, OT>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
   if (q_dtype == B200DF_Q_F32)
-    return launch_gather<float, uint16_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+    return launch_gather<float, uint16_t, OT>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
   if (elem == 1)
-    return launch_gather<double, uint8_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
-  return launch_gather<double, uint16_t>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+    return launch_gather<double, uint8_t, OT>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
+  return launch_gather<double, uint16_t, OT>(g, wf, sf, q, n, flags, dist, grad, type, centers, stream);
 }
 
 }  // namespace
@@ -930,9 +944,12 @@ static int resolve_elem(const b200df_group* group, int flags, int* elem)
   return B200DF_OK;
 }
 
-int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self,
-                                  const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
-                                  double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream)
+}  // extern "C"
+
+template <typename OT>
+static int gradients_device_impl(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q_dev,
+                                 int q_dtype, int64_t n, int flags, OT* dist_dev, OT* grad_dev, uint8_t* type_dev,
+                                 OT* centers_dev, void* stream)
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q_dev && dist_dev && grad_dev && type_dev)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
@@ -952,9 +969,9 @@ int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world
 
 // Host-buffer entry: chunks of states travel H2D -> kernel -> D2H on two streams, so the (large) result copies of
 // one chunk overlap the kernel of the next.
-int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
-                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
-                           double* centers)
+template <typename OT>
+static int gradients_host_impl(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                               int q_dtype, int64_t n, int flags, OT* dist, OT* grad, uint8_t* type, OT* centers)
 {
   B200DF_REQUIRE(group && n >= 0 && (n == 0 || (q && dist && grad && type)), "bad arguments");
   B200DF_REQUIRE(q_dtype == B200DF_Q_F32 || q_dtype == B200DF_Q_F64, "unknown q dtype");
@@ -987,9 +1004,9 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
 
   // Small calls (CHOMP evaluates one trajectory, ~100 waypoints, per iteration): one mapped pinned buffer carries the
   // joint values in and the results out, so the call is one launch and one synchronise instead of five staged copies.
-  const size_t o_q = 0, o_d = up((size_t)n * row), o_g = o_d + up(n * S * sizeof(double)),
-               o_t = o_g + up(n * S * 3 * sizeof(double)), o_c = o_t + up(n * S),
-               total = o_c + (centers ? up(n * S * 3 * sizeof(double)) : 0);
+  const size_t o_q = 0, o_d = up((size_t)n * row), o_g = o_d + up(n * S * sizeof(OT)),
+               o_t = o_g + up(n * S * 3 * sizeof(OT)), o_c = o_t + up(n * S),
+               total = o_c + (centers ? up(n * S * 3 * sizeof(OT)) : 0);
   if (total <= kSmallGradBytes && small_batch_enabled())
   {
     void* dpin = nullptr;
@@ -1013,20 +1030,20 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
     void* a_g = pinned_alias(grad);
     void* a_t = pinned_alias(type);
     void* a_c = pinned_alias(centers);
-    rc = dispatch_gather(g, wf, sf, elem, dp + o_q, q_dtype, n, flags, static_cast<double*>(a_d ? a_d : dp + o_d),
-                         static_cast<double*>(a_g ? a_g : dp + o_g), static_cast<uint8_t*>(a_t ? a_t : dp + o_t),
-                         centers ? static_cast<double*>(a_c ? a_c : dp + o_c) : nullptr, ctx->stream[0]);
+    rc = dispatch_gather(g, wf, sf, elem, dp + o_q, q_dtype, n, flags, static_cast<OT*>(a_d ? a_d : dp + o_d),
+                         static_cast<OT*>(a_g ? a_g : dp + o_g), static_cast<uint8_t*>(a_t ? a_t : dp + o_t),
+                         centers ? static_cast<OT*>(a_c ? a_c : dp + o_c) : nullptr, ctx->stream[0]);
     e = cudaStreamSynchronize(ctx->stream[0]);
     if (!rc && e == cudaSuccess)
     {
       if (!a_d)
-        std::memcpy(dist, hp + o_d, n * S * sizeof(double));
+        std::memcpy(dist, hp + o_d, n * S * sizeof(OT));
       if (!a_g)
-        std::memcpy(grad, hp + o_g, n * S * 3 * sizeof(double));
+        std::memcpy(grad, hp + o_g, n * S * 3 * sizeof(OT));
       if (!a_t)
         std::memcpy(type, hp + o_t, n * S);
       if (centers && !a_c)
-        std::memcpy(centers, hp + o_c, n * S * 3 * sizeof(double));
+        std::memcpy(centers, hp + o_c, n * S * 3 * sizeof(OT));
     }
     return finish(rc);
   }
@@ -1034,8 +1051,8 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
   // Large calls: chunks of states travel H2D -> kernel -> D2H on two streams of the cached context, so the (large)
   // result copies of one chunk overlap the kernel of the next.
   const int64_t chunk = std::min<int64_t>(n, 16384);
-  const size_t want[5] = { std::max<size_t>(chunk * row, 1), chunk * S * sizeof(double), chunk * S * 3 * sizeof(double),
-                           chunk * S, centers ? chunk * S * 3 * sizeof(double) : 0 };
+  const size_t want[5] = { std::max<size_t>(chunk * row, 1), chunk * S * sizeof(OT), chunk * S * 3 * sizeof(OT),
+                           chunk * S, centers ? chunk * S * 3 * sizeof(OT) : 0 };
   for (int k = 0; k < 2 && e == cudaSuccess; ++k)
   {
     e = Pool::ensure_stream(ctx, k);
@@ -1053,18 +1070,18 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
                         st);
     if (e != cudaSuccess)
       break;
-    rc = dispatch_gather(g, wf, sf, elem, buf[0], q_dtype, m, flags, static_cast<double*>(buf[1]),
-                         static_cast<double*>(buf[2]), static_cast<uint8_t*>(buf[3]),
-                         centers ? static_cast<double*>(buf[4]) : nullptr, st);
+    rc = dispatch_gather(g, wf, sf, elem, buf[0], q_dtype, m, flags, static_cast<OT*>(buf[1]),
+                         static_cast<OT*>(buf[2]), static_cast<uint8_t*>(buf[3]),
+                         centers ? static_cast<OT*>(buf[4]) : nullptr, st);
     if (rc)
       break;
-    e = cudaMemcpyAsync(dist + s * S, buf[1], m * S * sizeof(double), cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(dist + s * S, buf[1], m * S * sizeof(OT), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(grad + s * S * 3, buf[2], m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(grad + s * S * 3, buf[2], m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(type + s * S, buf[3], m * S, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && centers)
-      e = cudaMemcpyAsync(centers + s * S * 3, buf[4], m * S * 3 * sizeof(double), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(centers + s * S * 3, buf[4], m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
   }
   for (int i = 0; i < 2; ++i)
   {
@@ -1075,6 +1092,37 @@ int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200d
       e = es;
   }
   return finish(rc);
+}
+
+extern "C" {
+int b200df_gradients_batch_device(const b200df_group* group, b200df_field* world, b200df_field* self,
+                                  const void* q_dev, int q_dtype, int64_t n, int flags, double* dist_dev,
+                                  double* grad_dev, uint8_t* type_dev, double* centers_dev, void* stream)
+{
+  return gradients_device_impl<double>(group, world, self, q_dev, q_dtype, n, flags, dist_dev, grad_dev, type_dev,
+                                       centers_dev, stream);
+}
+
+int b200df_gradients_batch(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                           int q_dtype, int64_t n, int flags, double* dist, double* grad, uint8_t* type,
+                           double* centers)
+{
+  return gradients_host_impl<double>(group, world, self, q, q_dtype, n, flags, dist, grad, type, centers);
+}
+
+int b200df_gradients_batch_device_f32(const b200df_group* group, b200df_field* world, b200df_field* self,
+                                      const void* q_dev, int q_dtype, int64_t n, int flags, float* dist_dev,
+                                      float* grad_dev, uint8_t* type_dev, float* centers_dev, void* stream)
+{
+  return gradients_device_impl<float>(group, world, self, q_dev, q_dtype, n, flags, dist_dev, grad_dev, type_dev,
+                                      centers_dev, stream);
+}
+
+int b200df_gradients_batch_f32(const b200df_group* group, b200df_field* world, b200df_field* self, const void* q,
+                               int q_dtype, int64_t n, int flags, float* dist, float* grad, uint8_t* type,
+                               float* centers)
+{
+  return gradients_host_impl<float>(group, world, self, q, q_dtype, n, flags, dist, grad, type, centers);
 }
 
 }  // extern "C"

@@ -335,21 +335,27 @@ class Group:
                                                    C.c_void_p(stream) if stream else None))
 
     def gradients(self, q, world=None, self_field=None, flags=B.CHECK_ROBOT | B.CHECK_INTRA, want_centers=True,
-                  out=None):
+                  out=None, out_dtype=np.float64):
         """out: optional dict of preallocated C-contiguous arrays (dist, grad, type, centers), e.g. views of pinned
-        host memory, to keep the result copies off the pageable path."""
+        host memory, to keep the result copies off the pageable path.  out_dtype=np.float32 takes the
+        single-precision-output entry point (b200df_gradients_batch_f32)."""
         q, dt = _q_array(q, self.model.n_vars)
         N, S = len(q), self.n_spheres
         out = out or {}
-        dist = out.get("dist") if out.get("dist") is not None else np.empty((N, S))
-        grad = out.get("grad") if out.get("grad") is not None else np.empty((N, S, 3))
+        ot = np.dtype(out_dtype)
+        assert ot in (np.dtype(np.float64), np.dtype(np.float32))
+        dist = out.get("dist") if out.get("dist") is not None else np.empty((N, S), dtype=ot)
+        grad = out.get("grad") if out.get("grad") is not None else np.empty((N, S, 3), dtype=ot)
         typ = out.get("type") if out.get("type") is not None else np.empty((N, S), dtype=np.uint8)
-        cen = (out.get("centers") if out.get("centers") is not None else np.empty((N, S, 3))) if want_centers else None
+        cen = (out.get("centers") if out.get("centers") is not None else np.empty((N, S, 3), dtype=ot)) \
+            if want_centers else None
         assert dist.shape == (N, S) and grad.shape == (N, S, 3) and typ.shape == (N, S)
-        B.check(B.load().b200df_gradients_batch(self.h, world.h if world else None,
-                                                self_field.h if self_field else None, q.ctypes.data_as(C.c_void_p), dt,
-                                                N, flags, B.ptr(dist, C.c_double), B.ptr(grad, C.c_double),
-                                                B.ptr(typ, C.c_uint8), B.ptr(cen, C.c_double) if want_centers else None))
+        assert dist.dtype == ot and grad.dtype == ot and (cen is None or cen.dtype == ot)
+        ct = C.c_double if ot == np.dtype(np.float64) else C.c_float
+        fn = B.load().b200df_gradients_batch if ot == np.dtype(np.float64) else B.load().b200df_gradients_batch_f32
+        B.check(fn(self.h, world.h if world else None, self_field.h if self_field else None,
+                   q.ctypes.data_as(C.c_void_p), dt, N, flags, B.ptr(dist, ct), B.ptr(grad, ct), B.ptr(typ, C.c_uint8),
+                   B.ptr(cen, ct) if want_centers else None))
         return dict(dist=dist, grad=grad, type=typ, centers=cen)
 
     def check_edges(self, qa, qb, segments, world=None, self_field=None, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT,

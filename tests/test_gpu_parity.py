@@ -579,6 +579,44 @@ def test_config5_gradients_within_tolerance(gpu, oracle):
     assert (got["type"] == 3).any() and (got["type"] == 2).any()
 
 
+def test_config5_full_size_1000x100_with_link_fields_and_f32_outputs(gpu, oracle):
+    """BASELINE config 5 at its full size: 1 000 trajectories x 100 waypoints, getCollisionGradients with the per-link
+    fields, environment and intra-group terms against the oracle (types exact, values within north_star's 1e-5 m),
+    through the fp64-output call and the single-precision-output call."""
+    from moveit_b200 import engine
+    from moveit_b200.binding import CHECK_LINK_FIELDS
+    desc = rd.panda()
+    objs = scenarios.random_scene()
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
+    o.env.build_link_fields()
+    e = EngineSetup(desc, scenarios.FIELD_A, objs)
+    fields, enabled = engine.link_distance_fields(e.model_desc, e.group_links, desc.acm_entry_matrix(),
+                                                  scenarios.FIELD_A["resolution"], scenarios.FIELD_A["max_distance"])
+    e.group.set_link_fields(fields, enabled)
+    traj = scenarios.chomp_trajectories(desc, 1000, 100).reshape(-1, desc.nvar)
+    assert len(traj) == 100_000
+    fl = CHECK_ROBOT | CHECK_INTRA | CHECK_LINK_FIELDS
+    got = e.group.gradients(traj, e.world, flags=fl)
+    ref = o.env.gradients_batch(traj, flags=7)
+    typ = ref["type"].astype(np.uint8)
+    assert np.array_equal(got["type"], typ)
+    fin = ref["dist"] < 1e300
+    assert np.array_equal(fin, got["dist"] < 1e300)
+    assert np.max(np.abs(got["dist"][fin] - ref["dist"][fin])) < 1e-5   # north_star tolerance: 1e-5 m
+    assert np.max(np.abs(got["grad"] - ref["grad"])) < 1e-5
+    assert np.max(np.abs(got["centers"] - ref["centers"])) < 1e-12
+    assert all((typ == t).any() for t in (0, 1, 2, 3))
+    g32 = e.group.gradients(traj, e.world, flags=fl, out_dtype=np.float32)
+    assert g32["dist"].dtype == np.float32 and np.array_equal(g32["type"], typ)
+    assert np.array_equal(fin, g32["dist"] < 1e30) and np.all(g32["dist"][~fin] == np.finfo(np.float32).max)
+    assert np.max(np.abs(g32["dist"][fin] - ref["dist"][fin])) < 1e-5
+    assert np.max(np.abs(g32["grad"] - ref["grad"])) < 1e-5
+    assert np.max(np.abs(g32["centers"] - ref["centers"])) < 1e-5
+    # the rounded values are exactly the fp64 results rounded once
+    assert np.array_equal(g32["grad"], got["grad"].astype(np.float32))
+    assert np.array_equal(g32["dist"][fin], got["dist"][fin].astype(np.float32))
+
+
 def test_gradients_with_link_distance_fields(gpu, oracle):
     """getSelfProximityGradients' per-link PosedDistanceField term (:395-418), including the reference's quirks: the
     gradient is mapped with the full pose (rotation + translation, Q6) and a link's sphere loop stops at the first

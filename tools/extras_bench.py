@@ -133,6 +133,38 @@ def run(with_oracle=True):
         out["config5_chomp_gradients"]["device_resident_ms"] = ms
         out["config5_chomp_gradients"]["device_resident_states_per_s"] = N / (ms * 1e-3)
         assert np.array_equal(dd.cpu().numpy(), pin["dist"]) and np.array_equal(td.cpu().numpy(), pin["type"])
+        # single-precision outputs (b200df_gradients_batch_f32): 29 instead of 57 bytes per sphere over PCIe
+        pin32 = dict(dist=torch.empty((N, S), dtype=torch.float32).pin_memory().numpy(),
+                     grad=torch.empty((N, S, 3), dtype=torch.float32).pin_memory().numpy(),
+                     type=torch.empty((N, S), dtype=torch.uint8).pin_memory().numpy(),
+                     centers=torch.empty((N, S, 3), dtype=torch.float32).pin_memory().numpy())
+        e.group.gradients(tq, e.world, flags=fl, out=pin32, out_dtype=np.float32)
+        t = best_of(lambda: e.group.gradients(tq, e.world, flags=fl, out=pin32, out_dtype=np.float32), 3)
+        c5 = out["config5_chomp_gradients"]
+        c5["f32_out_pinned_ms"] = 1e3 * t
+        c5["f32_out_d2h_bytes"] = N * S * (4 + 12 + 1 + 12)
+        fin = pin["dist"] < 1e300
+        c5["f32_out_max_abs_diff_vs_f64"] = float(max(np.max(np.abs(pin32["dist"][fin] - pin["dist"][fin])),
+                                                       np.max(np.abs(pin32["grad"] - pin["grad"])),
+                                                       np.max(np.abs(pin32["centers"] - pin["centers"]))))
+        assert np.array_equal(pin32["type"], pin["type"]) and c5["f32_out_max_abs_diff_vs_f64"] < 1e-5
+        d32 = torch.empty((N, S), dtype=torch.float32, device="cuda")
+        g32 = torch.empty((N, S, 3), dtype=torch.float32, device="cuda")
+        c32 = torch.empty((N, S, 3), dtype=torch.float32, device="cuda")
+
+        def dev32():
+            B.check(B.load().b200df_gradients_batch_device_f32(
+                e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F64, N, fl, C.c_void_p(d32.data_ptr()),
+                C.c_void_p(g32.data_ptr()), C.c_void_p(td.data_ptr()), C.c_void_p(c32.data_ptr()),
+                C.c_void_p(st.cuda_stream)))
+        dev32()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            dev32()
+        e1.record()
+        torch.cuda.synchronize()
+        c5["f32_out_device_resident_ms"] = e0.elapsed_time(e1) / 5
     except ImportError:
         pass
 
