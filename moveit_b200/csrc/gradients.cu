@@ -283,7 +283,13 @@ __device__ __forceinline__ void field_taps_finish(const FieldDev& f, const doubl
 // consecutive threads on consecutive spheres of a state.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kGradStates = 32;    // states per CTA
-constexpr int kGradThreads = 128;
+#ifndef B200DF_GRAD_THREADS
+#define B200DF_GRAD_THREADS 128
+#endif
+#ifndef B200DF_GRAD_MINB
+#define B200DF_GRAD_MINB 1
+#endif
+constexpr int kGradThreads = B200DF_GRAD_THREADS;
 constexpr int kMaxStagedNbr = 1024;  // neighbour-table entries staged in shared memory (16 KB)
 
 // PosedDistanceField::getDistanceGradient's point mapping (collision_distance_field_types.h:156-160):
@@ -320,7 +326,7 @@ __device__ __forceinline__ float to_out<float>(double v)
 }
 
 template <typename QT, typename FT, typename OT, bool LF, int GS, int NT, bool COOP>
-__global__ void __launch_bounds__(NT) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
+__global__ void __launch_bounds__(NT, COOP ? 1 : B200DF_GRAD_MINB) gradients_gather_kernel(GroupDev g, FieldDev wf, FieldDev sf,
                                                                         const QT* __restrict__ q, long n, int flags,
                                                                         OT* __restrict__ out_dist,
                                                                         OT* __restrict__ out_grad,
