@@ -143,6 +143,7 @@ int field_prepare(b200df_field* f, FieldDev* view, cudaStream_t wait_on);
 bool edt_fast_applies(const b200df_field* f);
 int edt_fast(b200df_field* f, bool invert, void* out);
 // edt_tma.cu: the same two passes with TMA-moved tiles (nz a multiple of 16); -1 = tensor map not available
+void keep_async_pool(int device);  // validity.cu: the stream-ordered pool keeps its memory between calls
 bool edt_tma_applies(const b200df_field* f);
 int edt_tma(b200df_field* f, void* out);
 }

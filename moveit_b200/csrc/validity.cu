@@ -329,25 +329,6 @@ int64_t small_max_states()
   return e ? (int64_t)atoll(e) : (int64_t)16384;
 }
 
-// keeps the stream-ordered allocator from returning memory to the OS between calls (once per device)
-void keep_async_pool(int device)
-{
-  static std::mutex mu;
-  static std::vector<char> done;
-  std::lock_guard<std::mutex> lk(mu);
-  if ((int)done.size() <= device)
-    done.resize(device + 1, 0);
-  if (done[device])
-    return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
-  {
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
-  done[device] = 1;
-}
-
 // amb_idx (n ints) / amb_count (1 int): device scratch of the FAST path; allocated stream-ordered when null
 int run_verdict(const b200df_group* group, const FieldDev& wf_in, const FieldDev& sf_in, int elem, const void* q_dev,
                 int q_dtype, int64_t n, int flags, int precision, uint8_t* verdict_dev, cudaStream_t stream,
@@ -1292,3 +1273,25 @@ int b200df_check_batch(const b200df_group* group, b200df_field* world, b200df_fi
 }
 
 }  // extern "C"
+
+namespace b200df
+{
+// keeps the stream-ordered allocator from returning memory to the OS between calls (once per device)
+void keep_async_pool(int device)
+{
+  static std::mutex mu;
+  static std::vector<char> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)done.size() <= device)
+    done.resize(device + 1, 0);
+  if (done[device])
+    return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+  {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[device] = 1;
+}
+}  // namespace b200df

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -339,27 +340,48 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
 
 // SELF: the self-field lookups are compiled in only when the call asks for them (code size again)
 // PAIRS: likewise the whole intra-group pair machinery (a checkRobotCollision batch does not need it)
-template <typename QT, typename FT, int B, bool PAIRS, bool PAIR_SMEM, bool FULL, bool SELF>
+// MODE 0: one sweep; 1: first pass of two (appends the states left at 0 to surv_idx); 2: second pass (walks `list`)
+template <typename QT, typename FT, int B, bool PAIRS, bool PAIR_SMEM, bool FULL, bool SELF, int MODE>
 __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant__ FastTables T, FastLookup wf,
                                                           FastLookup sf, const int2* __restrict__ pair_T_global,
                                                           const QT* __restrict__ q, long n, int flags,
                                                           uint8_t* __restrict__ verdict, int* __restrict__ amb_idx,
-                                                          int* __restrict__ amb_count, int n_pair_smem)
+                                                          int* __restrict__ amb_count, int n_pair_smem,
+                                                          const int* __restrict__ list,
+                                                          const int* __restrict__ list_count,
+                                                          int* __restrict__ surv_idx, int* __restrict__ surv_count)
 {
+  // Two-pass form (fast_launch): pass A (field lookups only, no pair code, three times the resident warps) appends the
+  // states it leaves at verdict 0 to surv_idx; pass B (pairs only) walks that list - `list` non-null: slot -> state
+  // through the list, rows gathered, only verdicts 1 / 2 written.  A state that already collides with the world costs
+  // pass B nothing, where the fused sweep drags it along as a masked lane until the whole warp collides.
   extern __shared__ float fsm[];
   const int tid = threadIdx.x;
   const long base = (long)blockIdx.x * B;
+  constexpr bool LIST = MODE == 2;
+  const long total = LIST ? (long)*list_count : n;
+  if (LIST && base >= total)
+    return;
   // (kept as a run-time value in the PAIRS variant: the constant-folded form of that variant measured 1.5 % slower)
   const bool do_pairs = PAIRS && (flags & B200DF_CHECK_INTRA) != 0 && T.n_partners > 0;
   float* slots = fsm;                                                    // [n_slots][12][B]
   float* stc = slots + T.n_slots * 12 * B;                               // [n_store_spheres][3][B]
   float* stb = stc + (do_pairs ? T.n_store_spheres * 3 * B : 0);         // [n_store_links][3][B]
   float* qs = stb + (do_pairs ? T.n_store_links * 3 * B : 0);            // [B][n_vars]
+  const bool active = base + tid < total;
+  const long state = LIST ? (active ? (long)list[base + tid] : 0L) : base + tid;
+  if (LIST)
   {
-    const int total = B * T.n_vars;
+    const QT* src = q + state * T.n_vars;
+    for (int v = 0; v < T.n_vars; ++v)
+      qs[tid * T.n_vars + v] = active ? (float)src[v] : 0.f;
+  }
+  else
+  {
+    const int count = B * T.n_vars;
     const long limit = (n - base) * T.n_vars;
     const QT* src = q + base * T.n_vars;
-    for (int e = tid; e < total; e += B)
+    for (int e = tid; e < count; e += B)
       qs[e] = (e < limit) ? (float)src[e] : 0.f;  // fp64 joint values are rounded once (covered by the margins)
   }
   // the pair thresholds are read once per sphere-pair test by every warp: keep them in shared memory when they fit
@@ -371,8 +393,6 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
       pair_T_shared[e] = pair_T_global[e];
   }
   __syncthreads();
-  const long state = base + tid;
-  const bool active = state < n;
   const float* my_q = qs + tid * T.n_vars;
   float* my_slots = slots + tid;
   float* my_stc = stc + tid;
@@ -510,12 +530,27 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
     if (__all_sync(0xffffffffu, hit_m < 0))
       break;
   }
+  const int v = oor ? 2 : (hit_m < 0 ? 1 : (amb_m < 0 ? 2 : 0));
   if (active)
   {
-    const int v = oor ? 2 : (hit_m < 0 ? 1 : (amb_m < 0 ? 2 : 0));
-    verdict[state] = (uint8_t)v;
+    if (!LIST || v != 0)  // a listed state already holds the 0 of the first pass
+      verdict[state] = (uint8_t)v;
     if (v == 2)
       amb_idx[atomicAdd(amb_count, 1)] = (int)state;
+  }
+  if (MODE == 1)
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, active && v == 0);
+    if (m)
+    {
+      const int lane = tid & 31;
+      int at = 0;
+      if (lane == __ffs(m) - 1)
+        at = atomicAdd(surv_count, __popc(m));
+      at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+      if ((m >> lane) & 1u)
+        surv_idx[at + __popc(m & ((1u << lane) - 1u))] = (int)state;
+    }
   }
 }
 
@@ -821,27 +856,54 @@ FastLookup make_fast_lookup(const FieldDev& f)
 
 constexpr long kPairSmemMax = 1024;  // sphere pairs whose thresholds are staged in shared memory (8 KB)
 
+struct TwoPass  // see the kernel's header comment
+{
+  const int* list = nullptr;
+  const int* list_count = nullptr;
+  int* surv_idx = nullptr;
+  int* surv_count = nullptr;
+};
+
 template <typename QT, typename FT, int B>
 int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, const QT* q, long n, int flags,
-                uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream)
+                uint8_t* verdict, int* amb_idx, int* amb_count, size_t bytes, cudaStream_t stream,
+                TwoPass tp = TwoPass())
 {
   const bool pairs = (flags & B200DF_CHECK_INTRA) && g->fast->tables.n_partners > 0;
   const int n_pair_smem = (pairs && g->dev.n_pair_consts <= kPairSmemMax) ? (int)g->dev.n_pair_consts : 0;
   bytes += (size_t)n_pair_smem * sizeof(int2);
+  {
+    // measurement knob: unused shared memory per CTA, to see what fewer resident warps cost (tools/fast_loop.py)
+    static const long pad = getenv("B200DF_FAST_PAD_SMEM") ? atol(getenv("B200DF_FAST_PAD_SMEM")) : 0;
+    bytes += (size_t)std::max(0L, pad);
+  }
   const unsigned grid = (unsigned)((n + B - 1) / B);
   auto go = [&](auto kernel) -> cudaError_t {
     const cudaError_t e = allow_dynamic_smem(kernel, bytes);
     if (e != cudaSuccess)
       return e;
     kernel<<<grid, B, bytes, stream>>>(g->fast->tables, make_fast_lookup(wf), make_fast_lookup(sf), g->fast->pair_T, q, n,
-                                       flags, verdict, amb_idx, amb_count, n_pair_smem);
+                                       flags, verdict, amb_idx, amb_count, n_pair_smem, tp.list, tp.list_count,
+                                       tp.surv_idx, tp.surv_count);
     return cudaSuccess;
   };
   const bool fl = g->fast->needs_full;
   const bool self = (flags & B200DF_CHECK_SELF) != 0;
   auto pick = [&](auto with_pairs, auto pair_smem, auto full) -> cudaError_t {
     constexpr bool W = decltype(with_pairs)::value, P = decltype(pair_smem)::value, F = decltype(full)::value;
-    return self ? go(validity_fast_kernel<QT, FT, B, W, P, F, true>) : go(validity_fast_kernel<QT, FT, B, W, P, F, false>);
+    if constexpr (!W)
+    {
+      if (tp.surv_idx)  // first pass of two: field lookups only
+        return self ? go(validity_fast_kernel<QT, FT, B, W, P, F, true, 1>) :
+                      go(validity_fast_kernel<QT, FT, B, W, P, F, false, 1>);
+    }
+    else
+    {
+      if (tp.list)  // second pass: pairs only
+        return go(validity_fast_kernel<QT, FT, B, W, P, F, false, 2>);
+    }
+    return self ? go(validity_fast_kernel<QT, FT, B, W, P, F, true, 0>) :
+                  go(validity_fast_kernel<QT, FT, B, W, P, F, false, 0>);
   };
   using T_ = std::true_type;
   using F_ = std::false_type;
@@ -859,31 +921,61 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
 
 namespace
 {
+// smallest batch the two-pass form is used for: below it the second launch and the list cost more than they save
+constexpr long kTwoPassMinStates = 1L << 18;
+
+bool two_pass_enabled()
+{
+  static const bool on = !(getenv("B200DF_FAST_TWO_PASS") && atoi(getenv("B200DF_FAST_TWO_PASS")) == 0);
+  return on;
+}
+
 template <typename QT>
 int fast_launch_typed(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, int field_elem, const QT* q, long n,
                       int flags, uint8_t* verdict, int* amb_idx, int* amb_count, cudaStream_t stream)
 {
   const FastTables& T = g->fast->tables;
-  const bool pairs = (flags & B200DF_CHECK_INTRA) && T.n_partners > 0;
-  auto smem = [&](int block) {
+  const bool has_pairs = (flags & B200DF_CHECK_INTRA) && T.n_partners > 0;
+  auto smem = [&](int block, bool pairs) {
     size_t fl = (size_t)T.n_slots * 12 + T.n_vars;
     if (pairs)
       fl += (size_t)T.n_store_spheres * 3 + (size_t)T.n_store_links * 3;
     return fl * block * sizeof(float);
   };
-  B200DF_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), stream));
-  const size_t b128 = smem(128);
-  if (b128 <= 100 * 1024)
-  {
+  auto launch = [&](int fl, TwoPass tp) -> int {
+    const bool pairs = (fl & B200DF_CHECK_INTRA) && T.n_partners > 0;
+    const size_t b128 = smem(128, pairs);
+    if (b128 <= 100 * 1024)
+    {
+      if (field_elem == 1)
+        return launch_fast<QT, uint8_t, 128>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b128, stream, tp);
+      return launch_fast<QT, uint16_t, 128>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b128, stream, tp);
+    }
+    const size_t b32 = smem(32, pairs);
+    B200DF_REQUIRE(b32 <= 220 * 1024, "robot too large for the per-state shared-memory layout");
     if (field_elem == 1)
-      return launch_fast<QT, uint8_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
-    return launch_fast<QT, uint16_t, 128>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b128, stream);
-  }
-  const size_t b32 = smem(32);
-  B200DF_REQUIRE(b32 <= 220 * 1024, "robot too large for the per-state shared-memory layout");
-  if (field_elem == 1)
-    return launch_fast<QT, uint8_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
-  return launch_fast<QT, uint16_t, 32>(g, wf, sf, q, n, flags, verdict, amb_idx, amb_count, b32, stream);
+      return launch_fast<QT, uint8_t, 32>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b32, stream, tp);
+    return launch_fast<QT, uint16_t, 32>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b32, stream, tp);
+  };
+  B200DF_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), stream));
+  const int field_flags = flags & (B200DF_CHECK_ROBOT | B200DF_CHECK_SELF);
+  if (!has_pairs || !field_flags || n < kTwoPassMinStates || !two_pass_enabled())
+    return launch(flags, TwoPass());
+  // pass A: the field lookups of every state; pass B: the sphere pairs of the states pass A left at 0
+  int* surv = nullptr;
+  keep_async_pool(g->device);
+  B200DF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&surv), ((size_t)n + 1) * sizeof(int), stream));
+  B200DF_CUDA(cudaMemsetAsync(surv, 0, sizeof(int), stream));
+  TwoPass a, b;
+  a.surv_count = surv;
+  a.surv_idx = surv + 1;
+  b.list_count = surv;
+  b.list = surv + 1;
+  int rc = launch(field_flags, a);
+  if (!rc)
+    rc = launch(flags & ~(B200DF_CHECK_ROBOT | B200DF_CHECK_SELF), b);
+  cudaFreeAsync(surv, stream);
+  return rc;
 }
 }  // namespace
 
