@@ -47,6 +47,10 @@ def ncu_counters(path, precision):
         return {"dram_bytes_per_state": (k["dram_bytes_read"] + k["dram_bytes_write"]) / n,
                 "l2_sector_bytes_per_state": 32.0 * (k.get("lts_sectors_read", 0) + k.get("lts_sectors_write", 0)) / n,
                 "warp_instructions_per_state": k.get("warp_instructions", 0) / n, "kernel": k.get("kernel"),
+                "passes": [{"kernel": p.get("kernel", "")[:110], "share_of_call": p["duration_us_under_ncu"] /
+                            max(k.get("duration_us_under_ncu", 0.0), 1e-9),
+                            "issue_active_pct": p.get("issue_active_pct"), "warps_active_pct": p.get("warps_active_pct"),
+                            "registers": p.get("registers")} for p in k.get("passes", [])],
                 "source": os.path.relpath(path, ROOT) + " <- " + str(d.get("report"))}
     except Exception:
         return None
@@ -719,14 +723,17 @@ def main():
                          "peak_source": peak_src,
                          "issue": issue_roofline(counters, per_gpu_rate, clocks),
                          "l2": l2_roofline(counters, per_gpu_rate, clocks),
-                         "kernel": ("validity_fast_kernel<float, unsigned char, 128, pair thresholds in smem, simple joints, no self field> "
-                                    "(+ validity_small_kernel on the undecided "
+                         "kernel": ("validity_fast_kernel<float, unsigned char, 128, simple joints, no self field> twice: "
+                                    "the field pass over every state (no pair code), then the pair pass over the "
+                                    "states it left at 0 (+ validity_small_kernel on the undecided "
                                     "states)" if args.precision == "fast" else "validity_kernel<float, unsigned char, 64>"),
-                         "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out); traffic = ncu "
-                                 "dram bytes/state of the committed capture x states per launch. The fused "
-                                 "FK+lookup+pair kernel executes ~13 k warp instructions per 32 states and is "
-                                 "issue/latency bound by construction (DESIGN.md section 4): `issue` and `l2` are the "
-                                 "resources it actually loads; the HBM-bound kernel of this path is the EDT, see "
+                         "passes": counters.get("passes") if counters else None,
+                         "note": "37 algorithmic bytes/state (fp32 joint values in, verdict byte out) over the whole "
+                                 "call; traffic / issue / l2 = ncu counters of the committed capture of ONE call "
+                                 "(both passes summed) per state x this run's states. The FK+lookup and FK+pair "
+                                 "kernels execute some hundred warp instructions per state and are issue/latency "
+                                 "bound by construction (DESIGN.md section 4): `issue` and `l2` are the resources "
+                                 "they actually load; the HBM-bound kernel of this path is the EDT, see "
                                  "edt_ms.field_b_roofline"},
             "colliding_fraction": colliding / n,
             "field_replication_bytes": replicated_bytes,

@@ -942,9 +942,11 @@ static int scatter_host_points(b200df_field* f, const double* xyz, int64_t n, ui
   }
   const bool mirror = vol == f->occ && value == 1 && !orv && f->bits && f->bits_valid;
   const int wpr = bits_wpr(f->grid.n[2]);
-  const int64_t kSlicePoints = (int64_t)(4 << 20) / 24;  // ~4 MB of points per slice
+  const int64_t kSlicePoints = (int64_t)(2 << 20) / 24;  // ~2 MB of points per slice
   const unsigned hw = std::thread::hardware_concurrency();
-  const int n_workers = (int)std::min<int64_t>(std::min<unsigned>((unsigned)b200df_field::kEdtStreams, std::max(1u, hw / 2)),
+  // (B200DF_ADD_POINTS_WORKERS: measurement knob; workers beyond the field's four side streams share them)
+  static const int max_workers = getenv("B200DF_ADD_POINTS_WORKERS") ? atoi(getenv("B200DF_ADD_POINTS_WORKERS")) : 8;
+  const int n_workers = (int)std::min<int64_t>(std::min<unsigned>((unsigned)std::max(1, max_workers), std::max(1u, hw / 2)),
                                                n / kSlicePoints);
   if (n_workers <= 1)
   {
@@ -973,7 +975,7 @@ static int scatter_host_points(b200df_field* f, const double* xyz, int64_t n, ui
     if (p0 >= p1)
       return;
     cudaError_t e = cudaSetDevice(f->device);
-    cudaStream_t st = f->edt_streams[w];
+    cudaStream_t st = f->edt_streams[w % b200df_field::kEdtStreams];
     // sub-slices keep the copy engine busy while this thread is still staging the rest of its share
     for (int64_t q0 = p0; q0 < p1 && e == cudaSuccess; q0 += kSlicePoints)
     {

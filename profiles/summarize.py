@@ -29,6 +29,19 @@ KEYS = [
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
     "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
     "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
@@ -102,6 +115,7 @@ def traffic(path, out, states=None):
         with open(out) as f:
             data = json.load(f)
     data["report"] = os.path.basename(path)
+    seen = set()
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         key = "fast" if "validity_fast_kernel" in name else "exact" if name.startswith("validity_kernel") or \
@@ -111,16 +125,35 @@ def traffic(path, out, states=None):
         n = float(states) if states else val(r, "launch__grid_size") * val(r, "launch__block_size")
         dur = val(r, "gpu__time_duration.sum")
         dur_us = dur * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[col["gpu__time_duration.sum"]], 1.0)
-        data[key] = {"kernel": name[:160], "states_per_launch": n,
-                     "dram_bytes_read": val(r, "dram__bytes_read.sum", True),
-                     "dram_bytes_write": val(r, "dram__bytes_write.sum", True),
-                     "lts_sectors_read": val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
-                     "lts_sectors_write": val(r, "lts__t_sectors.sum") - val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
-                     "lts_sector_hit_pct": val(r, "lts__t_sector_hit_rate.pct"),
-                     "warp_instructions": val(r, "smsp__inst_executed.sum"),
-                     "duration_us_under_ncu": dur_us,
-                     "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                     "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active")}
+        one = {"kernel": name[:160], "states_per_launch": n,
+               "dram_bytes_read": val(r, "dram__bytes_read.sum", True),
+               "dram_bytes_write": val(r, "dram__bytes_write.sum", True),
+               "lts_sectors_read": val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
+               "lts_sectors_write": val(r, "lts__t_sectors.sum") - val(r, "lts__t_sectors_srcunit_tex_op_read.sum"),
+               "lts_sector_hit_pct": val(r, "lts__t_sector_hit_rate.pct"),
+               "warp_instructions": val(r, "smsp__inst_executed.sum"),
+               "duration_us_under_ncu": dur_us,
+               "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "registers": val(r, "launch__registers_per_thread"),
+               "grid": val(r, "launch__grid_size")}
+        if key in seen:
+            # the call runs several kernels of this kind (FAST: the field pass, then the pair pass over the survivors):
+            # the per-call counters are their sums, the per-pass rows are kept beside them
+            tot = data[key]
+            for f_ in ("dram_bytes_read", "dram_bytes_write", "lts_sectors_read", "lts_sectors_write",
+                       "warp_instructions", "duration_us_under_ncu"):
+                tot[f_] += one[f_]
+            tot["kernel"] = tot["passes"][0]["kernel"][:70] + " ... + " + one["kernel"][:70]
+            tot["issue_active_pct"] = sum(p_["issue_active_pct"] * p_["duration_us_under_ncu"]
+                                          for p_ in tot["passes"] + [one]) / tot["duration_us_under_ncu"]
+            tot["warps_active_pct"] = sum(p_["warps_active_pct"] * p_["duration_us_under_ncu"]
+                                          for p_ in tot["passes"] + [one]) / tot["duration_us_under_ncu"]
+            tot["passes"].append(one)
+        else:
+            seen.add(key)
+            data[key] = dict(one)
+            data[key]["passes"] = [one]
     with open(out, "w") as f:
         json.dump(data, f, indent=1)
         f.write("\n")
