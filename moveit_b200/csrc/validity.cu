@@ -996,7 +996,11 @@ static int check_batch_narrowed(const b200df_group* group, const FieldDev& wf, c
   const int64_t cs = 1 << 18;
   const int64_t n_chunks = (n + cs - 1) / cs;
   const unsigned hw = std::thread::hardware_concurrency();
-  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(Ctx::kLanes, std::max(2u, hw / 2)), n_chunks));
+  // lanes: one per hardware thread of the host, at most kLanes (B200DF_NARROW_LANES overrides: measurement knob;
+  // 16-core box, 10 M states: 4 lanes 4.95e8 states/s, 8 6.87e8, 12 7.05e8, 16 7.66e8)
+  static const int lanes_env = getenv("B200DF_NARROW_LANES") ? atoi(getenv("B200DF_NARROW_LANES")) : 0;
+  const int64_t lanes_want = lanes_env > 0 ? lanes_env : (int64_t)std::max(2u, hw);
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(Ctx::kLanes, lanes_want), n_chunks));
   // lane buffers: [fp32 rows | verdict bytes], pinned and device
   const size_t v_at = ((size_t)cs * row32 + 255) & ~size_t(255);
   const size_t lane_bytes = v_at + (size_t)cs;

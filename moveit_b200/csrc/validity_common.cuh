@@ -656,7 +656,7 @@ struct b200df_group::StagePool
     void* hstage[kSlots] = {};
     size_t hstage_bytes[kSlots] = {};
     // lanes of the narrowing path (pageable fp64 rows -> fp32 screening): one independent pipeline per host thread
-    static constexpr int kLanes = 8;
+    static constexpr int kLanes = 16;
     struct Lane
     {
       cudaStream_t st = nullptr;

@@ -319,9 +319,12 @@ class Group:
             B.load().b200df_group_destroy(self.h)
             self.h = None
 
-    def check(self, q, world=None, self_field=None, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT):
+    def check(self, q, world=None, self_field=None, flags=B.CHECK_ROBOT, precision=B.PRECISION_EXACT, out=None):
+        """out: optional preallocated uint8 [n] (a caller's reused verdict buffer)"""
         q, dt = _q_array(q, self.model.n_vars)
-        out = np.empty(len(q), dtype=np.uint8)
+        if out is None:
+            out = np.empty(len(q), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (len(q),) and out.flags.c_contiguous
         B.check(B.load().b200df_check_batch(self.h, world.h if world else None, self_field.h if self_field else None,
                                             q.ctypes.data_as(C.c_void_p), dt, len(q), flags, precision,
                                             B.ptr(out, C.c_uint8)))
