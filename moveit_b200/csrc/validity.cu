@@ -20,6 +20,7 @@
 //
 // Compiled with --fmad=false so that mul/add round like the reference's non-FMA x86-64 build.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -999,7 +1000,24 @@ static int check_batch_narrowed(const b200df_group* group, const FieldDev& wf, c
   // lanes: one per hardware thread of the host, at most kLanes (B200DF_NARROW_LANES overrides: measurement knob;
   // 16-core box, 10 M states: 4 lanes 4.95e8 states/s, 8 6.87e8, 12 7.05e8, 16 7.66e8)
   static const int lanes_env = getenv("B200DF_NARROW_LANES") ? atoi(getenv("B200DF_NARROW_LANES")) : 0;
-  const int64_t lanes_want = lanes_env > 0 ? lanes_env : (int64_t)std::max(2u, hw);
+  // the host's threads are shared with whoever else stages at the same time: other calls of this process (one per
+  // device under b200df_multi) and, under torchrun, the other ranks of the node (LOCAL_WORLD_SIZE)
+  static std::atomic<int> active_calls{ 0 };
+  struct ActiveCall
+  {
+    std::atomic<int>& c;
+    int now;
+    explicit ActiveCall(std::atomic<int>& counter) : c(counter), now(++counter)
+    {
+    }
+    ~ActiveCall()
+    {
+      --c;
+    }
+  } active(active_calls);
+  static const int local_ranks = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+  const unsigned sharers = (unsigned)std::max(1, active.now) * (unsigned)local_ranks;
+  const int64_t lanes_want = lanes_env > 0 ? lanes_env : (int64_t)std::max(2u, hw / sharers);
   const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(Ctx::kLanes, lanes_want), n_chunks));
   // lane buffers: [fp32 rows | verdict bytes], pinned and device
   const size_t v_at = ((size_t)cs * row32 + 255) & ~size_t(255);

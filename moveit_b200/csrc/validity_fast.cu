@@ -453,6 +453,10 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
           sure_mask = maybe_mask = 0u;
       }
       const unsigned warp_mask = __reduce_or_sync(0xffffffffu, maybe_mask);
+      // nothing to look up, nothing to keep for later links and no partner within reach of any lane: the link's
+      // spheres need not be posed at all (the pair pass of the two-pass form, or a call that asks for pairs only)
+      if (PAIRS && !do_robot && !self_here && !stored && warp_mask == 0u)
+        continue;
       for (int s0 = gl.sphere_begin; s0 < gl.sphere_end; s0 += kBatch)
       {
         const int cnt = min(kBatch, gl.sphere_end - s0);
