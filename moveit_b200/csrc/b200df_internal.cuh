@@ -70,6 +70,26 @@ struct ThreadDeviceScope
   ~ThreadDeviceScope();
 };
 
+// Bounds-checked debug build (-DB200DF_BOUNDS_CHECK, `python tools/build_variant.py checked all -DB200DF_BOUNDS_CHECK`):
+// every computed index into a voxel array or a device-side list is tested before use and a violation stops the kernel
+// (printf + trap, which the host sees as a launch failure).  compute-sanitizer is closed on the pool this was developed
+// on; tests/test_gpu_parity.py::test_bounds_checked_build_runs_every_kernel_family runs tools/sanitize_smoke.py on this
+// build.  Compiled out otherwise.
+#ifdef B200DF_BOUNDS_CHECK
+#define B200DF_CHECK_INDEX(idx, limit)                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (!((long long)(idx) >= 0 && (long long)(idx) < (long long)(limit)))                                             \
+    {                                                                                                                  \
+      printf("b200df bounds check failed: %s:%d index %lld limit %lld\n", __FILE__, __LINE__, (long long)(idx),        \
+             (long long)(limit));                                                                                      \
+      __trap();                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+#else
+#define B200DF_CHECK_INDEX(idx, limit) ((void)0)
+#endif
+
 // Geometry of a voxel grid as the kernels see it (voxel_grid.h:367-399).
 struct GridDev
 {

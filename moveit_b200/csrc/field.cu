@@ -55,6 +55,7 @@ __global__ void scatter_points_kernel(GridDev g, const double* __restrict__ xyz,
   if (!world_to_grid(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], ix, iy, iz))
     return;
   const long r = ix * g.stride1 + iy * g.stride2 + iz;
+  B200DF_CHECK_INDEX(r, (long long)g.n[0] * g.stride1);
   if (or_value)
     vol[r] |= value;  // only used with the same value from every thread of a launch: benign race
   else
@@ -72,6 +73,7 @@ __global__ void scatter_voxels_kernel(GridDev g, const int32_t* __restrict__ ijk
   const int ix = ijk[3 * i], iy = ijk[3 * i + 1], iz = ijk[3 * i + 2];
   if (ix < 0 || ix >= g.n[0] || iy < 0 || iy >= g.n[1] || iz < 0 || iz >= g.n[2])
     return;
+  B200DF_CHECK_INDEX(ix * g.stride1 + iy * g.stride2 + iz, (long long)g.n[0] * g.stride1);
   vol[ix * g.stride1 + iy * g.stride2 + iz] = value;
 }
 
@@ -172,7 +174,10 @@ __global__ void rasterize_kernel(BodyDev b, const double* __restrict__ xs, int n
   }
   int ix, iy, iz;
   if (world_to_grid(g, px, py, pz, ix, iy, iz))
+  {
+    B200DF_CHECK_INDEX(ix * g.stride1 + iy * g.stride2 + iz, (long long)g.n[0] * g.stride1);
     vol[ix * g.stride1 + iy * g.stride2 + iz] = value;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -316,6 +321,7 @@ __global__ void octree_scatter_kernel(GridDev g, const double* __restrict__ leav
   int gx, gy, gz;
   if (!world_to_grid(g, x, y, z, gx, gy, gz))
     return;
+  B200DF_CHECK_INDEX(gx * g.stride1 + gy * g.stride2 + gz, (long long)g.n[0] * g.stride1);
   vol[gx * g.stride1 + gy * g.stride2 + gz] = value;
   if (bits)
     atomicOr(&bits[((long)gx * g.n[1] + gy) * wpr + (gz >> 5)], 1u << (gz & 31));

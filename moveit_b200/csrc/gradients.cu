@@ -230,7 +230,10 @@ __device__ __forceinline__ void field_taps_load(const FieldDev& f, double x, dou
   const long off[7] = { 0, f.g.stride1, -f.g.stride1, f.g.stride2, -f.g.stride2, 1, -1 };
 #pragma unroll
   for (int k = 0; k < 7; ++k)
+  {
+    B200DF_CHECK_INDEX(idx + off[k], (long long)f.g.n[0] * f.g.stride1);
     t.v[k] = (int)static_cast<const FT*>(f.d2)[idx + off[k]];
+  }
   if (f.neg)
   {
 #pragma unroll

@@ -155,11 +155,13 @@ __global__ void __launch_bounds__(B) validity_kernel(GroupDev g, LookupDev wf, L
               if (do_robot)
               {
                 widx[k] = cell_index(wf, cx[k], cy[k], cz[k], win[k]);
+                B200DF_CHECK_INDEX(widx[k], (long long)(wf.lim[0] + 2) * wf.stride1);
                 wv[k] = (int)static_cast<const FT*>(wf.d2)[widx[k]];
               }
               if (self_here)
               {
                 sidx[k] = cell_index(sf, cx[k], cy[k], cz[k], sin_[k]);
+                B200DF_CHECK_INDEX(sidx[k], (long long)(sf.lim[0] + 2) * sf.stride1);
                 sv[k] = (int)static_cast<const FT*>(sf.d2)[sidx[k]];
               }
               if (stored)

@@ -495,6 +495,8 @@ __device__ __forceinline__ bool inset_cell(const GridDev& g, double x, double y,
 template <typename FT>
 __device__ __forceinline__ double cell_dist(const FieldDev& f, long idx)
 {
+  B200DF_CHECK_INDEX(idx, (long long)f.g.n[0] * f.g.stride1);
+  B200DF_CHECK_INDEX(static_cast<const FT*>(f.d2)[idx], f.max_d2 + 1);
   double d = f.sqrt_table[static_cast<const FT*>(f.d2)[idx]];
   if (f.neg)
     d = d - f.sqrt_table[static_cast<const FT*>(f.neg)[idx]];
@@ -511,7 +513,10 @@ __device__ __forceinline__ bool sphere_collides(const FieldDev& f, double x, dou
   if (!inset_cell(f.g, x, y, z, idx))
     return false;
   if (!f.neg)
+  {
+    B200DF_CHECK_INDEX(idx, (long long)f.g.n[0] * f.g.stride1);
     return (int)static_cast<const FT*>(f.d2)[idx] < thr;  // host-resolved, exactly equivalent threshold
+  }
   const double dist = cell_dist<FT>(f, idx);
   return (max_prop > dist) && (radius - dist > tol);
 }

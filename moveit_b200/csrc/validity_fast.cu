@@ -303,6 +303,7 @@ __device__ __forceinline__ int cell_margin(const FastLookup& f, int ix, int iy, 
 {
   const bool in = ((unsigned)(ix - 1) < f.lim[0]) & ((unsigned)(iy - 1) < f.lim[1]) & ((unsigned)(iz - 1) < f.lim[2]);
   const unsigned idx = in ? (unsigned)(ix * f.stride1 + iy * f.stride2 + iz) : 0u;
+  B200DF_CHECK_INDEX(idx, (long long)(f.lim[0] + 2) * f.stride1);
   const int v = (int)static_cast<const FT*>(f.d2)[idx] - thr;
   return in ? v : 0x3fffffff;
 }
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   float* qs = stb + (do_pairs ? T.n_store_links * 3 * B : 0);            // [B][n_vars]
   const bool active = base + tid < total;
   const long state = LIST ? (active ? (long)list[base + tid] : 0L) : base + tid;
+  B200DF_CHECK_INDEX(active ? state : 0L, n);  // padding lanes of the last CTA touch nothing
   if (LIST)
   {
     const QT* src = q + state * T.n_vars;
@@ -540,7 +542,11 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
     if (!LIST || v != 0)  // a listed state already holds the 0 of the first pass
       verdict[state] = (uint8_t)v;
     if (v == 2)
-      amb_idx[atomicAdd(amb_count, 1)] = (int)state;
+    {
+      const int at = atomicAdd(amb_count, 1);
+      B200DF_CHECK_INDEX(at, n);
+      amb_idx[at] = (int)state;
+    }
   }
   if (MODE == 1)
   {
@@ -553,7 +559,10 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
         at = atomicAdd(surv_count, __popc(m));
       at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
       if ((m >> lane) & 1u)
+      {
+        B200DF_CHECK_INDEX(at + __popc(m & ((1u << lane) - 1u)), n);
         surv_idx[at + __popc(m & ((1u << lane) - 1u))] = (int)state;
+      }
     }
   }
 }

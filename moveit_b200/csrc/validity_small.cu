@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDe
       {
         bool in;
         const unsigned idx = cell_index(wf, cx, cy, cz, in);
+        B200DF_CHECK_INDEX(idx, (long long)(wf.lim[0] + 2) * wf.stride1);
         const int d2 = (int)static_cast<const FT*>(wf.d2)[idx];
         hit |= voxel_hits<FT>(wf, idx, in, d2, radius, thr, g.tol, g.max_prop);
       }
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) validity_small_kernel(GroupDev g, SmallDe
       {
         bool in;
         const unsigned idx = cell_index(sf, cx, cy, cz, in);
+        B200DF_CHECK_INDEX(idx, (long long)(sf.lim[0] + 2) * sf.stride1);
         const int d2 = (int)static_cast<const FT*>(sf.d2)[idx];
         hit |= voxel_hits<FT>(sf, idx, in, d2, radius, thr, g.tol, g.max_prop);
       }

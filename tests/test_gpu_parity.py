@@ -1208,3 +1208,22 @@ def test_check_route_reports_the_kernel_and_why_fast_is_not_used(gpu, oracle):
     assert r == B.ROUTE_EXACT and (w & B.NOFAST_SIGNED)
     es2 = EngineSetup(rd.panda(), scenarios.FIELD_A, scenarios.random_scene(), signed=True)
     assert route(es2, 1_000_000) == (B.ROUTE_FAST, 0)  # radius > tolerance everywhere: the negative field is irrelevant
+
+
+def test_bounds_checked_build_runs_every_kernel_family(gpu):
+    """compute-sanitizer is closed on the pool, so the library is also built with -DB200DF_BOUNDS_CHECK
+    (moveit_b200/libb200df_checked.so, __graft_entry__.build): every computed voxel / list index is tested on the device
+    before use and a violation traps.  tools/sanitize_smoke.py drives every kernel family on that build."""
+    import os
+    import subprocess
+    import sys
+    from moveit_b200 import build as b
+    lib = b.OUT_CHECKED
+    if not os.path.exists(lib):
+        pytest.skip("libb200df_checked.so is not built (python -m moveit_b200.build --checked)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200DF_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_smoke.py")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "sanitize_smoke ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "bounds check failed" not in r.stdout + r.stderr
