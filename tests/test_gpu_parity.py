@@ -245,6 +245,39 @@ def test_group_with_self_field(gpu, oracle):
     assert only_self.sum() > 0  # arm spheres do reach link0's voxels
 
 
+def test_two_pass_fast_equals_exact_and_oracle(gpu, oracle):
+    """Large FAST batches run in two passes (field lookups of every state, then the sphere pairs of the states left at
+    0 through a device-side list).  Batches just above the switch-over (2^18 states, a ragged tail, fp32 and fp64 rows,
+    world only / world + self field) against the fp64 kernel on every state and against the oracle on a slice; the
+    colliding set must not depend on which form ran (the same states in a batch below the switch-over)."""
+    from moveit_b200.binding import PRECISION_FAST, PRECISION_EXACT
+    desc = rd.panda()
+    objs = scenarios.random_scene(seed=77)
+    q0 = np.zeros(desc.nvar)
+    o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, group="panda_arm", self_state=q0)
+    sp = self_field_points(o.model_desc, desc, o.group_links, o.model.fk(q0))
+    e = EngineSetup(desc, scenarios.FIELD_A, objs, group="panda_arm", self_points=sp)
+    n = (1 << 18) + 12345
+    q32 = desc.sample_states(n, 4242, np.float32)
+    for flags, fields in ((CHECK_ROBOT | CHECK_INTRA, (e.world, None)),
+                          (CHECK_ROBOT | CHECK_SELF | CHECK_INTRA, (e.world, e.self_field)),
+                          (CHECK_SELF | CHECK_INTRA, (None, e.self_field))):
+        fast = e.group.check(q32, fields[0], fields[1], flags=flags, precision=PRECISION_FAST)
+        exact = e.group.check(q32, fields[0], fields[1], flags=flags, precision=PRECISION_EXACT)
+        assert np.array_equal(fast, exact), flags
+        assert set(np.unique(fast)) <= {0, 1}
+        if flags == (CHECK_ROBOT | CHECK_INTRA):
+            assert 0.05 < fast.mean() < 0.95 and 0 < (fast & ~e.group.check(q32, e.world, flags=CHECK_ROBOT)).sum()
+        below = e.group.check(q32[:100_000], fields[0], fields[1], flags=flags, precision=PRECISION_FAST)  # one sweep
+        assert np.array_equal(below, fast[:100_000])
+    q64 = q32.astype(np.float64) + 1e-9  # not representable in fp32: the undecided states are redone on these values
+    flags = CHECK_ROBOT | CHECK_SELF | CHECK_INTRA
+    fast64 = e.group.check(q64, e.world, e.self_field, flags=flags, precision=PRECISION_FAST)
+    assert np.array_equal(fast64, e.group.check(q64, e.world, e.self_field, flags=flags, precision=PRECISION_EXACT))
+    ref = o.env.check_batch(q64[-20000:], mode=3, n_threads=8)
+    assert np.array_equal(fast64[-20000:], ref)
+
+
 def test_signed_world_field_verdicts(gpu, oracle):
     """use_signed_distance_field: the verdict kernels skip the negative field when it cannot matter (radius >
     tolerance: in an occupied cell both predicates collide, in a free cell the negative distance is 0) - every kernel
