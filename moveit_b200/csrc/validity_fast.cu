@@ -111,9 +111,10 @@ __device__ __forceinline__ void applyf(const float* t, float x, float y, float z
 }
 
 // joint value in fp32; mimic joints evaluate mult*v+off in fp64 like the exact kernel and round once
-__device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, bool& out_of_range)
+template <typename QP>
+__device__ __forceinline__ float jointf(const FLink& l, const QP* q, int k, bool& out_of_range)
 {
-  float v = q[l.var + k];
+  float v = (float)q[l.var + k];  // fp64 joint values are rounded once (covered by the margins)
   if (l.is_mimic)
     v = (float)(l.mimic_mult * (double)v + l.mimic_off);
   out_of_range |= !(fabsf(v) <= l.vmax);
@@ -123,9 +124,11 @@ __device__ __forceinline__ float jointf(const FLink& l, const float* q, int k, b
 // FULL: floating joints, planar joints and revolute joints about an oblique axis are compiled only into the kernel
 // variant for robots that have one (the hot kernel is sensitive to code size: the quaternion branch alone cost 6 % on a
 // Panda, whose joints are all fixed, prismatic or revolute about a coordinate axis)
-template <bool FULL>
-__device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float* slots, int B, float* cur,
-                                          bool& out_of_range)
+// saved: when non-null the robot has at most one branch point and its transform is parked in these 12 registers
+// instead of a shared-memory slot (the pair pass of the two-pass form: 48 bytes per state less)
+template <bool FULL, typename QP>
+__device__ __forceinline__ void fk_step_f(const FLink& l, const QP* q, float* slots, int B, float* cur,
+                                          bool& out_of_range, float* saved = nullptr)
 {
   float base[12];
   if (l.parent < 0)
@@ -142,6 +145,12 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
 #pragma unroll
       for (int k = 0; k < 12; ++k)
         par[k] = cur[k];
+    }
+    else if (saved)
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        par[k] = saved[k];
     }
     else
     {
@@ -278,9 +287,18 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const float* q, float*
   }
   if (l.store_slot >= 0)
   {
+    if (saved)
+    {
 #pragma unroll
-    for (int k = 0; k < 12; ++k)
-      slots[(l.store_slot * 12 + k) * B] = cur[k];
+      for (int k = 0; k < 12; ++k)
+        saved[k] = cur[k];
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 12; ++k)
+        slots[(l.store_slot * 12 + k) * B] = cur[k];
+    }
   }
 }
 
@@ -357,28 +375,26 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   // through the list, rows gathered, only verdicts 1 / 2 written.  A state that already collides with the world costs
   // pass B nothing, where the fused sweep drags it along as a masked lane until the whole warp collides.
   extern __shared__ float fsm[];
+  constexpr bool LIST = MODE == 2;
   const int tid = threadIdx.x;
   const long base = (long)blockIdx.x * B;
-  constexpr bool LIST = MODE == 2;
   const long total = LIST ? (long)*list_count : n;
   if (LIST && base >= total)
     return;
   // (kept as a run-time value in the PAIRS variant: the constant-folded form of that variant measured 1.5 % slower)
   const bool do_pairs = PAIRS && (flags & B200DF_CHECK_INTRA) != 0 && T.n_partners > 0;
+  // the pair pass keeps a lone branch-point transform in registers and reads its joint values straight from the
+  // gathered rows (L1 / L2 hits: the field pass has just read them): 84 bytes of shared memory per state less, one
+  // more CTA per SM
+  const bool slot_in_regs = LIST && T.n_slots <= 1;
   float* slots = fsm;                                                    // [n_slots][12][B]
-  float* stc = slots + T.n_slots * 12 * B;                               // [n_store_spheres][3][B]
+  float* stc = slots + (slot_in_regs ? 0 : T.n_slots * 12 * B);          // [n_store_spheres][3][B]
   float* stb = stc + (do_pairs ? T.n_store_spheres * 3 * B : 0);         // [n_store_links][3][B]
-  float* qs = stb + (do_pairs ? T.n_store_links * 3 * B : 0);            // [B][n_vars]
+  float* qs = stb + (do_pairs ? T.n_store_links * 3 * B : 0);            // [B][n_vars], not in the pair pass
   const bool active = base + tid < total;
   const long state = LIST ? (active ? (long)list[base + tid] : 0L) : base + tid;
   B200DF_CHECK_INDEX(active ? state : 0L, n);  // padding lanes of the last CTA touch nothing
-  if (LIST)
-  {
-    const QT* src = q + state * T.n_vars;
-    for (int v = 0; v < T.n_vars; ++v)
-      qs[tid * T.n_vars + v] = active ? (float)src[v] : 0.f;
-  }
-  else
+  if (!LIST)
   {
     const int count = B * T.n_vars;
     const long limit = (n - base) * T.n_vars;
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   }
   // the pair thresholds are read once per sphere-pair test by every warp: keep them in shared memory when they fit
   // (L1 is nearly all shared-memory carve-out here and what is left is thrashed by the voxel gathers)
-  int2* pair_T_shared = reinterpret_cast<int2*>(qs + B * T.n_vars);
+  int2* pair_T_shared = reinterpret_cast<int2*>(qs + (LIST ? 0 : B * T.n_vars));
   if (PAIR_SMEM)
   {
     for (int e = tid; e < n_pair_smem; e += B)
@@ -396,6 +412,8 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   }
   __syncthreads();
   const float* my_q = qs + tid * T.n_vars;
+  const QT* my_row = q + state * T.n_vars;  // padding lanes: row 0, values unused
+  float saved[12];
   float* my_slots = slots + tid;
   float* my_stc = stc + tid;
   float* my_stb = stb + tid;
@@ -411,7 +429,10 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
   for (int i = 0; i < T.n_links; ++i)
   {
     const FLink& l = T.links[i];
-    fk_step_f<FULL>(l, my_q, my_slots, B, cur, oor);
+    if (LIST)
+      fk_step_f<FULL>(l, my_row, my_slots, B, cur, oor, slot_in_regs ? saved : nullptr);
+    else
+      fk_step_f<FULL>(l, my_q, my_slots, B, cur, oor);
     const int gs = l.gslot;
     if (gs < 0)
       continue;
@@ -950,22 +971,24 @@ int fast_launch_typed(const b200df_group* g, const FieldDev& wf, const FieldDev&
 {
   const FastTables& T = g->fast->tables;
   const bool has_pairs = (flags & B200DF_CHECK_INTRA) && T.n_partners > 0;
-  auto smem = [&](int block, bool pairs) {
-    size_t fl = (size_t)T.n_slots * 12 + T.n_vars;
+  // (the pair pass of the two-pass form keeps neither the joint values nor a lone branch-point slot in shared memory)
+  auto smem = [&](int block, bool pairs, bool pair_pass) {
+    size_t fl = pair_pass ? (T.n_slots <= 1 ? 0 : (size_t)T.n_slots * 12) : (size_t)T.n_slots * 12 + T.n_vars;
     if (pairs)
       fl += (size_t)T.n_store_spheres * 3 + (size_t)T.n_store_links * 3;
     return fl * block * sizeof(float);
   };
   auto launch = [&](int fl, TwoPass tp) -> int {
     const bool pairs = (fl & B200DF_CHECK_INTRA) && T.n_partners > 0;
-    const size_t b128 = smem(128, pairs);
+    const bool pair_pass = tp.list != nullptr;
+    const size_t b128 = smem(128, pairs, pair_pass);
     if (b128 <= 100 * 1024)
     {
       if (field_elem == 1)
         return launch_fast<QT, uint8_t, 128>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b128, stream, tp);
       return launch_fast<QT, uint16_t, 128>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b128, stream, tp);
     }
-    const size_t b32 = smem(32, pairs);
+    const size_t b32 = smem(32, pairs, pair_pass);
     B200DF_REQUIRE(b32 <= 220 * 1024, "robot too large for the per-state shared-memory layout");
     if (field_elem == 1)
       return launch_fast<QT, uint8_t, 32>(g, wf, sf, q, n, fl, verdict, amb_idx, amb_count, b32, stream, tp);
