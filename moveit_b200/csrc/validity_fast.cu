@@ -302,15 +302,18 @@ __device__ __forceinline__ void fk_step_f(const FLink& l, const QP* q, float* sl
   }
 }
 
-// one axis of the world->grid mapping: cell, and whether the exact cell could be the lower / upper neighbour
-__device__ __forceinline__ int axis_cell(float p, float oo, float k, float delta, int& alt)
+// one axis of the world->grid mapping: the cell and the position inside it (0 .. 1)
+__device__ __forceinline__ int axis_cell(float p, float oo, float k, float& frac)
 {
   const float g = fmaf(p, oo, k);
   const float fl = floorf(g);
-  const float frac = g - fl;
-  const int c = (int)fl;  // |g| far outside the grid saturates and fails the range test like the exact kernel
-  alt = frac < delta ? -1 : (frac > 1.f - delta ? 1 : 0);
-  return c;
+  frac = g - fl;
+  return (int)fl;  // |g| far outside the grid saturates and fails the range test like the exact kernel
+}
+// could the exact cell be the lower (-1) / upper (+1) neighbour?
+__device__ __forceinline__ int axis_alt(float frac, float delta)
+{
+  return frac < delta ? -1 : (frac > 1.f - delta ? 1 : 0);
 }
 
 // Flags are carried as signed margins and combined with integer min / max (one instruction each) instead of bools
@@ -332,17 +335,23 @@ __device__ __forceinline__ void sphere_field(const FastLookup& f, float x, float
                                              int& sure, int& maybe)
 {
   const float delta = fmaf(eps, f.oo, f.gerr);
-  int ax, ay, az;
-  const int ix = axis_cell(x, f.oo, f.k[0], delta, ax);
-  const int iy = axis_cell(y, f.oo, f.k[1], delta, ay);
-  const int iz = axis_cell(z, f.oo, f.k[2], delta, az);
+  float fx, fy, fz;
+  const int ix = axis_cell(x, f.oo, f.k[0], fx);
+  const int iy = axis_cell(y, f.oo, f.k[1], fy);
+  const int iz = axis_cell(z, f.oo, f.k[2], fz);
   const int s0 = cell_margin<FT>(f, ix, iy, iz, thr);
-  if ((ax | ay | az) == 0)  // the common case: the centre is clear of every voxel face
+  // the common case: the centre is clear of every voxel face, |frac - 1/2| <= 1/2 - delta on all three axes (one
+  // subtraction and one compare per axis; the per-axis directions are only worked out on the rare path).  The two
+  // roundings of this form (frac - 1/2 and 1/2 - delta, <= 1.5e-8 each) are covered by 1.2e-7 of extra margin, which
+  // sends 4e-5 more of the states to the exact kernel.
+  const float clear = 0.5f - delta - 1.2e-7f;
+  if ((fabsf(fx - 0.5f) <= clear) & (fabsf(fy - 0.5f) <= clear) & (fabsf(fz - 0.5f) <= clear))
   {
     sure = min(sure, s0);
     maybe = min(maybe, s0);
     return;
   }
+  const int ax = axis_alt(fx, delta), ay = axis_alt(fy, delta), az = axis_alt(fz, delta);
   // near a face: the exact cell is one of up to 8 candidates; the verdict is settled only if they all agree
   int worst = s0, best = s0;  // all collide <=> the largest margin is negative; any collides <=> the smallest is
   for (int m = 1; m < 8; ++m)

@@ -688,6 +688,28 @@ int main(int argc, char** argv)
     for (const core::AttachedBody& b : attached)
       ref_state.attachBody(b);
     std::vector<std::uint8_t> v(n);
+    if (const char* reps_env = std::getenv("B200DF_DRIVER_BENCH_REPS"))
+    {
+      // CollisionEnvB200::checkCollisionBatch at scale: the states of the file (pageable fp64 rows, the shape a planner
+      // holds) through the C++ env, all three checks; one warm-up call builds the cache entry
+      const int reps = std::max(1, std::atoi(reps_env));
+      const int all = B200DF_CHECK_SELF | B200DF_CHECK_INTRA | B200DF_CHECK_ROBOT;
+      bool ok = env->checkCollisionBatch(req, q.data(), n, acm_ptr, all, ref_state, v.data());
+      double best = 1e300;
+      for (int k = 0; k < reps; ++k)
+      {
+        const auto t0 = std::chrono::steady_clock::now();
+        ok = env->checkCollisionBatch(req, q.data(), n, acm_ptr, all, ref_state, v.data()) && ok;
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      }
+      std::int64_t colliding = 0;
+      for (std::uint8_t x : v)
+        colliding += x;
+      std::printf("bench_batch ok=%d states=%lld best_s=%.6f states_per_s=%.6e colliding=%lld errors=%zu\n", ok ? 1 : 0,
+                  (long long)n, best, (double)n / best, (long long)colliding, env->errorCount());
+      writeFile(prefix + ".all.u8", v);
+      return ok ? 0 : 1;
+    }
     env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_ROBOT, ref_state, v.data());
     writeFile(prefix + ".robot.u8", v);
     env->checkCollisionBatch(req, q.data(), n, acm_ptr, B200DF_CHECK_SELF | B200DF_CHECK_INTRA, ref_state, v.data());

@@ -168,6 +168,36 @@ def run(with_oracle=True):
     except ImportError:
         pass
 
+    # CollisionEnvB200::checkCollisionBatch (the C++ env of the plugin) at scale, from pageable fp64 rows
+    try:
+        import subprocess
+        import tempfile
+        from moveit_b200 import scenario_io
+        import runpy
+        exe = runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "moveit_b200",
+                                          "host", "build_host.py"))["build"]()
+        with tempfile.TemporaryDirectory() as td:
+            scen, states, prefix = os.path.join(td, "scen.txt"), os.path.join(td, "q.f64"), os.path.join(td, "out")
+            scenario_io.write_scenario(scen, desc, scenarios.FIELD_A, scenarios.random_scene())
+            nb = 4_000_000
+            qb = desc.sample_states(nb, scenarios.SEED_STATES, np.float32).astype(np.float64)
+            qb.tofile(states)
+            r = subprocess.run([exe, scen, states, prefix], capture_output=True, text=True,
+                               env=dict(os.environ, B200DF_DRIVER_BENCH_REPS="5"))
+            line = [l for l in r.stdout.splitlines() if l.startswith("bench_batch")]
+            if r.returncode == 0 and line:
+                kv = dict(t.split("=") for t in line[0].split()[1:])
+                got = np.fromfile(prefix + ".all.u8", dtype=np.uint8)
+                ref = e.group.check(qb, e.world, flags=B.CHECK_ROBOT | B.CHECK_INTRA, precision=B.PRECISION_FAST)
+                out["cpp_env_checkCollisionBatch"] = {
+                    "states": nb, "states_per_s": float(kv["states_per_s"]), "ms": 1e3 * float(kv["best_s"]),
+                    "input": "pageable fp64 rows through CollisionEnvB200::checkCollisionBatch (host_driver)",
+                    "verdicts_match_c_abi_call": bool(np.array_equal(got, ref)), "errors": int(kv["errors"])}
+            else:
+                out["cpp_env_checkCollisionBatch"] = {"failed": (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:  # the extras never take the bench line down
+        out["cpp_env_checkCollisionBatch"] = {"failed": repr(ex)[:300]}
+
     # small calls, the granularity the reference's callers use (tools/latency_probe.py has the full sweep)
     small = {}
     q256 = q[:256].copy()
