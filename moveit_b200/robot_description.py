@@ -413,6 +413,14 @@ def pr2_like():
             if r.shapes[a]:
                 break
             a = r.parent[a]
+    # ... and the pairs that collide in every random state (grandparent / grandchild cylinders overlap by construction):
+    # what the Setup Assistant's "always in collision" rule finds (moveit_setup_assistant/src/tools/
+    # compute_default_collisions.cpp:474-547, >= 95 % of the samples; tools/pr2_default_collisions.py reproduces the
+    # list with the oracle's sphere decomposition) and the real PR2's SRDF disables likewise
+    for side in ("r", "l"):
+        p = side + "_"
+        r.disabled_pairs += [("torso_lift_link", p + "shoulder_lift_link"), (p + "shoulder_pan_link", p + "upper_arm_link"),
+                             (p + "upper_arm_link", p + "forearm_link"), (p + "forearm_link", p + "gripper_palm_link")]
     r.groups = {
         "right_arm": ["r_shoulder_pan_joint", "r_shoulder_lift_joint", "r_upper_arm_roll_joint", "r_elbow_flex_joint",
                       "r_forearm_roll_joint", "r_wrist_flex_joint", "r_wrist_roll_joint"],

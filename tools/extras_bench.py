@@ -243,6 +243,16 @@ def run(with_oracle=True):
     out["config4_pr2_like"] = {"states": len(q4), "ms": 1e3 * t, "states_per_s": len(q4) / t,
                                "exact_states_per_s": len(q4) / tx,
                                "links": pr2.n_links, "spheres": int(e4.group.n_spheres)}
+    # the self-collision part on its own (the "full ACM self-collision pairs" of BASELINE config 4), 1 M states: random
+    # states of this tree nearly always touch the scene, the pair tests are where its verdicts are not a foregone
+    # conclusion (adjacent and always-colliding pairs disabled like an SRDF does)
+    q4b = pr2.sample_states(1_000_000, 13, np.float32)
+    v4 = e4.group.check(q4b, None, flags=B.CHECK_INTRA, precision=B.PRECISION_FAST)
+    ts = best_of(lambda: e4.group.check(q4b, None, flags=B.CHECK_INTRA, precision=B.PRECISION_FAST), 3)
+    out["config4_pr2_like"].update({"self_collision_states": len(q4b), "self_collision_states_per_s": len(q4b) / ts,
+                                    "self_collision_colliding_fraction": float(v4.mean()),
+                                    "robot_and_intra_colliding_fraction": float(e4.group.check(
+                                        q4, e4.world, flags=fl, precision=B.PRECISION_FAST).mean())})
     if oracle:
         o = OracleSetup(oracle, desc, scenarios.FIELD_A, objs, self_state=np.zeros(desc.nvar))
         sample = traj[:20000]
