@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <type_traits>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -599,6 +600,240 @@ __global__ void __launch_bounds__(B) validity_fast_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Pair tests, ONE WARP PER STATE (robots with many spheres and link pairs).
+//
+// The one-thread-per-state kernels keep a state's stored centres in a shared-memory column; a PR2-sized tree (33 links,
+// 124 spheres, ~480 enabled link pairs) needs 1.9 KB per state there, which leaves the pair pass THREE warps per SM.
+// Here a warp owns one state: lane i builds joint matrix i (all sincos at once), twelve lanes walk the chain with one
+// matrix entry each, the lanes then pose the spheres and the bounding centres four at a time, and the enabled link
+// pairs are dealt out one per lane (bounding-sphere prune with its two thresholds, then the sphere pairs of the pairs
+// that pass).  5 KB of shared memory per warp, 44 warps per SM.  Same tables, same thresholds and the same error
+// analysis as the one-thread-per-state kernel: every transform entry is a three-term FMA chain of fp32 factors, which
+// is what the per-link bounds (9.1 u per product) assume; a pair is "surely touching" / "possibly touching" by the same
+// integer comparisons.  Verdicts: 1 = certain, 2 = the exact kernel decides, 0 = certainly no pair touches.
+// Floating joints are not built here (robots that have one stay on the other path).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = 4;
+
+__device__ __forceinline__ float entryf(const float* a, const float* b, int r, int c)  // (a * b)[r][c], like mulf
+{
+  const float a0 = a[4 * r], a1 = a[4 * r + 1], a2 = a[4 * r + 2];
+  const float acc = c == 3 ? fmaf(a0, b[3], a[4 * r + 3]) : a0 * b[c];
+  return fmaf(a2, b[8 + c], fmaf(a1, b[4 + c], acc));
+}
+
+// the joint's own transform (fixed: identity; the same formulas as fk_step_f, written out as a matrix)
+template <bool FULL, typename QP>
+__device__ __forceinline__ void joint_matrix_f(const FLink& l, const QP* q, float* j, bool& out_of_range)
+{
+#pragma unroll
+  for (int k = 0; k < 12; ++k)
+    j[k] = (k == 0 || k == 5 || k == 10) ? 1.f : 0.f;
+  if (l.joint_type == B200DF_JOINT_PRISMATIC)
+  {
+    const float v = jointf(l, q, 0, out_of_range);
+    j[3] = l.ax * v;
+    j[7] = l.ay * v;
+    j[11] = l.az * v;
+  }
+  else if (l.joint_type == B200DF_JOINT_REVOLUTE || (FULL && l.joint_type == B200DF_JOINT_PLANAR))
+  {
+    const bool planar = FULL && l.joint_type == B200DF_JOINT_PLANAR;
+    if (planar)
+    {
+      j[3] = jointf(l, q, 0, out_of_range);
+      j[7] = jointf(l, q, 1, out_of_range);
+    }
+    const float v = jointf(l, q, planar ? 2 : 0, out_of_range);
+    float s, c;
+    if (FULL)
+      sincosf(v, &s, &c);
+    else
+      sincos_small(v, &s, &c);
+    const int kind = planar ? 3 : l.jkind;
+    if (FULL && kind == 0)
+    {
+      const float tt = 1.f - c;
+      j[0] = fmaf(tt, l.x2, c);
+      j[1] = fmaf(tt, l.xy, -l.az * s);
+      j[2] = fmaf(tt, l.xz, l.ay * s);
+      j[4] = fmaf(tt, l.xy, l.az * s);
+      j[5] = fmaf(tt, l.y2, c);
+      j[6] = fmaf(tt, l.yz, -l.ax * s);
+      j[8] = fmaf(tt, l.xz, -l.ay * s);
+      j[9] = fmaf(tt, l.yz, l.ax * s);
+      j[10] = fmaf(tt, l.z2, c);
+    }
+    else
+    {
+      const float sg = planar ? s : (kind == 1 ? l.ax : (kind == 2 ? l.ay : l.az)) * s;
+      if (kind == 3)
+      {
+        j[0] = c;
+        j[1] = -sg;
+        j[4] = sg;
+        j[5] = c;
+      }
+      else if (kind == 2)
+      {
+        j[0] = c;
+        j[2] = sg;
+        j[8] = -sg;
+        j[10] = c;
+      }
+      else
+      {
+        j[5] = c;
+        j[6] = -sg;
+        j[9] = sg;
+        j[10] = c;
+      }
+    }
+  }
+}
+
+template <typename QT, bool FULL>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+    validity_fast_warp_pairs_kernel(const __grid_constant__ FastTables T, const FastTables* __restrict__ Tg,
+                                    const int* __restrict__ maps, const int2* __restrict__ pair_T,
+                                    const QT* __restrict__ q, long n, uint8_t* __restrict__ verdict,
+                                    int* __restrict__ amb_idx, int* __restrict__ amb_count,
+                                    const int* __restrict__ list, const int* __restrict__ list_count)
+{
+  extern __shared__ float wsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long slot = (long)blockIdx.x * kWarpsPerCta + warp;
+  const long total = list ? (long)*list_count : n;
+  if (slot >= total)
+    return;  // whole warps leave; nothing below synchronises across warps
+  const long state = list ? (long)list[slot] : slot;
+  B200DF_CHECK_INDEX(state, n);
+  const int L = T.n_links, G = T.n_glinks, S = T.n_spheres, P = T.n_partners;
+  const int* sph_link = maps;
+  const int* glink_link = sph_link + S;
+  const int* owner = glink_link + G;
+  const int* partner_glink = owner + P;
+  float* Tm = wsm + (size_t)warp * ((size_t)L * 24 + 16 + (size_t)S * 3 + (size_t)G * 3 + (size_t)P);  // [L][12] transforms
+  float* J = Tm + (size_t)L * 12;                                                          // [L][12] joint matrices
+  float* TMP = J + (size_t)L * 12;                                                         // [16]
+  float* C = TMP + 16;                                                                     // [S][3] sphere centres
+  float* BC = C + (size_t)S * 3;                                                           // [G][3] bounding centres
+  const QT* row = q + state * T.n_vars;
+  bool oor = false;
+  for (int i = lane; i < L; i += 32)
+  {
+    float j[12];
+    joint_matrix_f<FULL>(Tg->links[i], row, j, oor);
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      J[i * 12 + k] = j[k];
+  }
+  __syncwarp();
+  {
+    const int e = lane < 12 ? lane : 0;  // lanes 12..31 shadow lane 0 and do not store
+    const int r = e >> 2, c = e & 3;
+    for (int i = 0; i < L; ++i)
+    {
+      const FLink& l = T.links[i];  // warp-uniform: constant bank
+      float out;
+      if (l.parent < 0)
+        out = l.origin_is_identity ? J[i * 12 + e] : entryf(l.origin, J + i * 12, r, c);
+      else
+      {
+        const float* par = Tm + l.parent * 12;
+        if (l.joint_type == B200DF_JOINT_FIXED)
+          out = l.origin_is_identity ? par[e] : entryf(par, l.origin, r, c);
+        else if (l.origin_is_identity)
+          out = entryf(par, J + i * 12, r, c);
+        else
+        {
+          const float base = entryf(par, l.origin, r, c);
+          if (lane < 12)
+            TMP[e] = base;
+          __syncwarp();
+          out = entryf(TMP, J + i * 12, r, c);
+        }
+      }
+      if (lane < 12)
+        Tm[i * 12 + e] = out;
+      __syncwarp();
+    }
+  }
+  for (int sidx = lane; sidx < S; sidx += 32)
+  {
+    const FSphere sp = Tg->sph[sidx];
+    applyf(Tm + sph_link[sidx] * 12, sp.x, sp.y, sp.z, C[3 * sidx], C[3 * sidx + 1], C[3 * sidx + 2]);
+  }
+  for (int gidx = lane; gidx < G; gidx += 32)
+  {
+    const FGLink& gl = Tg->glinks[gidx];
+    applyf(Tm + glink_link[gidx] * 12, gl.bs[0], gl.bs[1], gl.bs[2], BC[3 * gidx], BC[3 * gidx + 1], BC[3 * gidx + 2]);
+  }
+  __syncwarp();
+  // phase 1: the bounding-sphere prune of every enabled link pair, one pair per lane; the pairs that may touch are
+  // queued (bit 31: the prune CERTAINLY passes, so a certain sphere contact is a certain collision)
+  unsigned* queue = reinterpret_cast<unsigned*>(BC + (size_t)G * 3);  // [P]
+  int n_queued = 0;
+  for (int p0 = 0; p0 < P; p0 += 32)
+  {
+    const int p = p0 + lane;
+    bool sure = false, maybe = false;
+    if (p < P)
+    {
+      const int own = owner[p], pg = partner_glink[p];
+      const int n_sure = Tg->partners[p].n_sure, n_maybe = Tg->partners[p].n_maybe;
+      const float dx = BC[3 * pg] - BC[3 * own], dy = BC[3 * pg + 1] - BC[3 * own + 1], dz = BC[3 * pg + 2] - BC[3 * own + 2];
+      const int d2 = __float_as_int(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+      sure = d2 + n_sure < 0;
+      maybe = d2 + n_maybe < 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, maybe);
+    if (maybe)
+      queue[n_queued + __popc(m & ((1u << lane) - 1u))] = (unsigned)p | (sure ? 0x80000000u : 0u);
+    n_queued += __popc(m);
+  }
+  __syncwarp();
+  // phase 2: the sphere pairs of one queued link pair at a time, dealt out over the lanes
+  bool hit = false, amb = false;
+  for (int k = 0; k < n_queued && !hit; ++k)
+  {
+    const unsigned entry = queue[k];
+    const int p = (int)(entry & 0x7fffffffu);
+    const FPartner& pr = T.partners[p];  // warp-uniform from here on: constant bank
+    const FGLink& gl = T.glinks[owner[p]];
+    const int ps0 = T.glinks[partner_glink[p]].sphere_begin;
+    const int cnt = pr.count, n_pairs = (gl.sphere_end - gl.sphere_begin) * cnt;
+    const int2* t0 = pair_T + gl.pair_const_begin + pr.const_offset;
+    int a_sure = 0x7fffffff, a_maybe = 0x7fffffff;
+    for (int idx = lane; idx < n_pairs; idx += 32)
+    {
+      const int io = idx / cnt, mm = idx - io * cnt;
+      const int so = gl.sphere_begin + io, sq = ps0 + mm;
+      const float ex = C[3 * so] - C[3 * sq], ey = C[3 * so + 1] - C[3 * sq + 1], ez = C[3 * so + 2] - C[3 * sq + 2];
+      const int e2 = __float_as_int(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+      const int2 th = t0[(long)io * gl.pair_const_stride + mm];
+      a_sure = __viaddmin_s32(e2, th.x, a_sure);
+      a_maybe = __viaddmin_s32(e2, th.y, a_maybe);
+    }
+    hit = (entry >> 31) != 0u && __any_sync(0xffffffffu, a_sure < 0);
+    amb = amb || __any_sync(0xffffffffu, a_maybe < 0);
+  }
+  oor = __any_sync(0xffffffffu, oor);
+  if (lane == 0)
+  {
+    const int v = oor ? 2 : (hit ? 1 : (amb ? 2 : 0));
+    if (!list || v != 0)  // a listed state already holds the 0 of the field pass
+      verdict[state] = (uint8_t)v;
+    if (v == 2)
+    {
+      const int at = atomicAdd(amb_count, 1);
+      B200DF_CHECK_INDEX(at, n);
+      amb_idx[at] = (int)state;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host: tables + forward error analysis
 // ------------------------------------------------------------------------------------------------------------
 double norm3(const double* v)
@@ -622,6 +857,12 @@ struct b200df_group::FastPath
 {
   FastTables tables;
   int2* pair_T = nullptr;  // device: {-bits(lo2), -(bits(hi2) + 1)} per sphere pair, see the pair loop
+  // the warp-per-state pair kernel (robots whose per-state shared-memory column leaves the one-thread-per-state pair
+  // pass a handful of warps per SM): the tables again in global memory, where 32 lanes may read 32 different entries,
+  // plus the flat maps it needs
+  FastTables* d_tables = nullptr;
+  int* d_warp_maps = nullptr;  // [sph_link[S] | glink_link[G] | owner_glink[P] | partner_glink[P]]
+  bool warp_ok = false;        // no floating joint (the one joint type that kernel does not build)
   bool ok = false;
   bool needs_full = false;  // a floating / planar / oblique-axis revolute joint: the kernel variant that knows them
 };
@@ -843,6 +1084,35 @@ int fast_create(b200df_group* g)
   DeviceGuard dg(g->device);
   B200DF_CUDA(cudaMalloc(&fp->pair_T, pair_T.size() * sizeof(int2)));
   B200DF_CUDA(cudaMemcpy(fp->pair_T, pair_T.data(), pair_T.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  {
+    std::vector<int> maps((size_t)S + G + 2 * (size_t)P, 0);
+    int* sph_link = maps.data();
+    int* glink_link = sph_link + S;
+    int* owner = glink_link + G;
+    int* partner_glink = owner + P;
+    bool has_floating = false;
+    for (int i = 0; i < L; ++i)
+      has_floating = has_floating || m->links[i].joint_type == B200DF_JOINT_FLOATING;
+    for (int gs = 0; gs < G; ++gs)
+    {
+      const DevGroupLink& gl = g->glinks[gs];
+      glink_link[gs] = gl.link;
+      for (int sp = gl.sphere_begin; sp < gl.sphere_end; ++sp)
+        sph_link[sp] = gl.link;
+      for (int pp = gl.partner_begin; pp < gl.partner_end; ++pp)
+      {
+        owner[pp] = gs;
+        for (int h = 0; h < G; ++h)
+          if (g->glinks[h].store_link == g->partners[pp].store_link)
+            partner_glink[pp] = h;
+      }
+    }
+    B200DF_CUDA(cudaMalloc(&fp->d_tables, sizeof(FastTables)));
+    B200DF_CUDA(cudaMemcpy(fp->d_tables, &T, sizeof(FastTables), cudaMemcpyHostToDevice));
+    B200DF_CUDA(cudaMalloc(&fp->d_warp_maps, maps.size() * sizeof(int)));
+    B200DF_CUDA(cudaMemcpy(fp->d_warp_maps, maps.data(), maps.size() * sizeof(int), cudaMemcpyHostToDevice));
+    fp->warp_ok = !has_floating;
+  }
   fp->ok = true;
   g->fast = fp.release();
   return B200DF_OK;
@@ -853,6 +1123,8 @@ void fast_destroy(b200df_group* g)
   if (!g->fast)
     return;
   cudaFree(g->fast->pair_T);
+  cudaFree(g->fast->d_tables);
+  cudaFree(g->fast->d_warp_maps);
   delete g->fast;
   g->fast = nullptr;
 }
@@ -1005,7 +1277,39 @@ int fast_launch_typed(const b200df_group* g, const FieldDev& wf, const FieldDev&
   };
   B200DF_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), stream));
   const int field_flags = flags & (B200DF_CHECK_ROBOT | B200DF_CHECK_SELF);
-  if (!has_pairs || !field_flags || n < kTwoPassMinStates || !two_pass_enabled())
+  // the pair tests one warp per state (list may be null: every state)
+  auto launch_warp_pairs = [&](const int* list, const int* list_count) -> int {
+    const size_t per_warp = ((size_t)T.n_links * 24 + 16 + (size_t)T.n_spheres * 3 + (size_t)T.n_glinks * 3 +
+                             (size_t)T.n_partners) * sizeof(float);
+    const size_t bytes = per_warp * kWarpsPerCta;
+    const unsigned grid = (unsigned)((n + kWarpsPerCta - 1) / kWarpsPerCta);
+    auto go = [&](auto kernel) -> cudaError_t {
+      const cudaError_t e = allow_dynamic_smem(kernel, bytes);
+      if (e != cudaSuccess)
+        return e;
+      kernel<<<grid, 32 * kWarpsPerCta, bytes, stream>>>(T, g->fast->d_tables, g->fast->d_warp_maps, g->fast->pair_T, q, n,
+                                                         verdict, amb_idx, amb_count, list, list_count);
+      return cudaSuccess;
+    };
+    B200DF_CUDA(g->fast->needs_full ? go(validity_fast_warp_pairs_kernel<QT, true>) :
+                                      go(validity_fast_warp_pairs_kernel<QT, false>));
+    B200DF_LAUNCHED();
+    B200DF_CUDA(cudaGetLastError());
+    return B200DF_OK;
+  };
+  // robots whose stored centres leave the one-thread-per-state pair pass a few warps per SM (its 128-state CTA does
+  // not fit): the pair tests go to the warp-per-state kernel, behind the field pass when field lookups are asked for
+  static const bool warp_pairs_on = !(getenv("B200DF_FAST_WARP_PAIRS") && atoi(getenv("B200DF_FAST_WARP_PAIRS")) == 0);
+  const bool heavy = has_pairs && g->fast->warp_ok && warp_pairs_on && smem(128, true, false) > 100 * 1024 &&
+                     ((size_t)T.n_links * 24 + 16 + (size_t)T.n_spheres * 3 + (size_t)T.n_glinks * 3 + (size_t)T.n_partners) *
+                             sizeof(float) * kWarpsPerCta <= 200 * 1024;
+  if (getenv("B200DF_DEBUG_FAST"))
+    fprintf(stderr, "b200df fast: links %d glinks %d spheres %d partners %d slots %d store_spheres %d store_links %d "
+                    "smem128 %zu heavy %d warp_ok %d\n", T.n_links, T.n_glinks, T.n_spheres, T.n_partners, T.n_slots,
+            T.n_store_spheres, T.n_store_links, smem(128, true, false), (int)heavy, (int)g->fast->warp_ok);
+  if (heavy && !field_flags)
+    return launch_warp_pairs(nullptr, nullptr);
+  if (!has_pairs || !field_flags || (!heavy && (n < kTwoPassMinStates || !two_pass_enabled())))
     return launch(flags, TwoPass());
   // pass A: the field lookups of every state; pass B: the sphere pairs of the states pass A left at 0
   int* surv = nullptr;
@@ -1019,7 +1323,7 @@ int fast_launch_typed(const b200df_group* g, const FieldDev& wf, const FieldDev&
   b.list = surv + 1;
   int rc = launch(field_flags, a);
   if (!rc)
-    rc = launch(flags & ~(B200DF_CHECK_ROBOT | B200DF_CHECK_SELF), b);
+    rc = heavy ? launch_warp_pairs(b.list, b.list_count) : launch(flags & ~(B200DF_CHECK_ROBOT | B200DF_CHECK_SELF), b);
   cudaFreeAsync(surv, stream);
   return rc;
 }

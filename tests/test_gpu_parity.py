@@ -460,6 +460,22 @@ def test_config4_pr2_like_fast_equals_exact(gpu, oracle):
         assert np.array_equal(raw[raw != 2], exact[raw != 2])
         print("pr2_like flags=%d undecided %.4f colliding %.3f" % (flags, (raw == 2).mean(), exact.mean()))
         assert (raw == 2).mean() < 0.1
+    # the self-collision part alone, where the verdicts of this tree are not a foregone conclusion: FAST runs the pair
+    # tests one warp per state for a robot of this size (validity_fast_warp_pairs_kernel), on its own and behind the
+    # field pass in an empty world; fp32 and fp64 rows; against the fp64 kernel on every state and the oracle on a slice
+    o = OracleSetup(oracle, desc, scenarios.FIELD_DEFAULT, [], self_state=np.zeros(desc.nvar))
+    empty = EngineSetup(desc, scenarios.FIELD_DEFAULT, [])
+    exact = empty.group.check(q, None, flags=CHECK_INTRA, precision=0)
+    assert 0.3 < exact.mean() < 0.95
+    assert np.array_equal(exact, empty.group.check(q, None, flags=CHECK_INTRA, precision=1))
+    raw = empty.group.check(q, None, flags=CHECK_INTRA, precision=3)
+    assert np.array_equal(raw[raw != 2], exact[raw != 2]) and (raw == 2).mean() < 0.1
+    both = empty.group.check(q, empty.world, flags=CHECK_ROBOT | CHECK_INTRA, precision=1)
+    assert np.array_equal(both, exact)  # nothing to hit in an empty world
+    q64 = q[:70_000].astype(np.float64) + 1e-9
+    f64 = empty.group.check(q64, None, flags=CHECK_INTRA, precision=1)
+    assert np.array_equal(f64, empty.group.check(q64, None, flags=CHECK_INTRA, precision=0))
+    assert np.array_equal(f64[:5000], o.env.check_batch(q64[:5000], mode=2, n_threads=8))
 
 
 def _interpolate_reference(qa, qb, K, angular):
