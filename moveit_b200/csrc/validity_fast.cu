@@ -66,7 +66,8 @@ struct FPartner
   // negated bit patterns of the squared-distance thresholds below which the prune certainly / possibly passes:
   // min(exact-cull threshold + margin, doBoundingSpheresIntersect threshold (Q2) - / + its margin)
   int n_sure, n_maybe;
-  int pad[2];
+  int div_magic;  // floor(idx / count) == (idx * div_magic) >> 16 for every sphere-pair index of this link pair
+  int pad;
 };
 
 struct FastTables  // passed by value: lives in the constant bank, read with warp-uniform indices
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta)
     int a_sure = 0x7fffffff, a_maybe = 0x7fffffff;
     for (int idx = lane; idx < n_pairs; idx += 32)
     {
-      const int io = idx / cnt, mm = idx - io * cnt;
+      const int io = pr.div_magic ? (idx * pr.div_magic) >> 16 : idx / cnt, mm = idx - io * cnt;
       const int so = gl.sphere_begin + io, sq = ps0 + mm;
       const float ex = C[3 * so] - C[3 * sq], ey = C[3 * so + 1] - C[3 * sq + 1], ez = C[3 * so + 2] - C[3 * sq + 2];
       const int e2 = __float_as_int(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
@@ -1069,6 +1070,13 @@ int fast_create(b200df_group* g)
       };
       f.n_sure = -fbits(std::min(tight_hi, lo2(rs, Eb)));
       f.n_maybe = -fbits(std::min(tight_hi, hi2(rs, Eb)));
+      {
+        const int cnt = std::max(1, pr.count), n_pairs = (gl.sphere_end - gl.sphere_begin) * cnt;
+        f.div_magic = 65536 / cnt + 1;
+        for (int idx = 0; idx < n_pairs; ++idx)  // 128 spheres at most: the products stay far below 2^31
+          if ((int)(((long)idx * f.div_magic) >> 16) != idx / cnt)
+            f.div_magic = 0;  // never seen; the kernel then divides
+      }
       for (int s = gl.sphere_begin; s < gl.sphere_end; ++s)
         for (int mm = 0; mm < pr.count; ++mm)
         {
