@@ -955,6 +955,19 @@ int b200df_check_batch_device(const b200df_group* group, b200df_field* world, b2
 __attribute__((target("avx2"))) static void narrow_rows_avx2(float* dst, const double* src, size_t count)
 {
   size_t k = 0;
+  // the page-locked staging buffer is read next by the GPU's copy engine, not by this core: non-temporal stores skip
+  // the read-for-ownership of every destination line (a third of the memory traffic of this loop)
+  static const bool stream_stores = !(getenv("B200DF_NARROW_NT") && atoi(getenv("B200DF_NARROW_NT")) == 0);
+  if (stream_stores && ((uintptr_t)dst & 31) == 0)
+  {
+    for (; k + 8 <= count; k += 8)
+    {
+      const __m128 a = _mm256_cvtpd_ps(_mm256_loadu_pd(src + k));
+      const __m128 b = _mm256_cvtpd_ps(_mm256_loadu_pd(src + k + 4));
+      _mm256_stream_ps(dst + k, _mm256_set_m128(b, a));
+    }
+    _mm_sfence();
+  }
   for (; k + 8 <= count; k += 8)
   {
     const __m128 a = _mm256_cvtpd_ps(_mm256_loadu_pd(src + k));
