@@ -1058,7 +1058,9 @@ static int gradients_host_impl(const b200df_group* group, b200df_field* world, b
   }
 
   // Large calls: chunks of states travel H2D -> kernel -> D2H on two streams of the cached context, so the (large)
-  // result copies of one chunk overlap the kernel of the next.
+  // result copies of one chunk overlap the kernel of the next.  Result arrays in ordinary pageable memory (what a
+  // planner's own vectors are) are not handed to the driver, whose staged copy runs at a third of the PCIe rate: each
+  // chunk lands in a page-locked slot and a few host threads move it on while the next chunk computes and copies.
   const int64_t chunk = std::min<int64_t>(n, 16384);
   const size_t want[5] = { std::max<size_t>(chunk * row, 1), chunk * S * sizeof(OT), chunk * S * 3 * sizeof(OT),
                            chunk * S, centers ? chunk * S * 3 * sizeof(OT) : 0 };
@@ -1069,7 +1071,41 @@ static int gradients_host_impl(const b200df_group* group, b200df_field* world, b
       if (want[b])
         e = Pool::ensure_scratch(ctx, 5 * k + b, want[b]);
   }
+  auto is_pinned = [](const void* host) {
+    cudaPointerAttributes a;
+    const bool yes = host && cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+  };
+  static const bool stage_env = !(getenv("B200DF_GRAD_STAGE_OUT") && atoi(getenv("B200DF_GRAD_STAGE_OUT")) == 0);
+  const bool stage_out = stage_env && !(is_pinned(dist) && is_pinned(grad) && is_pinned(type) && (!centers || is_pinned(centers)));
+  const size_t s_d = 0, s_g = s_d + up(want[1]), s_t = s_g + up(want[2]), s_c = s_t + up(want[3]),
+               slot_bytes = s_c + up(want[4]);
+  char* pin = nullptr;
+  if (stage_out && e == cudaSuccess)
+  {
+    void* dpin = nullptr;
+    e = Pool::ensure_pin(ctx, 2 * slot_bytes, &dpin);
+    pin = static_cast<char*>(ctx->pin);
+  }
+  auto drain = [&](int slot, int64_t s, int64_t m) {  // chunk [s, s + m) has landed in `slot`: on to the caller's arrays
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream[slot]);
+    if (es != cudaSuccess)
+    {
+      if (e == cudaSuccess)
+        e = es;
+      return;
+    }
+    const char* src = pin + (size_t)slot * slot_bytes;
+    const CopyJob jobs[4] = { { dist + s * S, src + s_d, (size_t)m * S * sizeof(OT) },
+                              { grad + s * S * 3, src + s_g, (size_t)m * S * 3 * sizeof(OT) },
+                              { type + s * S, src + s_t, (size_t)m * S },
+                              { centers ? centers + s * S * 3 : nullptr, src + s_c,
+                                centers ? (size_t)m * S * 3 * sizeof(OT) : 0 } };
+    parallel_copy_many(jobs, 4);
+  };
   int k = 0;
+  int64_t prev_s = -1, prev_m = 0;
   for (int64_t s = 0; s < n && !rc && e == cudaSuccess; s += chunk, k ^= 1)
   {
     const int64_t m = std::min<int64_t>(chunk, n - s);
@@ -1084,14 +1120,29 @@ static int gradients_host_impl(const b200df_group* group, b200df_field* world, b
                          centers ? static_cast<OT*>(buf[4]) : nullptr, st);
     if (rc)
       break;
-    e = cudaMemcpyAsync(dist + s * S, buf[1], m * S * sizeof(OT), cudaMemcpyDeviceToHost, st);
+    char* slot = stage_out ? pin + (size_t)k * slot_bytes : nullptr;
+    e = cudaMemcpyAsync(stage_out ? static_cast<void*>(slot + s_d) : static_cast<void*>(dist + s * S), buf[1],
+                        m * S * sizeof(OT), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(grad + s * S * 3, buf[2], m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(stage_out ? static_cast<void*>(slot + s_g) : static_cast<void*>(grad + s * S * 3), buf[2],
+                          m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(type + s * S, buf[3], m * S, cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(stage_out ? static_cast<void*>(slot + s_t) : static_cast<void*>(type + s * S), buf[3], m * S,
+                          cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && centers)
-      e = cudaMemcpyAsync(centers + s * S * 3, buf[4], m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(stage_out ? static_cast<void*>(slot + s_c) : static_cast<void*>(centers + s * S * 3), buf[4],
+                          m * S * 3 * sizeof(OT), cudaMemcpyDeviceToHost, st);
+    if (stage_out)
+    {
+      // the chunk before this one sits in the other slot: move it on while this one computes and copies
+      if (prev_s >= 0 && e == cudaSuccess)
+        drain(k ^ 1, prev_s, prev_m);
+      prev_s = s;
+      prev_m = m;
+    }
   }
+  if (stage_out && prev_s >= 0 && !rc && e == cudaSuccess)
+    drain(k ^ 1, prev_s, prev_m);
   for (int i = 0; i < 2; ++i)
   {
     if (!ctx->stream[i])

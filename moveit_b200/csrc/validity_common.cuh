@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -835,6 +836,48 @@ inline void parallel_memcpy(void* dst, const void* src, size_t bytes)
     workers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
   }
   std::memcpy(dst, src, std::min(piece, bytes));
+  for (std::thread& w : workers)
+    w.join();
+}
+
+// several host copies at once: the pieces (>= 1 MB) of all jobs are dealt out over up to 16 threads
+struct CopyJob
+{
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+inline void parallel_copy_many(const CopyJob* jobs, int n_jobs)
+{
+  struct Piece
+  {
+    char* dst;
+    const char* src;
+    size_t len;
+  };
+  std::vector<Piece> pieces;
+  const size_t kPiece = size_t(1) << 20;
+  for (int j = 0; j < n_jobs; ++j)
+    for (size_t off = 0; off < jobs[j].bytes; off += kPiece)
+      pieces.push_back({ static_cast<char*>(jobs[j].dst) + off, static_cast<const char*>(jobs[j].src) + off,
+                         std::min(kPiece, jobs[j].bytes - off) });
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t n_threads = std::min<size_t>(std::min<size_t>(16, std::max<unsigned>(1, hw)), pieces.size() / 2);
+  if (n_threads <= 1)
+  {
+    for (const Piece& p : pieces)
+      std::memcpy(p.dst, p.src, p.len);
+    return;
+  }
+  std::atomic<size_t> next{ 0 };
+  auto work = [&] {
+    for (size_t i = next++; i < pieces.size(); i = next++)
+      std::memcpy(pieces[i].dst, pieces[i].src, pieces[i].len);
+  };
+  std::vector<std::thread> workers;
+  for (size_t t = 1; t < n_threads; ++t)
+    workers.emplace_back(work);
+  work();
   for (std::thread& w : workers)
     w.join();
 }

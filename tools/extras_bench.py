@@ -143,6 +143,12 @@ def run(with_oracle=True):
         c5 = out["config5_chomp_gradients"]
         c5["f32_out_pinned_ms"] = 1e3 * t
         c5["f32_out_d2h_bytes"] = N * S * (4 + 12 + 1 + 12)
+        pg32 = dict(dist=np.zeros((N, S), np.float32), grad=np.zeros((N, S, 3), np.float32),
+                    type=np.zeros((N, S), np.uint8), centers=np.zeros((N, S, 3), np.float32))
+        t = best_of(lambda: e.group.gradients(traj, e.world, flags=fl, out=pg32, out_dtype=np.float32), 3)
+        c5["f32_out_pageable_ms"] = 1e3 * t
+        assert np.array_equal(pg32["dist"], pin32["dist"]) and np.array_equal(pg32["type"], pin32["type"]) and \
+            np.array_equal(pg["grad"], pin["grad"]) and np.array_equal(pg["centers"], pin["centers"])
         fin = pin["dist"] < 1e300
         c5["f32_out_max_abs_diff_vs_f64"] = float(max(np.max(np.abs(pin32["dist"][fin] - pin["dist"][fin])),
                                                        np.max(np.abs(pin32["grad"] - pin["grad"])),
