@@ -1,6 +1,8 @@
 // Internal declarations shared by the b200df translation units (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstring>
 
 #include <atomic>
 #include <cstdarg>
@@ -69,6 +71,34 @@ struct ThreadDeviceScope
   explicit ThreadDeviceScope(int dev);
   ~ThreadDeviceScope();
 };
+
+// host copy INTO a page-locked staging buffer that the GPU's copy engine reads next: non-temporal stores skip the
+// read-for-ownership of the destination lines
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) inline void stream_copy_avx2(char* dst, const char* src, size_t bytes)
+{
+  const size_t head = std::min(bytes, (size_t)((32 - ((uintptr_t)dst & 31)) & 31));
+  std::memcpy(dst, src, head);
+  size_t k = head;
+  for (; k + 32 <= bytes; k += 32)
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + k), _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + k)));
+  _mm_sfence();
+  std::memcpy(dst + k, src + k, bytes - k);
+}
+#endif
+inline void stream_copy(void* dst, const void* src, size_t bytes)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && bytes >= 4096)
+  {
+    stream_copy_avx2(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+    return;
+  }
+#endif
+  std::memcpy(dst, src, bytes);
+}
 
 // Bounds-checked debug build (-DB200DF_BOUNDS_CHECK, `python tools/build_variant.py checked all -DB200DF_BOUNDS_CHECK`):
 // every computed index into a voxel array or a device-side list is tested before use and a violation stops the kernel

@@ -988,7 +988,7 @@ static int scatter_host_points(b200df_field* f, const double* xyz, int64_t n, ui
     {
       const int64_t q1 = std::min<int64_t>(p1, q0 + kSlicePoints);
       const size_t off = (size_t)q0 * 24, len = (size_t)(q1 - q0) * 24;
-      std::memcpy(f->pts_pin + off, reinterpret_cast<const char*>(xyz) + off, len);
+      stream_copy(f->pts_pin + off, reinterpret_cast<const char*>(xyz) + off, len);
       e = cudaMemcpyAsync(reinterpret_cast<char*>(f->pts_dev) + off, f->pts_pin + off, len, cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess)
         break;
