@@ -666,6 +666,38 @@ def test_config5_full_size_1000x100_with_link_fields_and_f32_outputs(gpu, oracle
     assert np.array_equal(g32["dist"][fin], got["dist"][fin].astype(np.float32))
 
 
+def test_device_resident_gradient_entry_points_match_the_host_buffer_ones(gpu):
+    """b200df_gradients_batch_device / _device_f32 (results stay on the GPU, nothing synchronises) against the host-buffer
+    calls on the same states, for a small batch (CTA-per-state variant) and a large one, into pageable arrays (staged
+    by the library) and page-locked ones."""
+    import ctypes as C
+    import torch
+    from moveit_b200 import binding as B
+    desc = rd.panda()
+    e = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
+    fl = CHECK_ROBOT | CHECK_INTRA
+    for n in (100, 40_000):
+        q = scenarios.chomp_trajectories(desc, n // 100, 100).reshape(-1, desc.nvar)
+        S = int(e.group.n_spheres)
+        qd = torch.from_numpy(q).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        for dt, fn, kw in ((torch.float64, B.load().b200df_gradients_batch_device, {}),
+                           (torch.float32, B.load().b200df_gradients_batch_device_f32, dict(out_dtype=np.float32))):
+            dd = torch.empty((n, S), dtype=dt, device="cuda")
+            gd = torch.empty((n, S, 3), dtype=dt, device="cuda")
+            td = torch.empty((n, S), dtype=torch.uint8, device="cuda")
+            cd = torch.empty((n, S, 3), dtype=dt, device="cuda")
+            B.check(fn(e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F64, n, fl, C.c_void_p(dd.data_ptr()),
+                       C.c_void_p(gd.data_ptr()), C.c_void_p(td.data_ptr()), C.c_void_p(cd.data_ptr()), C.c_void_p(st)))
+            torch.cuda.synchronize()
+            host = e.group.gradients(q, e.world, flags=fl, **kw)  # pageable outputs
+            pin = {k: torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory().numpy() for k, v in host.items()}
+            e.group.gradients(q, e.world, flags=fl, out=pin, **kw)
+            for got in (host, pin):
+                assert np.array_equal(got["dist"], dd.cpu().numpy()) and np.array_equal(got["grad"], gd.cpu().numpy())
+                assert np.array_equal(got["type"], td.cpu().numpy()) and np.array_equal(got["centers"], cd.cpu().numpy())
+
+
 def test_gradients_with_link_distance_fields(gpu, oracle):
     """getSelfProximityGradients' per-link PosedDistanceField term (:395-418), including the reference's quirks: the
     gradient is mapped with the full pose (rotation + translation, Q6) and a link's sphere loop stops at the first
