@@ -1246,7 +1246,11 @@ int launch_fast(const b200df_group* g, const FieldDev& wf, const FieldDev& sf, c
 namespace
 {
 // smallest batch the two-pass form is used for: below it the second launch and the list cost more than they save
-constexpr long kTwoPassMinStates = 1L << 18;
+// (B200DF_FAST_TWO_PASS_MIN overrides: measurement knob; 65 536 states: fused 0.073 ms, two passes 0.090; 131 072: 0.124
+// against 0.107; 200 000: 0.173 against 0.163)
+constexpr long kTwoPassMinStatesDefault = 1L << 17;
+static const long kTwoPassMinStates =
+    getenv("B200DF_FAST_TWO_PASS_MIN") ? atol(getenv("B200DF_FAST_TWO_PASS_MIN")) : kTwoPassMinStatesDefault;
 
 bool two_pass_enabled()
 {

@@ -247,7 +247,7 @@ def test_group_with_self_field(gpu, oracle):
 
 def test_two_pass_fast_equals_exact_and_oracle(gpu, oracle):
     """Large FAST batches run in two passes (field lookups of every state, then the sphere pairs of the states left at
-    0 through a device-side list).  Batches just above the switch-over (2^18 states, a ragged tail, fp32 and fp64 rows,
+    0 through a device-side list).  Batches above the switch-over at 2^17 states (2^18 + a ragged tail, fp32 and fp64 rows,
     world only / world + self field) against the fp64 kernel on every state and against the oracle on a slice; the
     colliding set must not depend on which form ran (the same states in a batch below the switch-over)."""
     from moveit_b200.binding import PRECISION_FAST, PRECISION_EXACT

@@ -20,7 +20,7 @@ def main():
     desc = rd.panda()
     e = EngineSetup(desc, scenarios.FIELD_A, scenarios.random_scene())
     fl = B.CHECK_ROBOT | B.CHECK_INTRA
-    n = 1 << 18  # the smallest batch that takes the two-pass FAST form
+    n = 1 << 18  # large enough for the two-pass FAST form (>= 2^17 states)
     q = desc.sample_states(n + 1000, scenarios.SEED_STATES, np.float32)
     fast = e.group.check(q[:n], e.world, flags=fl, precision=B.PRECISION_FAST)
     exact = e.group.check(q[:n], e.world, flags=fl, precision=B.PRECISION_EXACT)
