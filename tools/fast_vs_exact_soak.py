@@ -33,12 +33,17 @@ def main(batches=10, n=10_000_000):
     seed, n_links, floating, kw = FUZZ_CASES[4]  # the floating-root tree of the fuzz tests (quaternion joint in FAST)
     cases.append(("fuzz_floating_root", random_robot(100 + seed, n_links, floating, **kw), scenarios.FIELD_DEFAULT,
                   scenarios.random_scene(seed=200 + seed, n_boxes=6, n_cylinders=3)))
+    # the PR2-like tree, self-collision only (72 % colliding): FAST runs its pair tests one warp per state there
+    cases.append(("pr2_like_self_collision", rd.pr2_like(), scenarios.FIELD_DEFAULT, None))
+    n_full = n
     for name, desc, field, objs in cases:
-        e = EngineSetup(desc, field, objs)
+        self_only = objs is None
+        n = max(1, n_full // 10) if self_only else n_full  # the fp64 kernels take 40 ms per million states of this tree
+        e = EngineSetup(desc, field, objs or [])
         lo = np.array([l[0] for l in desc.limits], dtype=np.float32)
         hi = np.array([l[1] for l in desc.limits], dtype=np.float32)
         lo_t, hi_t = torch.from_numpy(lo).cuda(), torch.from_numpy(hi).cuda()
-        flags = B.CHECK_ROBOT | B.CHECK_INTRA
+        flags = B.CHECK_INTRA if self_only else B.CHECK_ROBOT | B.CHECK_INTRA
         for b in range(batches):
             g = torch.Generator(device="cuda")
             g.manual_seed(1000 * (b + 1) + len(name))
@@ -51,7 +56,8 @@ def main(batches=10, n=10_000_000):
             v = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(4)]
             # 4 = the one-CTA-per-state kernel (what small batches run on), forced at this batch size
             for k, prec in enumerate((B.PRECISION_EXACT, B.PRECISION_FAST, 3, 4)):
-                e.group.check_device(q.data_ptr(), B.Q_F32, n, v[k].data_ptr(), e.world, None, flags, prec, stream)
+                e.group.check_device(q.data_ptr(), B.Q_F32, n, v[k].data_ptr(), None if self_only else e.world, None, flags,
+                                     prec, stream)
             torch.cuda.synchronize()
             diff = int((v[0] != v[1]).sum().item()) + int((v[0] != v[3]).sum().item())
             und = float((v[2] == 2).sum().item()) / n
