@@ -26,7 +26,7 @@ def main():
     vd = torch.empty(n, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     run = lambda: B.check(B.load().b200df_check_batch_device(
-        e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F32, n, fl, B.PRECISION_FAST,
+        e.group.h, e.world.h, None, C.c_void_p(qd.data_ptr()), B.Q_F32, n, fl, int(os.environ.get("FAST_LOOP_PRECISION", B.PRECISION_FAST)),
         C.c_void_p(vd.data_ptr()), C.c_void_p(st)))
     for _ in range(3):
         run()
